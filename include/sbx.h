@@ -1,0 +1,202 @@
+/*
+ * sbx.h -- C ABI of the B200 (sm_100a) spectrogram frame transform.
+ *
+ * Drop-in boundary for spectrogram-rs's frame path.  Every entry point names the reference
+ * interface it replaces (paths relative to the reference repository root).  Plain pointers and
+ * sizes only; no C++/torch types; never throws or aborts across the boundary -- every failure is
+ * an sbx_status plus a message retrievable with sbx_last_error().
+ *
+ * Symbols:  N = window length in samples, P = pad factor, M = P*N = FFT length,
+ *           K = M/2 - 1 output bins (N-1 at the reference's P = 2), H = output rows.
+ *
+ * Threading: a plan is NOT thread-safe (one plan <-> one CUDA stream <-> one caller at a time,
+ * like the reference's `&mut self`); distinct plans are independent.
+ */
+#ifndef SBX_H
+#define SBX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define SBX_API __declspec(dllexport)
+#else
+#define SBX_API __attribute__((visibility("default")))
+#endif
+
+#define SBX_ABI_VERSION 1u
+
+typedef struct sbx_plan sbx_plan;   /* opaque; owns device tables, scratch and a CUDA stream */
+typedef struct sbx_live sbx_live;   /* opaque; pinned ring + CUDA graph for one live stream */
+typedef int32_t sbx_status;
+
+enum {
+    SBX_OK = 0,
+    SBX_NOT_ENOUGH_SAMPLES = 1,   /* the reference's `None` (src/fourier/fft.rs:72) */
+    SBX_ERR_INVALID_ARGUMENT = -1,
+    SBX_ERR_UNSUPPORTED = -2,     /* configuration outside what the kernels cover */
+    SBX_ERR_CUDA = -3,            /* CUDA runtime / driver failure, or no usable GPU */
+    SBX_ERR_OUT_OF_MEMORY = -4,
+    SBX_ERR_BUFFER_TOO_SMALL = -5
+};
+
+enum { SBX_INTERP_CUBIC = 0,      /* cubic_interpolate, the interpolator the reference wires in
+                                     (src/fourier/interpolated_frequency_sample.rs:46-48,88-105) */
+       SBX_INTERP_COSINE = 1 };   /* cosine_interpolate (ibid. :78-86; README behaviour) */
+
+enum { SBX_SCHEME_MONO = 0,       /* ColorScheme::new_mono: colour = gradient(dB), alpha = 255
+                                     (src/colorscheme.rs:67-70) */
+       SBX_SCHEME_STEREO = 1 };   /* ColorScheme::new_stereo: colour = gradient(l/(|l|+|r|)),
+                                     alpha = normalised dB (src/colorscheme.rs:63-66) */
+
+/*
+ * Everything the reference hard-codes as literals (SURVEY.md section 5 "Config"), as one struct.
+ * Fill with sbx_config_default() first, then override.
+ */
+typedef struct sbx_config {
+    uint32_t struct_size;   /* = sizeof(sbx_config); ABI guard */
+    uint32_t abi_version;   /* = SBX_ABI_VERSION */
+    float    sample_rate;   /* Hz.  FastFourierTransform::new(sample_rate, ..) src/fourier/fft.rs:18 */
+    uint32_t window_n;      /* N = (period * sample_rate) as usize, src/fourier/fft.rs:19,41 */
+    uint32_t pad_factor;    /* P; the reference hard-codes 2 (src/fourier/fft.rs:21,44) */
+    uint32_t hop;           /* (stride * sample_rate) as usize, src/fourier/audio_transform.rs:35 */
+    uint32_t rows_h;        /* H; TEXTURE_HEIGHT = 1024, src/widgets/simple_spectrogram.rs:35 */
+    uint32_t channels;      /* PCM layout of the BATCH/LIVE entry points: 1 = mono (treated as the
+                               (s,s) duplication of src/devices/audio_input_list_model.rs:66-69),
+                               2 = interleaved (l,r).  The single-frame entry points always take
+                               interleaved (l,r) like AudioTransform::process. */
+    double   f_min, f_max;  /* 32.0 .. 22030.0, src/widgets/simple_spectrogram.rs:107 */
+    float    db_min, db_max;/* -70, -10, src/colorscheme.rs:16-17 */
+    float    db_eps;        /* 1e-7, src/colorscheme.rs:60 */
+    uint32_t interp;        /* SBX_INTERP_* */
+    uint32_t scheme;        /* SBX_SCHEME_* */
+    int32_t  device;        /* CUDA device ordinal */
+    uint32_t reserved;
+    uint8_t  lut_rgb[768];  /* 256 x (r,g,b): gradient.eval_continuous((i+0.5)/256), i = 0..255
+                               (src/colorscheme.rs:69).  See sbx_builtin_lut(). */
+} sbx_config;
+
+/* Reference defaults: 48 kHz, N 4096, P 2, hop 512, H 1024, 32..22030 Hz, -70..-10 dB, eps 1e-7,
+ * CUBIC, mono scheme, Magma, stereo PCM, device 0. */
+SBX_API void sbx_config_default(sbx_config *cfg);
+
+/* Built-in 256-entry ramps: "magma", "viridis", "inferno", "plasma"
+ * (src/colorscheme.rs:131-132,138-139).  Returns SBX_ERR_INVALID_ARGUMENT for other names. */
+SBX_API sbx_status sbx_builtin_lut(const char *name, uint8_t lut_rgb[768]);
+
+/* (period * sample_rate) as usize -- src/fourier/fft.rs:19,41 -- and
+ * (stride * sample_rate) as usize -- src/fourier/audio_transform.rs:35 (f32 multiply, truncation). */
+SBX_API uint32_t sbx_samples_from_seconds(float seconds, float sample_rate);
+
+/* ---- plan lifetime: replaces FastFourierTransform::new (src/fourier/fft.rs:18-31), which
+ * re-plans FFTW on every sample-rate change (src/widgets/simple_spectrogram.rs:214-219). ---- */
+SBX_API sbx_status sbx_plan_create(const sbx_config *cfg, sbx_plan **out_plan);
+SBX_API void       sbx_plan_destroy(sbx_plan *plan);
+
+/* Message for the last failing call on this plan (plan may be NULL: last error of a failed
+ * sbx_plan_create on this thread).  Never NULL. */
+SBX_API const char *sbx_last_error(const sbx_plan *plan);
+
+/* AudioTransform::sample_rate / num_input_samples (src/fourier/audio_transform.rs:7-8),
+ * FastFourierTransform::num_output_frequencies (src/fourier/fft.rs:33). */
+SBX_API float    sbx_sample_rate(const sbx_plan *plan);
+SBX_API uint32_t sbx_num_input_samples(const sbx_plan *plan);       /* N */
+SBX_API uint32_t sbx_num_output_frequencies(const sbx_plan *plan);  /* K */
+SBX_API uint32_t sbx_fft_length(const sbx_plan *plan);              /* M */
+SBX_API uint32_t sbx_rows(const sbx_plan *plan);                    /* H */
+SBX_API uint32_t sbx_hop(const sbx_plan *plan);
+SBX_API uint32_t sbx_channels(const sbx_plan *plan);
+
+/* Frames the sliding window yields over n_samples samples: frame f covers [f*hop, f*hop+N)
+ * (src/fourier/audio_transform.rs:37-41). */
+SBX_API uint64_t sbx_num_frames(const sbx_plan *plan, uint64_t n_samples);
+
+/* ---- single frame, HOST buffers ---------------------------------------------------------- */
+
+/* Exact drop-in for FastFourierTransform::process (src/fourier/fft.rs:43-99).
+ * lr: n_avail interleaved (l,r) samples (only the first N are used); out_lr: K interleaved (L,R).
+ * Returns SBX_NOT_ENOUGH_SAMPLES when n_avail < N (the reference's None). */
+SBX_API sbx_status sbx_process_magnitudes(sbx_plan *plan, const float *lr, uint32_t n_avail, float *out_lr);
+
+/* Replaces the body of SimpleSpectrogram::snapshot's frame loop
+ * (src/widgets/simple_spectrogram.rs:136-161): one frame -> one RGBA8 column of H rows,
+ * rgba[4*row], row 0 = top = highest frequency (the `height - py - 1` flip at :150). */
+SBX_API sbx_status sbx_process_column(sbx_plan *plan, const float *lr, uint32_t n_avail, uint8_t *rgba);
+
+/* InterpolatedFrequencySample::magnitude_in + ColorScheme::color_for on caller-supplied spectra
+ * (src/fourier/interpolated_frequency_sample.rs:60-75, src/colorscheme.rs:55-71):
+ * mags_lr = n_frames x K x (L,R)  ->  rgba = n_frames x H x 4.  This is the "identical
+ * normalised inputs" entry point of the bit-exactness contract. */
+SBX_API sbx_status sbx_colorize_magnitudes(sbx_plan *plan, const float *mags_lr, uint64_t n_frames, uint8_t *rgba);
+
+/* ---- offline batch ------------------------------------------------------------------------ */
+
+/* AudioStreamTransform::process (src/fourier/audio_transform.rs:34-42) + the column loop over a
+ * whole recording.  pcm: n_samples x channels f32 (HOST memory, pinned or pageable);
+ * rgba: frames x H x 4, frame-major (frame f's column at rgba + f*H*4).  Host<->device copies are
+ * chunked and overlapped inside the call.  *frames_out = frames written. */
+SBX_API sbx_status sbx_process_batch(sbx_plan *plan, const float *pcm, uint64_t n_samples,
+                                     uint8_t *rgba, uint64_t rgba_capacity_frames, uint64_t *frames_out);
+
+/* Same, DEVICE pointers, asynchronous on the plan's stream (sbx_synchronize() to wait).
+ * d_pcm must be 16-byte aligned. */
+SBX_API sbx_status sbx_process_batch_device(sbx_plan *plan, const float *d_pcm, uint64_t n_samples,
+                                            uint8_t *d_rgba, uint64_t rgba_capacity_frames, uint64_t *frames_out);
+
+/* Batched FastFourierTransform::process: DEVICE pointers, d_mags_lr = frames x K x (L,R).
+ * (Also the feed format of GPUSpectrogram's texture upload, src/widgets/gpu_spectrogram.rs:255-275.) */
+SBX_API sbx_status sbx_magnitudes_batch_device(sbx_plan *plan, const float *d_pcm, uint64_t n_samples,
+                                               float *d_mags_lr, uint64_t capacity_frames, uint64_t *frames_out);
+
+/* ---- streams ------------------------------------------------------------------------------ */
+/* Use the caller's CUDA stream (a cudaStream_t passed as void*; NULL restores the plan's own). */
+SBX_API sbx_status sbx_set_stream(sbx_plan *plan, void *cuda_stream);
+SBX_API sbx_status sbx_synchronize(sbx_plan *plan);
+/* Kernel launches issued by this plan since creation (bench.py's gpu_launches evidence). */
+SBX_API uint64_t   sbx_launch_count(const sbx_plan *plan);
+
+/* ---- introspection for the bit-exactness tests ------------------------------------------- */
+/* The log-frequency bin map the plan computed on the host: per row py (0 = lowest frequency)
+ * the sampling plan of magnitude_in(f0..f1): first sample frequency f0, step (f1-f0)/n, count n
+ * (src/log_scaling.rs:114-119, src/fourier/interpolated_frequency_sample.rs:60-67).
+ * Any output pointer may be NULL.  Arrays have H entries. */
+SBX_API sbx_status sbx_get_bin_map(const sbx_plan *plan, float *f0, float *step, uint32_t *n, float *period);
+/* 255 power thresholds: LUT index of power p is #{i : p >= thr[i]} -- the exact step function
+ * of color_for's dB/normalise/floor(t*256) chain (src/colorscheme.rs:59-61,69). */
+SBX_API sbx_status sbx_get_color_thresholds(const sbx_plan *plan, float thr[255]);
+/* The f32 periodic Hann window the plan uploaded (src/fourier/fft.rs:59-63); N entries. */
+SBX_API sbx_status sbx_get_window(const sbx_plan *plan, float *w);
+
+/* ---- live path: the SPSC ring + hop cursor of L1/L2 --------------------------------------- */
+/* Pinned-host ring of (l,r) samples (capacity as HeapRb::new(4096),
+ * src/devices/audio_input_list_model.rs:30) with AudioStreamTransform's cursor semantics
+ * (src/fourier/audio_transform.rs:34-42) and one captured CUDA graph
+ * (H2D -> fused kernel -> D2H) per frame. */
+SBX_API sbx_status sbx_live_create(sbx_plan *plan, uint32_t ring_capacity_samples, sbx_live **out_live);
+SBX_API void       sbx_live_destroy(sbx_live *live);
+/* Producer side (the cpal callback, src/devices/audio_input_list_model.rs:66-72): pushes up to
+ * n_samples frames of `channels` floats (mono is duplicated to (s,s)); returns how many fit. */
+SBX_API uint32_t   sbx_live_push(sbx_live *live, const float *samples, uint32_t n_samples, uint32_t channels);
+/* Consumer side: one iteration of AudioStreamTransform::process's closure -- transform the first
+ * N buffered samples without consuming them, then skip(hop) (also when the frame failed, as the
+ * reference does).  SBX_OK + one RGBA column, or SBX_NOT_ENOUGH_SAMPLES. */
+SBX_API sbx_status sbx_live_pop_column(sbx_live *live, uint8_t *rgba);
+SBX_API sbx_status sbx_live_pop_magnitudes(sbx_live *live, float *out_lr);
+SBX_API uint32_t   sbx_live_buffered(const sbx_live *live);
+
+/* ---- pinned host memory helpers (for callers without a CUDA binding) --------------------- */
+SBX_API void *sbx_host_alloc(size_t bytes);
+SBX_API void  sbx_host_free(void *p);
+
+/* Library/ABI version and the SM architecture the kernels were compiled for ("sm_100a"). */
+SBX_API uint32_t    sbx_abi_version(void);
+SBX_API const char *sbx_build_arch(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SBX_H */

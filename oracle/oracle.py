@@ -1,0 +1,199 @@
+"""ctypes loader for the CPU oracle (oracle/stft_oracle.c).  TEST INFRASTRUCTURE: imported only by
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liboracle.so")
+
+INTERP_CUBIC, INTERP_COSINE = 0, 1
+
+
+class OrcParams(C.Structure):
+    _fields_ = [("sample_rate", C.c_float), ("window_n", C.c_uint32), ("pad_factor", C.c_uint32),
+                ("hop", C.c_uint32), ("rows_h", C.c_uint32), ("f_min", C.c_double), ("f_max", C.c_double),
+                ("db_min", C.c_float), ("db_max", C.c_float), ("db_eps", C.c_float),
+                ("interp", C.c_uint32), ("stereo_scheme", C.c_uint32)]
+
+
+def build(force=False):
+    src = os.path.join(HERE, "stft_oracle.c")
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", HERE, "-B", "liboracle.so"], check=True, capture_output=True)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB_PATH)
+        f32p, u8p, u32p = C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.POINTER(C.c_uint32)
+        L.orc_hann.restype = C.c_float
+        L.orc_hann.argtypes = [C.c_uint32, C.c_uint32]
+        L.orc_num_output_frequencies.restype = C.c_uint32
+        L.orc_num_output_frequencies.argtypes = [C.c_uint32, C.c_uint32]
+        L.orc_frame_magnitudes.restype = C.c_int
+        L.orc_frame_magnitudes.argtypes = [f32p, C.c_uint32, C.c_uint32, C.c_uint32, f32p]
+        L.orc_window_pad.restype = None
+        L.orc_window_pad.argtypes = [f32p, C.c_uint32, C.c_uint32, f32p]
+        L.orc_split_scale.restype = None
+        L.orc_split_scale.argtypes = [f32p, C.c_uint32, C.c_uint32, f32p]
+        L.orc_fft_c2c_f32.restype = C.c_int
+        L.orc_fft_c2c_f32.argtypes = [f32p, f32p, C.c_uint32]
+        L.orc_row_edge.restype = C.c_float
+        L.orc_row_edge.argtypes = [C.c_double, C.c_double, C.c_uint32, C.c_uint32]
+        L.orc_period.restype = C.c_float
+        L.orc_period.argtypes = [C.c_uint32, C.c_float]
+        L.orc_bin_map_row.restype = None
+        L.orc_bin_map_row.argtypes = [C.c_double, C.c_double, C.c_uint32, C.c_uint32, C.c_float, C.c_uint32,
+                                      f32p, f32p, u32p]
+        L.orc_normalised_db.restype = C.c_float
+        L.orc_normalised_db.argtypes = [C.c_float] * 5
+        L.orc_gradient_index.restype = C.c_uint32
+        L.orc_gradient_index.argtypes = [C.c_float]
+        L.orc_color_index.restype = C.c_uint32
+        L.orc_color_index.argtypes = [C.c_float] * 5
+        L.orc_column_from_magnitudes.restype = None
+        L.orc_column_from_magnitudes.argtypes = [C.POINTER(OrcParams), f32p, u8p, u8p]
+        L.orc_rows_from_magnitudes.restype = None
+        L.orc_rows_from_magnitudes.argtypes = [C.POINTER(OrcParams), f32p, f32p]
+        L.orc_column.restype = C.c_int
+        L.orc_column.argtypes = [C.POINTER(OrcParams), f32p, C.c_uint32, u8p, u8p]
+        L.orc_num_frames.restype = C.c_uint64
+        L.orc_num_frames.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32]
+        L.orc_hop_from_stride.restype = C.c_uint32
+        L.orc_hop_from_stride.argtypes = [C.c_float, C.c_float]
+        L.orc_window_from_period.restype = C.c_uint32
+        L.orc_window_from_period.argtypes = [C.c_float, C.c_float]
+        L.orc_batch.restype = C.c_int64
+        L.orc_batch.argtypes = [C.POINTER(OrcParams), f32p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64,
+                                u8p, u8p, f32p, C.c_int]
+        L.orc_max_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _f32(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _u8(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def params(sample_rate=48000.0, window_n=4096, pad_factor=2, hop=512, rows_h=1024, f_min=32.0, f_max=22030.0,
+           db_min=-70.0, db_max=-10.0, db_eps=1e-7, interp=INTERP_CUBIC, stereo_scheme=0):
+    return OrcParams(sample_rate, window_n, pad_factor, hop, rows_h, f_min, f_max, db_min, db_max, db_eps,
+                     interp, stereo_scheme)
+
+
+def num_output_frequencies(n, pad):
+    return int(lib().orc_num_output_frequencies(n, pad))
+
+
+def hann(n):
+    L = lib()
+    return np.array([L.orc_hann(i, n) for i in range(n)], dtype=np.float32)
+
+
+def frame_magnitudes(lr, n, pad):
+    """lr: (>=n, 2) float32.  Returns (K, 2) float32 or None (the reference's None)."""
+    lr = np.ascontiguousarray(lr, dtype=np.float32)
+    out = np.empty((num_output_frequencies(n, pad), 2), dtype=np.float32)
+    st = lib().orc_frame_magnitudes(_f32(lr), lr.shape[0], n, pad, _f32(out))
+    if st == 1:
+        return None
+    if st != 0:
+        raise RuntimeError("orc_frame_magnitudes failed")
+    return out
+
+
+def window_pad(lr, n, pad):
+    lr = np.ascontiguousarray(lr, dtype=np.float32)
+    z = np.empty((n * pad, 2), dtype=np.float32)
+    lib().orc_window_pad(_f32(lr), n, pad, _f32(z))
+    return z
+
+
+def split_scale(zf, n, pad):
+    zf = np.ascontiguousarray(zf, dtype=np.float32)
+    out = np.empty((num_output_frequencies(n, pad), 2), dtype=np.float32)
+    lib().orc_split_scale(_f32(zf), n, pad, _f32(out))
+    return out
+
+
+def fft_c2c_f32(z):
+    z = np.ascontiguousarray(z, dtype=np.float32)
+    out = np.empty_like(z)
+    if lib().orc_fft_c2c_f32(_f32(z), _f32(out), z.shape[0]) != 0:
+        raise RuntimeError("orc_fft_c2c_f32 failed")
+    return out
+
+
+def bin_map(p):
+    """Returns (f0, step, n, period) arrays for every row of the params' log-frequency map."""
+    L = lib()
+    k = num_output_frequencies(p.window_n, p.pad_factor)
+    period = L.orc_period(k, p.sample_rate)
+    f0 = np.empty(p.rows_h, np.float32)
+    step = np.empty(p.rows_h, np.float32)
+    n = np.empty(p.rows_h, np.uint32)
+    a, b, c = C.c_float(), C.c_float(), C.c_uint32()
+    for py in range(p.rows_h):
+        L.orc_bin_map_row(p.f_min, p.f_max, py, p.rows_h, period, k, C.byref(a), C.byref(b), C.byref(c))
+        f0[py], step[py], n[py] = a.value, b.value, c.value
+    return f0, step, n, np.float32(period)
+
+
+def column_from_magnitudes(p, mags_lr, lut_rgb):
+    mags_lr = np.ascontiguousarray(mags_lr, dtype=np.float32)
+    lut_rgb = np.ascontiguousarray(lut_rgb, dtype=np.uint8)
+    out = np.empty((p.rows_h, 4), dtype=np.uint8)
+    lib().orc_column_from_magnitudes(C.byref(p), _f32(mags_lr), _u8(lut_rgb), _u8(out))
+    return out
+
+
+def rows_from_magnitudes(p, mags_lr):
+    mags_lr = np.ascontiguousarray(mags_lr, dtype=np.float32)
+    out = np.empty((p.rows_h, 2), dtype=np.float32)
+    lib().orc_rows_from_magnitudes(C.byref(p), _f32(mags_lr), _f32(out))
+    return out
+
+
+def color_index(l, r, db_min=-70.0, db_max=-10.0, db_eps=1e-7):
+    return int(lib().orc_color_index(l, r, db_min, db_max, db_eps))
+
+
+def num_frames(n_samples, n, hop):
+    return int(lib().orc_num_frames(n_samples, n, hop))
+
+
+def batch(p, pcm, channels, lut_rgb, want_rgba=True, want_mags=False, frame_lo=0, frame_hi=None, threads=1):
+    """pcm: float32 (n_samples,) mono or (n_samples, 2).  Returns (rgba or None, mags or None)."""
+    pcm = np.ascontiguousarray(pcm, dtype=np.float32)
+    n_samples = pcm.shape[0]
+    total = num_frames(n_samples, p.window_n, p.hop)
+    if frame_hi is None or frame_hi > total:
+        frame_hi = total
+    count = max(0, frame_hi - frame_lo)
+    k = num_output_frequencies(p.window_n, p.pad_factor)
+    rgba = np.empty((count, p.rows_h, 4), np.uint8) if want_rgba else None
+    mags = np.empty((count, k, 2), np.float32) if want_mags else None
+    lut_rgb = np.ascontiguousarray(lut_rgb, dtype=np.uint8)
+    if count:
+        got = lib().orc_batch(C.byref(p), _f32(pcm), n_samples, channels, frame_lo, frame_hi, _u8(lut_rgb),
+                              _u8(rgba) if want_rgba else None, _f32(mags) if want_mags else None, threads)
+        if got != count:
+            raise RuntimeError(f"orc_batch returned {got}, expected {count}")
+    return rgba, mags
+
+
+def max_threads():
+    return int(lib().orc_max_threads())

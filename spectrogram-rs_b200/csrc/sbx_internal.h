@@ -1,0 +1,68 @@
+// sbx_internal.h -- host-side plan object shared by sbx_plan.cu and sbx_live.cu (not installed).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/sbx.h"
+#include "stft_kernels.cuh"
+
+struct sbx_plan {
+    sbx_config cfg;
+    uint32_t n, pad, m, k_out, rows, hop, channels;
+    int log2n, log2pad;
+    float period, scale;
+
+    // host copies of the tables (for introspection and the bit-exactness tests)
+    std::vector<float> h_window;
+    std::vector<sbx::RowMap> h_rowmap;
+    std::vector<float> h_thr;           // 512
+    std::vector<float> h_cos_w;
+
+    // device tables
+    float *d_window = nullptr;
+    float2 *d_tw = nullptr;
+    sbx::RowMap *d_rowmap = nullptr;
+    float *d_cos_w = nullptr;
+    float *d_thr = nullptr;
+    uint32_t *d_lut = nullptr;
+
+    // single-frame staging (host pinned + device)
+    float *h_frame = nullptr;           // N x 2 floats in, reused for K x 2 out
+    uint8_t *h_col = nullptr;           // H x 4
+    float *d_frame = nullptr;           // N x 2
+    float *d_mags1 = nullptr;           // K x 2
+    uint8_t *d_col = nullptr;           // H x 4
+
+    // batch pipeline slots (host-pointer batch entry point)
+    static constexpr int kSlots = 3;
+    struct Slot {
+        cudaStream_t stream = nullptr;
+        float *d_pcm = nullptr;
+        uint8_t *d_rgba = nullptr;
+        float *h_pcm = nullptr;         // pinned bounce buffers (used when the caller's memory is pageable)
+        uint8_t *h_rgba = nullptr;
+        cudaEvent_t done = nullptr;
+        // pending pageable copy-out
+        uint8_t *pending_dst = nullptr;
+        size_t pending_bytes = 0;
+    } slots[kSlots];
+    uint64_t chunk_frames = 0;
+
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;      // current stream (own or caller's)
+    uint64_t launches = 0;
+    mutable std::string last_error;
+
+    sbx::KernelArgs base_args() const;
+};
+
+namespace sbx {
+// launches the fused kernel for `channels`-layout PCM on `stream`
+sbx_status launch_fused(sbx_plan *p, int channels, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba,
+                        float *d_mags, cudaStream_t stream);
+sbx_status launch_colourise(sbx_plan *p, const float *d_mags, uint64_t n_frames, uint8_t *d_rgba, cudaStream_t stream);
+sbx_status fail(const sbx_plan *p, sbx_status st, const std::string &msg);
+sbx_status cuda_fail(const sbx_plan *p, cudaError_t e, const char *what);
+}  // namespace sbx

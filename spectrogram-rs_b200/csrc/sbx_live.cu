@@ -1,0 +1,175 @@
+// sbx_live.cu -- the live path: a pinned-host SPSC ring of (l,r) samples with the cursor semantics
+// of AudioStreamTransform::process (src/fourier/audio_transform.rs:34-42) and one captured CUDA
+// graph (H2D copy -> fused kernel -> D2H copy) per frame.
+//
+// Producer = the audio callback thread (src/devices/audio_input_list_model.rs:63-79), consumer =
+// the draw thread; exactly one of each, as in the reference (HeapRb::new(4096).split()).
+#include <atomic>
+#include <cstring>
+#include <new>
+
+#include "sbx_internal.h"
+
+struct sbx_live {
+    sbx_plan *plan = nullptr;
+    uint32_t capacity = 0;                 // samples
+    float *ring = nullptr;                 // pinned, capacity x (l,r)
+    std::atomic<uint64_t> head{0};         // total samples consumed
+    std::atomic<uint64_t> tail{0};         // total samples produced
+    float *h_in = nullptr;                 // pinned linearised window, N x 2
+    float *h_mags = nullptr;               // pinned K x 2
+    uint8_t *h_col = nullptr;              // pinned H x 4
+    float *d_in = nullptr;
+    float *d_mags = nullptr;
+    uint8_t *d_col = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaGraphExec_t graph_col = nullptr, graph_mags = nullptr;
+};
+
+using sbx::cuda_fail;
+using sbx::fail;
+
+#define SBX_CUDA(plan, call)                                              \
+    do {                                                                  \
+        cudaError_t e__ = (call);                                         \
+        if (e__ != cudaSuccess) return cuda_fail((plan), e__, #call);     \
+    } while (0)
+
+static sbx_status build_graph(sbx_live *lv, bool column, cudaGraphExec_t *out)
+{
+    sbx_plan *p = lv->plan;
+    cudaGraph_t graph = nullptr;
+    SBX_CUDA(p, cudaStreamBeginCapture(lv->stream, cudaStreamCaptureModeThreadLocal));
+    cudaError_t e = cudaMemcpyAsync(lv->d_in, lv->h_in, (size_t)p->n * 2 * sizeof(float), cudaMemcpyHostToDevice, lv->stream);
+    sbx_status st = SBX_OK;
+    if (e == cudaSuccess)
+        st = sbx::launch_fused(p, 2, lv->d_in, 1, column ? lv->d_col : nullptr, column ? nullptr : lv->d_mags, lv->stream);
+    if (e == cudaSuccess && st == SBX_OK) {
+        e = column ? cudaMemcpyAsync(lv->h_col, lv->d_col, (size_t)p->rows * 4, cudaMemcpyDeviceToHost, lv->stream)
+                   : cudaMemcpyAsync(lv->h_mags, lv->d_mags, (size_t)p->k_out * 2 * sizeof(float), cudaMemcpyDeviceToHost, lv->stream);
+    }
+    cudaError_t e_end = cudaStreamEndCapture(lv->stream, &graph);
+    if (st != SBX_OK) { if (graph) cudaGraphDestroy(graph); return st; }
+    if (e != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return cuda_fail(p, e, "live graph capture"); }
+    if (e_end != cudaSuccess) return cuda_fail(p, e_end, "cudaStreamEndCapture");
+    e = cudaGraphInstantiate(out, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return cuda_fail(p, e, "cudaGraphInstantiate");
+    p->launches -= 1;                       // the captured launch did not execute
+    return SBX_OK;
+}
+
+extern "C" {
+
+SBX_API void sbx_live_destroy(sbx_live *lv)
+{
+    if (!lv) return;
+    if (lv->plan) cudaSetDevice(lv->plan->cfg.device);
+    if (lv->stream) cudaStreamSynchronize(lv->stream);
+    if (lv->graph_col) cudaGraphExecDestroy(lv->graph_col);
+    if (lv->graph_mags) cudaGraphExecDestroy(lv->graph_mags);
+    if (lv->ring) cudaFreeHost(lv->ring);
+    if (lv->h_in) cudaFreeHost(lv->h_in);
+    if (lv->h_mags) cudaFreeHost(lv->h_mags);
+    if (lv->h_col) cudaFreeHost(lv->h_col);
+    cudaFree(lv->d_in); cudaFree(lv->d_mags); cudaFree(lv->d_col);
+    if (lv->stream) cudaStreamDestroy(lv->stream);
+    delete lv;
+}
+
+SBX_API sbx_status sbx_live_create(sbx_plan *p, uint32_t ring_capacity_samples, sbx_live **out_live)
+{
+    if (out_live) *out_live = nullptr;
+    if (!p || !out_live) return SBX_ERR_INVALID_ARGUMENT;
+    if (ring_capacity_samples == 0) return fail(p, SBX_ERR_INVALID_ARGUMENT, "ring capacity must be >= 1");
+    SBX_CUDA(p, cudaSetDevice(p->cfg.device));
+    sbx_live *lv = new (std::nothrow) sbx_live();
+    if (!lv) return fail(p, SBX_ERR_OUT_OF_MEMORY, "out of host memory");
+    lv->plan = p;
+    lv->capacity = ring_capacity_samples;
+    cudaError_t e = cudaMallocHost(&lv->ring, (size_t)lv->capacity * 2 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMallocHost(&lv->h_in, (size_t)p->n * 2 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMallocHost(&lv->h_mags, (size_t)p->k_out * 2 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMallocHost(&lv->h_col, (size_t)p->rows * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&lv->d_in, (size_t)p->n * 2 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&lv->d_mags, (size_t)p->k_out * 2 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&lv->d_col, (size_t)p->rows * 4);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&lv->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { sbx_live_destroy(lv); return cuda_fail(p, e, "live buffers"); }
+    // one eager launch configures the kernel attributes outside of stream capture
+    std::memset(lv->h_in, 0, (size_t)p->n * 2 * sizeof(float));
+    e = cudaMemcpyAsync(lv->d_in, lv->h_in, (size_t)p->n * 2 * sizeof(float), cudaMemcpyHostToDevice, lv->stream);
+    sbx_status st = e == cudaSuccess ? sbx::launch_fused(p, 2, lv->d_in, 1, lv->d_col, lv->d_mags, lv->stream) : SBX_ERR_CUDA;
+    if (st == SBX_OK) e = cudaStreamSynchronize(lv->stream);
+    if (st == SBX_OK && e == cudaSuccess) st = build_graph(lv, true, &lv->graph_col);
+    if (st == SBX_OK && e == cudaSuccess) st = build_graph(lv, false, &lv->graph_mags);
+    if (e != cudaSuccess) st = cuda_fail(p, e, "live warm-up");
+    if (st != SBX_OK) { sbx_live_destroy(lv); return st; }
+    *out_live = lv;
+    return SBX_OK;
+}
+
+SBX_API uint32_t sbx_live_buffered(const sbx_live *lv)
+{
+    if (!lv) return 0;
+    return (uint32_t)(lv->tail.load(std::memory_order_acquire) - lv->head.load(std::memory_order_acquire));
+}
+
+// push_iter: writes as many samples as fit, drops the rest (ringbuf Producer::push_iter)
+SBX_API uint32_t sbx_live_push(sbx_live *lv, const float *samples, uint32_t n_samples, uint32_t channels)
+{
+    if (!lv || !samples || (channels != 1 && channels != 2)) return 0;
+    const uint64_t tail = lv->tail.load(std::memory_order_relaxed);
+    const uint64_t head = lv->head.load(std::memory_order_acquire);
+    const uint32_t free_slots = lv->capacity - (uint32_t)(tail - head);
+    const uint32_t n = n_samples < free_slots ? n_samples : free_slots;
+    for (uint32_t i = 0; i < n; ++i) {
+        float *dst = lv->ring + 2 * ((tail + i) % lv->capacity);
+        if (channels == 1) { dst[0] = samples[i]; dst[1] = samples[i]; }      // audio_input_list_model.rs:67
+        else { dst[0] = samples[2 * i]; dst[1] = samples[2 * i + 1]; }        // :70
+    }
+    lv->tail.store(tail + n, std::memory_order_release);
+    return n;
+}
+
+static sbx_status live_pop(sbx_live *lv, uint8_t *rgba, float *out_lr)
+{
+    if (!lv) return SBX_ERR_INVALID_ARGUMENT;
+    sbx_plan *p = lv->plan;
+    const uint64_t head = lv->head.load(std::memory_order_relaxed);
+    const uint64_t tail = lv->tail.load(std::memory_order_acquire);
+    const uint32_t avail = (uint32_t)(tail - head);
+    // input_stream.skip(stride_samples) runs whether or not the frame was produced (audio_transform.rs:38-39)
+    const uint32_t skip = p->hop < avail ? p->hop : avail;
+    if (avail < p->n) {
+        lv->head.store(head + skip, std::memory_order_release);
+        return SBX_NOT_ENOUGH_SAMPLES;
+    }
+    // linearise the window (non-consuming iter(), audio_transform.rs:38)
+    const uint32_t start = (uint32_t)(head % lv->capacity);
+    const uint32_t first = lv->capacity - start < p->n ? lv->capacity - start : p->n;
+    std::memcpy(lv->h_in, lv->ring + 2 * (size_t)start, (size_t)first * 2 * sizeof(float));
+    if (first < p->n) std::memcpy(lv->h_in + 2 * (size_t)first, lv->ring, (size_t)(p->n - first) * 2 * sizeof(float));
+    SBX_CUDA(p, cudaSetDevice(p->cfg.device));
+    SBX_CUDA(p, cudaGraphLaunch(rgba ? lv->graph_col : lv->graph_mags, lv->stream));
+    p->launches += 1;
+    SBX_CUDA(p, cudaStreamSynchronize(lv->stream));
+    if (rgba) std::memcpy(rgba, lv->h_col, (size_t)p->rows * 4);
+    else std::memcpy(out_lr, lv->h_mags, (size_t)p->k_out * 2 * sizeof(float));
+    lv->head.store(head + skip, std::memory_order_release);
+    return SBX_OK;
+}
+
+SBX_API sbx_status sbx_live_pop_column(sbx_live *lv, uint8_t *rgba)
+{
+    if (!lv || !rgba) return SBX_ERR_INVALID_ARGUMENT;
+    return live_pop(lv, rgba, nullptr);
+}
+
+SBX_API sbx_status sbx_live_pop_magnitudes(sbx_live *lv, float *out_lr)
+{
+    if (!lv || !out_lr) return SBX_ERR_INVALID_ARGUMENT;
+    return live_pop(lv, nullptr, out_lr);
+}
+
+}  // extern "C"

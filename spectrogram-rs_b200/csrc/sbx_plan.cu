@@ -1,0 +1,550 @@
+// sbx_plan.cu -- plan construction (host-computed tables), kernel dispatch and the C ABI of
+// include/sbx.h.  No CPU compute fallback exists: every transform entry point launches the sm_100a
+// kernels of stft_kernels.cuh or fails with SBX_ERR_CUDA / SBX_ERR_UNSUPPORTED.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <new>
+
+#include "luts.inc"
+#include "sbx_internal.h"
+#include "sbx_tables.h"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr uint32_t kMinLog2N = 8, kMaxLog2N = 13, kMaxLog2M = 14;
+
+int ilog2_exact(uint32_t v)
+{
+    if (v == 0 || (v & (v - 1)) != 0) return -1;
+    int l = 0;
+    while ((1u << l) < v) ++l;
+    return l;
+}
+
+template <class T> cudaError_t upload(T **dst, const void *src, size_t bytes)
+{
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(dst), bytes ? bytes : 16);
+    if (e != cudaSuccess) return e;
+    return bytes ? cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) : cudaSuccess;
+}
+
+}  // namespace
+
+namespace sbx {
+
+sbx_status fail(const sbx_plan *p, sbx_status st, const std::string &msg)
+{
+    if (p) p->last_error = msg; else g_create_error = msg;
+    return st;
+}
+sbx_status cuda_fail(const sbx_plan *p, cudaError_t e, const char *what)
+{
+    return fail(p, SBX_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+// ---- kernel dispatch ---------------------------------------------------------------------------
+template <int LOG2N, int LOG2PAD, int CH>
+cudaError_t launch_one(const KernelArgs &args, uint64_t n_frames, cudaStream_t stream)
+{
+    using G = Geom<LOG2N, LOG2PAD, CH>;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(fused_frames_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    const uint64_t ctas = (n_frames + G::FRAMES_PER_CTA - 1) / G::FRAMES_PER_CTA;
+    if (ctas == 0) return cudaSuccess;
+    if (ctas > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    fused_frames_kernel<G><<<(unsigned)ctas, G::THREADS, G::SMEM_BYTES, stream>>>(args);
+    return cudaGetLastError();
+}
+
+template <int LOG2N, int LOG2PAD>
+cudaError_t launch_ch(int channels, const KernelArgs &args, uint64_t n_frames, cudaStream_t stream)
+{
+    if constexpr (LOG2N + LOG2PAD > (int)kMaxLog2M) {
+        return cudaErrorInvalidConfiguration;
+    } else {
+        return channels == 1 ? launch_one<LOG2N, LOG2PAD, 1>(args, n_frames, stream)
+                             : launch_one<LOG2N, LOG2PAD, 2>(args, n_frames, stream);
+    }
+}
+
+template <int LOG2N>
+cudaError_t launch_pad(int log2pad, int channels, const KernelArgs &args, uint64_t n_frames, cudaStream_t stream)
+{
+    switch (log2pad) {
+        case 0: return launch_ch<LOG2N, 0>(channels, args, n_frames, stream);
+        case 1: return launch_ch<LOG2N, 1>(channels, args, n_frames, stream);
+        case 2: return launch_ch<LOG2N, 2>(channels, args, n_frames, stream);
+        default: return cudaErrorInvalidConfiguration;
+    }
+}
+
+sbx_status launch_fused(sbx_plan *p, int channels, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba,
+                        float *d_mags, cudaStream_t stream)
+{
+    KernelArgs a = p->base_args();
+    a.pcm = d_pcm;
+    a.rgba = d_rgba;
+    a.mags_out = d_mags;
+    a.n_frames = n_frames;
+    cudaError_t e;
+    switch (p->log2n) {
+        case 8: e = launch_pad<8>(p->log2pad, channels, a, n_frames, stream); break;
+        case 9: e = launch_pad<9>(p->log2pad, channels, a, n_frames, stream); break;
+        case 10: e = launch_pad<10>(p->log2pad, channels, a, n_frames, stream); break;
+        case 11: e = launch_pad<11>(p->log2pad, channels, a, n_frames, stream); break;
+        case 12: e = launch_pad<12>(p->log2pad, channels, a, n_frames, stream); break;
+        case 13: e = launch_pad<13>(p->log2pad, channels, a, n_frames, stream); break;
+        default: e = cudaErrorInvalidConfiguration; break;
+    }
+    if (e != cudaSuccess) return cuda_fail(p, e, "fused_frames_kernel launch");
+    if (n_frames) p->launches += 1;
+    return SBX_OK;
+}
+
+template <int LOG2M> cudaError_t launch_colourise_one(const KernelArgs &a, uint64_t n_frames, cudaStream_t stream)
+{
+    static bool configured[64] = {};
+    const int smem = (4 << LOG2M) + 512 * 4 + 256 * 4;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(colourise_kernel<LOG2M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    if (n_frames == 0) return cudaSuccess;
+    if (n_frames > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    colourise_kernel<LOG2M><<<(unsigned)n_frames, 256, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+sbx_status launch_colourise(sbx_plan *p, const float *d_mags, uint64_t n_frames, uint8_t *d_rgba, cudaStream_t stream)
+{
+    KernelArgs a = p->base_args();
+    a.mags_in = d_mags;
+    a.rgba = d_rgba;
+    a.n_frames = n_frames;
+    cudaError_t e;
+    switch (p->log2n + p->log2pad) {
+        case 8: e = launch_colourise_one<8>(a, n_frames, stream); break;
+        case 9: e = launch_colourise_one<9>(a, n_frames, stream); break;
+        case 10: e = launch_colourise_one<10>(a, n_frames, stream); break;
+        case 11: e = launch_colourise_one<11>(a, n_frames, stream); break;
+        case 12: e = launch_colourise_one<12>(a, n_frames, stream); break;
+        case 13: e = launch_colourise_one<13>(a, n_frames, stream); break;
+        case 14: e = launch_colourise_one<14>(a, n_frames, stream); break;
+        default: e = cudaErrorInvalidConfiguration; break;
+    }
+    if (e != cudaSuccess) return cuda_fail(p, e, "colourise_kernel launch");
+    if (n_frames) p->launches += 1;
+    return SBX_OK;
+}
+
+}  // namespace sbx
+
+sbx::KernelArgs sbx_plan::base_args() const
+{
+    sbx::KernelArgs a{};
+    a.window = d_window;
+    a.tw = d_tw;
+    a.rowmap = d_rowmap;
+    a.cos_w = d_cos_w;
+    a.thr = d_thr;
+    a.lut = d_lut;
+    a.hop = hop;
+    a.rows = rows;
+    a.k_out = k_out;
+    a.period = period;
+    a.k_max_f = (float)(k_out - 1);
+    a.scale = scale;
+    a.interp = (int)cfg.interp;
+    a.scheme = (int)cfg.scheme;
+    return a;
+}
+
+using sbx::cuda_fail;
+using sbx::fail;
+
+#define SBX_CUDA(plan, call)                                              \
+    do {                                                                  \
+        cudaError_t e__ = (call);                                         \
+        if (e__ != cudaSuccess) return cuda_fail((plan), e__, #call);     \
+    } while (0)
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+SBX_API uint32_t sbx_abi_version(void) { return SBX_ABI_VERSION; }
+SBX_API const char *sbx_build_arch(void) { return "sm_100a"; }
+
+SBX_API sbx_status sbx_builtin_lut(const char *name, uint8_t lut_rgb[768])
+{
+    if (!name || !lut_rgb) return SBX_ERR_INVALID_ARGUMENT;
+    const unsigned char *src = nullptr;
+    if (!std::strcmp(name, "magma")) src = SBX_LUT_MAGMA;
+    else if (!std::strcmp(name, "viridis")) src = SBX_LUT_VIRIDIS;
+    else if (!std::strcmp(name, "inferno")) src = SBX_LUT_INFERNO;
+    else if (!std::strcmp(name, "plasma")) src = SBX_LUT_PLASMA;
+    if (!src) return SBX_ERR_INVALID_ARGUMENT;
+    std::memcpy(lut_rgb, src, 768);
+    return SBX_OK;
+}
+
+SBX_API void sbx_config_default(sbx_config *cfg)
+{
+    if (!cfg) return;
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->struct_size = (uint32_t)sizeof(sbx_config);
+    cfg->abi_version = SBX_ABI_VERSION;
+    cfg->sample_rate = 48000.0f;
+    cfg->window_n = 4096;
+    cfg->pad_factor = 2;
+    cfg->hop = 512;
+    cfg->rows_h = 1024;
+    cfg->channels = 2;
+    cfg->f_min = 32.0;
+    cfg->f_max = 22030.0;
+    cfg->db_min = -70.0f;
+    cfg->db_max = -10.0f;
+    cfg->db_eps = 1e-7f;
+    cfg->interp = SBX_INTERP_CUBIC;
+    cfg->scheme = SBX_SCHEME_MONO;
+    cfg->device = 0;
+    std::memcpy(cfg->lut_rgb, SBX_LUT_MAGMA, 768);
+}
+
+SBX_API uint32_t sbx_samples_from_seconds(float seconds, float sample_rate)
+{
+    const float v = seconds * sample_rate;           // f32 multiply, then `as usize` (saturating)
+    if (!(v >= 0.0f)) return 0;
+    return v >= 4294967296.0f ? 0xffffffffu : (uint32_t)v;
+}
+
+SBX_API const char *sbx_last_error(const sbx_plan *plan)
+{
+    return plan ? plan->last_error.c_str() : g_create_error.c_str();
+}
+
+SBX_API void sbx_plan_destroy(sbx_plan *p)
+{
+    if (!p) return;
+    cudaSetDevice(p->cfg.device);
+    if (p->own_stream) cudaStreamSynchronize(p->own_stream);
+    for (auto &s : p->slots) {
+        if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
+        if (s.done) cudaEventDestroy(s.done);
+        cudaFree(s.d_pcm);
+        cudaFree(s.d_rgba);
+    }
+    cudaFree(p->d_window); cudaFree(p->d_tw); cudaFree(p->d_rowmap); cudaFree(p->d_cos_w);
+    cudaFree(p->d_thr); cudaFree(p->d_lut); cudaFree(p->d_frame); cudaFree(p->d_mags1); cudaFree(p->d_col);
+    if (p->h_frame) cudaFreeHost(p->h_frame);
+    if (p->h_col) cudaFreeHost(p->h_col);
+    if (p->own_stream) cudaStreamDestroy(p->own_stream);
+    delete p;
+}
+
+SBX_API sbx_status sbx_plan_create(const sbx_config *cfg, sbx_plan **out_plan)
+{
+    if (out_plan) *out_plan = nullptr;
+    if (!cfg || !out_plan) return fail(nullptr, SBX_ERR_INVALID_ARGUMENT, "cfg and out_plan must not be NULL");
+    if (cfg->struct_size != sizeof(sbx_config) || cfg->abi_version != SBX_ABI_VERSION)
+        return fail(nullptr, SBX_ERR_INVALID_ARGUMENT, "sbx_config size/version mismatch (call sbx_config_default first)");
+    const int log2n = ilog2_exact(cfg->window_n), log2pad = ilog2_exact(cfg->pad_factor);
+    if (cfg->window_n < 2) return fail(nullptr, SBX_ERR_INVALID_ARGUMENT, "window_n must be >= 2");
+    if (log2n < 0)
+        return fail(nullptr, SBX_ERR_UNSUPPORTED, "window_n must be a power of two (mixed-radix sizes such as the live app's 2400 are not implemented yet)");
+    if (log2n < (int)kMinLog2N || log2n > (int)kMaxLog2N)
+        return fail(nullptr, SBX_ERR_UNSUPPORTED, "window_n must be in [256, 8192]");
+    if (log2pad < 0 || log2pad > 2) return fail(nullptr, SBX_ERR_UNSUPPORTED, "pad_factor must be 1, 2 or 4");
+    if (log2n + log2pad > (int)kMaxLog2M)
+        return fail(nullptr, SBX_ERR_UNSUPPORTED, "window_n * pad_factor must be <= 16384 (the transform is held in one SM's shared memory)");
+    if (cfg->channels != 1 && cfg->channels != 2) return fail(nullptr, SBX_ERR_INVALID_ARGUMENT, "channels must be 1 or 2");
+    if (cfg->hop == 0) return fail(nullptr, SBX_ERR_INVALID_ARGUMENT, "hop must be >= 1");
+    if (cfg->rows_h == 0 || cfg->rows_h > (1u << 20)) return fail(nullptr, SBX_ERR_INVALID_ARGUMENT, "rows_h must be in [1, 2^20]");
+    if (!(cfg->f_min > 0.0) || !(cfg->f_max > cfg->f_min)) return fail(nullptr, SBX_ERR_INVALID_ARGUMENT, "need 0 < f_min < f_max");
+    if (!(cfg->sample_rate >= 1.0f) || !(cfg->sample_rate < 4.0e9f)) return fail(nullptr, SBX_ERR_INVALID_ARGUMENT, "sample_rate out of range");
+    if (!(cfg->db_max > cfg->db_min)) return fail(nullptr, SBX_ERR_INVALID_ARGUMENT, "need db_min < db_max");
+    if (!(cfg->db_eps >= 0.0f)) return fail(nullptr, SBX_ERR_INVALID_ARGUMENT, "db_eps must be >= 0");
+    if (cfg->interp > SBX_INTERP_COSINE) return fail(nullptr, SBX_ERR_INVALID_ARGUMENT, "unknown interp");
+    if (cfg->scheme > SBX_SCHEME_STEREO) return fail(nullptr, SBX_ERR_INVALID_ARGUMENT, "unknown scheme");
+
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(nullptr, SBX_ERR_CUDA, std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= n_dev) return fail(nullptr, SBX_ERR_INVALID_ARGUMENT, "device ordinal out of range");
+    SBX_CUDA(nullptr, cudaSetDevice(cfg->device));
+    cudaDeviceProp prop{};
+    SBX_CUDA(nullptr, cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10)
+        return fail(nullptr, SBX_ERR_CUDA, "kernels are compiled for sm_100a only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
+
+    sbx_plan *p = new (std::nothrow) sbx_plan();
+    if (!p) return fail(nullptr, SBX_ERR_OUT_OF_MEMORY, "out of host memory");
+    p->cfg = *cfg;
+    p->n = cfg->window_n;
+    p->pad = cfg->pad_factor;
+    p->m = p->n * p->pad;
+    p->k_out = p->m / 2 - 1;
+    p->rows = cfg->rows_h;
+    p->hop = cfg->hop;
+    p->channels = cfg->channels;
+    p->log2n = log2n;
+    p->log2pad = log2pad;
+
+    // ---- tables (host-computed once; the kernels never evaluate exp/log/cos) ---------------------
+    sbx::tables::HostTables t;
+    sbx::tables::build(*cfg, t);
+    p->period = t.period;
+    p->scale = t.scale;
+    p->h_window = t.window;
+    p->h_rowmap = t.rowmap;
+    p->h_cos_w = t.cos_w;
+    p->h_thr = t.thr;
+
+#define SBX_TRY(call)                                                                   \
+    do {                                                                                \
+        cudaError_t e__ = (call);                                                       \
+        if (e__ != cudaSuccess) {                                                       \
+            sbx_status st__ = e__ == cudaErrorMemoryAllocation ? SBX_ERR_OUT_OF_MEMORY : SBX_ERR_CUDA; \
+            fail(nullptr, st__, std::string(#call) + ": " + cudaGetErrorString(e__));   \
+            sbx_plan_destroy(p);                                                        \
+            return st__;                                                                \
+        }                                                                               \
+    } while (0)
+
+    SBX_TRY(upload(&p->d_window, p->h_window.data(), p->n * sizeof(float)));
+    SBX_TRY(upload(&p->d_tw, t.tw.data(), p->m * sizeof(float2)));
+    SBX_TRY(upload(&p->d_rowmap, p->h_rowmap.data(), p->rows * sizeof(sbx::RowMap)));
+    SBX_TRY(upload(&p->d_cos_w, p->h_cos_w.data(), p->h_cos_w.size() * sizeof(float)));
+    SBX_TRY(upload(&p->d_thr, p->h_thr.data(), 512 * sizeof(float)));
+    SBX_TRY(upload(&p->d_lut, t.lut, sizeof(t.lut)));
+    SBX_TRY(cudaMalloc(&p->d_frame, (size_t)p->n * 2 * sizeof(float)));
+    SBX_TRY(cudaMalloc(&p->d_mags1, (size_t)p->k_out * 2 * sizeof(float)));
+    SBX_TRY(cudaMalloc(&p->d_col, (size_t)p->rows * 4));
+    SBX_TRY(cudaMallocHost(&p->h_frame, (size_t)p->n * 2 * sizeof(float)));
+    SBX_TRY(cudaMallocHost(&p->h_col, (size_t)p->rows * 4));
+    SBX_TRY(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
+#undef SBX_TRY
+    p->stream = p->own_stream;
+    *out_plan = p;
+    return SBX_OK;
+}
+
+SBX_API float sbx_sample_rate(const sbx_plan *p) { return p ? p->cfg.sample_rate : 0.0f; }
+SBX_API uint32_t sbx_num_input_samples(const sbx_plan *p) { return p ? p->n : 0; }
+SBX_API uint32_t sbx_num_output_frequencies(const sbx_plan *p) { return p ? p->k_out : 0; }
+SBX_API uint32_t sbx_fft_length(const sbx_plan *p) { return p ? p->m : 0; }
+SBX_API uint32_t sbx_rows(const sbx_plan *p) { return p ? p->rows : 0; }
+SBX_API uint32_t sbx_hop(const sbx_plan *p) { return p ? p->hop : 0; }
+SBX_API uint32_t sbx_channels(const sbx_plan *p) { return p ? p->channels : 0; }
+SBX_API uint64_t sbx_launch_count(const sbx_plan *p) { return p ? p->launches : 0; }
+
+SBX_API uint64_t sbx_num_frames(const sbx_plan *p, uint64_t n_samples)
+{
+    if (!p || n_samples < p->n) return 0;
+    return (n_samples - p->n) / p->hop + 1;
+}
+
+SBX_API sbx_status sbx_set_stream(sbx_plan *p, void *cuda_stream)
+{
+    if (!p) return SBX_ERR_INVALID_ARGUMENT;
+    p->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : p->own_stream;
+    return SBX_OK;
+}
+
+SBX_API sbx_status sbx_synchronize(sbx_plan *p)
+{
+    if (!p) return SBX_ERR_INVALID_ARGUMENT;
+    SBX_CUDA(p, cudaSetDevice(p->cfg.device));
+    SBX_CUDA(p, cudaStreamSynchronize(p->stream));
+    return SBX_OK;
+}
+
+// ---- single frame, host buffers ----------------------------------------------------------------
+static sbx_status single_frame(sbx_plan *p, const float *lr, uint32_t n_avail, float *out_lr, uint8_t *rgba)
+{
+    if (!p) return SBX_ERR_INVALID_ARGUMENT;
+    if (!lr && n_avail) return fail(p, SBX_ERR_INVALID_ARGUMENT, "lr is NULL");
+    if (n_avail < p->n) return SBX_NOT_ENOUGH_SAMPLES;                 // fft.rs:72
+    SBX_CUDA(p, cudaSetDevice(p->cfg.device));
+    cudaStream_t s = p->stream;
+    std::memcpy(p->h_frame, lr, (size_t)p->n * 2 * sizeof(float));
+    SBX_CUDA(p, cudaMemcpyAsync(p->d_frame, p->h_frame, (size_t)p->n * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+    sbx_status st = sbx::launch_fused(p, 2, p->d_frame, 1, rgba ? p->d_col : nullptr, out_lr ? p->d_mags1 : nullptr, s);
+    if (st != SBX_OK) return st;
+    if (out_lr) SBX_CUDA(p, cudaMemcpyAsync(p->h_frame, p->d_mags1, (size_t)p->k_out * 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (rgba) SBX_CUDA(p, cudaMemcpyAsync(p->h_col, p->d_col, (size_t)p->rows * 4, cudaMemcpyDeviceToHost, s));
+    SBX_CUDA(p, cudaStreamSynchronize(s));
+    if (out_lr) std::memcpy(out_lr, p->h_frame, (size_t)p->k_out * 2 * sizeof(float));
+    if (rgba) std::memcpy(rgba, p->h_col, (size_t)p->rows * 4);
+    return SBX_OK;
+}
+
+SBX_API sbx_status sbx_process_magnitudes(sbx_plan *p, const float *lr, uint32_t n_avail, float *out_lr)
+{
+    if (p && !out_lr) return fail(p, SBX_ERR_INVALID_ARGUMENT, "out_lr is NULL");
+    return single_frame(p, lr, n_avail, out_lr, nullptr);
+}
+
+SBX_API sbx_status sbx_process_column(sbx_plan *p, const float *lr, uint32_t n_avail, uint8_t *rgba)
+{
+    if (p && !rgba) return fail(p, SBX_ERR_INVALID_ARGUMENT, "rgba is NULL");
+    return single_frame(p, lr, n_avail, nullptr, rgba);
+}
+
+SBX_API sbx_status sbx_colorize_magnitudes(sbx_plan *p, const float *mags_lr, uint64_t n_frames, uint8_t *rgba)
+{
+    if (!p) return SBX_ERR_INVALID_ARGUMENT;
+    if (n_frames == 0) return SBX_OK;
+    if (!mags_lr || !rgba) return fail(p, SBX_ERR_INVALID_ARGUMENT, "NULL buffer");
+    SBX_CUDA(p, cudaSetDevice(p->cfg.device));
+    cudaStream_t s = p->stream;
+    const size_t in_bytes = (size_t)n_frames * p->k_out * 2 * sizeof(float), out_bytes = (size_t)n_frames * p->rows * 4;
+    float *d_in = nullptr;
+    uint8_t *d_out = nullptr;
+    cudaError_t e = cudaMalloc(&d_in, in_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, out_bytes);
+    if (e != cudaSuccess) { cudaFree(d_in); return cuda_fail(p, e, "cudaMalloc(colourise buffers)"); }
+    sbx_status st = SBX_OK;
+    e = cudaMemcpyAsync(d_in, mags_lr, in_bytes, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) st = sbx::launch_colourise(p, d_in, n_frames, d_out, s);
+    if (e == cudaSuccess && st == SBX_OK) e = cudaMemcpyAsync(rgba, d_out, out_bytes, cudaMemcpyDeviceToHost, s);
+    cudaError_t e2 = cudaStreamSynchronize(s);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (st != SBX_OK) return st;
+    if (e != cudaSuccess) return cuda_fail(p, e, "colourise copy");
+    if (e2 != cudaSuccess) return cuda_fail(p, e2, "colourise sync");
+    return SBX_OK;
+}
+
+// ---- batch, device buffers ---------------------------------------------------------------------
+static sbx_status batch_device(sbx_plan *p, const float *d_pcm, uint64_t n_samples, uint8_t *d_rgba, float *d_mags,
+                               uint64_t capacity_frames, uint64_t *frames_out)
+{
+    if (frames_out) *frames_out = 0;
+    if (!p) return SBX_ERR_INVALID_ARGUMENT;
+    const uint64_t frames = sbx_num_frames(p, n_samples);
+    if (frames == 0) return SBX_OK;
+    if (!d_pcm || (!d_rgba && !d_mags)) return fail(p, SBX_ERR_INVALID_ARGUMENT, "NULL device buffer");
+    if (frames > capacity_frames) return fail(p, SBX_ERR_BUFFER_TOO_SMALL, "output capacity is smaller than the frame count");
+    if ((reinterpret_cast<uintptr_t>(d_pcm) & 15u) != 0) return fail(p, SBX_ERR_INVALID_ARGUMENT, "d_pcm must be 16-byte aligned");
+    SBX_CUDA(p, cudaSetDevice(p->cfg.device));
+    sbx_status st = sbx::launch_fused(p, (int)p->channels, d_pcm, frames, d_rgba, d_mags, p->stream);
+    if (st == SBX_OK && frames_out) *frames_out = frames;
+    return st;
+}
+
+SBX_API sbx_status sbx_process_batch_device(sbx_plan *p, const float *d_pcm, uint64_t n_samples, uint8_t *d_rgba,
+                                            uint64_t rgba_capacity_frames, uint64_t *frames_out)
+{
+    if (p && !d_rgba && sbx_num_frames(p, n_samples)) return fail(p, SBX_ERR_INVALID_ARGUMENT, "d_rgba is NULL");
+    return batch_device(p, d_pcm, n_samples, d_rgba, nullptr, rgba_capacity_frames, frames_out);
+}
+
+SBX_API sbx_status sbx_magnitudes_batch_device(sbx_plan *p, const float *d_pcm, uint64_t n_samples, float *d_mags_lr,
+                                               uint64_t capacity_frames, uint64_t *frames_out)
+{
+    if (p && !d_mags_lr && sbx_num_frames(p, n_samples)) return fail(p, SBX_ERR_INVALID_ARGUMENT, "d_mags_lr is NULL");
+    return batch_device(p, d_pcm, n_samples, nullptr, d_mags_lr, capacity_frames, frames_out);
+}
+
+// ---- batch, host buffers: chunked, H2D / kernel / D2H overlapped over kSlots streams -------------
+SBX_API sbx_status sbx_process_batch(sbx_plan *p, const float *pcm, uint64_t n_samples, uint8_t *rgba,
+                                     uint64_t rgba_capacity_frames, uint64_t *frames_out)
+{
+    if (frames_out) *frames_out = 0;
+    if (!p) return SBX_ERR_INVALID_ARGUMENT;
+    const uint64_t frames = sbx_num_frames(p, n_samples);
+    if (frames == 0) return SBX_OK;
+    if (!pcm || !rgba) return fail(p, SBX_ERR_INVALID_ARGUMENT, "NULL host buffer");
+    if (frames > rgba_capacity_frames) return fail(p, SBX_ERR_BUFFER_TOO_SMALL, "rgba capacity is smaller than the frame count");
+    SBX_CUDA(p, cudaSetDevice(p->cfg.device));
+
+    if (p->chunk_frames == 0) {
+        // ~32 MiB of RGBA per chunk, even frame count (mono pairs), at least 2 frames
+        uint64_t cf = ((uint64_t)32 << 20) / ((uint64_t)p->rows * 4);
+        cf = cf < 2 ? 2 : (cf & ~1ull);
+        const size_t pcm_bytes = ((size_t)(cf - 1) * p->hop + p->n) * p->channels * sizeof(float);
+        for (auto &s : p->slots) {
+            SBX_CUDA(p, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+            SBX_CUDA(p, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+            SBX_CUDA(p, cudaMalloc(&s.d_pcm, pcm_bytes));
+            SBX_CUDA(p, cudaMalloc(&s.d_rgba, (size_t)cf * p->rows * 4));
+        }
+        p->chunk_frames = cf;
+    }
+    // order after whatever the caller queued on the plan stream
+    SBX_CUDA(p, cudaStreamSynchronize(p->stream));
+    const uint64_t cf = p->chunk_frames;
+    uint64_t chunk = 0;
+    for (uint64_t f0 = 0; f0 < frames; f0 += cf, ++chunk) {
+        sbx_plan::Slot &s = p->slots[chunk % sbx_plan::kSlots];
+        const uint64_t nf = frames - f0 < cf ? frames - f0 : cf;
+        const size_t samples = (size_t)(nf - 1) * p->hop + p->n;
+        SBX_CUDA(p, cudaMemcpyAsync(s.d_pcm, pcm + (size_t)f0 * p->hop * p->channels,
+                                    samples * p->channels * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+        sbx_status st = sbx::launch_fused(p, (int)p->channels, s.d_pcm, nf, s.d_rgba, nullptr, s.stream);
+        if (st != SBX_OK) return st;
+        SBX_CUDA(p, cudaMemcpyAsync(rgba + (size_t)f0 * p->rows * 4, s.d_rgba, (size_t)nf * p->rows * 4,
+                                    cudaMemcpyDeviceToHost, s.stream));
+    }
+    for (auto &s : p->slots) SBX_CUDA(p, cudaStreamSynchronize(s.stream));
+    if (frames_out) *frames_out = frames;
+    return SBX_OK;
+}
+
+// ---- introspection -----------------------------------------------------------------------------
+SBX_API sbx_status sbx_get_bin_map(const sbx_plan *p, float *f0, float *step, uint32_t *n, float *period)
+{
+    if (!p) return SBX_ERR_INVALID_ARGUMENT;
+    for (uint32_t py = 0; py < p->rows; ++py) {
+        if (f0) f0[py] = p->h_rowmap[py].f0;
+        if (step) step[py] = p->h_rowmap[py].step;
+        if (n) n[py] = p->h_rowmap[py].n;
+    }
+    if (period) *period = p->period;
+    return SBX_OK;
+}
+
+SBX_API sbx_status sbx_get_color_thresholds(const sbx_plan *p, float thr[255])
+{
+    if (!p || !thr) return SBX_ERR_INVALID_ARGUMENT;
+    std::memcpy(thr, p->h_thr.data(), 255 * sizeof(float));
+    return SBX_OK;
+}
+
+SBX_API sbx_status sbx_get_window(const sbx_plan *p, float *w)
+{
+    if (!p || !w) return SBX_ERR_INVALID_ARGUMENT;
+    std::memcpy(w, p->h_window.data(), p->n * sizeof(float));
+    return SBX_OK;
+}
+
+SBX_API void *sbx_host_alloc(size_t bytes)
+{
+    void *ptr = nullptr;
+    if (cudaMallocHost(&ptr, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return ptr;
+}
+SBX_API void sbx_host_free(void *ptr)
+{
+    if (ptr) cudaFreeHost(ptr);
+}
+
+}  // extern "C"

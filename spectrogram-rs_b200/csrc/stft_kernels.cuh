@@ -1,0 +1,520 @@
+// stft_kernels.cuh -- sm_100a device code of the fused frame transform.
+//
+//   PCM window -> Hann -> (implicit) zero-pad -> M-point C2C FFT in shared memory -> L/R split,
+//   2/N scale -> log-frequency resample -> dB step function -> LUT -> packed RGBA column
+//
+// One CTA transforms one complex sequence z[n] = a[n] + i b[n] of N windowed samples:
+//   stereo PCM : a = left, b = right of ONE frame      (reference packing, src/fourier/fft.rs:57)
+//   mono PCM   : a = frame 2c, b = frame 2c+1           (two frames share one transform; the
+//                reference's (s,s) duplication gives L == R == |S[k]|*2/N)
+// and the same conjugate-symmetry split (src/fourier/fft.rs:81-89) separates the two real
+// sequences afterwards.
+//
+// FFT structure (see tools/fft_model.py for the numpy model of the index math):
+//   * the zero padding is never materialised: the radix-P DIF step over a sequence whose last
+//     (P-1)N entries are zero degenerates to P sub-transforms of length N over z[n]*W_M^(n*q0);
+//   * each sub-transform is an in-place radix-(2^rem,16,16,..) DIF, natural order in,
+//     digit-reversed order out; bin kk = P*k + q0 lives at position q0*N + digitrev(k);
+//   * 16 points per thread per pass in registers, one __syncthreads per pass;
+//   * shared memory holds float2, XOR-swizzled at 16-byte granularity so that both the strided
+//     passes (half-warp = one 128 B row) and the final stride-1 pass (thread = one 128 B row,
+//     float4 accesses) are bank-conflict free.
+#pragma once
+#ifdef SBX_EMU
+#include "emu_shim.h"      // tests/emu: host emulation of the phase functions below (test-only)
+#else
+#include <cuda_runtime.h>
+#endif
+#include <stdint.h>
+
+namespace sbx {
+
+struct RowMap {            // one output row py (0 = lowest frequency) of the log-frequency bin map
+    float f0;              // first sample frequency            (lin_space start)
+    float step;            // (f1 - f0) / n                     (lin_space step)
+    uint32_t n;            // samples averaged for this row
+    uint32_t aux;          // offset of this row's first entry in the cosine-weight table
+};
+
+struct KernelArgs {
+    const float *pcm;            // device PCM, CH floats per sample
+    uint8_t *rgba;               // frames x H x 4 or nullptr
+    float *mags_out;             // frames x K x 2 or nullptr
+    const float *mags_in;        // colourise-only kernel: frames x K x 2
+    const float *window;         // [N] periodic Hann, f32, host-computed (fft.rs:59-63)
+    const float2 *tw;            // [M] W_M^t = exp(-2 pi i t / M), f64-computed, rounded once
+    const RowMap *rowmap;        // [H]
+    const float *cos_w;          // COSINE interpolation weights per (row, sample) or nullptr
+    const float *thr;            // [512] 255 colour-index thresholds (+inf pad), 255 alpha thresholds
+    const uint32_t *lut;         // [256] packed r | g<<8 | b<<16 | 255<<24
+    unsigned long long n_frames;
+    uint32_t hop, rows, k_out;
+    float period;                // 2K / sr   (interpolated_frequency_sample.rs:52-54)
+    float k_max_f;               // (K-1) as f32
+    float scale;                 // 2 / N     (fft.rs:92)
+    int interp;                  // 0 cubic, 1 cosine
+    int scheme;                  // 0 mono gradient, 1 stereo pan gradient
+};
+
+// ----------------------------------------------------------------------------------------------
+// complex helpers and small DFT butterflies (forward, exp(-i...))
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 mul_neg_i(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
+
+#define SBX_RSQRT2 0.70710678118654752440f
+#define SBX_COS_PI_8 0.92387953251128675613f
+#define SBX_SIN_PI_8 0.38268343236508977173f
+
+__device__ __forceinline__ void bf2(float2 &a, float2 &b)
+{
+    float2 t = csub(a, b);
+    a = cadd(a, b);
+    b = t;
+}
+
+// 4-point DFT: y_q = sum_r a_r (-i)^(r q), outputs in natural order
+__device__ __forceinline__ void bf4(float2 &a0, float2 &a1, float2 &a2, float2 &a3)
+{
+    float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = csub(a1, a3);
+    a0 = cadd(t0, t2);
+    a2 = csub(t0, t2);
+    a1 = make_float2(t1.x + t3.y, t1.y - t3.x);
+    a3 = make_float2(t1.x - t3.y, t1.y + t3.x);
+}
+
+template <int R> struct Butterfly;
+
+template <> struct Butterfly<2> {
+    static __device__ __forceinline__ void run(float2 (&v)[2]) { bf2(v[0], v[1]); }
+};
+template <> struct Butterfly<4> {
+    static __device__ __forceinline__ void run(float2 (&v)[4]) { bf4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct Butterfly<8> {
+    // 8 = 2 x 4: n = a + 2a', k = b + 4c
+    static __device__ __forceinline__ void run(float2 (&v)[8])
+    {
+        bf4(v[0], v[2], v[4], v[6]);            // a = 0 : t[0][b] in v[0],v[2],v[4],v[6]
+        bf4(v[1], v[3], v[5], v[7]);            // a = 1 : t[1][b] in v[1],v[3],v[5],v[7]
+        // t[1][b] *= W8^b
+        v[3] = make_float2((v[3].x + v[3].y) * SBX_RSQRT2, (v[3].y - v[3].x) * SBX_RSQRT2);
+        v[5] = mul_neg_i(v[5]);
+        v[7] = make_float2((v[7].y - v[7].x) * SBX_RSQRT2, -(v[7].x + v[7].y) * SBX_RSQRT2);
+        // X[b] = t0 + t1, X[b+4] = t0 - t1
+        float2 x0 = cadd(v[0], v[1]), x4 = csub(v[0], v[1]);
+        float2 x1 = cadd(v[2], v[3]), x5 = csub(v[2], v[3]);
+        float2 x2 = cadd(v[4], v[5]), x6 = csub(v[4], v[5]);
+        float2 x3 = cadd(v[6], v[7]), x7 = csub(v[6], v[7]);
+        v[0] = x0; v[1] = x1; v[2] = x2; v[3] = x3; v[4] = x4; v[5] = x5; v[6] = x6; v[7] = x7;
+    }
+};
+template <> struct Butterfly<16> {
+    // 16 = 4 x 4: n = a + 4a', k = b + 4c;  X[b+4c] = sum_a (W16^(ab) sum_a' x[a+4a'] W4^(a'b)) W4^(ac)
+    static __device__ __forceinline__ void run(float2 (&v)[16])
+    {
+        bf4(v[0], v[4], v[8], v[12]);           // a = 0: t[0][b] at v[4b]
+        bf4(v[1], v[5], v[9], v[13]);           // a = 1: t[1][b] at v[1+4b]
+        bf4(v[2], v[6], v[10], v[14]);          // a = 2
+        bf4(v[3], v[7], v[11], v[15]);          // a = 3
+        const float2 w1 = make_float2(SBX_COS_PI_8, -SBX_SIN_PI_8);
+        const float2 w3 = make_float2(SBX_SIN_PI_8, -SBX_COS_PI_8);
+        const float2 w9 = make_float2(-SBX_COS_PI_8, SBX_SIN_PI_8);
+        // b = 1: W16^a
+        v[5] = cmul(v[5], w1);
+        v[6] = make_float2((v[6].x + v[6].y) * SBX_RSQRT2, (v[6].y - v[6].x) * SBX_RSQRT2);    // W16^2
+        v[7] = cmul(v[7], w3);
+        // b = 2: W16^(2a)
+        v[9] = make_float2((v[9].x + v[9].y) * SBX_RSQRT2, (v[9].y - v[9].x) * SBX_RSQRT2);    // W16^2
+        v[10] = mul_neg_i(v[10]);                                                              // W16^4
+        v[11] = make_float2((v[11].y - v[11].x) * SBX_RSQRT2, -(v[11].x + v[11].y) * SBX_RSQRT2); // W16^6
+        // b = 3: W16^(3a)
+        v[13] = cmul(v[13], w3);
+        v[14] = make_float2((v[14].y - v[14].x) * SBX_RSQRT2, -(v[14].x + v[14].y) * SBX_RSQRT2); // W16^6
+        v[15] = cmul(v[15], w9);
+        // outer 4-point DFTs over a for each b: inputs t[a][b] = v[a+4b], outputs X[b+4c] -> slot a=c
+        bf4(v[0], v[1], v[2], v[3]);            // b = 0 -> X[0],X[4],X[8],X[12]
+        bf4(v[4], v[5], v[6], v[7]);            // b = 1 -> X[1],X[5],X[9],X[13]
+        bf4(v[8], v[9], v[10], v[11]);          // b = 2 -> X[2],X[6],X[10],X[14]
+        bf4(v[12], v[13], v[14], v[15]);        // b = 3 -> X[3],X[7],X[11],X[15]
+        // now v[c + 4b] = X[b + 4c]: transpose the 4x4 to natural order
+        float2 t;
+        t = v[1]; v[1] = v[4]; v[4] = t;
+        t = v[2]; v[2] = v[8]; v[8] = t;
+        t = v[3]; v[3] = v[12]; v[12] = t;
+        t = v[6]; v[6] = v[9]; v[9] = t;
+        t = v[7]; v[7] = v[13]; v[13] = t;
+        t = v[11]; v[11] = v[14]; v[14] = t;
+    }
+};
+
+// ----------------------------------------------------------------------------------------------
+// compile-time geometry
+// ----------------------------------------------------------------------------------------------
+template <int LOG2N_, int LOG2PAD_, int CH_> struct Geom {
+    static constexpr int LOG2N = LOG2N_, LOG2PAD = LOG2PAD_, CH = CH_;
+    static constexpr int N = 1 << LOG2N, PAD = 1 << LOG2PAD, LOG2M = LOG2N + LOG2PAD, M = 1 << LOG2M;
+    static constexpr int REM = LOG2N & 3;                  // first pass radix 2^REM when REM != 0
+    static constexpr int NPASS = LOG2N / 4 + (REM ? 1 : 0);
+    static constexpr int THREADS = (M / 16) < 64 ? 64 : ((M / 16) > 512 ? 512 : (M / 16));
+    static constexpr int FRAMES_PER_CTA = CH == 1 ? 2 : 1;
+    static constexpr int SMEM_BYTES = M * 8 + 512 * 4 + 256 * 4;
+    static __host__ __device__ constexpr int log2r(int p) { return (REM != 0 && p == 0) ? REM : 4; }
+    static __host__ __device__ constexpr int log2stride(int p)                 // log2 of the butterfly stride of pass p
+    {
+        int s = LOG2N;
+        for (int i = 0; i <= p; ++i) s -= log2r(i);
+        return s;
+    }
+};
+
+// shared-memory swizzles -----------------------------------------------------------------------
+// transform buffer: element index -> physical float2 slot; permutes the eight 16-byte chunks of
+// every 128-byte row by the row number
+__device__ __forceinline__ int zsw(int i) { return i ^ (((i >> 4) & 7) << 1); }
+
+// magnitude buffer (indexed by bin kk = j + 1): the split phase writes bins that differ by
+// multiples of M/16 (8 lanes) and M/256 (the other half-warp); fold those bits into the bank
+template <int LOG2M> __device__ __forceinline__ int msw(int kk)
+{
+    if constexpr (LOG2M >= 12)
+        return kk ^ (((kk >> (LOG2M - 4)) & 7) | (((kk >> (LOG2M - 8)) & 1) << 3));
+    else
+        return kk ^ ((kk >> (LOG2M - 4)) & 7);
+}
+
+// position <-> bin (digit reversal of the sub-transform index; see tools/fft_model.py)
+template <class G> __device__ __forceinline__ int bin_of_pos(int pos)
+{
+    const int rem = pos & (G::N - 1), q0 = pos >> G::LOG2N;
+    int k = 0, shift = G::LOG2N, kshift = 0;
+#pragma unroll
+    for (int p = 0; p < G::NPASS; ++p) {
+        const int lr = G::log2r(p);
+        shift -= lr;
+        k |= ((rem >> shift) & ((1 << lr) - 1)) << kshift;
+        kshift += lr;
+    }
+    return (k << G::LOG2PAD) | q0;
+}
+template <class G> __device__ __forceinline__ int pos_of_bin(int kk)
+{
+    const int q0 = kk & (G::PAD - 1);
+    int k = kk >> G::LOG2PAD;
+    int pos = q0 << G::LOG2N, shift = G::LOG2N;
+#pragma unroll
+    for (int p = 0; p < G::NPASS; ++p) {
+        const int lr = G::log2r(p);
+        shift -= lr;
+        pos |= (k & ((1 << lr) - 1)) << shift;
+        k >>= lr;
+    }
+    return pos;
+}
+
+// ----------------------------------------------------------------------------------------------
+// DIF passes
+// ----------------------------------------------------------------------------------------------
+
+// Pass 0: global PCM -> window -> sub-transform premultiply -> radix butterfly -> twiddle -> smem
+template <class G>
+__device__ __forceinline__ void pass_first(float2 *z, const KernelArgs &a, unsigned long long frame0, bool second_valid)
+{
+    constexpr int LR = G::log2r(0), R = 1 << LR, LS = G::log2stride(0), S = 1 << LS;
+    constexpr int PER_SUB = G::N / R, COUNT = G::PAD * PER_SUB;
+    const float *pa = a.pcm + frame0 * (unsigned long long)a.hop * G::CH;
+    const float *pb = pa + a.hop;                                    // mono: the next frame
+    for (int w = threadIdx.x; w < COUNT; w += G::THREADS) {
+        const int q0 = w / PER_SUB, lo = w % PER_SUB;
+        float2 v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int n = lo + r * S;
+            const float wn = __ldg(a.window + n);
+            float2 s;
+            if constexpr (G::CH == 2) {
+                s = __ldg(reinterpret_cast<const float2 *>(pa) + n);
+            } else {
+                s.x = __ldg(pa + n);
+                s.y = second_valid ? __ldg(pb + n) : 0.0f;
+            }
+            s.x *= wn;  s.y *= wn;                                   // fft.rs:57-63 (complex * f32)
+            if (q0 != 0) s = cmul(s, __ldg(a.tw + ((n * q0) & (G::M - 1))));
+            v[r] = s;
+        }
+        Butterfly<R>::run(v);
+        const int base = (q0 << G::LOG2N) + lo;
+        z[zsw(base)] = v[0];
+#pragma unroll
+        for (int q = 1; q < R; ++q) {
+            float2 y = v[q];
+            if constexpr (G::NPASS > 1) y = cmul(y, __ldg(a.tw + ((lo * q) << G::LOG2PAD)));   // W_N^(lo q)
+            z[zsw(base + q * S)] = y;
+        }
+    }
+}
+
+// Pass P >= 1: in-place radix-16 butterflies at stride S = 2^LS; the last pass (S = 1) moves whole
+// 128-byte rows with float4 accesses
+template <class G, int P>
+__device__ __forceinline__ void pass_inplace(float2 *z, const KernelArgs &a)
+{
+    constexpr int LS = G::log2stride(P), S = 1 << LS;
+    constexpr int COUNT = G::M / 16;
+    constexpr int PER_SUB_LOG2 = G::LOG2N - 4;
+    for (int w = threadIdx.x; w < COUNT; w += G::THREADS) {
+        float2 v[16];
+        if constexpr (S == 1) {
+            // row w holds elements 16w .. 16w+15
+            float4 *row = reinterpret_cast<float4 *>(z) + (w << 3);
+            const int key = w & 7;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float4 t = row[c ^ key];
+                v[2 * c] = make_float2(t.x, t.y);
+                v[2 * c + 1] = make_float2(t.z, t.w);
+            }
+            Butterfly<16>::run(v);
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                row[c ^ key] = make_float4(v[2 * c].x, v[2 * c].y, v[2 * c + 1].x, v[2 * c + 1].y);
+        } else {
+            const int blk = w >> PER_SUB_LOG2, u = w & ((1 << PER_SUB_LOG2) - 1);
+            const int lo = u & (S - 1), hi = u >> LS;
+            const int base = (blk << G::LOG2N) + (hi << (LS + 4)) + lo;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) v[r] = z[zsw(base + r * S)];
+            Butterfly<16>::run(v);
+            z[zsw(base)] = v[0];
+            // twiddle W_(16 S)^(lo q) = W_M^(lo q M/(16 S))
+            constexpr int TSHIFT = G::LOG2M - 4 - LS;
+#pragma unroll
+            for (int q = 1; q < 16; ++q)
+                z[zsw(base + q * S)] = cmul(v[q], __ldg(a.tw + ((lo * q) << TSHIFT)));
+        }
+    }
+}
+
+template <class G, int P> struct RunPasses {
+    static __device__ __forceinline__ void run(float2 *z, const KernelArgs &a)
+    {
+        if constexpr (P < G::NPASS) {
+            pass_inplace<G, P>(z, a);
+            __syncthreads();
+            RunPasses<G, P + 1>::run(z, a);
+        }
+    }
+};
+
+// ----------------------------------------------------------------------------------------------
+// L/R split (fft.rs:81-95): bins kk = 1 .. M/2-1, a = Z[kk], b = Z[M-kk]
+//   L = |a + conj b| / 2 * (2/N),  R = |a - conj b| / 2 * (2/N)
+// split_read: every thread reads its pairs into registers; (barrier); split_write: (L,R) is
+// written over the transform buffer, indexed by kk
+// ----------------------------------------------------------------------------------------------
+template <class G> struct SplitRegs {
+    static constexpr int PAIRS = G::M / 2;
+    static constexpr int PER_THREAD = (PAIRS + G::THREADS - 1) / G::THREADS;
+    float2 mag[PER_THREAD];
+    int kks[PER_THREAD];
+};
+
+template <class G>
+__device__ __forceinline__ void split_read(const float2 *z, const KernelArgs &a, SplitRegs<G> &r)
+{
+#pragma unroll
+    for (int i = 0; i < SplitRegs<G>::PER_THREAD; ++i) {
+        const int v = threadIdx.x + i * G::THREADS;
+        r.kks[i] = 0;
+        r.mag[i] = make_float2(0.0f, 0.0f);
+        if (v < SplitRegs<G>::PAIRS) {
+            const int pos = ((v >> 3) << 4) | (v & 7);      // low digit < 8  <=>  kk < M/2
+            const int kk = bin_of_pos<G>(pos);
+            if (kk != 0) {
+                const float2 x = z[zsw(pos)];
+                const float2 y = z[zsw(pos_of_bin<G>(G::M - kk))];
+                const float lx = x.x + y.x, ly = x.y - y.y;   // a + conj b
+                const float rx = x.x - y.x, ry = x.y + y.y;   // a - conj b
+                const float l = sqrtf(lx * lx + ly * ly) * 0.5f;
+                const float rr = sqrtf(rx * rx + ry * ry) * 0.5f;
+                r.mag[i] = make_float2(l * a.scale, rr * a.scale);
+                r.kks[i] = kk;
+            }
+        }
+    }
+}
+
+template <class G>
+__device__ __forceinline__ void split_write(float2 *z, const SplitRegs<G> &r)
+{
+#pragma unroll
+    for (int i = 0; i < SplitRegs<G>::PER_THREAD; ++i)
+        if (r.kks[i] != 0) z[msw<G::LOG2M>(r.kks[i])] = r.mag[i];
+}
+
+// ----------------------------------------------------------------------------------------------
+// log-frequency resample + colour  (interpolated_frequency_sample.rs:60-105, colorscheme.rs:55-71,
+// simple_spectrogram.rs:141-161).  Everything here is written with explicitly rounded intrinsics
+// (no FMA contraction) in the reference's operation order: given identical magnitudes the result is
+// bit-identical to the CPU oracle.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float cubic1(float y0, float y1, float y2, float y3, float mu, float mu2, float mu3)
+{
+    const float a0 = __fadd_rn(__fsub_rn(__fsub_rn(y3, y2), y0), y1);
+    const float a1 = __fsub_rn(__fsub_rn(y0, y1), a0);
+    const float a2 = __fsub_rn(y2, y0);
+    return __fadd_rn(__fadd_rn(__fmul_rn(a0, mu3), __fmul_rn(a1, mu2)), __fadd_rn(__fmul_rn(a2, mu), y1));
+}
+
+// number of thresholds <= p  (thr ascending, thr[255] = +inf); NaN -> 0
+__device__ __forceinline__ int step_index(const float *thr, float p)
+{
+    int pos = 0;
+#pragma unroll
+    for (int s = 128; s >= 1; s >>= 1)
+        if (thr[pos + s - 1] <= p) pos += s;
+    return pos;
+}
+
+template <int LOG2M, bool PAIR, int THREADS>
+__device__ __forceinline__ void resample_colour(const float2 *mags, const float *thr, const uint32_t *lut,
+                                                const KernelArgs &a, unsigned long long frame0, bool second_valid)
+{
+    const int k_last = (int)a.k_out - 1;
+    uint32_t *outA = reinterpret_cast<uint32_t *>(a.rgba) + frame0 * a.rows;
+    uint32_t *outB = outA + a.rows;
+    for (uint32_t py = threadIdx.x; py < a.rows; py += THREADS) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.rowmap) + py);
+        const float f0 = __uint_as_float(raw.x), step = __uint_as_float(raw.y);
+        const uint32_t n = raw.z;
+        float ax = 0.0f, ay = 0.0f;
+        for (uint32_t s = 0; s < n; ++s) {
+            const float fq = __fadd_rn(f0, __fmul_rn((float)s, step));          // lin_space
+            float x = __fmul_rn(fq, a.period);                                   // index_of
+            x = fminf(fmaxf(x, 0.0f), a.k_max_f);
+            const float fl = floorf(x);
+            const int x1 = (int)fl;
+            float vx, vy;
+            if (a.interp == 0) {                                                 // cubic_interpolate
+                const float mu = __fsub_rn(x, fl);
+                const float mu2 = __fmul_rn(mu, mu), mu3 = __fmul_rn(mu, mu2);
+                const int x0 = x1 > 0 ? x1 - 1 : 0;
+                const int x2 = min(x1 + 1, k_last), x3 = min(x1 + 2, k_last);
+                const float2 y0 = mags[msw<LOG2M>(x0 + 1)], y1 = mags[msw<LOG2M>(x1 + 1)];
+                const float2 y2 = mags[msw<LOG2M>(x2 + 1)], y3 = mags[msw<LOG2M>(x3 + 1)];
+                vx = cubic1(y0.x, y1.x, y2.x, y3.x, mu, mu2, mu3);
+                vy = cubic1(y0.y, y1.y, y2.y, y3.y, mu, mu2, mu3);
+            } else {                                                             // cosine_interpolate
+                int hi = (int)ceilf(x);
+                const int lo_b = min(x1 + 1, k_last);
+                hi = min(max(hi, lo_b), k_last);
+                const float t = __ldg(a.cos_w + raw.w + s);                      // (1 - cos(frac*pi)) / 2, host libm
+                const float omt = __fsub_rn(1.0f, t);
+                const float2 yl = mags[msw<LOG2M>(x1 + 1)], yh = mags[msw<LOG2M>(hi + 1)];
+                vx = __fadd_rn(__fmul_rn(yl.x, omt), __fmul_rn(yh.x, t));
+                vy = __fadd_rn(__fmul_rn(yl.y, omt), __fmul_rn(yh.y, t));
+            }
+            ax = __fadd_rn(ax, vx);
+            ay = __fadd_rn(ay, vy);
+        }
+        const float nf = (float)n;
+        ax = __fdiv_rn(ax, nf);
+        ay = __fdiv_rn(ay, nf);
+        const uint32_t row = a.rows - 1u - py;                                   // simple_spectrogram.rs:150
+        if constexpr (PAIR) {
+            // mono: (ax, ay) are the L(=R) magnitudes of frames A and B
+            const float pA = __fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ax, ax));
+            const float pB = __fadd_rn(__fmul_rn(ay, ay), __fmul_rn(ay, ay));
+            if (a.scheme == 0) {
+                outA[row] = lut[step_index(thr, pA)];
+                if (second_valid) outB[row] = lut[step_index(thr, pB)];
+            } else {
+                // l == r: pan = l / (|l| + |r|) = 0.5 (NaN -> index 0 when l == 0)
+                const uint32_t panA = ax != 0.0f && ax == ax ? 128u : 0u, panB = ay != 0.0f && ay == ay ? 128u : 0u;
+                outA[row] = (lut[panA] & 0x00ffffffu) | ((uint32_t)step_index(thr + 256, pA) << 24);
+                if (second_valid) outB[row] = (lut[panB] & 0x00ffffffu) | ((uint32_t)step_index(thr + 256, pB) << 24);
+            }
+        } else {
+            const float p = __fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay));    // norm_sqr
+            if (a.scheme == 0) {
+                outA[row] = lut[step_index(thr, p)];
+            } else {
+                const double pan = (double)ax / (double)__fadd_rn(fabsf(ax), fabsf(ay));
+                const double v = floor(pan * 256.0);
+                const uint32_t idx = !(v >= 0.0) ? 0u : (v > 255.0 ? 255u : (uint32_t)v);
+                outA[row] = (lut[idx] & 0x00ffffffu) | ((uint32_t)step_index(thr + 256, p) << 24);
+            }
+        }
+    }
+}
+
+#ifndef SBX_EMU
+// ----------------------------------------------------------------------------------------------
+// kernels
+// ----------------------------------------------------------------------------------------------
+template <class G>
+__global__ void __launch_bounds__(G::THREADS) fused_frames_kernel(const KernelArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *z = reinterpret_cast<float2 *>(smem_raw);
+    float *thr = reinterpret_cast<float *>(smem_raw + (size_t)G::M * 8);
+    uint32_t *lut = reinterpret_cast<uint32_t *>(thr + 512);
+
+    const unsigned long long frame0 = (unsigned long long)blockIdx.x * G::FRAMES_PER_CTA;
+    const bool second_valid = G::CH == 1 && frame0 + 1 < a.n_frames;
+
+    for (int i = threadIdx.x; i < 512; i += G::THREADS) thr[i] = __ldg(a.thr + i);
+    for (int i = threadIdx.x; i < 256; i += G::THREADS) lut[i] = __ldg(a.lut + i);
+
+    pass_first<G>(z, a, frame0, second_valid);
+    __syncthreads();
+    RunPasses<G, 1>::run(z, a);
+    {
+        SplitRegs<G> regs;
+        split_read<G>(z, a, regs);
+        __syncthreads();
+        split_write<G>(z, regs);
+    }
+    __syncthreads();
+
+    if (a.mags_out != nullptr) {
+        float2 *out = reinterpret_cast<float2 *>(a.mags_out) + frame0 * a.k_out;
+        for (uint32_t j = threadIdx.x; j < a.k_out; j += G::THREADS) {
+            const float2 m = z[msw<G::LOG2M>((int)j + 1)];
+            if constexpr (G::CH == 1) {
+                out[j] = make_float2(m.x, m.x);
+                if (second_valid) out[a.k_out + j] = make_float2(m.y, m.y);
+            } else {
+                out[j] = m;
+            }
+        }
+    }
+    if (a.rgba != nullptr)
+        resample_colour<G::LOG2M, G::CH == 1, G::THREADS>(z, thr, lut, a, frame0, second_valid);
+}
+
+// magnitudes (frames x K x (L,R), device) -> RGBA columns: the resample/colour stage alone
+template <int LOG2M>
+__global__ void __launch_bounds__(256) colourise_kernel(const KernelArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *z = reinterpret_cast<float2 *>(smem_raw);
+    float *thr = reinterpret_cast<float *>(smem_raw + ((size_t)4 << LOG2M));      // M/2 float2
+    uint32_t *lut = reinterpret_cast<uint32_t *>(thr + 512);
+    const unsigned long long frame = blockIdx.x;
+    for (int i = threadIdx.x; i < 512; i += 256) thr[i] = __ldg(a.thr + i);
+    for (int i = threadIdx.x; i < 256; i += 256) lut[i] = __ldg(a.lut + i);
+    const float2 *in = reinterpret_cast<const float2 *>(a.mags_in) + frame * a.k_out;
+    for (uint32_t j = threadIdx.x; j < a.k_out; j += 256) z[msw<LOG2M>((int)j + 1)] = __ldg(in + j);
+    __syncthreads();
+    resample_colour<LOG2M, false, 256>(z, thr, lut, a, frame, false);
+}
+
+#endif  // SBX_EMU
+
+}  // namespace sbx

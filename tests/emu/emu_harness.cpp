@@ -1,0 +1,136 @@
+// emu_harness.cpp -- TEST INFRASTRUCTURE (see emu_shim.h).  Runs one CTA of the fused kernel on
+// the host by calling each barrier-delimited phase of stft_kernels.cuh for every thread id in
+// turn, with the product's own host tables (sbx_tables.h).
+#define SBX_EMU 1
+#include "../../spectrogram-rs_b200/csrc/stft_kernels.cuh"
+#include "../../spectrogram-rs_b200/csrc/sbx_tables.h"
+
+#include <vector>
+
+namespace {
+
+template <class G, int P> struct EmuPasses {
+    static void run(float2 *z, const sbx::KernelArgs &a)
+    {
+        if constexpr (P < G::NPASS) {
+            for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::pass_inplace<G, P>(z, a); }
+            EmuPasses<G, P + 1>::run(z, a);
+        }
+    }
+};
+
+// one CTA: frames frame0 (.. frame0+1 for mono) -> mags (FRAMES_PER_CTA x K x 2) and rgba
+template <class G>
+int emu_cta(const sbx::KernelArgs &a, unsigned long long frame0, float *mags_out, uint8_t *rgba)
+{
+    std::vector<float2> z(G::M);
+    const bool second_valid = G::CH == 1 && frame0 + 1 < a.n_frames;
+    for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::pass_first<G>(z.data(), a, frame0, second_valid); }
+    EmuPasses<G, 1>::run(z.data(), a);
+    std::vector<sbx::SplitRegs<G>> regs(G::THREADS);
+    for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::split_read<G>(z.data(), a, regs[t]); }
+    for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::split_write<G>(z.data(), regs[t]); }
+    if (mags_out) {
+        for (uint32_t j = 0; j < a.k_out; ++j) {
+            const float2 m = z[sbx::msw<G::LOG2M>((int)j + 1)];
+            float *o = mags_out + (size_t)frame0 * a.k_out * 2;
+            if (G::CH == 1) {
+                o[2 * j] = m.x; o[2 * j + 1] = m.x;
+                if (second_valid) { o[2 * (a.k_out + j)] = m.y; o[2 * (a.k_out + j) + 1] = m.y; }
+            } else { o[2 * j] = m.x; o[2 * j + 1] = m.y; }
+        }
+    }
+    if (rgba) {
+        sbx::KernelArgs b = a;
+        b.rgba = rgba;
+        for (int t = 0; t < G::THREADS; ++t) {
+            threadIdx.x = t;
+            sbx::resample_colour<G::LOG2M, G::CH == 1, G::THREADS>(z.data(), a.thr, a.lut, b, frame0, second_valid);
+        }
+    }
+    return 0;
+}
+
+template <int LOG2N, int LOG2PAD>
+int emu_dispatch_ch(int ch, const sbx::KernelArgs &a, unsigned long long f0, float *mags, uint8_t *rgba)
+{
+    if constexpr (LOG2N + LOG2PAD > 14) return -2;
+    else return ch == 1 ? emu_cta<sbx::Geom<LOG2N, LOG2PAD, 1>>(a, f0, mags, rgba)
+                        : emu_cta<sbx::Geom<LOG2N, LOG2PAD, 2>>(a, f0, mags, rgba);
+}
+template <int LOG2N>
+int emu_dispatch_pad(int lp, int ch, const sbx::KernelArgs &a, unsigned long long f0, float *mags, uint8_t *rgba)
+{
+    switch (lp) {
+        case 0: return emu_dispatch_ch<LOG2N, 0>(ch, a, f0, mags, rgba);
+        case 1: return emu_dispatch_ch<LOG2N, 1>(ch, a, f0, mags, rgba);
+        case 2: return emu_dispatch_ch<LOG2N, 2>(ch, a, f0, mags, rgba);
+    }
+    return -2;
+}
+
+int ilog2(uint32_t v) { int l = 0; while ((1u << l) < v) ++l; return (1u << l) == v ? l : -1; }
+
+}  // namespace
+
+extern "C" {
+
+// Whole batch through the emulated kernel.  pcm: n_samples x channels.  Outputs may be NULL.
+// Returns frames processed or a negative error.
+__attribute__((visibility("default")))
+long long emu_batch(const sbx_config *cfg, const float *pcm, unsigned long long n_samples,
+                    float *mags_lr, uint8_t *rgba)
+{
+    sbx::tables::HostTables t;
+    sbx::tables::build(*cfg, t);
+    if (n_samples < t.n) return 0;
+    const unsigned long long frames = (n_samples - t.n) / cfg->hop + 1;
+    sbx::KernelArgs a{};
+    a.pcm = pcm;
+    a.window = t.window.data();
+    a.tw = reinterpret_cast<const float2 *>(t.tw.data());
+    a.rowmap = t.rowmap.data();
+    a.cos_w = t.cos_w.data();
+    a.thr = t.thr.data();
+    a.lut = t.lut;
+    a.n_frames = frames;
+    a.hop = cfg->hop; a.rows = t.rows; a.k_out = t.k_out;
+    a.period = t.period; a.k_max_f = (float)(t.k_out - 1); a.scale = t.scale;
+    a.interp = (int)cfg->interp; a.scheme = (int)cfg->scheme;
+    const int ln = ilog2(t.n), lp = ilog2(t.pad), ch = (int)cfg->channels;
+    if (ln < 8 || ln > 13 || lp < 0) return -2;
+    const int per = ch == 1 ? 2 : 1;
+    for (unsigned long long f0 = 0; f0 < frames; f0 += per) {
+        int st;
+        switch (ln) {
+            case 8: st = emu_dispatch_pad<8>(lp, ch, a, f0, mags_lr, rgba); break;
+            case 9: st = emu_dispatch_pad<9>(lp, ch, a, f0, mags_lr, rgba); break;
+            case 10: st = emu_dispatch_pad<10>(lp, ch, a, f0, mags_lr, rgba); break;
+            case 11: st = emu_dispatch_pad<11>(lp, ch, a, f0, mags_lr, rgba); break;
+            case 12: st = emu_dispatch_pad<12>(lp, ch, a, f0, mags_lr, rgba); break;
+            case 13: st = emu_dispatch_pad<13>(lp, ch, a, f0, mags_lr, rgba); break;
+            default: st = -2;
+        }
+        if (st != 0) return st;
+    }
+    return (long long)frames;
+}
+
+// host tables of the product, exposed so CPU tests can compare them with the oracle bit for bit
+__attribute__((visibility("default")))
+int emu_tables(const sbx_config *cfg, float *window, float *f0, float *step, uint32_t *n, float *period, float *thr512)
+{
+    sbx::tables::HostTables t;
+    sbx::tables::build(*cfg, t);
+    if (window) memcpy(window, t.window.data(), t.n * sizeof(float));
+    for (uint32_t py = 0; py < t.rows; ++py) {
+        if (f0) f0[py] = t.rowmap[py].f0;
+        if (step) step[py] = t.rowmap[py].step;
+        if (n) n[py] = t.rowmap[py].n;
+    }
+    if (period) *period = t.period;
+    if (thr512) memcpy(thr512, t.thr.data(), 512 * sizeof(float));
+    return 0;
+}
+
+}  // extern "C"
