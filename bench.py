@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- STFT frames/s of the fused sm_100a frame transform (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of synthetic input: F frames per GPU of the
+cfg1 geometry ("batched 4096-pt frames": 48 kHz mono log sweep, N 4096, zero-padded to M 8192,
+hop 512, H 1024 rows, Magma).  Multi-GPU = time-block sharding: rank r owns frames [rF, (r+1)F) of
+one long recording, i.e. its own sample block including the N-hop halo, and there is no data-path
+collective -- torch.distributed is used only for the barrier and the max-over-ranks
+of the device time.  Weak scaling: F per GPU is fixed.
+
+Rank 0 prints ONE JSON line.  `value` is kernel throughput with the PCM resident in HBM (CUDA
+events on the launching stream); `e2e` goes through the host-pointer C-ABI call sbx_process_batch
+with pinned host buffers, H2D and D2H inside the timed region; `roofline` compares the
+algorithmic bytes (hop*4 in + H*4 out per frame) with the measured HBM copy peak;
+`cpu_baseline` is the CPU oracle (a port of the reference's path; the Rust+FFTW reference itself
+cannot be built in this image) timed on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# cfg1 geometry
+SR, N, PAD, HOP, ROWS = 48000.0, 4096, 2, 512, 1024
+B_FRAME = HOP * 1 * 4 + ROWS * 4          # algorithmic bytes per frame (mono in, RGBA out)
+FLOPS_FRAME = 5 * (N * PAD) * 13          # 5 M log2 M, the C2C figure SURVEY.md quotes
+WORKLOAD = "cfg1-batched: 48 kHz mono log sweep 20 Hz-20 kHz, N=4096 Hann, zero-pad to M=8192, hop 512, H=1024 log rows 32-22030 Hz, cubic resample, Magma"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_rate(frames_budget_s=12.0, threads=None):
+    """frames/s of the CPU oracle on this box's host cores, on a bounded sample of the workload."""
+    from oracle import oracle
+    from tests import signals
+    threads = threads or oracle.max_threads()
+    lut = signals.lut("magma")
+    p = oracle.params(sample_rate=SR, window_n=N, pad_factor=PAD, hop=HOP, rows_h=ROWS)
+    sweep = signals.log_sweep(int(SR * 60))
+
+    def run(frames):
+        ns = (frames - 1) * HOP + N
+        x = np.resize(sweep, ns)
+        t0 = time.perf_counter()
+        oracle.batch(p, x, 1, lut, want_rgba=True, threads=threads)
+        return time.perf_counter() - t0
+
+    run(threads * 8)                                    # warm-up (tables, page faults)
+    probe = threads * 64
+    t = run(probe)
+    frames = int(max(probe, min(2_000_000, probe * frames_budget_s / max(t, 1e-6))))
+    dt = run(frames)
+    return frames / dt, threads, f"{frames} frames of the workload ({dt:.1f} s, {threads} pthreads over frames, oracle radix-2 f32 FFT standing in for FFTW)"
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port), all host threads."""
+    if rank != 0:
+        return
+    rates = []
+    threads, sample = None, ""
+    for i in range(args.warmup + args.steps):
+        rate, threads, sample = cpu_reference_rate(frames_budget_s=min(8.0, 120.0 / max(1, args.steps + args.warmup)))
+        if i >= args.warmup:
+            rates.append(rate)
+    value = float(np.mean(rates))
+    peaks, src = measured_peaks()
+    out = {
+        "impl": "reference", "metric": "stft_frames_per_sec", "value": value, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "CPU path; n_gpus is the arm it is paired with"},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=1 << 20, help="frames per GPU per step")
+    ap.add_argument("--e2e-frames", type=int, default=1 << 17, help="frames per GPU per end-to-end step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the transform has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import spectrogram_rs_b200 as sbx
+    from tests import signals
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    F = args.frames
+    plan = sbx.Plan(sample_rate=SR, window_n=N, pad_factor=PAD, hop=HOP, rows_h=ROWS, channels=1, lut="magma", device=local_rank)
+    # a non-default stream: sbx_set_stream(NULL) means "the plan's own stream", and the CUDA events
+    # below must be recorded on the stream the kernels are launched on
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    plan.set_stream(stream.cuda_stream)
+
+    # ---- synthetic input: this rank's time block of one long tiled sweep, generated on the device ----
+    sweep = torch.from_numpy(signals.log_sweep(int(SR * 60))).cuda()
+    L = sweep.numel()
+    n_samples = (F - 1) * HOP + N
+    offset = (rank * F * HOP) % L
+    reps = (offset + n_samples + L - 1) // L
+    pcm = sweep.repeat(reps)[offset:offset + n_samples].contiguous()
+    rgba = torch.empty((F, ROWS, 4), dtype=torch.uint8, device="cuda")
+    in_bytes, out_bytes = pcm.numel() * 4, rgba.numel()
+    log(f"[rank {rank}] F={F} frames/GPU/step, input {in_bytes / 1e9:.2f} GB, output {out_bytes / 1e9:.2f} GB (both > L2: no flush needed)")
+
+    def step():
+        got = plan.process_batch_device(pcm, n_samples, rgba, F)
+        assert got == F
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = plan.launch_count
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record(stream)
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record(stream)
+    barrier()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    clocks = sampler.stop()
+    launches = plan.launch_count - launches0
+    total_ms = max_over_ranks(total_ms)
+    ms_per_step = total_ms / args.steps
+    value = world * F / (ms_per_step * 1e-3)
+    kernel_ms = float(np.mean(per_launch_ms))            # one launch per step: the fused kernel
+
+    # ---- end to end through the host-pointer C ABI: pinned host PCM in, pinned host RGBA out ----------
+    Fe = args.e2e_frames
+    ns_e = (Fe - 1) * HOP + N
+    h_pcm = torch.empty(ns_e, dtype=torch.float32).pin_memory()
+    h_pcm.copy_(pcm[:ns_e].cpu())
+    h_rgba = torch.empty((Fe, ROWS, 4), dtype=torch.uint8).pin_memory()
+    plan.set_stream(None)
+    for _ in range(2):
+        plan.process_batch_ptr(h_pcm.data_ptr(), ns_e, h_rgba.data_ptr(), Fe)
+    e2e_steps = max(3, min(args.steps, 10))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        got = plan.process_batch_ptr(h_pcm.data_ptr(), ns_e, h_rgba.data_ptr(), Fe)
+        checksum = int(h_rgba[0, 0, 0])                  # the step's result is read on the host
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * Fe * e2e_steps / e2e_s
+    assert got == Fe and torch.equal(h_rgba[:64].cuda(), rgba[:64])
+    plan.set_stream(stream.cuda_stream)
+
+    peaks, peak_src = measured_peaks()
+    achieved = (F * B_FRAME / 1e9) / (kernel_ms * 1e-3)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")   # written from the ncu --set full capture
+    if os.path.exists(tpath):
+        try:
+            t = json.load(open(tpath))
+            traffic = t["dram_bytes_per_frame"] * F
+        except Exception:
+            traffic = None
+
+    out = {
+        "metric": "stft_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": F, "sharding": "time-block with N-hop halo, no collectives",
+                   "l2": "inputs (%.2f GB) and outputs (%.2f GB) per step exceed the 126 MB L2" % (in_bytes / 1e9, out_bytes / 1e9),
+                   "bytes_per_frame": B_FRAME},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
+                     "kernel": "fused_frames_kernel<Geom<12,1,1>>", "kernel_ms": kernel_ms,
+                     "fp32_tflops_5MlogM": value / world * FLOPS_FRAME / 1e12,
+                     "note": "path is FP32/shared-memory bound at this hop (44-87 flop/B vs a 12 flop/B ridge, SURVEY.md D6)"},
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": ns_e * 4, "d2h_bytes_per_step": Fe * ROWS * 4,
+                "frames_per_gpu_per_step": Fe, "steps": e2e_steps, "api": "sbx_process_batch (host pointers, pinned)"},
+        "gpu_launches": launches * world,
+        "clocks": clocks,
+    }
+
+    if rank == 0 and not args.no_extras:
+        try:
+            out["extra"] = extras(sbx, signals, torch)
+        except Exception as exc:                            # extras must never lose the headline line
+            out["extra"] = {"error": repr(exc)}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, cores, sample = cpu_reference_rate()
+        out["cpu_baseline"] = {"value": rate, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def extras(sbx, signals, torch):
+    """Secondary measurements reported beside the headline: cfg3 throughput, cfg2 live latency."""
+    res = {}
+    # cfg3 geometry: 96 kHz mono, N 8192 -> M 16384, hop 256, Viridis
+    n3, hop3, F3 = 8192, 256, 1 << 18
+    plan = sbx.Plan(sample_rate=96000.0, window_n=n3, pad_factor=2, hop=hop3, rows_h=1024, channels=1, lut="viridis",
+                    device=torch.cuda.current_device())
+    stream = torch.cuda.current_stream()                 # main() made a side stream current
+    assert stream.cuda_stream != 0
+    plan.set_stream(stream.cuda_stream)
+    ns = (F3 - 1) * hop3 + n3
+    x = torch.from_numpy(signals.sweeps_plus_noise(1 << 22, 96000.0)).cuda()
+    x = x.repeat((ns + x.numel() - 1) // x.numel())[:ns].contiguous()
+    out = torch.empty((F3, 1024, 4), dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        plan.process_batch_device(x, ns, out, F3)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record(stream)
+    for _ in range(5):
+        plan.process_batch_device(x, ns, out, F3)
+    b.record(stream)
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 5
+    res["cfg3_frames_per_s"] = F3 / (ms * 1e-3)
+    res["cfg3_workload"] = "96 kHz mono, N=8192 -> M=16384, hop 256, H=1024, Viridis, %d frames/step" % F3
+    res["cfg3_hbm_frac"] = res["cfg3_frames_per_s"] * (hop3 * 4 + 4096) / 1e9 / measured_peaks()[0]["hbm_gbs"]
+    plan.close()
+    del x, out
+
+    # cfg2: live single stream, 48 kHz stereo, 2048-pt frames pushed one at a time through the pinned ring
+    plan = sbx.Plan(sample_rate=48000.0, window_n=2048, pad_factor=2, hop=2048, rows_h=1024, channels=2, lut="magma",
+                    device=torch.cuda.current_device())
+    live = plan.live(4096)
+    lr = signals.stereo_loopback(2048 * 64)
+    col = np.empty((1024, 4), np.uint8)
+    lat = []
+    for i in range(11000):
+        blk = lr[(i % 64) * 2048:(i % 64 + 1) * 2048]
+        t0 = time.perf_counter_ns()
+        live.push(blk)
+        live.pop_column(col)
+        t1 = time.perf_counter_ns()
+        if i >= 1000:
+            lat.append((t1 - t0) * 1e-3)
+    lat = np.array(lat)
+    res["cfg2_live_latency_us"] = {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
+                                   "mean": float(lat.mean()), "samples": int(lat.size),
+                                   "what": "push 2048 stereo samples into the pinned ring + pop one RGBA column (CUDA graph H2D->kernel->D2H + sync), timed on the host through ctypes"}
+    live.close()
+    plan.close()
+    return res
+
+
+if __name__ == "__main__":
+    main()

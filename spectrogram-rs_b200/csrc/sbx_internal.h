@@ -29,7 +29,7 @@ struct sbx_plan {
     uint32_t *d_lut = nullptr;
 
     // single-frame staging (host pinned + device)
-    float *h_frame = nullptr;           // N x 2 floats in, reused for K x 2 out
+    float *h_frame = nullptr;           // max(N, K) x 2 floats: N x 2 in, reused for K x 2 out
     uint8_t *h_col = nullptr;           // H x 4
     float *d_frame = nullptr;           // N x 2
     float *d_mags1 = nullptr;           // K x 2

@@ -336,7 +336,7 @@ SBX_API sbx_status sbx_plan_create(const sbx_config *cfg, sbx_plan **out_plan)
     SBX_TRY(cudaMalloc(&p->d_frame, (size_t)p->n * 2 * sizeof(float)));
     SBX_TRY(cudaMalloc(&p->d_mags1, (size_t)p->k_out * 2 * sizeof(float)));
     SBX_TRY(cudaMalloc(&p->d_col, (size_t)p->rows * 4));
-    SBX_TRY(cudaMallocHost(&p->h_frame, (size_t)p->n * 2 * sizeof(float)));
+    SBX_TRY(cudaMallocHost(&p->h_frame, (size_t)(p->n > p->k_out ? p->n : p->k_out) * 2 * sizeof(float)));
     SBX_TRY(cudaMallocHost(&p->h_col, (size_t)p->rows * 4));
     SBX_TRY(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
 #undef SBX_TRY

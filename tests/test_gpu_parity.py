@@ -1,0 +1,212 @@
+"""-m gpu: the CUDA path, called through the C ABI (libsbx_b200.so), against the CPU oracle.
+
+Tolerances (BASELINE.json north_star):
+  * magnitudes: max |gpu - oracle| <= 1e-5 * frame peak   (f32 FFT vs the oracle's f32 FFT; the
+    literal per-bin relative error is meaningless on leakage-floor bins)
+  * bin map / thresholds / window: bit-exact
+  * RGBA from identical magnitudes: bit-exact
+  * RGBA end to end: every pixel within one LUT step, and at most 0.1 % of pixels differing at all
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests import signals
+
+pytestmark = pytest.mark.gpu
+
+MAG_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def sbx():
+    import spectrogram_rs_b200 as s
+    return s
+
+
+def _pcm(channels, n_samples, seed=0):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    if channels == 1:
+        return (signals.log_sweep(n_samples) + 0.02 * rng.standard_normal(n_samples)).astype(np.float32)
+    return signals.stereo_loopback(n_samples, seed=seed + 1)
+
+
+def _lut_index_image(rgba, lut):
+    """Map RGBA pixels back to LUT indices (ramps used here have unique entries)."""
+    key = {tuple(int(v) for v in c): i for i, c in enumerate(lut)}
+    flat = rgba.reshape(-1, 4)
+    return np.array([key[tuple(int(v) for v in px[:3])] for px in flat]).reshape(rgba.shape[:-1])
+
+
+CASES = [
+    # (N, P, channels, hop, H, interp)
+    (256, 2, 2, 64, 64, 0),
+    (512, 2, 1, 128, 128, 0),
+    (1024, 4, 2, 256, 256, 1),
+    (2048, 2, 2, 2048, 1024, 0),       # cfg2 geometry
+    (4096, 2, 1, 512, 1024, 0),        # cfg1 / cfg4 geometry
+    (4096, 2, 2, 512, 1024, 1),
+    (8192, 2, 1, 256, 1024, 0),        # cfg3 geometry
+    (4096, 4, 1, 512, 2048, 0),        # cfg5 geometry (N = 4096)
+    (2048, 1, 2, 512, 512, 0),
+    (256, 1, 1, 100, 77, 0),           # ragged hop / odd H
+]
+
+
+@pytest.mark.parametrize("n,pad,ch,hop,rows,interp", CASES)
+def test_batch_matches_oracle(sbx, magma, n, pad, ch, hop, rows, interp):
+    import torch
+    frames = 7                                        # odd: exercises the half-filled mono pair
+    n_samples = n + hop * (frames - 1) + 5
+    pcm = _pcm(ch, n_samples)
+    p = oracle.params(window_n=n, pad_factor=pad, hop=hop, rows_h=rows, interp=interp)
+    o_rgba, o_mags = oracle.batch(p, pcm, ch, magma, want_mags=True)
+
+    with sbx.Plan(window_n=n, pad_factor=pad, hop=hop, rows_h=rows, channels=ch, interp=interp, lut=magma) as plan:
+        assert plan.num_frames(n_samples) == frames == oracle.num_frames(n_samples, n, hop)
+        d_pcm = torch.from_numpy(pcm).cuda()
+        d_mags = torch.zeros((frames, plan.k, 2), dtype=torch.float32, device="cuda")
+        d_rgba = torch.zeros((frames, rows, 4), dtype=torch.uint8, device="cuda")
+        assert plan.magnitudes_batch_device(d_pcm, n_samples, d_mags, frames) == frames
+        assert plan.process_batch_device(d_pcm, n_samples, d_rgba, frames) == frames
+        plan.synchronize()
+        g_mags, g_rgba = d_mags.cpu().numpy(), d_rgba.cpu().numpy()
+        # host-pointer batch entry point gives the same bytes
+        h_rgba = plan.process_batch(pcm)
+        assert np.array_equal(h_rgba, g_rgba)
+        # magnitudes
+        peak = np.abs(o_mags).max(axis=(1, 2), keepdims=True)
+        assert (np.abs(g_mags - o_mags) / peak).max() <= MAG_TOL
+        # identical normalised inputs -> bit-exact RGBA
+        assert np.array_equal(plan.colorize_magnitudes(g_mags), np.stack(
+            [oracle.column_from_magnitudes(p, g_mags[f], magma) for f in range(frames)]))
+        assert np.array_equal(plan.colorize_magnitudes(o_mags), o_rgba)
+        # fused kernel == its own magnitudes run through the colour stage
+        assert np.array_equal(plan.colorize_magnitudes(g_mags), g_rgba)
+        # end to end
+        assert np.array_equal(g_rgba[..., 3], o_rgba[..., 3])
+        di = np.abs(_lut_index_image(g_rgba, magma) - _lut_index_image(o_rgba, magma))
+        assert di.max() <= 1
+        assert (di != 0).mean() <= 1e-3
+
+
+@pytest.mark.parametrize("n,pad", [(256, 2), (2048, 2), (4096, 2), (1024, 4)])
+def test_single_frame_entry_points(sbx, magma, n, pad):
+    lr = signals.stereo_loopback(n + 10)
+    p = oracle.params(window_n=n, pad_factor=pad, rows_h=256)
+    with sbx.Plan(window_n=n, pad_factor=pad, rows_h=256, lut=magma) as plan:
+        assert plan.process_magnitudes(lr[: n - 1]) is None          # the reference's None
+        assert plan.process_column(lr[: n - 1]) is None
+        g = plan.process_magnitudes(lr)
+        o = oracle.frame_magnitudes(lr, n, pad)
+        assert g.shape == o.shape == (n * pad // 2 - 1, 2)
+        assert np.abs(g - o).max() <= MAG_TOL * np.abs(o).max()
+        col = plan.process_column(lr)
+        assert np.array_equal(col, plan.colorize_magnitudes(g)[0])
+        ocol = oracle.column_from_magnitudes(p, g, magma)
+        assert np.array_equal(col, ocol)
+
+
+def test_tables_bit_exact(sbx, magma):
+    for kw in (dict(window_n=4096, pad_factor=2, rows_h=1024, sample_rate=48000.0),
+               dict(window_n=8192, pad_factor=2, rows_h=1024, sample_rate=96000.0),
+               dict(window_n=1024, pad_factor=4, rows_h=2048, sample_rate=48000.0),
+               dict(window_n=2048, pad_factor=2, rows_h=333, sample_rate=44100.0, f_min=20.0, f_max=20000.0)):
+        with sbx.Plan(lut=magma, **kw) as plan:
+            p = oracle.params(**kw)
+            f0, step, n, period = plan.bin_map()
+            of0, ostep, on, operiod = oracle.bin_map(p)
+            assert np.array_equal(f0.view(np.uint32), of0.view(np.uint32))
+            assert np.array_equal(step.view(np.uint32), ostep.view(np.uint32))
+            assert np.array_equal(n, on)
+            assert np.float32(period).view(np.uint32) == np.float32(operiod).view(np.uint32)
+            assert np.array_equal(plan.window().view(np.uint32), oracle.hann(kw["window_n"]).view(np.uint32))
+
+
+def test_known_answer_sine(sbx, magma):
+    """K1/K2: unit sine at exact padded bin k0 -> L[k0-1] = 0.5; L-only input -> R ~ 0."""
+    n, pad, k0 = 4096, 2, 400
+    t = np.arange(n, dtype=np.float64)
+    s = np.sin(2 * np.pi * k0 * t / (n * pad)).astype(np.float32)
+    with sbx.Plan(window_n=n, pad_factor=pad, lut=magma) as plan:
+        m = plan.process_magnitudes(np.stack([s, s], 1))
+        assert abs(m[k0 - 1, 0] - 0.5) < 2e-6 and abs(m[k0 - 1, 1] - 0.5) < 2e-6
+        assert abs(m[k0 + 1, 0] - 0.25) < 2e-6                      # +-2 padded bins = +-1 Hann bin
+        assert abs(m[k0, 0] - 0.42441318) < 2e-6
+        assert m[k0 + 7, 0] < 1e-6
+        m = plan.process_magnitudes(np.stack([s, np.zeros_like(s)], 1))
+        assert abs(m[k0 - 1, 0] - 0.5) < 2e-6 and m[:, 1].max() < 1e-6
+
+
+def test_mono_equals_duplicated_stereo(sbx, magma):
+    """channels=1 is defined as the (s,s) duplication of audio_input_list_model.rs:66-69."""
+    import torch
+    n, hop, frames = 1024, 256, 6
+    ns = n + hop * (frames - 1)
+    x = signals.white_noise(ns)
+    with sbx.Plan(window_n=n, hop=hop, rows_h=256, channels=1, lut=magma) as pm, \
+            sbx.Plan(window_n=n, hop=hop, rows_h=256, channels=2, lut=magma) as ps:
+        a = torch.zeros((frames, 256, 4), dtype=torch.uint8, device="cuda")
+        b = torch.zeros_like(a)
+        pm.process_batch_device(torch.from_numpy(x).cuda(), ns, a, frames)
+        ps.process_batch_device(torch.from_numpy(np.stack([x, x], 1)).cuda(), ns, b, frames)
+        pm.synchronize(); ps.synchronize()
+        ia, ib = _lut_index_image(a.cpu().numpy(), magma), _lut_index_image(b.cpu().numpy(), magma)
+        assert np.abs(ia - ib).max() <= 1 and (ia != ib).mean() <= 1e-3
+
+
+def test_time_block_sharding_is_exact(sbx, magma):
+    """frames [lo, hi) computed from the sample block [lo*hop, (hi-1)*hop + N) equal the
+    same frames of the unsharded run, byte for byte."""
+    n, hop = 2048, 256
+    ns = n + hop * 40
+    x = signals.log_sweep(ns)
+    with sbx.Plan(window_n=n, hop=hop, rows_h=512, channels=1, lut=magma) as plan:
+        whole = plan.process_batch(x)
+        total = whole.shape[0]
+        parts = []
+        for g in range(3):
+            lo, hi = total * g // 3, total * (g + 1) // 3
+            parts.append(plan.process_batch(x[lo * hop:(hi - 1) * hop + n]))
+        assert np.array_equal(np.concatenate(parts), whole)
+
+
+def test_live_ring_semantics(sbx, magma):
+    """sbx_live_*: non-consuming window, skip(hop) even on the failing attempt, push drops overflow."""
+    n, hop = 2048, 2048
+    lr = signals.stereo_loopback(n * 3)
+    with sbx.Plan(window_n=n, hop=hop, rows_h=1024, lut=magma) as plan:
+        live = plan.live(4096)
+        assert live.pop_column() is None
+        assert live.push(lr[:4000]) == 4000
+        assert live.push(lr[4000:4200]) == 96                       # capacity 4096
+        c0 = live.pop_column()
+        assert np.array_equal(c0, plan.process_column(lr[:n]))
+        assert live.buffered() == 4096 - hop
+        c1 = live.pop_column()
+        assert np.array_equal(c1, plan.process_column(lr[hop:hop + n]))
+        assert live.buffered() == 0
+        live.push(lr[:100])
+        assert live.pop_column() is None and live.buffered() == 0   # skip also on failure
+        m = None
+        live.push(lr[:n])
+        m = live.pop_magnitudes()
+        assert np.array_equal(m, plan.process_magnitudes(lr[:n]))
+        live.close()
+
+
+def test_errors_do_not_abort(sbx, magma):
+    with pytest.raises(sbx.SbxError) as e:
+        sbx.Plan(window_n=2400, lut=magma)                          # the live app's size: not yet supported
+    assert e.value.status == -2
+    with pytest.raises(sbx.SbxError):
+        sbx.Plan(window_n=8192, pad_factor=4, lut=magma)
+    with pytest.raises(sbx.SbxError):
+        sbx.Plan(window_n=1024, hop=0, lut=magma)
+    with sbx.Plan(window_n=1024, lut=magma) as plan:
+        import torch
+        small = torch.zeros((1, 1024, 4), dtype=torch.uint8, device="cuda")
+        pcm = torch.zeros(1024 * 2 * 4, device="cuda")
+        with pytest.raises(sbx.SbxError) as e:
+            plan.process_batch_device(pcm, 1024 * 4, small, 1)
+        assert e.value.status == -5
