@@ -17,13 +17,17 @@ struct sbx_plan {
     // host copies of the tables (for introspection and the bit-exactness tests)
     std::vector<float> h_window;
     std::vector<sbx::RowMap> h_rowmap;
-    std::vector<float> h_thr;           // 512
-    std::vector<float> h_cos_w;
+    std::vector<float> h_thr_raw;       // [2][256] bare thresholds
+    float guess_a[2] = {0, 0}, guess_b[2] = {0, 0};
+    uint32_t n_chunks = 0;
 
     // device tables
     float *d_window = nullptr;
-    float2 *d_tw = nullptr;
+    float2 *d_wtw = nullptr;
+    float2 *d_twp = nullptr;
     sbx::RowMap *d_rowmap = nullptr;
+    sbx::RowChunk *d_chunks = nullptr;
+    float *d_samp_x = nullptr;
     float *d_cos_w = nullptr;
     float *d_thr = nullptr;
     uint32_t *d_lut = nullptr;

@@ -115,7 +115,7 @@ sbx_status launch_fused(sbx_plan *p, int channels, const float *d_pcm, uint64_t 
 template <int LOG2M> cudaError_t launch_colourise_one(const KernelArgs &a, uint64_t n_frames, cudaStream_t stream)
 {
     static bool configured[64] = {};
-    const int smem = (4 << LOG2M) + 512 * 4 + 256 * 4;
+    const int smem = (8 << LOG2M) + 2 * sbx::THR_STRIDE * 4 + 256 * 4;
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !configured[dev]) {
@@ -157,17 +157,21 @@ sbx::KernelArgs sbx_plan::base_args() const
 {
     sbx::KernelArgs a{};
     a.window = d_window;
-    a.tw = d_tw;
+    a.wtw = d_wtw;
+    a.twp = d_twp;
     a.rowmap = d_rowmap;
+    a.chunks = d_chunks;
+    a.n_chunks = n_chunks;
+    a.samp_x = d_samp_x;
     a.cos_w = d_cos_w;
     a.thr = d_thr;
     a.lut = d_lut;
     a.hop = hop;
     a.rows = rows;
     a.k_out = k_out;
-    a.period = period;
-    a.k_max_f = (float)(k_out - 1);
     a.scale = scale;
+    a.db_eps = cfg.db_eps;
+    for (int i = 0; i < 2; ++i) { a.guess_a[i] = guess_a[i]; a.guess_b[i] = guess_b[i]; }
     a.interp = (int)cfg.interp;
     a.scheme = (int)cfg.scheme;
     return a;
@@ -249,7 +253,8 @@ SBX_API void sbx_plan_destroy(sbx_plan *p)
         cudaFree(s.d_pcm);
         cudaFree(s.d_rgba);
     }
-    cudaFree(p->d_window); cudaFree(p->d_tw); cudaFree(p->d_rowmap); cudaFree(p->d_cos_w);
+    cudaFree(p->d_window); cudaFree(p->d_wtw); cudaFree(p->d_twp); cudaFree(p->d_rowmap); cudaFree(p->d_chunks);
+    cudaFree(p->d_samp_x); cudaFree(p->d_cos_w);
     cudaFree(p->d_thr); cudaFree(p->d_lut); cudaFree(p->d_frame); cudaFree(p->d_mags1); cudaFree(p->d_col);
     if (p->h_frame) cudaFreeHost(p->h_frame);
     if (p->h_col) cudaFreeHost(p->h_col);
@@ -311,10 +316,15 @@ SBX_API sbx_status sbx_plan_create(const sbx_config *cfg, sbx_plan **out_plan)
     sbx::tables::build(*cfg, t);
     p->period = t.period;
     p->scale = t.scale;
+    if (!t.ok) {
+        delete p;
+        return fail(nullptr, SBX_ERR_UNSUPPORTED, "a row of the bin map averages more samples than the shared-memory scratch holds");
+    }
     p->h_window = t.window;
     p->h_rowmap = t.rowmap;
-    p->h_cos_w = t.cos_w;
-    p->h_thr = t.thr;
+    p->h_thr_raw = t.thr_raw;
+    p->n_chunks = (uint32_t)t.chunks.size();
+    for (int i = 0; i < 2; ++i) { p->guess_a[i] = t.guess_a[i]; p->guess_b[i] = t.guess_b[i]; }
 
 #define SBX_TRY(call)                                                                   \
     do {                                                                                \
@@ -328,10 +338,13 @@ SBX_API sbx_status sbx_plan_create(const sbx_config *cfg, sbx_plan **out_plan)
     } while (0)
 
     SBX_TRY(upload(&p->d_window, p->h_window.data(), p->n * sizeof(float)));
-    SBX_TRY(upload(&p->d_tw, t.tw.data(), p->m * sizeof(float2)));
+    SBX_TRY(upload(&p->d_wtw, t.wtw.data(), t.wtw.size() * sizeof(float)));
+    SBX_TRY(upload(&p->d_twp, t.twp.data(), t.twp.size() * sizeof(float)));
     SBX_TRY(upload(&p->d_rowmap, p->h_rowmap.data(), p->rows * sizeof(sbx::RowMap)));
-    SBX_TRY(upload(&p->d_cos_w, p->h_cos_w.data(), p->h_cos_w.size() * sizeof(float)));
-    SBX_TRY(upload(&p->d_thr, p->h_thr.data(), 512 * sizeof(float)));
+    SBX_TRY(upload(&p->d_chunks, t.chunks.data(), t.chunks.size() * sizeof(sbx::RowChunk)));
+    SBX_TRY(upload(&p->d_samp_x, t.samp_x.data(), t.samp_x.size() * sizeof(float)));
+    SBX_TRY(upload(&p->d_cos_w, t.cos_w.data(), t.cos_w.size() * sizeof(float)));
+    SBX_TRY(upload(&p->d_thr, t.thr.data(), t.thr.size() * sizeof(float)));
     SBX_TRY(upload(&p->d_lut, t.lut, sizeof(t.lut)));
     SBX_TRY(cudaMalloc(&p->d_frame, (size_t)p->n * 2 * sizeof(float)));
     SBX_TRY(cudaMalloc(&p->d_mags1, (size_t)p->k_out * 2 * sizeof(float)));
@@ -525,7 +538,7 @@ SBX_API sbx_status sbx_get_bin_map(const sbx_plan *p, float *f0, float *step, ui
 SBX_API sbx_status sbx_get_color_thresholds(const sbx_plan *p, float thr[255])
 {
     if (!p || !thr) return SBX_ERR_INVALID_ARGUMENT;
-    std::memcpy(thr, p->h_thr.data(), 255 * sizeof(float));
+    std::memcpy(thr, p->h_thr_raw.data(), 255 * sizeof(float));
     return SBX_OK;
 }
 

@@ -86,11 +86,25 @@ struct HostTables {
     uint32_t n = 0, pad = 0, m = 0, k_out = 0, rows = 0;
     float period = 0.0f, scale = 0.0f;
     std::vector<float> window;          // [N]
-    std::vector<float> tw;              // [M] x (re, im)
+    std::vector<float> wtw;             // [(P-1) N] x (re, im): window[n] * W_M^(n q0)
+    std::vector<float> twp;             // per-pass twiddle planes x (re, im), see KernelArgs::twp
     std::vector<RowMap> rowmap;         // [H]
-    std::vector<float> cos_w;           // COSINE weights per (row, sample)
-    std::vector<float> thr;             // [512]
+    std::vector<RowChunk> chunks;       // rows grouped so that a chunk's samples fit the kernel's scratch area
+    std::vector<float> samp_x;          // per (row, sample): clamped fractional bin
+    std::vector<float> cos_w;           // per (row, sample): cosine weight (COSINE only)
+    std::vector<float> thr;             // [2][THR_STRIDE] with sentinels
+    std::vector<float> thr_raw;         // [2][256] the bare thresholds (introspection)
+    float guess_a[2], guess_b[2];
     uint32_t lut[256];
+    bool ok = true;                     // false: a row has more samples than the scratch area holds
+};
+
+// radix plan of the length-N sub-transform: first pass radix 2^(log2n % 4) when that is not 1, then 16s
+struct RadixPlan {
+    int log2n, rem, npass;
+    explicit RadixPlan(int l) : log2n(l), rem(l & 3), npass(l / 4 + ((l & 3) ? 1 : 0)) {}
+    int log2r(int p) const { return (rem != 0 && p == 0) ? rem : 4; }
+    int log2stride(int p) const { int s = log2n; for (int i = 0; i <= p; ++i) s -= log2r(i); return s; }
 };
 
 inline void build(const sbx_config &cfg, HostTables &t)
@@ -107,11 +121,29 @@ inline void build(const sbx_config &cfg, HostTables &t)
     t.window.resize(t.n);
     for (uint32_t i = 0; i < t.n; ++i) t.window[i] = hann_f32(i, t.n);
 
-    t.tw.resize((size_t)t.m * 2);
-    for (uint32_t k = 0; k < t.m; ++k) {
-        const double ang = -2.0 * M_PI * (double)k / (double)t.m;
-        t.tw[2 * (size_t)k] = (float)std::cos(ang);
-        t.tw[2 * (size_t)k + 1] = (float)std::sin(ang);
+    // sub-transform premultiply: window[n] * W_M^(n q0), q0 = 1..P-1 (f64 product of the f32 window)
+    t.wtw.assign((size_t)(t.pad - 1) * t.n * 2, 0.0f);
+    for (uint32_t q0 = 1; q0 < t.pad; ++q0)
+        for (uint32_t i = 0; i < t.n; ++i) {
+            const double ang = -2.0 * M_PI * (double)(((uint64_t)i * q0) % t.m) / (double)t.m;
+            const size_t o = ((size_t)(q0 - 1) * t.n + i) * 2;
+            t.wtw[o] = (float)((double)t.window[i] * std::cos(ang));
+            t.wtw[o + 1] = (float)((double)t.window[i] * std::sin(ang));
+        }
+
+    // per-pass twiddle planes: plane j of pass p holds W_(S_p R_p)^(2^j lo), lo < S_p
+    int log2n = 0;
+    while ((1u << log2n) < t.n) ++log2n;
+    const RadixPlan rp(log2n);
+    t.twp.clear();
+    for (int p = 0; p + 1 < rp.npass; ++p) {
+        const uint32_t s = 1u << rp.log2stride(p), span = s << rp.log2r(p);
+        for (int j = 0; j < TW_PLANES; ++j)
+            for (uint32_t lo = 0; lo < s; ++lo) {
+                const double ang = -2.0 * M_PI * (double)(((uint64_t)lo << j) % span) / (double)span;
+                t.twp.push_back((float)std::cos(ang));
+                t.twp.push_back((float)std::sin(ang));
+            }
     }
 
     t.rowmap.resize(t.rows);
@@ -130,26 +162,58 @@ inline void build(const sbx_config &cfg, HostTables &t)
         total_samples += n;
         t.rowmap[py] = rm;
     }
+    // per-sample positions: index_of(lin_space(f0..f1, n)[s])  (ifs.rs:67-69, :24-31), and the cosine weights
+    t.samp_x.resize(total_samples);
     t.cos_w.clear();
-    if (cfg.interp == SBX_INTERP_COSINE) {
-        // (1 - cos(frac * PI)) / 2 per (row, sample), f32, host libm -- ifs.rs:82-83
-        const float pi = 3.14159265358979323846f;
-        t.cos_w.resize(total_samples);
-        for (uint32_t py = 0; py < t.rows; ++py) {
-            const RowMap &rm = t.rowmap[py];
-            for (uint32_t s = 0; s < rm.n; ++s) {
-                const float fq = rm.f0 + (float)s * rm.step;
-                const float x = index_of(fq, t.period, t.k_out);
+    if (cfg.interp == SBX_INTERP_COSINE) t.cos_w.resize(total_samples);
+    const float pi = 3.14159265358979323846f;
+    for (uint32_t py = 0; py < t.rows; ++py) {
+        const RowMap &rm = t.rowmap[py];
+        for (uint32_t s = 0; s < rm.n; ++s) {
+            const float fq = rm.f0 + (float)s * rm.step;
+            const float x = index_of(fq, t.period, t.k_out);
+            t.samp_x[rm.aux + s] = x;
+            if (cfg.interp == SBX_INTERP_COSINE) {
                 const float off = x - std::floor(x);
-                t.cos_w[rm.aux + s] = (1.0f - cosf(off * pi)) / 2.0f;
+                t.cos_w[rm.aux + s] = (1.0f - cosf(off * pi)) / 2.0f;                  // ifs.rs:82-83
             }
         }
     }
+    // row chunks: greedy, a chunk's samples must fit the kernel's scratch area ((M/2) * 16/17 slots)
+    const uint32_t cap = (uint32_t)((((uint64_t)t.m / 2) * 16) / 17);
+    t.chunks.clear();
+    t.ok = true;
+    RowChunk ck = {0, 0, 0, 0};
+    for (uint32_t py = 0; py < t.rows; ++py) {
+        const RowMap &rm = t.rowmap[py];
+        if (rm.n > cap) t.ok = false;
+        if (ck.samp_end - ck.samp_begin + rm.n > cap && ck.row_end > ck.row_begin) {
+            t.chunks.push_back(ck);
+            ck.row_begin = py; ck.samp_begin = rm.aux;
+        }
+        ck.row_end = py + 1;
+        ck.samp_end = rm.aux + rm.n;
+    }
+    t.chunks.push_back(ck);
 
-    t.thr.resize(512);
+    t.thr_raw.resize(512);
     const sbx_config c = cfg;
-    step_thresholds([&c](float pw) { return colour_step(pw, c); }, t.thr.data());
-    step_thresholds([&c](float pw) { return alpha_step(pw, c); }, t.thr.data() + 256);
+    step_thresholds([&c](float pw) { return colour_step(pw, c); }, t.thr_raw.data());
+    step_thresholds([&c](float pw) { return alpha_step(pw, c); }, t.thr_raw.data() + 256);
+    // device layout per set: [-inf, thr[0..254], +inf, pad...]
+    t.thr.assign(2 * THR_STRIDE, std::numeric_limits<float>::infinity());
+    for (int set = 0; set < 2; ++set) {
+        float *dst = t.thr.data() + set * THR_STRIDE;
+        dst[0] = -std::numeric_limits<float>::infinity();
+        for (int i = 0; i < 255; ++i) dst[1 + i] = t.thr_raw[set * 256 + i];
+    }
+    // guess of the step: t = (10 log10(x) - db_min) / (db_max - db_min) * levels = log2(x) * a + b
+    const double range = (double)cfg.db_max - (double)cfg.db_min;
+    for (int set = 0; set < 2; ++set) {
+        const double levels = set == 0 ? 256.0 : 255.0;
+        t.guess_a[set] = (float)(10.0 * std::log10(2.0) * levels / range);
+        t.guess_b[set] = (float)(-(double)cfg.db_min * levels / range);
+    }
 
     for (int i = 0; i < 256; ++i)
         t.lut[i] = (uint32_t)cfg.lut_rgb[3 * i] | ((uint32_t)cfg.lut_rgb[3 * i + 1] << 8) |

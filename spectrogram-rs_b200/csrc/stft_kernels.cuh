@@ -36,25 +36,39 @@ struct RowMap {            // one output row py (0 = lowest frequency) of the lo
     uint32_t aux;          // offset of this row's first entry in the cosine-weight table
 };
 
+struct RowChunk {          // consecutive rows whose interpolated samples fit the shared scratch area
+    uint32_t row_begin, row_end;       // rows [row_begin, row_end)
+    uint32_t samp_begin, samp_end;     // their entries in the per-sample tables
+};
+
 struct KernelArgs {
     const float *pcm;            // device PCM, CH floats per sample
     uint8_t *rgba;               // frames x H x 4 or nullptr
     float *mags_out;             // frames x K x 2 or nullptr
     const float *mags_in;        // colourise-only kernel: frames x K x 2
     const float *window;         // [N] periodic Hann, f32, host-computed (fft.rs:59-63)
-    const float2 *tw;            // [M] W_M^t = exp(-2 pi i t / M), f64-computed, rounded once
+    const float2 *wtw;           // [(P-1) N] window[n] * W_M^(n q0), q0 = 1..P-1 (sub-transform premultiply)
+    const float2 *twp;           // per DIF pass p: TW_PLANES planes of S_p entries, plane j = W_(S_p R_p)^(2^j lo)
     const RowMap *rowmap;        // [H]
-    const float *cos_w;          // COSINE interpolation weights per (row, sample) or nullptr
-    const float *thr;            // [512] 255 colour-index thresholds (+inf pad), 255 alpha thresholds
+    const RowChunk *chunks;      // [n_chunks]
+    const float *samp_x;         // per (row, sample): clamped fractional bin index_of(f0 + s*step)
+    const float *cos_w;          // per (row, sample): cosine weight (1 - cos(frac*pi))/2, or nullptr
+    const float *thr;            // [2][264] step thresholds with sentinels: colour index, alpha
     const uint32_t *lut;         // [256] packed r | g<<8 | b<<16 | 255<<24
     unsigned long long n_frames;
-    uint32_t hop, rows, k_out;
-    float period;                // 2K / sr   (interpolated_frequency_sample.rs:52-54)
-    float k_max_f;               // (K-1) as f32
+    uint32_t hop, rows, k_out, n_chunks;
     float scale;                 // 2 / N     (fft.rs:92)
+    float guess_a[2], guess_b[2];// step guess = log2(p + eps) * a + b   (colour, alpha)
+    float db_eps;
     int interp;                  // 0 cubic, 1 cosine
     int scheme;                  // 0 mono gradient, 1 stereo pan gradient
 };
+
+constexpr int TW_PLANES = 4;     // twiddle planes stored per pass: W^(1,2,4,8 * lo)
+#ifndef SBX_TW_LOADS
+#define SBX_TW_LOADS 2           // planes actually loaded per butterfly (1: W^lo; 2: + W^4lo; 4: all); rest by products
+#endif
+constexpr int THR_STRIDE = 264;  // floats per threshold set: [-inf, thr[0..254], +inf, pad]
 
 // ----------------------------------------------------------------------------------------------
 // complex helpers and small DFT butterflies (forward, exp(-i...))
@@ -66,6 +80,26 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b)
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 __device__ __forceinline__ float2 mul_neg_i(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
+__device__ __forceinline__ float2 csqr(float2 a) { return make_float2(a.x * a.x - a.y * a.y, 2.0f * (a.x * a.y)); }
+
+__device__ __forceinline__ float fast_sqrt(float x)
+{
+#ifdef SBX_EMU
+    return sqrtf(x);
+#else
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));     // MUFU.SQRT: ~1 ulp, sqrt(0) = 0
+    return r;
+#endif
+}
+__device__ __forceinline__ float fast_log2(float x)
+{
+#ifdef SBX_EMU
+    return log2f(x);
+#else
+    return __log2f(x);
+#endif
+}
 
 #define SBX_RSQRT2 0.70710678118654752440f
 #define SBX_COS_PI_8 0.92387953251128675613f
@@ -163,7 +197,7 @@ template <int LOG2N_, int LOG2PAD_, int CH_> struct Geom {
     static constexpr int NPASS = LOG2N / 4 + (REM ? 1 : 0);
     static constexpr int THREADS = (M / 16) < 64 ? 64 : ((M / 16) > 512 ? 512 : (M / 16));
     static constexpr int FRAMES_PER_CTA = CH == 1 ? 2 : 1;
-    static constexpr int SMEM_BYTES = M * 8 + 512 * 4 + 256 * 4;
+    static constexpr int SMEM_BYTES = M * 8 + 2 * THR_STRIDE * 4 + 256 * 4;
     static __host__ __device__ constexpr int log2r(int p) { return (REM != 0 && p == 0) ? REM : 4; }
     static __host__ __device__ constexpr int log2stride(int p)                 // log2 of the butterfly stride of pass p
     {
@@ -171,6 +205,14 @@ template <int LOG2N_, int LOG2PAD_, int CH_> struct Geom {
         for (int i = 0; i <= p; ++i) s -= log2r(i);
         return s;
     }
+    static __host__ __device__ constexpr int tw_offset(int p)                  // first entry of pass p in KernelArgs::twp
+    {
+        int o = 0;
+        for (int i = 0; i < p; ++i) o += TW_PLANES << log2stride(i);
+        return o;
+    }
+    static constexpr int TW_TOTAL = tw_offset(NPASS - 1);                      // the last pass has no twiddles
+    static constexpr int SCRATCH = ((M / 2) * 16) / 17;                        // resample scratch slots (padded 17/16)
 };
 
 // shared-memory swizzles -----------------------------------------------------------------------
@@ -217,6 +259,41 @@ template <class G> __device__ __forceinline__ int pos_of_bin(int kk)
     return pos;
 }
 
+// v[q] *= w^q for q = 1..R-1, where plane[j * plane_stride] = w^(2^j) are exactly rounded table
+// values.  SBX_TW_LOADS of the planes are read; the other powers are products of at most three
+// table values (loads are the scarce resource: the kernel is L1/shared-memory-pipe bound).
+template <int R>
+__device__ __forceinline__ void apply_twiddles(float2 (&v)[R], const float2 *plane, int plane_stride)
+{
+    const float2 w1 = __ldg(plane);
+    v[1] = cmul(v[1], w1);
+    if constexpr (R >= 4) {
+        const float2 w2 = SBX_TW_LOADS >= 4 ? __ldg(plane + plane_stride) : csqr(w1);
+        const float2 w3 = cmul(w2, w1);
+        v[2] = cmul(v[2], w2);
+        v[3] = cmul(v[3], w3);
+        if constexpr (R >= 8) {
+            const float2 w4 = SBX_TW_LOADS >= 2 ? __ldg(plane + 2 * plane_stride) : csqr(w2);
+            const float2 w5 = cmul(w4, w1), w6 = cmul(w4, w2), w7 = cmul(w4, w3);
+            v[4] = cmul(v[4], w4);
+            v[5] = cmul(v[5], w5);
+            v[6] = cmul(v[6], w6);
+            v[7] = cmul(v[7], w7);
+            if constexpr (R >= 16) {
+                const float2 w8 = SBX_TW_LOADS >= 4 ? __ldg(plane + 3 * plane_stride) : csqr(w4);
+                v[8] = cmul(v[8], w8);
+                v[9] = cmul(v[9], cmul(w8, w1));
+                v[10] = cmul(v[10], cmul(w8, w2));
+                v[11] = cmul(v[11], cmul(w8, w3));
+                v[12] = cmul(v[12], cmul(w8, w4));
+                v[13] = cmul(v[13], cmul(w8, w5));
+                v[14] = cmul(v[14], cmul(w8, w6));
+                v[15] = cmul(v[15], cmul(w8, w7));
+            }
+        }
+    }
+}
+
 // ----------------------------------------------------------------------------------------------
 // DIF passes
 // ----------------------------------------------------------------------------------------------
@@ -230,12 +307,11 @@ __device__ __forceinline__ void pass_first(float2 *z, const KernelArgs &a, unsig
     const float *pa = a.pcm + frame0 * (unsigned long long)a.hop * G::CH;
     const float *pb = pa + a.hop;                                    // mono: the next frame
     for (int w = threadIdx.x; w < COUNT; w += G::THREADS) {
-        const int q0 = w / PER_SUB, lo = w % PER_SUB;
+        const int q0 = w / PER_SUB, lo = w % PER_SUB;                // q0 is warp-uniform (PER_SUB % 32 == 0)
         float2 v[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int n = lo + r * S;
-            const float wn = __ldg(a.window + n);
             float2 s;
             if constexpr (G::CH == 2) {
                 s = __ldg(reinterpret_cast<const float2 *>(pa) + n);
@@ -243,19 +319,19 @@ __device__ __forceinline__ void pass_first(float2 *z, const KernelArgs &a, unsig
                 s.x = __ldg(pa + n);
                 s.y = second_valid ? __ldg(pb + n) : 0.0f;
             }
-            s.x *= wn;  s.y *= wn;                                   // fft.rs:57-63 (complex * f32)
-            if (q0 != 0) s = cmul(s, __ldg(a.tw + ((n * q0) & (G::M - 1))));
+            if (q0 == 0) {
+                const float wn = __ldg(a.window + n);
+                s.x *= wn;  s.y *= wn;                               // fft.rs:57-63 (complex * f32)
+            } else {
+                s = cmul(s, __ldg(a.wtw + (q0 - 1) * G::N + n));     // window and W_M^(n q0) in one factor
+            }
             v[r] = s;
         }
         Butterfly<R>::run(v);
+        if constexpr (G::NPASS > 1) apply_twiddles<R>(v, a.twp + lo, S);   // W_N^(lo q)
         const int base = (q0 << G::LOG2N) + lo;
-        z[zsw(base)] = v[0];
 #pragma unroll
-        for (int q = 1; q < R; ++q) {
-            float2 y = v[q];
-            if constexpr (G::NPASS > 1) y = cmul(y, __ldg(a.tw + ((lo * q) << G::LOG2PAD)));   // W_N^(lo q)
-            z[zsw(base + q * S)] = y;
-        }
+        for (int q = 0; q < R; ++q) z[zsw(base + q * S)] = v[q];
     }
 }
 
@@ -290,12 +366,9 @@ __device__ __forceinline__ void pass_inplace(float2 *z, const KernelArgs &a)
 #pragma unroll
             for (int r = 0; r < 16; ++r) v[r] = z[zsw(base + r * S)];
             Butterfly<16>::run(v);
-            z[zsw(base)] = v[0];
-            // twiddle W_(16 S)^(lo q) = W_M^(lo q M/(16 S))
-            constexpr int TSHIFT = G::LOG2M - 4 - LS;
+            apply_twiddles<16>(v, a.twp + G::tw_offset(P) + lo, S);        // W_(16 S)^(lo q)
 #pragma unroll
-            for (int q = 1; q < 16; ++q)
-                z[zsw(base + q * S)] = cmul(v[q], __ldg(a.tw + ((lo * q) << TSHIFT)));
+            for (int q = 0; q < 16; ++q) z[zsw(base + q * S)] = v[q];
         }
     }
 }
@@ -340,8 +413,8 @@ __device__ __forceinline__ void split_read(const float2 *z, const KernelArgs &a,
                 const float2 y = z[zsw(pos_of_bin<G>(G::M - kk))];
                 const float lx = x.x + y.x, ly = x.y - y.y;   // a + conj b
                 const float rx = x.x - y.x, ry = x.y + y.y;   // a - conj b
-                const float l = sqrtf(lx * lx + ly * ly) * 0.5f;
-                const float rr = sqrtf(rx * rx + ry * ry) * 0.5f;
+                const float l = fast_sqrt(lx * lx + ly * ly) * 0.5f;
+                const float rr = fast_sqrt(rx * rx + ry * ry) * 0.5f;
                 r.mag[i] = make_float2(l * a.scale, rr * a.scale);
                 r.kks[i] = kk;
             }
@@ -371,104 +444,140 @@ __device__ __forceinline__ float cubic1(float y0, float y1, float y2, float y3, 
     return __fadd_rn(__fadd_rn(__fmul_rn(a0, mu3), __fmul_rn(a1, mu2)), __fadd_rn(__fmul_rn(a2, mu), y1));
 }
 
-// number of thresholds <= p  (thr ascending, thr[255] = +inf); NaN -> 0
-__device__ __forceinline__ int step_index(const float *thr, float p)
+// Step function of p: the number of thresholds <= p.  ts = [-inf, thr[0..254], +inf]; the guess
+// log2(p + eps) * ga + gb is the same dB chain evaluated with the fast log, and is corrected against
+// the exact host-computed thresholds, so the result is exact whatever the error of the guess.
+__device__ __forceinline__ int step_index(const float *ts, float p, float eps, float ga, float gb)
 {
-    int pos = 0;
-#pragma unroll
-    for (int s = 128; s >= 1; s >>= 1)
-        if (thr[pos + s - 1] <= p) pos += s;
-    return pos;
+    const float t = fast_log2(p + eps) * ga + gb;
+    int idx = (int)fminf(fmaxf(t, 0.0f), 255.0f);           // NaN -> 0
+    while (idx < 255 && p >= ts[idx + 1]) ++idx;
+    while (idx > 0 && p < ts[idx]) --idx;
+    return idx;
 }
 
-template <int LOG2M, bool PAIR, int THREADS>
-__device__ __forceinline__ void resample_colour(const float2 *mags, const float *thr, const uint32_t *lut,
-                                                const KernelArgs &a, unsigned long long frame0, bool second_valid)
+__device__ __forceinline__ int scratch_slot(int g) { return g + (g >> 4); }   // 17/16 padding
+
+// One interpolated sample (both channels) at fractional bin x -- magnitude_at (ifs.rs:46-48)
+template <int LOG2M>
+__device__ __forceinline__ float2 interp_sample(const float2 *mags, const KernelArgs &a, float x, int k_last, uint32_t g)
+{
+    const float fl = floorf(x);
+    const int x1 = (int)fl;
+    float2 v;
+    if (a.interp == 0) {                                                     // cubic_interpolate
+        const float mu = __fsub_rn(x, fl);
+        const float mu2 = __fmul_rn(mu, mu), mu3 = __fmul_rn(mu, mu2);
+        const int x0 = x1 > 0 ? x1 - 1 : 0;
+        const int x2 = min(x1 + 1, k_last), x3 = min(x1 + 2, k_last);
+        const float2 y0 = mags[msw<LOG2M>(x0 + 1)], y1 = mags[msw<LOG2M>(x1 + 1)];
+        const float2 y2 = mags[msw<LOG2M>(x2 + 1)], y3 = mags[msw<LOG2M>(x3 + 1)];
+        v.x = cubic1(y0.x, y1.x, y2.x, y3.x, mu, mu2, mu3);
+        v.y = cubic1(y0.y, y1.y, y2.y, y3.y, mu, mu2, mu3);
+    } else {                                                                 // cosine_interpolate
+        int hi = (int)ceilf(x);
+        const int lo_b = min(x1 + 1, k_last);
+        hi = min(max(hi, lo_b), k_last);
+        const float t = __ldg(a.cos_w + g);                                  // host libm cosf
+        const float omt = __fsub_rn(1.0f, t);
+        const float2 yl = mags[msw<LOG2M>(x1 + 1)], yh = mags[msw<LOG2M>(hi + 1)];
+        v.x = __fadd_rn(__fmul_rn(yl.x, omt), __fmul_rn(yh.x, t));
+        v.y = __fadd_rn(__fmul_rn(yl.y, omt), __fmul_rn(yh.y, t));
+    }
+    return v;
+}
+
+// Phase A of a row chunk: one lane per (row, sample); consecutive lanes read consecutive bins
+template <int LOG2M, int THREADS>
+__device__ __forceinline__ void resample_samples(const float2 *mags, float2 *scratch, const KernelArgs &a, const RowChunk ck)
 {
     const int k_last = (int)a.k_out - 1;
+    for (uint32_t g = ck.samp_begin + threadIdx.x; g < ck.samp_end; g += THREADS)
+        scratch[scratch_slot((int)(g - ck.samp_begin))] = interp_sample<LOG2M>(mags, a, __ldg(a.samp_x + g), k_last, g);
+}
+
+// Phase B: one thread per row: sequential mean of its samples (the reference's summation order,
+// ifs.rs:71-73), dB step, LUT, packed RGBA store
+template <bool PAIR, int THREADS>
+__device__ __forceinline__ void colour_rows(const float2 *scratch, const float *thr, const uint32_t *lut,
+                                            const KernelArgs &a, const RowChunk ck, unsigned long long frame0, bool second_valid)
+{
     uint32_t *outA = reinterpret_cast<uint32_t *>(a.rgba) + frame0 * a.rows;
     uint32_t *outB = outA + a.rows;
-    for (uint32_t py = threadIdx.x; py < a.rows; py += THREADS) {
+    for (uint32_t py = ck.row_begin + threadIdx.x; py < ck.row_end; py += THREADS) {
         const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.rowmap) + py);
-        const float f0 = __uint_as_float(raw.x), step = __uint_as_float(raw.y);
         const uint32_t n = raw.z;
+        const int first = (int)(raw.w - ck.samp_begin);
         float ax = 0.0f, ay = 0.0f;
         for (uint32_t s = 0; s < n; ++s) {
-            const float fq = __fadd_rn(f0, __fmul_rn((float)s, step));          // lin_space
-            float x = __fmul_rn(fq, a.period);                                   // index_of
-            x = fminf(fmaxf(x, 0.0f), a.k_max_f);
-            const float fl = floorf(x);
-            const int x1 = (int)fl;
-            float vx, vy;
-            if (a.interp == 0) {                                                 // cubic_interpolate
-                const float mu = __fsub_rn(x, fl);
-                const float mu2 = __fmul_rn(mu, mu), mu3 = __fmul_rn(mu, mu2);
-                const int x0 = x1 > 0 ? x1 - 1 : 0;
-                const int x2 = min(x1 + 1, k_last), x3 = min(x1 + 2, k_last);
-                const float2 y0 = mags[msw<LOG2M>(x0 + 1)], y1 = mags[msw<LOG2M>(x1 + 1)];
-                const float2 y2 = mags[msw<LOG2M>(x2 + 1)], y3 = mags[msw<LOG2M>(x3 + 1)];
-                vx = cubic1(y0.x, y1.x, y2.x, y3.x, mu, mu2, mu3);
-                vy = cubic1(y0.y, y1.y, y2.y, y3.y, mu, mu2, mu3);
-            } else {                                                             // cosine_interpolate
-                int hi = (int)ceilf(x);
-                const int lo_b = min(x1 + 1, k_last);
-                hi = min(max(hi, lo_b), k_last);
-                const float t = __ldg(a.cos_w + raw.w + s);                      // (1 - cos(frac*pi)) / 2, host libm
-                const float omt = __fsub_rn(1.0f, t);
-                const float2 yl = mags[msw<LOG2M>(x1 + 1)], yh = mags[msw<LOG2M>(hi + 1)];
-                vx = __fadd_rn(__fmul_rn(yl.x, omt), __fmul_rn(yh.x, t));
-                vy = __fadd_rn(__fmul_rn(yl.y, omt), __fmul_rn(yh.y, t));
-            }
-            ax = __fadd_rn(ax, vx);
-            ay = __fadd_rn(ay, vy);
+            const float2 v = scratch[scratch_slot(first + (int)s)];
+            ax = __fadd_rn(ax, v.x);
+            ay = __fadd_rn(ay, v.y);
         }
         const float nf = (float)n;
         ax = __fdiv_rn(ax, nf);
         ay = __fdiv_rn(ay, nf);
         const uint32_t row = a.rows - 1u - py;                                   // simple_spectrogram.rs:150
+        const float *thr_a = thr + THR_STRIDE;
         if constexpr (PAIR) {
             // mono: (ax, ay) are the L(=R) magnitudes of frames A and B
             const float pA = __fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ax, ax));
             const float pB = __fadd_rn(__fmul_rn(ay, ay), __fmul_rn(ay, ay));
             if (a.scheme == 0) {
-                outA[row] = lut[step_index(thr, pA)];
-                if (second_valid) outB[row] = lut[step_index(thr, pB)];
+                outA[row] = lut[step_index(thr, pA, a.db_eps, a.guess_a[0], a.guess_b[0])];
+                if (second_valid) outB[row] = lut[step_index(thr, pB, a.db_eps, a.guess_a[0], a.guess_b[0])];
             } else {
-                // l == r: pan = l / (|l| + |r|) = 0.5 (NaN -> index 0 when l == 0)
-                const uint32_t panA = ax != 0.0f && ax == ax ? 128u : 0u, panB = ay != 0.0f && ay == ay ? 128u : 0u;
-                outA[row] = (lut[panA] & 0x00ffffffu) | ((uint32_t)step_index(thr + 256, pA) << 24);
-                if (second_valid) outB[row] = (lut[panB] & 0x00ffffffu) | ((uint32_t)step_index(thr + 256, pB) << 24);
+                // l == r: pan = l / (|l| + |r|) = 0.5 for finite l > 0, else NaN or negative -> index 0
+                const uint32_t panA = (ax > 0.0f && ax < 3.0e38f) ? 128u : 0u, panB = (ay > 0.0f && ay < 3.0e38f) ? 128u : 0u;
+                outA[row] = (lut[panA] & 0x00ffffffu) | ((uint32_t)step_index(thr_a, pA, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
+                if (second_valid)
+                    outB[row] = (lut[panB] & 0x00ffffffu) | ((uint32_t)step_index(thr_a, pB, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
             }
         } else {
             const float p = __fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay));    // norm_sqr
             if (a.scheme == 0) {
-                outA[row] = lut[step_index(thr, p)];
+                outA[row] = lut[step_index(thr, p, a.db_eps, a.guess_a[0], a.guess_b[0])];
             } else {
                 const double pan = (double)ax / (double)__fadd_rn(fabsf(ax), fabsf(ay));
                 const double v = floor(pan * 256.0);
                 const uint32_t idx = !(v >= 0.0) ? 0u : (v > 255.0 ? 255u : (uint32_t)v);
-                outA[row] = (lut[idx] & 0x00ffffffu) | ((uint32_t)step_index(thr + 256, p) << 24);
+                outA[row] = (lut[idx] & 0x00ffffffu) | ((uint32_t)step_index(thr_a, p, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
             }
         }
     }
 }
 
-#ifndef SBX_EMU
 // ----------------------------------------------------------------------------------------------
 // kernels
 // ----------------------------------------------------------------------------------------------
+#ifndef SBX_EMU
+template <int LOG2M, bool PAIR, int THREADS>
+__device__ __forceinline__ void resample_colour(float2 *z, const float *thr, const uint32_t *lut, const KernelArgs &a,
+                                                unsigned long long frame0, bool second_valid)
+{
+    float2 *scratch = z + (1 << (LOG2M - 1));                 // the upper half of the transform buffer is free
+    for (uint32_t c = 0; c < a.n_chunks; ++c) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.chunks) + c);
+        const RowChunk ck = {raw.x, raw.y, raw.z, raw.w};
+        if (c != 0) __syncthreads();
+        resample_samples<LOG2M, THREADS>(z, scratch, a, ck);
+        __syncthreads();
+        colour_rows<PAIR, THREADS>(scratch, thr, lut, a, ck, frame0, second_valid);
+    }
+}
+
 template <class G>
 __global__ void __launch_bounds__(G::THREADS) fused_frames_kernel(const KernelArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *z = reinterpret_cast<float2 *>(smem_raw);
     float *thr = reinterpret_cast<float *>(smem_raw + (size_t)G::M * 8);
-    uint32_t *lut = reinterpret_cast<uint32_t *>(thr + 512);
+    uint32_t *lut = reinterpret_cast<uint32_t *>(thr + 2 * THR_STRIDE);
 
     const unsigned long long frame0 = (unsigned long long)blockIdx.x * G::FRAMES_PER_CTA;
     const bool second_valid = G::CH == 1 && frame0 + 1 < a.n_frames;
 
-    for (int i = threadIdx.x; i < 512; i += G::THREADS) thr[i] = __ldg(a.thr + i);
+    for (int i = threadIdx.x; i < 2 * THR_STRIDE; i += G::THREADS) thr[i] = __ldg(a.thr + i);
     for (int i = threadIdx.x; i < 256; i += G::THREADS) lut[i] = __ldg(a.lut + i);
 
     pass_first<G>(z, a, frame0, second_valid);
@@ -504,17 +613,16 @@ __global__ void __launch_bounds__(256) colourise_kernel(const KernelArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *z = reinterpret_cast<float2 *>(smem_raw);
-    float *thr = reinterpret_cast<float *>(smem_raw + ((size_t)4 << LOG2M));      // M/2 float2
-    uint32_t *lut = reinterpret_cast<uint32_t *>(thr + 512);
+    float *thr = reinterpret_cast<float *>(smem_raw + ((size_t)8 << LOG2M));      // M float2 (mags + scratch)
+    uint32_t *lut = reinterpret_cast<uint32_t *>(thr + 2 * THR_STRIDE);
     const unsigned long long frame = blockIdx.x;
-    for (int i = threadIdx.x; i < 512; i += 256) thr[i] = __ldg(a.thr + i);
+    for (int i = threadIdx.x; i < 2 * THR_STRIDE; i += 256) thr[i] = __ldg(a.thr + i);
     for (int i = threadIdx.x; i < 256; i += 256) lut[i] = __ldg(a.lut + i);
     const float2 *in = reinterpret_cast<const float2 *>(a.mags_in) + frame * a.k_out;
     for (uint32_t j = threadIdx.x; j < a.k_out; j += 256) z[msw<LOG2M>((int)j + 1)] = __ldg(in + j);
     __syncthreads();
     resample_colour<LOG2M, false, 256>(z, thr, lut, a, frame, false);
 }
-
 #endif  // SBX_EMU
 
 }  // namespace sbx

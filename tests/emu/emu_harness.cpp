@@ -43,9 +43,11 @@ int emu_cta(const sbx::KernelArgs &a, unsigned long long frame0, float *mags_out
     if (rgba) {
         sbx::KernelArgs b = a;
         b.rgba = rgba;
-        for (int t = 0; t < G::THREADS; ++t) {
-            threadIdx.x = t;
-            sbx::resample_colour<G::LOG2M, G::CH == 1, G::THREADS>(z.data(), a.thr, a.lut, b, frame0, second_valid);
+        float2 *scratch = z.data() + G::M / 2;
+        for (uint32_t c = 0; c < a.n_chunks; ++c) {
+            const sbx::RowChunk ck = a.chunks[c];
+            for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::resample_samples<G::LOG2M, G::THREADS>(z.data(), scratch, b, ck); }
+            for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::colour_rows<G::CH == 1, G::THREADS>(scratch, a.thr, a.lut, b, ck, frame0, second_valid); }
         }
     }
     return 0;
@@ -87,15 +89,21 @@ long long emu_batch(const sbx_config *cfg, const float *pcm, unsigned long long 
     const unsigned long long frames = (n_samples - t.n) / cfg->hop + 1;
     sbx::KernelArgs a{};
     a.pcm = pcm;
+    if (!t.ok) return -2;
     a.window = t.window.data();
-    a.tw = reinterpret_cast<const float2 *>(t.tw.data());
+    a.wtw = reinterpret_cast<const float2 *>(t.wtw.data());
+    a.twp = reinterpret_cast<const float2 *>(t.twp.data());
     a.rowmap = t.rowmap.data();
+    a.chunks = t.chunks.data();
+    a.n_chunks = (uint32_t)t.chunks.size();
+    a.samp_x = t.samp_x.data();
     a.cos_w = t.cos_w.data();
     a.thr = t.thr.data();
     a.lut = t.lut;
     a.n_frames = frames;
     a.hop = cfg->hop; a.rows = t.rows; a.k_out = t.k_out;
-    a.period = t.period; a.k_max_f = (float)(t.k_out - 1); a.scale = t.scale;
+    a.scale = t.scale; a.db_eps = cfg->db_eps;
+    for (int i = 0; i < 2; ++i) { a.guess_a[i] = t.guess_a[i]; a.guess_b[i] = t.guess_b[i]; }
     a.interp = (int)cfg->interp; a.scheme = (int)cfg->scheme;
     const int ln = ilog2(t.n), lp = ilog2(t.pad), ch = (int)cfg->channels;
     if (ln < 8 || ln > 13 || lp < 0) return -2;
@@ -129,7 +137,7 @@ int emu_tables(const sbx_config *cfg, float *window, float *f0, float *step, uin
         if (n) n[py] = t.rowmap[py].n;
     }
     if (period) *period = t.period;
-    if (thr512) memcpy(thr512, t.thr.data(), 512 * sizeof(float));
+    if (thr512) memcpy(thr512, t.thr_raw.data(), 512 * sizeof(float));
     return 0;
 }
 
