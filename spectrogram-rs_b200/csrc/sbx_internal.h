@@ -27,8 +27,8 @@ struct sbx_plan {
     float2 *d_twp = nullptr;
     sbx::RowMap *d_rowmap = nullptr;
     sbx::RowChunk *d_chunks = nullptr;
-    float *d_samp_x = nullptr;
-    float *d_cos_w = nullptr;
+    uint2 *d_samp = nullptr;
+    int taps_clamped = 0;
     float *d_thr = nullptr;
     uint32_t *d_lut = nullptr;
 

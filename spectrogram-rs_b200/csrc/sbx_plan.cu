@@ -115,7 +115,7 @@ sbx_status launch_fused(sbx_plan *p, int channels, const float *d_pcm, uint64_t 
 template <int LOG2M> cudaError_t launch_colourise_one(const KernelArgs &a, uint64_t n_frames, cudaStream_t stream)
 {
     static bool configured[64] = {};
-    const int smem = (8 << LOG2M) + 2 * sbx::THR_STRIDE * 4 + 256 * 4;
+    const int smem = 8 << LOG2M;
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !configured[dev]) {
@@ -162,8 +162,8 @@ sbx::KernelArgs sbx_plan::base_args() const
     a.rowmap = d_rowmap;
     a.chunks = d_chunks;
     a.n_chunks = n_chunks;
-    a.samp_x = d_samp_x;
-    a.cos_w = d_cos_w;
+    a.samp = d_samp;
+    a.taps_clamped = taps_clamped;
     a.thr = d_thr;
     a.lut = d_lut;
     a.hop = hop;
@@ -254,7 +254,7 @@ SBX_API void sbx_plan_destroy(sbx_plan *p)
         cudaFree(s.d_rgba);
     }
     cudaFree(p->d_window); cudaFree(p->d_wtw); cudaFree(p->d_twp); cudaFree(p->d_rowmap); cudaFree(p->d_chunks);
-    cudaFree(p->d_samp_x); cudaFree(p->d_cos_w);
+    cudaFree(p->d_samp);
     cudaFree(p->d_thr); cudaFree(p->d_lut); cudaFree(p->d_frame); cudaFree(p->d_mags1); cudaFree(p->d_col);
     if (p->h_frame) cudaFreeHost(p->h_frame);
     if (p->h_col) cudaFreeHost(p->h_col);
@@ -324,6 +324,7 @@ SBX_API sbx_status sbx_plan_create(const sbx_config *cfg, sbx_plan **out_plan)
     p->h_rowmap = t.rowmap;
     p->h_thr_raw = t.thr_raw;
     p->n_chunks = (uint32_t)t.chunks.size();
+    p->taps_clamped = t.taps_clamped ? 1 : 0;
     for (int i = 0; i < 2; ++i) { p->guess_a[i] = t.guess_a[i]; p->guess_b[i] = t.guess_b[i]; }
 
 #define SBX_TRY(call)                                                                   \
@@ -342,8 +343,7 @@ SBX_API sbx_status sbx_plan_create(const sbx_config *cfg, sbx_plan **out_plan)
     SBX_TRY(upload(&p->d_twp, t.twp.data(), t.twp.size() * sizeof(float)));
     SBX_TRY(upload(&p->d_rowmap, p->h_rowmap.data(), p->rows * sizeof(sbx::RowMap)));
     SBX_TRY(upload(&p->d_chunks, t.chunks.data(), t.chunks.size() * sizeof(sbx::RowChunk)));
-    SBX_TRY(upload(&p->d_samp_x, t.samp_x.data(), t.samp_x.size() * sizeof(float)));
-    SBX_TRY(upload(&p->d_cos_w, t.cos_w.data(), t.cos_w.size() * sizeof(float)));
+    SBX_TRY(upload(&p->d_samp, t.samp.data(), t.samp.size() * sizeof(uint32_t)));
     SBX_TRY(upload(&p->d_thr, t.thr.data(), t.thr.size() * sizeof(float)));
     SBX_TRY(upload(&p->d_lut, t.lut, sizeof(t.lut)));
     SBX_TRY(cudaMalloc(&p->d_frame, (size_t)p->n * 2 * sizeof(float)));

@@ -90,8 +90,8 @@ struct HostTables {
     std::vector<float> twp;             // per-pass twiddle planes x (re, im), see KernelArgs::twp
     std::vector<RowMap> rowmap;         // [H]
     std::vector<RowChunk> chunks;       // rows grouped so that a chunk's samples fit the kernel's scratch area
-    std::vector<float> samp_x;          // per (row, sample): clamped fractional bin
-    std::vector<float> cos_w;           // per (row, sample): cosine weight (COSINE only)
+    std::vector<uint32_t> samp;         // per (row, sample): {floor(x), weight bits}, see KernelArgs::samp
+    bool taps_clamped = false;          // some cubic tap falls outside [0, K-1]
     std::vector<float> thr;             // [2][THR_STRIDE] with sentinels
     std::vector<float> thr_raw;         // [2][256] the bare thresholds (introspection)
     float guess_a[2], guess_b[2];
@@ -162,21 +162,26 @@ inline void build(const sbx_config &cfg, HostTables &t)
         total_samples += n;
         t.rowmap[py] = rm;
     }
-    // per-sample positions: index_of(lin_space(f0..f1, n)[s])  (ifs.rs:67-69, :24-31), and the cosine weights
-    t.samp_x.resize(total_samples);
-    t.cos_w.clear();
-    if (cfg.interp == SBX_INTERP_COSINE) t.cos_w.resize(total_samples);
+    // per-sample positions x = index_of(lin_space(f0..f1, n)[s])  (ifs.rs:67-69, :24-31), stored as
+    // floor(x) and the interpolation weight: mu = x - floor(x) (cubic, ifs.rs:90) or
+    // (1 - cos((x - low) * PI)) / 2 (cosine, ifs.rs:82-83; f32, host libm)
+    t.samp.resize(total_samples * 2);
+    t.taps_clamped = false;
     const float pi = 3.14159265358979323846f;
     for (uint32_t py = 0; py < t.rows; ++py) {
         const RowMap &rm = t.rowmap[py];
         for (uint32_t s = 0; s < rm.n; ++s) {
             const float fq = rm.f0 + (float)s * rm.step;
             const float x = index_of(fq, t.period, t.k_out);
-            t.samp_x[rm.aux + s] = x;
-            if (cfg.interp == SBX_INTERP_COSINE) {
-                const float off = x - std::floor(x);
-                t.cos_w[rm.aux + s] = (1.0f - cosf(off * pi)) / 2.0f;                  // ifs.rs:82-83
-            }
+            const float fl = std::floor(x);
+            const float off = x - fl;
+            const float w = cfg.interp == SBX_INTERP_COSINE ? (1.0f - cosf(off * pi)) / 2.0f : off;
+            const uint32_t x1 = (uint32_t)fl;
+            if (x1 < 1 || x1 + 2 > t.k_out - 1) t.taps_clamped = true;
+            uint32_t wbits;
+            std::memcpy(&wbits, &w, 4);
+            t.samp[2 * (size_t)(rm.aux + s)] = x1;
+            t.samp[2 * (size_t)(rm.aux + s) + 1] = wbits;
         }
     }
     // row chunks: greedy, a chunk's samples must fit the kernel's scratch area ((M/2) * 16/17 slots)

@@ -51,8 +51,8 @@ struct KernelArgs {
     const float2 *twp;           // per DIF pass p: TW_PLANES planes of S_p entries, plane j = W_(S_p R_p)^(2^j lo)
     const RowMap *rowmap;        // [H]
     const RowChunk *chunks;      // [n_chunks]
-    const float *samp_x;         // per (row, sample): clamped fractional bin index_of(f0 + s*step)
-    const float *cos_w;          // per (row, sample): cosine weight (1 - cos(frac*pi))/2, or nullptr
+    const uint2 *samp;           // per (row, sample): {floor(x) as int, weight as f32 bits}, x = index_of(f0 + s*step);
+                                 //   weight = x - floor(x) (CUBIC) or (1 - cos(frac*pi))/2 (COSINE, host libm)
     const float *thr;            // [2][264] step thresholds with sentinels: colour index, alpha
     const uint32_t *lut;         // [256] packed r | g<<8 | b<<16 | 255<<24
     unsigned long long n_frames;
@@ -62,6 +62,7 @@ struct KernelArgs {
     float db_eps;
     int interp;                  // 0 cubic, 1 cosine
     int scheme;                  // 0 mono gradient, 1 stereo pan gradient
+    int taps_clamped;            // 1 if any cubic tap index needs clamping to [0, K-1] (spectrum edges)
 };
 
 constexpr int TW_PLANES = 4;     // twiddle planes stored per pass: W^(1,2,4,8 * lo)
@@ -197,7 +198,7 @@ template <int LOG2N_, int LOG2PAD_, int CH_> struct Geom {
     static constexpr int NPASS = LOG2N / 4 + (REM ? 1 : 0);
     static constexpr int THREADS = (M / 16) < 64 ? 64 : ((M / 16) > 512 ? 512 : (M / 16));
     static constexpr int FRAMES_PER_CTA = CH == 1 ? 2 : 1;
-    static constexpr int SMEM_BYTES = M * 8 + 2 * THR_STRIDE * 4 + 256 * 4;
+    static constexpr int SMEM_BYTES = M * 8;
     static __host__ __device__ constexpr int log2r(int p) { return (REM != 0 && p == 0) ? REM : 4; }
     static __host__ __device__ constexpr int log2stride(int p)                 // log2 of the butterfly stride of pass p
     {
@@ -213,51 +214,65 @@ template <int LOG2N_, int LOG2PAD_, int CH_> struct Geom {
     }
     static constexpr int TW_TOTAL = tw_offset(NPASS - 1);                      // the last pass has no twiddles
     static constexpr int SCRATCH = ((M / 2) * 16) / 17;                        // resample scratch slots (padded 17/16)
+
+    // bin kk = PAD*k + q0 lives at position q0*N + digitrev(k): a pure bit permutation of kk
+    static __host__ __device__ constexpr int pos_of_bin(int kk)
+    {
+        const int q0 = kk & (PAD - 1);
+        int k = kk >> LOG2PAD;
+        int pos = q0 << LOG2N, shift = LOG2N;
+        for (int p = 0; p < NPASS; ++p) {
+            const int lr = log2r(p);
+            shift -= lr;
+            pos |= (k & ((1 << lr) - 1)) << shift;
+            k >>= lr;
+        }
+        return pos;
+    }
+    static __host__ __device__ constexpr int pos_bit(int j)                    // position bit that bin bit j maps to
+    {
+        const int p = pos_of_bin(1 << j);
+        int b = 0;
+        while ((1 << b) < p) ++b;
+        return b;
+    }
+    // Swizzle key (3 bits, XOR-linear in the position bits >= 4).  Key bit b = position bit 4+b, XORed
+    // with one "external" position bit: the split phase reads positions that differ in the bits the
+    // lowest bin bits map to (sub-transform select, first-pass digit), so those are folded in too.
+    static __host__ __device__ constexpr int key_ext_src(int b)
+    {
+        bool used[3] = {false, false, false};
+        int ext[3] = {-1, -1, -1};
+        for (int j = 0; j < 3; ++j) {
+            const int pb = pos_bit(j);
+            if (pb >= 4 && pb <= 6) used[pb - 4] = true;
+        }
+        int next = 0;
+        for (int j = 0; j < 3; ++j) {
+            const int pb = pos_bit(j);
+            if (pb > 6) {
+                while (next < 3 && used[next]) ++next;
+                if (next < 3) { ext[next] = pb; used[next] = true; }
+            }
+        }
+        return ext[b];
+    }
+    static __host__ __device__ constexpr int zkey(int i)
+    {
+        int k = (i >> 4) & 7;
+        if (key_ext_src(0) >= 0) k ^= (i >> key_ext_src(0)) & 1;
+        if (key_ext_src(1) >= 0) k ^= ((i >> key_ext_src(1)) & 1) << 1;
+        if (key_ext_src(2) >= 0) k ^= ((i >> key_ext_src(2)) & 1) << 2;
+        return k;
+    }
+    // element index -> physical float2 slot: permutes the eight 16-byte chunks of every 128-byte row.
+    // XOR-linear: zsw(a | b) = zsw(a) ^ zsw(b) for bit-disjoint a, b.
+    static __host__ __device__ constexpr int zsw(int i) { return i ^ (zkey(i) << 1); }
 };
 
-// shared-memory swizzles -----------------------------------------------------------------------
-// transform buffer: element index -> physical float2 slot; permutes the eight 16-byte chunks of
-// every 128-byte row by the row number
-__device__ __forceinline__ int zsw(int i) { return i ^ (((i >> 4) & 7) << 1); }
-
-// magnitude buffer (indexed by bin kk = j + 1): the split phase writes bins that differ by
-// multiples of M/16 (8 lanes) and M/256 (the other half-warp); fold those bits into the bank
-template <int LOG2M> __device__ __forceinline__ int msw(int kk)
-{
-    if constexpr (LOG2M >= 12)
-        return kk ^ (((kk >> (LOG2M - 4)) & 7) | (((kk >> (LOG2M - 8)) & 1) << 3));
-    else
-        return kk ^ ((kk >> (LOG2M - 4)) & 7);
-}
-
-// position <-> bin (digit reversal of the sub-transform index; see tools/fft_model.py)
-template <class G> __device__ __forceinline__ int bin_of_pos(int pos)
-{
-    const int rem = pos & (G::N - 1), q0 = pos >> G::LOG2N;
-    int k = 0, shift = G::LOG2N, kshift = 0;
-#pragma unroll
-    for (int p = 0; p < G::NPASS; ++p) {
-        const int lr = G::log2r(p);
-        shift -= lr;
-        k |= ((rem >> shift) & ((1 << lr) - 1)) << kshift;
-        kshift += lr;
-    }
-    return (k << G::LOG2PAD) | q0;
-}
-template <class G> __device__ __forceinline__ int pos_of_bin(int kk)
-{
-    const int q0 = kk & (G::PAD - 1);
-    int k = kk >> G::LOG2PAD;
-    int pos = q0 << G::LOG2N, shift = G::LOG2N;
-#pragma unroll
-    for (int p = 0; p < G::NPASS; ++p) {
-        const int lr = G::log2r(p);
-        shift -= lr;
-        pos |= (k & ((1 << lr) - 1)) << shift;
-        k >>= lr;
-    }
-    return pos;
-}
+// Physical slot of element (base + off): `off` is a compile-time multiple of 16 whose bits are clear
+// in `base`, `bx` = G::zsw(base).  One LOP3 (or nothing) per access instead of a full swizzle.
+#define SBX_ZAT(G, bx, off) (((bx) ^ (G::zkey(off) << 1)) + (off))
 
 // v[q] *= w^q for q = 1..R-1, where plane[j * plane_stride] = w^(2^j) are exactly rounded table
 // values.  SBX_TW_LOADS of the planes are read; the other powers are products of at most three
@@ -329,9 +344,9 @@ __device__ __forceinline__ void pass_first(float2 *z, const KernelArgs &a, unsig
         }
         Butterfly<R>::run(v);
         if constexpr (G::NPASS > 1) apply_twiddles<R>(v, a.twp + lo, S);   // W_N^(lo q)
-        const int base = (q0 << G::LOG2N) + lo;
+        const int bx = G::zsw((q0 << G::LOG2N) + lo);
 #pragma unroll
-        for (int q = 0; q < R; ++q) z[zsw(base + q * S)] = v[q];
+        for (int q = 0; q < R; ++q) z[SBX_ZAT(G, bx, q * S)] = v[q];
     }
 }
 
@@ -348,7 +363,7 @@ __device__ __forceinline__ void pass_inplace(float2 *z, const KernelArgs &a)
         if constexpr (S == 1) {
             // row w holds elements 16w .. 16w+15
             float4 *row = reinterpret_cast<float4 *>(z) + (w << 3);
-            const int key = w & 7;
+            const int key = G::zkey(w << 4);
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 float4 t = row[c ^ key];
@@ -362,13 +377,13 @@ __device__ __forceinline__ void pass_inplace(float2 *z, const KernelArgs &a)
         } else {
             const int blk = w >> PER_SUB_LOG2, u = w & ((1 << PER_SUB_LOG2) - 1);
             const int lo = u & (S - 1), hi = u >> LS;
-            const int base = (blk << G::LOG2N) + (hi << (LS + 4)) + lo;
+            const int bx = G::zsw((blk << G::LOG2N) + (hi << (LS + 4)) + lo);
 #pragma unroll
-            for (int r = 0; r < 16; ++r) v[r] = z[zsw(base + r * S)];
+            for (int r = 0; r < 16; ++r) v[r] = z[SBX_ZAT(G, bx, r * S)];
             Butterfly<16>::run(v);
             apply_twiddles<16>(v, a.twp + G::tw_offset(P) + lo, S);        // W_(16 S)^(lo q)
 #pragma unroll
-            for (int q = 0; q < 16; ++q) z[zsw(base + q * S)] = v[q];
+            for (int q = 0; q < 16; ++q) z[SBX_ZAT(G, bx, q * S)] = v[q];
         }
     }
 }
@@ -387,47 +402,53 @@ template <class G, int P> struct RunPasses {
 // ----------------------------------------------------------------------------------------------
 // L/R split (fft.rs:81-95): bins kk = 1 .. M/2-1, a = Z[kk], b = Z[M-kk]
 //   L = |a + conj b| / 2 * (2/N),  R = |a - conj b| / 2 * (2/N)
-// split_read: every thread reads its pairs into registers; (barrier); split_write: (L,R) is
-// written over the transform buffer, indexed by kk
+// Thread t owns bins kk = t | (p << log2 THREADS).  pos_of_bin is a bit permutation and the swizzle is
+// XOR-linear, so slot(kk) = zsw(pos(t)) ^ const(p); the partner M-kk = (T-t) | ((~p & mask) << log2 T)
+// for t != 0 splits the same way.  split_read: pairs -> registers; (barrier); split_write: (L,R) is
+// written over the lower half of the transform buffer in natural bin order (no swizzle).
 // ----------------------------------------------------------------------------------------------
 template <class G> struct SplitRegs {
     static constexpr int PAIRS = G::M / 2;
-    static constexpr int PER_THREAD = (PAIRS + G::THREADS - 1) / G::THREADS;
+    static constexpr int PER_THREAD = PAIRS / G::THREADS;
+    static_assert(PAIRS % G::THREADS == 0 && (G::THREADS & (G::THREADS - 1)) == 0, "split mapping");
     float2 mag[PER_THREAD];
-    int kks[PER_THREAD];
+};
+
+template <class G> struct SplitConst {
+    static __host__ __device__ constexpr int log2_threads() { int l = 0; while ((1 << l) < G::THREADS) ++l; return l; }
+    static constexpr int LT = log2_threads();
+    static constexpr int PMASK = (G::M >> LT) - 1;
+    static __host__ __device__ constexpr int own(int p) { return G::zsw(G::pos_of_bin(p << LT)); }
+    static __host__ __device__ constexpr int partner(int p) { return G::zsw(G::pos_of_bin(((~p) & PMASK) << LT)); }
+    static __host__ __device__ constexpr int partner_t0(int p) { return p == 0 ? 0 : G::zsw(G::pos_of_bin(G::M - (p << LT))); }
 };
 
 template <class G>
 __device__ __forceinline__ void split_read(const float2 *z, const KernelArgs &a, SplitRegs<G> &r)
 {
+    using C = SplitConst<G>;
+    const int tid = threadIdx.x;
+    const int own = G::zsw(G::pos_of_bin(tid));
+    const int par = G::zsw(G::pos_of_bin((G::THREADS - tid) & (G::THREADS - 1)));
 #pragma unroll
-    for (int i = 0; i < SplitRegs<G>::PER_THREAD; ++i) {
-        const int v = threadIdx.x + i * G::THREADS;
-        r.kks[i] = 0;
-        r.mag[i] = make_float2(0.0f, 0.0f);
-        if (v < SplitRegs<G>::PAIRS) {
-            const int pos = ((v >> 3) << 4) | (v & 7);      // low digit < 8  <=>  kk < M/2
-            const int kk = bin_of_pos<G>(pos);
-            if (kk != 0) {
-                const float2 x = z[zsw(pos)];
-                const float2 y = z[zsw(pos_of_bin<G>(G::M - kk))];
-                const float lx = x.x + y.x, ly = x.y - y.y;   // a + conj b
-                const float rx = x.x - y.x, ry = x.y + y.y;   // a - conj b
-                const float l = fast_sqrt(lx * lx + ly * ly) * 0.5f;
-                const float rr = fast_sqrt(rx * rx + ry * ry) * 0.5f;
-                r.mag[i] = make_float2(l * a.scale, rr * a.scale);
-                r.kks[i] = kk;
-            }
-        }
+    for (int p = 0; p < SplitRegs<G>::PER_THREAD; ++p) {
+        const float2 x = z[own ^ C::own(p)];
+        const float2 y = z[tid == 0 ? C::partner_t0(p) : (par ^ C::partner(p))];
+        const float lx = x.x + y.x, ly = x.y - y.y;   // a + conj b
+        const float rx = x.x - y.x, ry = x.y + y.y;   // a - conj b
+        const float l = fast_sqrt(lx * lx + ly * ly) * 0.5f;
+        const float rr = fast_sqrt(rx * rx + ry * ry) * 0.5f;
+        r.mag[p] = make_float2(l * a.scale, rr * a.scale);
     }
 }
 
 template <class G>
 __device__ __forceinline__ void split_write(float2 *z, const SplitRegs<G> &r)
 {
+    const int tid = threadIdx.x;
 #pragma unroll
-    for (int i = 0; i < SplitRegs<G>::PER_THREAD; ++i)
-        if (r.kks[i] != 0) z[msw<G::LOG2M>(r.kks[i])] = r.mag[i];
+    for (int p = 0; p < SplitRegs<G>::PER_THREAD; ++p)
+        if (p != 0 || tid != 0) z[tid | (p << SplitConst<G>::LT)] = r.mag[p];      // kk = 0 (DC) is dropped
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -451,49 +472,59 @@ __device__ __forceinline__ int step_index(const float *ts, float p, float eps, f
 {
     const float t = fast_log2(p + eps) * ga + gb;
     int idx = (int)fminf(fmaxf(t, 0.0f), 255.0f);           // NaN -> 0
-    while (idx < 255 && p >= ts[idx + 1]) ++idx;
-    while (idx > 0 && p < ts[idx]) --idx;
+    while (idx < 255 && p >= __ldg(ts + idx + 1)) ++idx;
+    while (idx > 0 && p < __ldg(ts + idx)) --idx;
     return idx;
 }
 
 __device__ __forceinline__ int scratch_slot(int g) { return g + (g >> 4); }   // 17/16 padding
 
-// One interpolated sample (both channels) at fractional bin x -- magnitude_at (ifs.rs:46-48)
-template <int LOG2M>
-__device__ __forceinline__ float2 interp_sample(const float2 *mags, const KernelArgs &a, float x, int k_last, uint32_t g)
+// One interpolated sample (both channels) -- magnitude_at (ifs.rs:46-48).  mags is indexed by bin
+// kk = j + 1; x1 = floor(x), w = the interpolation weight, both precomputed by the plan.
+template <bool CLAMP>
+__device__ __forceinline__ float2 interp_sample(const float2 *mags, const KernelArgs &a, int x1, float w, int k_last)
 {
-    const float fl = floorf(x);
-    const int x1 = (int)fl;
     float2 v;
-    if (a.interp == 0) {                                                     // cubic_interpolate
-        const float mu = __fsub_rn(x, fl);
+    if (a.interp == 0) {                                                     // cubic_interpolate, ifs.rs:88-105
+        const float mu = w;
         const float mu2 = __fmul_rn(mu, mu), mu3 = __fmul_rn(mu, mu2);
-        const int x0 = x1 > 0 ? x1 - 1 : 0;
-        const int x2 = min(x1 + 1, k_last), x3 = min(x1 + 2, k_last);
-        const float2 y0 = mags[msw<LOG2M>(x0 + 1)], y1 = mags[msw<LOG2M>(x1 + 1)];
-        const float2 y2 = mags[msw<LOG2M>(x2 + 1)], y3 = mags[msw<LOG2M>(x3 + 1)];
+        float2 y0, y1, y2, y3;
+        if constexpr (CLAMP) {
+            y0 = mags[(x1 > 0 ? x1 - 1 : 0) + 1];
+            y1 = mags[x1 + 1];
+            y2 = mags[min(x1 + 1, k_last) + 1];
+            y3 = mags[min(x1 + 2, k_last) + 1];
+        } else {
+            const float2 *m = mags + x1;
+            y0 = m[0]; y1 = m[1]; y2 = m[2]; y3 = m[3];
+        }
         v.x = cubic1(y0.x, y1.x, y2.x, y3.x, mu, mu2, mu3);
         v.y = cubic1(y0.y, y1.y, y2.y, y3.y, mu, mu2, mu3);
-    } else {                                                                 // cosine_interpolate
-        int hi = (int)ceilf(x);
-        const int lo_b = min(x1 + 1, k_last);
-        hi = min(max(hi, lo_b), k_last);
-        const float t = __ldg(a.cos_w + g);                                  // host libm cosf
-        const float omt = __fsub_rn(1.0f, t);
-        const float2 yl = mags[msw<LOG2M>(x1 + 1)], yh = mags[msw<LOG2M>(hi + 1)];
-        v.x = __fadd_rn(__fmul_rn(yl.x, omt), __fmul_rn(yh.x, t));
-        v.y = __fadd_rn(__fmul_rn(yl.y, omt), __fmul_rn(yh.y, t));
+    } else {                                                                 // cosine_interpolate, ifs.rs:78-86
+        const float omt = __fsub_rn(1.0f, w);
+        const float2 yl = mags[x1 + 1], yh = mags[min(x1 + 1, k_last) + 1];  // high = clamp(ceil x, low+1, K-1)
+        v.x = __fadd_rn(__fmul_rn(yl.x, omt), __fmul_rn(yh.x, w));
+        v.y = __fadd_rn(__fmul_rn(yl.y, omt), __fmul_rn(yh.y, w));
     }
     return v;
 }
 
 // Phase A of a row chunk: one lane per (row, sample); consecutive lanes read consecutive bins
-template <int LOG2M, int THREADS>
+template <int THREADS>
 __device__ __forceinline__ void resample_samples(const float2 *mags, float2 *scratch, const KernelArgs &a, const RowChunk ck)
 {
     const int k_last = (int)a.k_out - 1;
-    for (uint32_t g = ck.samp_begin + threadIdx.x; g < ck.samp_end; g += THREADS)
-        scratch[scratch_slot((int)(g - ck.samp_begin))] = interp_sample<LOG2M>(mags, a, __ldg(a.samp_x + g), k_last, g);
+    if (a.taps_clamped) {
+        for (uint32_t g = ck.samp_begin + threadIdx.x; g < ck.samp_end; g += THREADS) {
+            const uint2 sp = __ldg(a.samp + g);
+            scratch[scratch_slot((int)(g - ck.samp_begin))] = interp_sample<true>(mags, a, (int)sp.x, __uint_as_float(sp.y), k_last);
+        }
+    } else {
+        for (uint32_t g = ck.samp_begin + threadIdx.x; g < ck.samp_end; g += THREADS) {
+            const uint2 sp = __ldg(a.samp + g);
+            scratch[scratch_slot((int)(g - ck.samp_begin))] = interp_sample<false>(mags, a, (int)sp.x, __uint_as_float(sp.y), k_last);
+        }
+    }
 }
 
 // Phase B: one thread per row: sequential mean of its samples (the reference's summation order,
@@ -514,9 +545,11 @@ __device__ __forceinline__ void colour_rows(const float2 *scratch, const float *
             ax = __fadd_rn(ax, v.x);
             ay = __fadd_rn(ay, v.y);
         }
-        const float nf = (float)n;
-        ax = __fdiv_rn(ax, nf);
-        ay = __fdiv_rn(ay, nf);
+        if (n > 1) {                                                             // x / 1.0f == x exactly
+            const float nf = (float)n;
+            ax = __fdiv_rn(ax, nf);
+            ay = __fdiv_rn(ay, nf);
+        }
         const uint32_t row = a.rows - 1u - py;                                   // simple_spectrogram.rs:150
         const float *thr_a = thr + THR_STRIDE;
         if constexpr (PAIR) {
@@ -524,24 +557,24 @@ __device__ __forceinline__ void colour_rows(const float2 *scratch, const float *
             const float pA = __fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ax, ax));
             const float pB = __fadd_rn(__fmul_rn(ay, ay), __fmul_rn(ay, ay));
             if (a.scheme == 0) {
-                outA[row] = lut[step_index(thr, pA, a.db_eps, a.guess_a[0], a.guess_b[0])];
-                if (second_valid) outB[row] = lut[step_index(thr, pB, a.db_eps, a.guess_a[0], a.guess_b[0])];
+                outA[row] = __ldg(lut + step_index(thr, pA, a.db_eps, a.guess_a[0], a.guess_b[0]));
+                if (second_valid) outB[row] = __ldg(lut + step_index(thr, pB, a.db_eps, a.guess_a[0], a.guess_b[0]));
             } else {
                 // l == r: pan = l / (|l| + |r|) = 0.5 for finite l > 0, else NaN or negative -> index 0
                 const uint32_t panA = (ax > 0.0f && ax < 3.0e38f) ? 128u : 0u, panB = (ay > 0.0f && ay < 3.0e38f) ? 128u : 0u;
-                outA[row] = (lut[panA] & 0x00ffffffu) | ((uint32_t)step_index(thr_a, pA, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
+                outA[row] = (__ldg(lut + panA) & 0x00ffffffu) | ((uint32_t)step_index(thr_a, pA, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
                 if (second_valid)
-                    outB[row] = (lut[panB] & 0x00ffffffu) | ((uint32_t)step_index(thr_a, pB, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
+                    outB[row] = (__ldg(lut + panB) & 0x00ffffffu) | ((uint32_t)step_index(thr_a, pB, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
             }
         } else {
             const float p = __fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay));    // norm_sqr
             if (a.scheme == 0) {
-                outA[row] = lut[step_index(thr, p, a.db_eps, a.guess_a[0], a.guess_b[0])];
+                outA[row] = __ldg(lut + step_index(thr, p, a.db_eps, a.guess_a[0], a.guess_b[0]));
             } else {
                 const double pan = (double)ax / (double)__fadd_rn(fabsf(ax), fabsf(ay));
                 const double v = floor(pan * 256.0);
                 const uint32_t idx = !(v >= 0.0) ? 0u : (v > 255.0 ? 255u : (uint32_t)v);
-                outA[row] = (lut[idx] & 0x00ffffffu) | ((uint32_t)step_index(thr_a, p, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
+                outA[row] = (__ldg(lut + idx) & 0x00ffffffu) | ((uint32_t)step_index(thr_a, p, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
             }
         }
     }
@@ -552,15 +585,16 @@ __device__ __forceinline__ void colour_rows(const float2 *scratch, const float *
 // ----------------------------------------------------------------------------------------------
 #ifndef SBX_EMU
 template <int LOG2M, bool PAIR, int THREADS>
-__device__ __forceinline__ void resample_colour(float2 *z, const float *thr, const uint32_t *lut, const KernelArgs &a,
-                                                unsigned long long frame0, bool second_valid)
+__device__ __forceinline__ void resample_colour(float2 *z, const KernelArgs &a, unsigned long long frame0, bool second_valid)
 {
+    const float *thr = a.thr;
+    const uint32_t *lut = a.lut;
     float2 *scratch = z + (1 << (LOG2M - 1));                 // the upper half of the transform buffer is free
     for (uint32_t c = 0; c < a.n_chunks; ++c) {
         const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.chunks) + c);
         const RowChunk ck = {raw.x, raw.y, raw.z, raw.w};
         if (c != 0) __syncthreads();
-        resample_samples<LOG2M, THREADS>(z, scratch, a, ck);
+        resample_samples<THREADS>(z, scratch, a, ck);
         __syncthreads();
         colour_rows<PAIR, THREADS>(scratch, thr, lut, a, ck, frame0, second_valid);
     }
@@ -571,14 +605,9 @@ __global__ void __launch_bounds__(G::THREADS) fused_frames_kernel(const KernelAr
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *z = reinterpret_cast<float2 *>(smem_raw);
-    float *thr = reinterpret_cast<float *>(smem_raw + (size_t)G::M * 8);
-    uint32_t *lut = reinterpret_cast<uint32_t *>(thr + 2 * THR_STRIDE);
 
     const unsigned long long frame0 = (unsigned long long)blockIdx.x * G::FRAMES_PER_CTA;
     const bool second_valid = G::CH == 1 && frame0 + 1 < a.n_frames;
-
-    for (int i = threadIdx.x; i < 2 * THR_STRIDE; i += G::THREADS) thr[i] = __ldg(a.thr + i);
-    for (int i = threadIdx.x; i < 256; i += G::THREADS) lut[i] = __ldg(a.lut + i);
 
     pass_first<G>(z, a, frame0, second_valid);
     __syncthreads();
@@ -594,7 +623,7 @@ __global__ void __launch_bounds__(G::THREADS) fused_frames_kernel(const KernelAr
     if (a.mags_out != nullptr) {
         float2 *out = reinterpret_cast<float2 *>(a.mags_out) + frame0 * a.k_out;
         for (uint32_t j = threadIdx.x; j < a.k_out; j += G::THREADS) {
-            const float2 m = z[msw<G::LOG2M>((int)j + 1)];
+            const float2 m = z[j + 1];
             if constexpr (G::CH == 1) {
                 out[j] = make_float2(m.x, m.x);
                 if (second_valid) out[a.k_out + j] = make_float2(m.y, m.y);
@@ -604,7 +633,7 @@ __global__ void __launch_bounds__(G::THREADS) fused_frames_kernel(const KernelAr
         }
     }
     if (a.rgba != nullptr)
-        resample_colour<G::LOG2M, G::CH == 1, G::THREADS>(z, thr, lut, a, frame0, second_valid);
+        resample_colour<G::LOG2M, G::CH == 1, G::THREADS>(z, a, frame0, second_valid);
 }
 
 // magnitudes (frames x K x (L,R), device) -> RGBA columns: the resample/colour stage alone
@@ -612,16 +641,12 @@ template <int LOG2M>
 __global__ void __launch_bounds__(256) colourise_kernel(const KernelArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2 *z = reinterpret_cast<float2 *>(smem_raw);
-    float *thr = reinterpret_cast<float *>(smem_raw + ((size_t)8 << LOG2M));      // M float2 (mags + scratch)
-    uint32_t *lut = reinterpret_cast<uint32_t *>(thr + 2 * THR_STRIDE);
+    float2 *z = reinterpret_cast<float2 *>(smem_raw);                            // M float2 (mags + scratch)
     const unsigned long long frame = blockIdx.x;
-    for (int i = threadIdx.x; i < 2 * THR_STRIDE; i += 256) thr[i] = __ldg(a.thr + i);
-    for (int i = threadIdx.x; i < 256; i += 256) lut[i] = __ldg(a.lut + i);
     const float2 *in = reinterpret_cast<const float2 *>(a.mags_in) + frame * a.k_out;
-    for (uint32_t j = threadIdx.x; j < a.k_out; j += 256) z[msw<LOG2M>((int)j + 1)] = __ldg(in + j);
+    for (uint32_t j = threadIdx.x; j < a.k_out; j += 256) z[j + 1] = __ldg(in + j);
     __syncthreads();
-    resample_colour<LOG2M, false, 256>(z, thr, lut, a, frame, false);
+    resample_colour<LOG2M, false, 256>(z, a, frame, false);
 }
 #endif  // SBX_EMU
 

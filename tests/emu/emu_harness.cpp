@@ -32,7 +32,7 @@ int emu_cta(const sbx::KernelArgs &a, unsigned long long frame0, float *mags_out
     for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::split_write<G>(z.data(), regs[t]); }
     if (mags_out) {
         for (uint32_t j = 0; j < a.k_out; ++j) {
-            const float2 m = z[sbx::msw<G::LOG2M>((int)j + 1)];
+            const float2 m = z[j + 1];
             float *o = mags_out + (size_t)frame0 * a.k_out * 2;
             if (G::CH == 1) {
                 o[2 * j] = m.x; o[2 * j + 1] = m.x;
@@ -46,7 +46,7 @@ int emu_cta(const sbx::KernelArgs &a, unsigned long long frame0, float *mags_out
         float2 *scratch = z.data() + G::M / 2;
         for (uint32_t c = 0; c < a.n_chunks; ++c) {
             const sbx::RowChunk ck = a.chunks[c];
-            for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::resample_samples<G::LOG2M, G::THREADS>(z.data(), scratch, b, ck); }
+            for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::resample_samples<G::THREADS>(z.data(), scratch, b, ck); }
             for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::colour_rows<G::CH == 1, G::THREADS>(scratch, a.thr, a.lut, b, ck, frame0, second_valid); }
         }
     }
@@ -96,8 +96,8 @@ long long emu_batch(const sbx_config *cfg, const float *pcm, unsigned long long 
     a.rowmap = t.rowmap.data();
     a.chunks = t.chunks.data();
     a.n_chunks = (uint32_t)t.chunks.size();
-    a.samp_x = t.samp_x.data();
-    a.cos_w = t.cos_w.data();
+    a.samp = reinterpret_cast<const uint2 *>(t.samp.data());
+    a.taps_clamped = t.taps_clamped ? 1 : 0;
     a.thr = t.thr.data();
     a.lut = t.lut;
     a.n_frames = frames;
