@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsbx_b200.so")
+LIB_PATH = os.environ.get("SBX_LIB_PATH") or os.path.join(HERE, "libsbx_b200.so")   # override: kernel-variant experiments
 
 SBX_OK, SBX_NOT_ENOUGH_SAMPLES = 0, 1
 SBX_ERR_INVALID_ARGUMENT, SBX_ERR_UNSUPPORTED, SBX_ERR_CUDA, SBX_ERR_OUT_OF_MEMORY, SBX_ERR_BUFFER_TOO_SMALL = -1, -2, -3, -4, -5

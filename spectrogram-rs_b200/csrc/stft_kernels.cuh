@@ -65,6 +65,9 @@ struct KernelArgs {
     int taps_clamped;            // 1 if any cubic tap index needs clamping to [0, K-1] (spectrum edges)
 };
 
+#ifndef SBX_EPT_LOG2
+#define SBX_EPT_LOG2 4           // log2 of the transform points each thread owns per pass (4: M/16 threads, 5: M/32)
+#endif
 constexpr int TW_PLANES = 4;     // twiddle planes stored per pass: W^(1,2,4,8 * lo)
 #ifndef SBX_TW_LOADS
 #define SBX_TW_LOADS 2           // planes actually loaded per butterfly (1: W^lo; 2: + W^4lo; 4: all); rest by products
@@ -196,7 +199,7 @@ template <int LOG2N_, int LOG2PAD_, int CH_> struct Geom {
     static constexpr int N = 1 << LOG2N, PAD = 1 << LOG2PAD, LOG2M = LOG2N + LOG2PAD, M = 1 << LOG2M;
     static constexpr int REM = LOG2N & 3;                  // first pass radix 2^REM when REM != 0
     static constexpr int NPASS = LOG2N / 4 + (REM ? 1 : 0);
-    static constexpr int THREADS = (M / 16) < 64 ? 64 : ((M / 16) > 512 ? 512 : (M / 16));
+    static constexpr int THREADS = (M >> SBX_EPT_LOG2) < 64 ? 64 : ((M >> SBX_EPT_LOG2) > 512 ? 512 : (M >> SBX_EPT_LOG2));
     static constexpr int FRAMES_PER_CTA = CH == 1 ? 2 : 1;
     static constexpr int SMEM_BYTES = M * 8;
     static __host__ __device__ constexpr int log2r(int p) { return (REM != 0 && p == 0) ? REM : 4; }
@@ -421,24 +424,52 @@ template <class G> struct SplitConst {
     static __host__ __device__ constexpr int own(int p) { return G::zsw(G::pos_of_bin(p << LT)); }
     static __host__ __device__ constexpr int partner(int p) { return G::zsw(G::pos_of_bin(((~p) & PMASK) << LT)); }
     static __host__ __device__ constexpr int partner_t0(int p) { return p == 0 ? 0 : G::zsw(G::pos_of_bin(G::M - (p << LT))); }
+    // the bit of p that maps to position bit 0: p and p | (1 << B0) sit in one 16-byte chunk
+    static __host__ __device__ constexpr int pair_bit()
+    {
+        for (int b = 0; (1 << b) < (G::M / 2) / G::THREADS; ++b)
+            if (G::pos_of_bin(1 << (LT + b)) == 1) return b;
+        return -1;
+    }
+    static constexpr int B0 = pair_bit();
 };
+
+__device__ __forceinline__ float2 split_pair(float2 x, float2 y, float scale)
+{
+    const float lx = x.x + y.x, ly = x.y - y.y;   // a + conj b
+    const float rx = x.x - y.x, ry = x.y + y.y;   // a - conj b
+    const float l = fast_sqrt(lx * lx + ly * ly) * 0.5f;
+    const float rr = fast_sqrt(rx * rx + ry * ry) * 0.5f;
+    return make_float2(l * scale, rr * scale);
+}
 
 template <class G>
 __device__ __forceinline__ void split_read(const float2 *z, const KernelArgs &a, SplitRegs<G> &r)
 {
     using C = SplitConst<G>;
+    constexpr int PER = SplitRegs<G>::PER_THREAD;
     const int tid = threadIdx.x;
     const int own = G::zsw(G::pos_of_bin(tid));
     const int par = G::zsw(G::pos_of_bin((G::THREADS - tid) & (G::THREADS - 1)));
+    if constexpr (C::B0 >= 0) {
+        // 16-byte accesses: (pa, pb = pa | 1<<B0) share a chunk; the partners (M-kk) share one too, swapped
 #pragma unroll
-    for (int p = 0; p < SplitRegs<G>::PER_THREAD; ++p) {
-        const float2 x = z[own ^ C::own(p)];
-        const float2 y = z[tid == 0 ? C::partner_t0(p) : (par ^ C::partner(p))];
-        const float lx = x.x + y.x, ly = x.y - y.y;   // a + conj b
-        const float rx = x.x - y.x, ry = x.y + y.y;   // a - conj b
-        const float l = fast_sqrt(lx * lx + ly * ly) * 0.5f;
-        const float rr = fast_sqrt(rx * rx + ry * ry) * 0.5f;
-        r.mag[p] = make_float2(l * a.scale, rr * a.scale);
+        for (int pa = 0; pa < PER; ++pa) {
+            if ((pa >> C::B0) & 1) continue;
+            const int pb = pa | (1 << C::B0);
+            const float4 x = *reinterpret_cast<const float4 *>(z + (own ^ C::own(pa)));
+            float4 y = *reinterpret_cast<const float4 *>(z + (par ^ C::partner(pb)));   // .xy: partner of pb, .zw: of pa
+            if (tid == 0) {                                                             // M - kk carries into the p field
+                const float2 ya = z[C::partner_t0(pa)], yb = z[C::partner_t0(pb)];
+                y = make_float4(yb.x, yb.y, ya.x, ya.y);
+            }
+            r.mag[pa] = split_pair(make_float2(x.x, x.y), make_float2(y.z, y.w), a.scale);
+            r.mag[pb] = split_pair(make_float2(x.z, x.w), make_float2(y.x, y.y), a.scale);
+        }
+    } else {
+#pragma unroll
+        for (int p = 0; p < PER; ++p)
+            r.mag[p] = split_pair(z[own ^ C::own(p)], z[tid == 0 ? C::partner_t0(p) : (par ^ C::partner(p))], a.scale);
     }
 }
 
@@ -472,8 +503,13 @@ __device__ __forceinline__ int step_index(const float *ts, float p, float eps, f
 {
     const float t = fast_log2(p + eps) * ga + gb;
     int idx = (int)fminf(fmaxf(t, 0.0f), 255.0f);           // NaN -> 0
-    while (idx < 255 && p >= __ldg(ts + idx + 1)) ++idx;
-    while (idx > 0 && p < __ldg(ts + idx)) --idx;
+    const float lo = __ldg(ts + idx), hi = __ldg(ts + idx + 1);   // ts[0] = -inf, ts[256] = +inf
+    if (p >= hi) {
+        do { ++idx; } while (idx < 255 && p >= __ldg(ts + idx + 1));
+        if (idx > 255) idx = 255;
+    } else if (p < lo) {
+        do { --idx; } while (idx > 0 && p < __ldg(ts + idx));
+    }
     return idx;
 }
 
@@ -509,22 +545,34 @@ __device__ __forceinline__ float2 interp_sample(const float2 *mags, const Kernel
     return v;
 }
 
-// Phase A of a row chunk: one lane per (row, sample); consecutive lanes read consecutive bins
+// Phase A of a row chunk: one lane per (row, sample); consecutive lanes read consecutive bins.
+// The sample-table loads of four iterations are issued together (latency hiding).
+template <int THREADS, bool CLAMP>
+__device__ __forceinline__ void resample_samples_impl(const float2 *mags, float2 *scratch, const KernelArgs &a, const RowChunk ck)
+{
+    const int k_last = (int)a.k_out - 1;
+    const uint32_t count = ck.samp_end - ck.samp_begin;
+    const uint2 *tab = a.samp + ck.samp_begin;
+    for (uint32_t g0 = threadIdx.x; g0 < count; g0 += 4 * THREADS) {
+        uint2 sp[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t g = g0 + i * THREADS;
+            sp[i] = g < count ? __ldg(tab + g) : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t g = g0 + i * THREADS;
+            if (g < count)
+                scratch[scratch_slot((int)g)] = interp_sample<CLAMP>(mags, a, (int)sp[i].x, __uint_as_float(sp[i].y), k_last);
+        }
+    }
+}
 template <int THREADS>
 __device__ __forceinline__ void resample_samples(const float2 *mags, float2 *scratch, const KernelArgs &a, const RowChunk ck)
 {
-    const int k_last = (int)a.k_out - 1;
-    if (a.taps_clamped) {
-        for (uint32_t g = ck.samp_begin + threadIdx.x; g < ck.samp_end; g += THREADS) {
-            const uint2 sp = __ldg(a.samp + g);
-            scratch[scratch_slot((int)(g - ck.samp_begin))] = interp_sample<true>(mags, a, (int)sp.x, __uint_as_float(sp.y), k_last);
-        }
-    } else {
-        for (uint32_t g = ck.samp_begin + threadIdx.x; g < ck.samp_end; g += THREADS) {
-            const uint2 sp = __ldg(a.samp + g);
-            scratch[scratch_slot((int)(g - ck.samp_begin))] = interp_sample<false>(mags, a, (int)sp.x, __uint_as_float(sp.y), k_last);
-        }
-    }
+    if (a.taps_clamped) resample_samples_impl<THREADS, true>(mags, scratch, a, ck);
+    else resample_samples_impl<THREADS, false>(mags, scratch, a, ck);
 }
 
 // Phase B: one thread per row: sequential mean of its samples (the reference's summation order,
