@@ -56,6 +56,8 @@ def lib():
                                       f32p, f32p, u32p]
         L.orc_normalised_db.restype = C.c_float
         L.orc_normalised_db.argtypes = [C.c_float] * 5
+        L.orc_db_chain.restype = C.c_float
+        L.orc_db_chain.argtypes = [C.c_float] * 4
         L.orc_gradient_index.restype = C.c_uint32
         L.orc_gradient_index.argtypes = [C.c_float]
         L.orc_color_index.restype = C.c_uint32

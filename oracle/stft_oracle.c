@@ -319,12 +319,18 @@ static c32 orc_magnitude_in(const c32 *d, uint32_t len, float period, float f0, 
 /* ColorScheme::color_for, mono schemes (src/colorscheme.rs:16-17,55-71)      */
 /* ------------------------------------------------------------------------- */
 
+/* colorscheme.rs:60-61 on a power value p = l*l + r*r */
+ORC_API float orc_db_chain(float p, float db_min, float db_max, float db_eps)
+{
+    float db = 10.0f * log10f(p + db_eps);
+    return (db - db_min) / (db_max - db_min);
+}
+
 /* colorscheme.rs:59-61 */
 ORC_API float orc_normalised_db(float l, float r, float db_min, float db_max, float db_eps)
 {
-    float p = l * l + r * r;
-    float db = 10.0f * log10f(p + db_eps);
-    return (db - db_min) / (db_max - db_min);
+    float p = l * l + r * r;                                     /* norm_sqr */
+    return orc_db_chain(p, db_min, db_max, db_eps);
 }
 
 /* [unvendored] colorous 1.0.12 256-entry ramp gradients: idx = clamp(floor(t*256),0,255) */

@@ -1,0 +1,136 @@
+"""CPU: the C-ABI library loads, exports every symbol include/sbx.h declares, its struct layout matches
+the binding, and it fails loudly (no CPU fallback) when no GPU is present.  No compute calls."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "sbx.h")
+
+
+@pytest.fixture(scope="module")
+def binding():
+    import spectrogram_rs_b200 as s
+    return s.binding
+
+
+def _declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"SBX_API\s+[\w\s\*]+?\b(sbx_\w+)\s*\(", text)))
+
+
+def test_header_declares_the_expected_surface():
+    names = _declared_symbols()
+    for must in ("sbx_plan_create", "sbx_plan_destroy", "sbx_process_magnitudes", "sbx_process_column",
+                 "sbx_process_batch", "sbx_process_batch_device", "sbx_colorize_magnitudes", "sbx_get_bin_map",
+                 "sbx_live_push", "sbx_live_pop_column", "sbx_num_input_samples", "sbx_num_output_frequencies"):
+        assert must in names
+    assert len(names) >= 30
+
+
+def test_library_exports_every_declared_symbol(binding):
+    lib = binding.load()
+    declared = _declared_symbols()
+    assert sorted(binding.SYMBOLS) == declared, "binding.SYMBOLS and include/sbx.h disagree"
+    out = subprocess.run(["nm", "-D", "--defined-only", binding.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r"\bT (sbx_\w+)", out))
+    assert set(declared) <= exported
+    assert exported == set(declared), f"undeclared exports: {exported - set(declared)}"
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.sbx_abi_version() == 1 and lib.sbx_build_arch() == b"sm_100a"
+
+
+def test_library_is_sm100a_and_has_no_cufft_dependency(binding):
+    out = subprocess.run(["cuobjdump", "--list-elf", binding.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    ldd = subprocess.run(["ldd", binding.LIB_PATH], capture_output=True, text=True).stdout
+    assert "cufft" not in ldd.lower() and "torch" not in ldd.lower()
+
+
+def test_struct_layout_matches_the_header(binding):
+    src = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "sbx.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(sbx_config), offsetof(sbx_config, sample_rate),
+         offsetof(sbx_config, channels), offsetof(sbx_config, f_min), offsetof(sbx_config, db_min),
+         offsetof(sbx_config, interp), offsetof(sbx_config, device), offsetof(sbx_config, lut_rgb));
+  return 0; }'''
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "layout.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "layout")
+        subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
+        vals = [int(v) for v in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    S = binding.SbxConfig
+    assert vals == [C.sizeof(S), S.sample_rate.offset, S.channels.offset, S.f_min.offset, S.db_min.offset,
+                    S.interp.offset, S.device.offset, S.lut_rgb.offset]
+
+
+def test_defaults_are_the_reference_literals(binding):
+    lib = binding.load()
+    cfg = binding.SbxConfig()
+    lib.sbx_config_default(C.byref(cfg))
+    assert (cfg.struct_size, cfg.abi_version) == (C.sizeof(binding.SbxConfig), 1)
+    assert (cfg.sample_rate, cfg.window_n, cfg.pad_factor, cfg.hop, cfg.rows_h) == (48000.0, 4096, 2, 512, 1024)
+    assert (cfg.f_min, cfg.f_max) == (32.0, 22030.0)                         # simple_spectrogram.rs:107
+    assert (cfg.db_min, cfg.db_max) == (-70.0, -10.0)                        # colorscheme.rs:16-17
+    assert abs(cfg.db_eps - 1e-7) < 1e-12 and cfg.interp == 0 and cfg.scheme == 0
+    assert tuple(cfg.lut_rgb[:3]) == (0, 0, 4)                               # magma
+    assert lib.sbx_samples_from_seconds(0.05, 48000.0) == 2400               # fft.rs:19
+    assert lib.sbx_samples_from_seconds(2.0 / 1024.0, 48000.0) == 93         # audio_transform.rs:35
+    assert lib.sbx_samples_from_seconds(-1.0, 48000.0) == 0
+    lut = (C.c_uint8 * 768)()
+    assert lib.sbx_builtin_lut(b"viridis", lut) == 0 and tuple(lut[:3]) == (68, 1, 84)
+    assert lib.sbx_builtin_lut(b"nope", lut) == -1
+
+
+def test_null_and_invalid_arguments_return_codes(binding):
+    lib = binding.load()
+    h = C.c_void_p()
+    assert lib.sbx_plan_create(None, C.byref(h)) == -1
+    cfg = binding.SbxConfig()
+    lib.sbx_config_default(C.byref(cfg))
+    cfg.struct_size = 12
+    assert lib.sbx_plan_create(C.byref(cfg), C.byref(h)) == -1 and not h.value
+    assert b"size/version" in lib.sbx_last_error(None)
+    lib.sbx_config_default(C.byref(cfg))
+    cfg.window_n = 2400                                                       # the live app's non-power-of-two window
+    assert lib.sbx_plan_create(C.byref(cfg), C.byref(h)) == -2
+    lib.sbx_config_default(C.byref(cfg))
+    cfg.channels = 3                                                          # audio_input_list_model.rs:73-75
+    assert lib.sbx_plan_create(C.byref(cfg), C.byref(h)) == -1
+    lib.sbx_plan_destroy(None)
+    lib.sbx_live_destroy(None)
+    assert lib.sbx_num_input_samples(None) == 0 and lib.sbx_num_frames(None, 10) == 0
+    assert lib.sbx_process_magnitudes(None, None, 0, None) == -1
+    assert lib.sbx_live_push(None, None, 0, 2) == 0
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    """In the CPU-only container plan creation must fail with SBX_ERR_CUDA, not compute anything."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import spectrogram_rs_b200 as s
+    with pytest.raises(s.SbxError) as e:
+        s.Plan()
+    assert e.value.status == -3 and "no CPU fallback" in str(e.value)
+
+
+def test_product_does_not_reference_the_oracle():
+    """The oracle is test infrastructure: nothing under spectrogram-rs_b200/ may import, include or link it."""
+    pkg = os.path.join(ROOT, "spectrogram-rs_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".inc", ".hpp", ".cpp")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                for needle in ("liboracle", "libemu", "stft_oracle", "from oracle", "import oracle", "oracle/", "orc_"):
+                    assert needle not in text, f"{f} references the oracle ({needle})"

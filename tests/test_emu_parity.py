@@ -1,0 +1,114 @@
+"""CPU: the kernel's own phase functions (stft_kernels.cuh compiled for the host by tests/emu) and the
+product's host tables (sbx_tables.h) against the oracle.  This checks the index math, butterflies,
+swizzles, L/R split, resampling and the dB step function without a GPU; the GPU suite
+(test_gpu_parity.py) checks the same things through the C ABI on the device."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests import signals
+from tests.emu import emu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MAG_TOL = 1e-5
+
+CASES = [
+    # (N, P, channels, hop, H, interp)
+    (256, 2, 2, 64, 64, 0),
+    (512, 2, 1, 128, 128, 0),
+    (1024, 4, 2, 256, 256, 1),
+    (2048, 2, 2, 2048, 1024, 0),
+    (4096, 2, 1, 512, 1024, 0),
+    (4096, 2, 2, 512, 1024, 1),
+    (8192, 2, 1, 256, 1024, 0),
+    (4096, 4, 1, 512, 2048, 0),
+    (2048, 1, 2, 512, 512, 0),
+    (256, 1, 1, 100, 77, 0),
+    (1024, 2, 1, 1, 33, 0),
+]
+
+
+def _pcm(ch, ns, seed=0):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    if ch == 1:
+        return (signals.log_sweep(ns, duration=ns / 48000.0) + 0.02 * rng.standard_normal(ns)).astype(np.float32)
+    return signals.stereo_loopback(ns, seed=seed + 1)
+
+
+@pytest.mark.parametrize("n,pad,ch,hop,rows,interp", CASES)
+def test_emulated_kernel_matches_oracle(magma, n, pad, ch, hop, rows, interp):
+    ns = n + hop * 2 + 2
+    pcm = _pcm(ch, ns)
+    frames = oracle.num_frames(ns, n, hop)
+    cfg = emu.make_config(magma, window_n=n, pad_factor=pad, hop=hop, rows_h=rows, channels=ch, interp=interp)
+    mags, rgba = emu.batch(cfg, pcm)
+    p = oracle.params(window_n=n, pad_factor=pad, hop=hop, rows_h=rows, interp=interp)
+    o_rgba, o_mags = oracle.batch(p, pcm, ch, magma, want_mags=True)
+    assert mags.shape == o_mags.shape and rgba.shape == o_rgba.shape
+    peak = np.abs(o_mags).max(axis=(1, 2), keepdims=True)
+    assert (np.abs(mags - o_mags) / peak).max() <= MAG_TOL
+    # identical magnitudes -> bit-identical columns
+    rec = np.stack([oracle.column_from_magnitudes(p, mags[f], magma) for f in range(frames)])
+    assert np.array_equal(rec, rgba)
+    assert ((rgba != o_rgba).any(axis=2)).mean() <= 2e-3
+
+
+@pytest.mark.parametrize("name,kw,ch,lut", [
+    ("cfg1_sweep_mono", dict(sample_rate=48000.0, window_n=4096, pad_factor=2, hop=512, rows_h=1024), 1, "magma"),
+    ("cfg2_stereo_live", dict(sample_rate=48000.0, window_n=2048, pad_factor=2, hop=2048, rows_h=1024), 2, "magma"),
+    ("cfg3_96k_viridis", dict(sample_rate=96000.0, window_n=8192, pad_factor=2, hop=256, rows_h=1024), 1, "viridis"),
+    ("cfg5_pad4_n1024", dict(sample_rate=48000.0, window_n=1024, pad_factor=4, hop=128, rows_h=2048), 1, "magma"),
+    ("small_cosine", dict(sample_rate=44100.0, window_n=256, pad_factor=2, hop=64, rows_h=96, interp=1), 2, "viridis"),
+])
+def test_emulated_kernel_matches_golden(name, kw, ch, lut):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    cfg = emu.make_config(signals.lut(lut), channels=ch, **kw)
+    mags, rgba = emu.batch(cfg, g["pcm"])
+    peak = np.abs(g["mags"]).max(axis=(1, 2), keepdims=True)
+    assert (np.abs(mags - g["mags"]) / peak).max() <= MAG_TOL
+    assert ((rgba != g["rgba"]).any(axis=2)).mean() <= 2e-3
+    assert np.array_equal(rgba[..., 3], g["rgba"][..., 3])
+
+
+@pytest.mark.parametrize("kw", [
+    dict(window_n=4096, pad_factor=2, rows_h=1024, sample_rate=48000.0),
+    dict(window_n=8192, pad_factor=2, rows_h=1024, sample_rate=96000.0),
+    dict(window_n=1024, pad_factor=4, rows_h=2048, sample_rate=48000.0),
+    dict(window_n=2048, pad_factor=2, rows_h=333, sample_rate=44100.0, f_min=20.0, f_max=20000.0),
+])
+def test_host_tables_bit_exact(magma, kw):
+    """Window, bin map and period computed by the product's sbx_tables.h == the oracle's, bit for bit."""
+    t = emu.tables(emu.make_config(magma, **kw))
+    p = oracle.params(**kw)
+    f0, step, n, period = oracle.bin_map(p)
+    assert np.array_equal(t["f0"].view(np.uint32), f0.view(np.uint32))
+    assert np.array_equal(t["step"].view(np.uint32), step.view(np.uint32))
+    assert np.array_equal(t["n"], n)
+    assert np.float32(t["period"]).view(np.uint32) == np.float32(period).view(np.uint32)
+    assert np.array_equal(t["window"].view(np.uint32), oracle.hann(kw["window_n"]).view(np.uint32))
+
+
+@pytest.mark.parametrize("db", [(-70.0, -10.0, 1e-7), (-90.0, 0.0, 1e-9), (-40.0, -20.0, 1e-7)])
+def test_colour_thresholds_reproduce_the_db_chain(magma, db):
+    """step(p) = #{thr <= p} must equal clamp(floor(t * 256)) of the dB chain for every p: checked on
+    each threshold, its two neighbouring floats, and 200k random powers."""
+    db_min, db_max, eps = db
+    t = emu.tables(emu.make_config(magma, db_min=db_min, db_max=db_max, db_eps=eps))
+    thr = t["thr"][:255]
+    assert np.all(np.diff(thr) > 0)
+    L = oracle.lib()
+
+    rng = np.random.Generator(np.random.PCG64(5))
+    probes = [thr, np.nextafter(thr, np.float32(0)), np.nextafter(thr, np.float32(np.inf)),
+              (10.0 ** rng.uniform(-11, 1, 200000)).astype(np.float32), np.array([0.0, np.inf], np.float32)]
+    p_all = np.concatenate(probes).astype(np.float32)
+    got = np.searchsorted(thr, p_all, side="right")
+    # the oracle's dB chain evaluated on the power value itself (colorscheme.rs:60-61,69)
+    want = np.empty(p_all.size, np.int64)
+    for i, pv in enumerate(p_all):
+        tt = L.orc_db_chain(float(pv), db_min, db_max, eps)
+        want[i] = L.orc_gradient_index(tt)
+    assert np.array_equal(got, want)
