@@ -1,0 +1,163 @@
+// audio_transform.hpp -- C++17 host-side mirror of the reference's frame-transform interface over the C ABI
+// of include/sbx.h (the reference is Rust; no Rust toolchain exists in the build image -- INTEGRATION.md has
+// the Rust shim).  Same names, argument meaning and error behaviour as
+//   trait AudioTransform / struct AudioStreamTransform<T>   src/fourier/audio_transform.rs:4-42
+//   FastFourierTransform                                    src/fourier/fft.rs:11-99
+//   HeapRb::new(cap).split()                                src/devices/audio_input_list_model.rs:30
+// Header-only; link with -lsbx_b200.  All arithmetic happens in the library, on the GPU.
+#pragma once
+#include <atomic>
+#include <cstdint>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/sbx.h"
+
+namespace sbx {
+
+using StereoMagnitude = std::pair<float, float>;   // src/fourier/mod.rs:13
+using Period = float;                              // :14
+using Frequency = float;                           // :15
+static_assert(sizeof(StereoMagnitude) == 2 * sizeof(float), "(f32, f32) must be two packed floats");
+
+struct Error : std::runtime_error {
+    sbx_status status;
+    Error(sbx_status st, const std::string &msg) : std::runtime_error(msg), status(st) {}
+};
+
+// Single-producer single-consumer ring of (l, r) samples -- ringbuf::HeapRb as the reference uses it.
+class HeapRb {
+   public:
+    explicit HeapRb(size_t capacity) : buf_(capacity), cap_(capacity) {}
+    // Producer::push_iter: pushes while there is room, returns the number pushed (the rest is dropped)
+    template <class It> size_t push_iter(It first, It last)
+    {
+        const uint64_t tail = tail_.load(std::memory_order_relaxed), head = head_.load(std::memory_order_acquire);
+        size_t room = cap_ - static_cast<size_t>(tail - head), n = 0;
+        for (; first != last && n < room; ++first, ++n) buf_[(tail + n) % cap_] = *first;
+        tail_.store(tail + n, std::memory_order_release);
+        return n;
+    }
+    size_t push_mono(const float *data, size_t n)            // audio_input_list_model.rs:66-69
+    {
+        std::vector<StereoMagnitude> tmp(n);
+        for (size_t i = 0; i < n; ++i) tmp[i] = {data[i], data[i]};
+        return push_iter(tmp.begin(), tmp.end());
+    }
+    size_t push_interleaved(const float *data, size_t n_frames)   // :70-72
+    {
+        const StereoMagnitude *p = reinterpret_cast<const StereoMagnitude *>(data);
+        return push_iter(p, p + n_frames);
+    }
+    size_t len() const { return static_cast<size_t>(tail_.load(std::memory_order_acquire) - head_.load(std::memory_order_acquire)); }
+    // Consumer::iter(): copies up to `max` samples WITHOUT consuming them
+    size_t peek(StereoMagnitude *out, size_t max) const
+    {
+        const uint64_t head = head_.load(std::memory_order_relaxed);
+        const size_t n = std::min(max, len());
+        for (size_t i = 0; i < n; ++i) out[i] = buf_[(head + i) % cap_];
+        return n;
+    }
+    size_t skip(size_t n)                                     // Consumer::skip
+    {
+        n = std::min(n, len());
+        head_.store(head_.load(std::memory_order_relaxed) + n, std::memory_order_release);
+        return n;
+    }
+
+   private:
+    std::vector<StereoMagnitude> buf_;
+    size_t cap_;
+    std::atomic<uint64_t> head_{0}, tail_{0};
+};
+
+// trait AudioTransform (src/fourier/audio_transform.rs:4-11) as a C++ "concept by convention":
+//   using Output; Frequency sample_rate() const; size_t num_input_samples() const;
+//   std::optional<Output> process(const StereoMagnitude* samples, size_t n_available);
+
+// FastFourierTransform::new(sample_rate, period) drop-in (src/fourier/fft.rs:18-31)
+class GpuFrameTransform {
+   public:
+    using Output = std::vector<StereoMagnitude>;
+
+    GpuFrameTransform(Frequency sample_rate, Period period, const sbx_config *overrides = nullptr)
+    {
+        sbx_config cfg;
+        if (overrides) cfg = *overrides; else sbx_config_default(&cfg);
+        cfg.sample_rate = sample_rate;
+        cfg.window_n = sbx_samples_from_seconds(period, sample_rate);      // (period * sample_rate) as usize
+        const sbx_status st = sbx_plan_create(&cfg, &plan_);
+        if (st != SBX_OK) throw Error(st, sbx_last_error(nullptr));
+        sample_rate_ = sample_rate;
+    }
+    GpuFrameTransform(GpuFrameTransform &&o) noexcept : plan_(o.plan_), sample_rate_(o.sample_rate_) { o.plan_ = nullptr; }
+    GpuFrameTransform &operator=(GpuFrameTransform &&o) noexcept
+    {
+        if (this != &o) { sbx_plan_destroy(plan_); plan_ = o.plan_; sample_rate_ = o.sample_rate_; o.plan_ = nullptr; }
+        return *this;
+    }
+    GpuFrameTransform(const GpuFrameTransform &) = delete;
+    GpuFrameTransform &operator=(const GpuFrameTransform &) = delete;
+    ~GpuFrameTransform() { sbx_plan_destroy(plan_); }
+
+    Frequency sample_rate() const { return sample_rate_; }
+    size_t num_input_samples() const { return sbx_num_input_samples(plan_); }
+    size_t num_output_frequencies() const { return sbx_num_output_frequencies(plan_); }   // fft.rs:33
+    size_t rows() const { return sbx_rows(plan_); }
+    sbx_plan *plan() const { return plan_; }
+
+    // AudioTransform::process (fft.rs:43-99): nullopt when fewer than N samples are available (fft.rs:72)
+    std::optional<Output> process(const StereoMagnitude *samples, size_t n_available)
+    {
+        Output out(num_output_frequencies());
+        const sbx_status st = sbx_process_magnitudes(plan_, reinterpret_cast<const float *>(samples),
+                                                     static_cast<uint32_t>(n_available), reinterpret_cast<float *>(out.data()));
+        if (st == SBX_NOT_ENOUGH_SAMPLES) return std::nullopt;
+        if (st != SBX_OK) throw Error(st, sbx_last_error(plan_));
+        return out;
+    }
+    // the loop body of SimpleSpectrogram::snapshot (simple_spectrogram.rs:136-161): one RGBA8 column, row 0 = top
+    bool process_column(const StereoMagnitude *samples, size_t n_available, uint8_t *rgba)
+    {
+        const sbx_status st = sbx_process_column(plan_, reinterpret_cast<const float *>(samples),
+                                                 static_cast<uint32_t>(n_available), rgba);
+        if (st == SBX_NOT_ENOUGH_SAMPLES) return false;
+        if (st != SBX_OK) throw Error(st, sbx_last_error(plan_));
+        return true;
+    }
+
+   private:
+    sbx_plan *plan_ = nullptr;
+    Frequency sample_rate_ = 0;
+};
+
+// struct AudioStreamTransform<T> (src/fourier/audio_transform.rs:14-42); public fields, as in the reference
+template <class T> struct AudioStreamTransform {
+    HeapRb *input_stream;
+    T transform;
+    Period stride;
+
+    AudioStreamTransform(HeapRb *stream, T t, Period s) : input_stream(stream), transform(std::move(t)), stride(s) {}
+
+    // process(): calls `sink(output)` once per frame while a whole window is buffered.  As in the reference,
+    // skip(stride_samples) also runs after the failing attempt (:38-41).  Returns the number of frames.
+    template <class Sink> size_t process(Sink &&sink)
+    {
+        const size_t stride_samples = sbx_samples_from_seconds(stride, transform.sample_rate());
+        std::vector<StereoMagnitude> window(transform.num_input_samples());
+        size_t frames = 0;
+        for (;;) {
+            const size_t got = input_stream->peek(window.data(), window.size());
+            auto out = transform.process(window.data(), got);
+            input_stream->skip(stride_samples);
+            if (!out) return frames;
+            sink(std::move(*out));
+            ++frames;
+        }
+    }
+};
+
+}  // namespace sbx

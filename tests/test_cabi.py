@@ -134,3 +134,24 @@ def test_product_does_not_reference_the_oracle():
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 for needle in ("liboracle", "libemu", "stft_oracle", "from oracle", "import oracle", "oracle/", "orc_"):
                     assert needle not in text, f"{f} references the oracle ({needle})"
+
+
+def _build_cpp_example(tmpdir):
+    host = os.path.join(ROOT, "spectrogram-rs_b200", "host")
+    exe = os.path.join(str(tmpdir), "example_stream")
+    lib_dir = os.path.join(ROOT, "spectrogram-rs_b200")
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", os.path.join(host, "example_stream.cpp"),
+                    "-L", lib_dir, "-lsbx_b200", f"-Wl,-rpath,{lib_dir}", "-o", exe], check=True)
+    return exe
+
+
+def test_cpp_host_mirror_compiles_and_fails_loudly_without_gpu(binding, tmp_path):
+    """spectrogram-rs_b200/host/audio_transform.hpp (AudioTransform / AudioStreamTransform<T> / HeapRb mirror)."""
+    binding.load()
+    exe = _build_cpp_example(tmp_path)
+    import torch
+    out = subprocess.run([exe], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert out.returncode == 0, out.stderr
+    else:
+        assert out.returncode == 2 and "no CPU fallback" in out.stderr

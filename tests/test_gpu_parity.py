@@ -210,3 +210,16 @@ def test_errors_do_not_abort(sbx, magma):
         with pytest.raises(sbx.SbxError) as e:
             plan.process_batch_device(pcm, 1024 * 4, small, 1)
         assert e.value.status == -5
+
+
+def test_cpp_host_mirror_runs(tmp_path):
+    """The C++ mirror of AudioStreamTransform<T>: 4096 buffered samples, N 2048, hop 512 -> 5 frames; 1 kHz tone."""
+    import re
+    from tests.test_cabi import _build_cpp_example
+    import subprocess
+    out = subprocess.run([_build_cpp_example(tmp_path)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    m = re.search(r"frames=(\d+) k=(\d+) peak_bin=(\d+) peak=([\d.]+) column=1 alpha=255", out.stdout)
+    assert m, out.stdout
+    assert int(m.group(1)) == 5 and int(m.group(2)) == 2047
+    assert abs(int(m.group(3)) + 1 - 1000.0 * 4096 / 48000.0) <= 1 and 0.4 < float(m.group(4)) <= 0.5
