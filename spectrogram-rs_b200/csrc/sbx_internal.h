@@ -6,7 +6,7 @@
 #include <vector>
 
 #include "../../include/sbx.h"
-#include "stft_kernels.cuh"
+#include "stft_large.cuh"
 
 struct sbx_plan {
     sbx_config cfg;
@@ -29,6 +29,13 @@ struct sbx_plan {
     sbx::RowChunk *d_chunks = nullptr;
     uint2 *d_samp = nullptr;
     int taps_clamped = 0;
+
+    // large path (M > 16384): block-transform twiddles and per-launch scratch
+    bool large = false;
+    float2 *d_twp_block = nullptr;
+    float2 *d_zbuf = nullptr;           // [large_units][M]
+    float2 *d_magbuf = nullptr;         // [large_units][M/2]
+    uint32_t large_units = 0;           // scratch capacity in units (frame pairs / frames)
     float *d_thr = nullptr;
     uint32_t *d_lut = nullptr;
 
@@ -65,6 +72,8 @@ struct sbx_plan {
 namespace sbx {
 // launches the fused kernel for `channels`-layout PCM on `stream`
 sbx_status launch_fused(sbx_plan *p, int channels, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba,
+                        float *d_mags, cudaStream_t stream);
+sbx_status launch_large(sbx_plan *p, int channels, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba,
                         float *d_mags, cudaStream_t stream);
 sbx_status launch_colourise(sbx_plan *p, const float *d_mags, uint64_t n_frames, uint8_t *d_rgba, cudaStream_t stream);
 sbx_status fail(const sbx_plan *p, sbx_status st, const std::string &msg);

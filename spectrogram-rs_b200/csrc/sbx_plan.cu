@@ -16,7 +16,8 @@ namespace {
 
 thread_local std::string g_create_error;
 
-constexpr uint32_t kMinLog2N = 8, kMaxLog2N = 13, kMaxLog2M = 14;
+constexpr uint32_t kMinLog2N = 8, kMaxLog2M = 14;                      // fused (single-SM) kernel: N <= 8192, M <= 16384
+constexpr uint32_t kMaxLog2NLarge = 16, kMaxLog2MLarge = 18;             // multi-kernel path of stft_large.cuh
 
 int ilog2_exact(uint32_t v)
 {
@@ -92,6 +93,7 @@ cudaError_t launch_pad(int log2pad, int channels, const KernelArgs &args, uint64
 sbx_status launch_fused(sbx_plan *p, int channels, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba,
                         float *d_mags, cudaStream_t stream)
 {
+    if (p->large) return launch_large(p, channels, d_pcm, n_frames, d_rgba, d_mags, stream);
     KernelArgs a = p->base_args();
     a.pcm = d_pcm;
     a.rgba = d_rgba;
@@ -109,6 +111,85 @@ sbx_status launch_fused(sbx_plan *p, int channels, const float *d_pcm, uint64_t 
     }
     if (e != cudaSuccess) return cuda_fail(p, e, "fused_frames_kernel launch");
     if (n_frames) p->launches += 1;
+    return SBX_OK;
+}
+
+// ---- large path (M > 16384): four kernels per chunk of units --------------------------------------
+template <int LOG2N, int LOG2PAD, int CH>
+cudaError_t launch_large_one(const LargeArgs &la, bool want_rgba, cudaStream_t stream)
+{
+    using GL = GeomL<LOG2N, LOG2PAD>;
+    const unsigned units = la.units;
+    large_first_kernel<LOG2N, LOG2PAD, CH><<<units * GL::PAD * (LARGE_BLOCK / LARGE_THREADS), LARGE_THREADS, 0, stream>>>(la);
+    large_block_kernel<<<units * (GL::M / LARGE_BLOCK), LARGE_THREADS, 0, stream>>>(la);
+    large_split_kernel<LOG2N, LOG2PAD, CH><<<units * ((GL::M / 2) / LARGE_THREADS), LARGE_THREADS, 0, stream>>>(la);
+    if (want_rgba) large_colour_kernel<CH == 1><<<units, LARGE_THREADS, 0, stream>>>(la, la.magbuf, (size_t)GL::M / 2);
+    return cudaGetLastError();
+}
+
+template <int LOG2N, int LOG2PAD>
+cudaError_t launch_large_ch(int channels, const LargeArgs &la, bool want_rgba, cudaStream_t stream)
+{
+    if constexpr (LOG2N + LOG2PAD <= (int)kMaxLog2M || LOG2N + LOG2PAD > (int)kMaxLog2MLarge) {
+        return cudaErrorInvalidConfiguration;
+    } else {
+        return channels == 1 ? launch_large_one<LOG2N, LOG2PAD, 1>(la, want_rgba, stream)
+                             : launch_large_one<LOG2N, LOG2PAD, 2>(la, want_rgba, stream);
+    }
+}
+
+template <int LOG2N>
+cudaError_t launch_large_pad(int log2pad, int channels, const LargeArgs &la, bool want_rgba, cudaStream_t stream)
+{
+    switch (log2pad) {
+        case 0: return launch_large_ch<LOG2N, 0>(channels, la, want_rgba, stream);
+        case 1: return launch_large_ch<LOG2N, 1>(channels, la, want_rgba, stream);
+        case 2: return launch_large_ch<LOG2N, 2>(channels, la, want_rgba, stream);
+        default: return cudaErrorInvalidConfiguration;
+    }
+}
+
+sbx_status launch_large(sbx_plan *p, int channels, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba,
+                        float *d_mags, cudaStream_t stream)
+{
+    if (n_frames == 0) return SBX_OK;
+    if (p->large_units == 0) {
+        // scratch: (M + M/2) float2 per unit, about 512 MiB in total, at least one unit
+        const size_t per_unit = (size_t)p->m * 12;
+        uint64_t units = ((uint64_t)512 << 20) / per_unit;
+        units = units < 1 ? 1 : (units > 8192 ? 8192 : units);
+        cudaError_t e = cudaMalloc(&p->d_zbuf, units * (size_t)p->m * sizeof(float2));
+        if (e == cudaSuccess) e = cudaMalloc(&p->d_magbuf, units * (size_t)(p->m / 2) * sizeof(float2));
+        if (e != cudaSuccess) { cudaFree(p->d_zbuf); p->d_zbuf = nullptr; return cuda_fail(p, e, "cudaMalloc(large-transform scratch)"); }
+        p->large_units = (uint32_t)units;
+    }
+    const uint32_t per = channels == 1 ? 2 : 1;
+    const uint64_t total_units = (n_frames + per - 1) / per;
+    LargeArgs la{};
+    la.k = p->base_args();
+    la.k.pcm = d_pcm;
+    la.k.rgba = d_rgba;
+    la.k.mags_out = d_mags;
+    la.k.n_frames = n_frames;
+    la.twp_block = p->d_twp_block;
+    la.zbuf = p->d_zbuf;
+    la.magbuf = p->d_magbuf;
+    la.log2n = (uint32_t)p->log2n;
+    la.log2pad = (uint32_t)p->log2pad;
+    for (uint64_t u0 = 0; u0 < total_units; u0 += p->large_units) {
+        la.frame_base = u0 * per;
+        la.units = (uint32_t)(total_units - u0 < p->large_units ? total_units - u0 : p->large_units);
+        cudaError_t e;
+        switch (p->log2n) {
+            case 13: e = launch_large_pad<13>(p->log2pad, channels, la, d_rgba != nullptr, stream); break;
+            case 14: e = launch_large_pad<14>(p->log2pad, channels, la, d_rgba != nullptr, stream); break;
+            case 15: e = launch_large_pad<15>(p->log2pad, channels, la, d_rgba != nullptr, stream); break;
+            case 16: e = launch_large_pad<16>(p->log2pad, channels, la, d_rgba != nullptr, stream); break;
+            default: e = cudaErrorInvalidConfiguration; break;
+        }
+        if (e != cudaSuccess) return cuda_fail(p, e, "large-transform kernels launch");
+        p->launches += d_rgba != nullptr ? 4 : 3;
+    }
     return SBX_OK;
 }
 
@@ -131,6 +212,22 @@ template <int LOG2M> cudaError_t launch_colourise_one(const KernelArgs &a, uint6
 
 sbx_status launch_colourise(sbx_plan *p, const float *d_mags, uint64_t n_frames, uint8_t *d_rgba, cudaStream_t stream)
 {
+    if (p->large) {
+        if (n_frames == 0) return SBX_OK;
+        if (n_frames > 0x7fffffffull) return fail(p, SBX_ERR_INVALID_ARGUMENT, "too many frames");
+        LargeArgs la{};
+        la.k = p->base_args();
+        la.k.rgba = d_rgba;
+        la.k.n_frames = n_frames;
+        la.units = (uint32_t)n_frames;
+        // magnitudes are indexed by bin kk = j + 1: shift the caller's K x (L,R) rows by one entry
+        large_colour_kernel<false><<<(unsigned)n_frames, LARGE_THREADS, 0, stream>>>(
+            la, reinterpret_cast<const float2 *>(d_mags) - 1, (size_t)p->k_out);
+        cudaError_t el = cudaGetLastError();
+        if (el != cudaSuccess) return cuda_fail(p, el, "large_colour_kernel launch");
+        p->launches += 1;
+        return SBX_OK;
+    }
     KernelArgs a = p->base_args();
     a.mags_in = d_mags;
     a.rgba = d_rgba;
@@ -254,7 +351,7 @@ SBX_API void sbx_plan_destroy(sbx_plan *p)
         cudaFree(s.d_rgba);
     }
     cudaFree(p->d_window); cudaFree(p->d_wtw); cudaFree(p->d_twp); cudaFree(p->d_rowmap); cudaFree(p->d_chunks);
-    cudaFree(p->d_samp);
+    cudaFree(p->d_samp); cudaFree(p->d_twp_block); cudaFree(p->d_zbuf); cudaFree(p->d_magbuf);
     cudaFree(p->d_thr); cudaFree(p->d_lut); cudaFree(p->d_frame); cudaFree(p->d_mags1); cudaFree(p->d_col);
     if (p->h_frame) cudaFreeHost(p->h_frame);
     if (p->h_col) cudaFreeHost(p->h_col);
@@ -272,11 +369,13 @@ SBX_API sbx_status sbx_plan_create(const sbx_config *cfg, sbx_plan **out_plan)
     if (cfg->window_n < 2) return fail(nullptr, SBX_ERR_INVALID_ARGUMENT, "window_n must be >= 2");
     if (log2n < 0)
         return fail(nullptr, SBX_ERR_UNSUPPORTED, "window_n must be a power of two (mixed-radix sizes such as the live app's 2400 are not implemented yet)");
-    if (log2n < (int)kMinLog2N || log2n > (int)kMaxLog2N)
-        return fail(nullptr, SBX_ERR_UNSUPPORTED, "window_n must be in [256, 8192]");
+    if (log2n < (int)kMinLog2N || log2n > (int)kMaxLog2NLarge)
+        return fail(nullptr, SBX_ERR_UNSUPPORTED, "window_n must be in [256, 65536]");
     if (log2pad < 0 || log2pad > 2) return fail(nullptr, SBX_ERR_UNSUPPORTED, "pad_factor must be 1, 2 or 4");
-    if (log2n + log2pad > (int)kMaxLog2M)
-        return fail(nullptr, SBX_ERR_UNSUPPORTED, "window_n * pad_factor must be <= 16384 (the transform is held in one SM's shared memory)");
+    if (log2n + log2pad > (int)kMaxLog2MLarge)
+        return fail(nullptr, SBX_ERR_UNSUPPORTED, "window_n * pad_factor must be <= 262144");
+    if (log2n + log2pad > (int)kMaxLog2M && log2n < 13)
+        return fail(nullptr, SBX_ERR_UNSUPPORTED, "transforms longer than 16384 need window_n >= 8192");
     if (cfg->channels != 1 && cfg->channels != 2) return fail(nullptr, SBX_ERR_INVALID_ARGUMENT, "channels must be 1 or 2");
     if (cfg->hop == 0) return fail(nullptr, SBX_ERR_INVALID_ARGUMENT, "hop must be >= 1");
     if (cfg->rows_h == 0 || cfg->rows_h > (1u << 20)) return fail(nullptr, SBX_ERR_INVALID_ARGUMENT, "rows_h must be in [1, 2^20]");
@@ -323,6 +422,7 @@ SBX_API sbx_status sbx_plan_create(const sbx_config *cfg, sbx_plan **out_plan)
     p->h_window = t.window;
     p->h_rowmap = t.rowmap;
     p->h_thr_raw = t.thr_raw;
+    p->large = t.large;
     p->n_chunks = (uint32_t)t.chunks.size();
     p->taps_clamped = t.taps_clamped ? 1 : 0;
     for (int i = 0; i < 2; ++i) { p->guess_a[i] = t.guess_a[i]; p->guess_b[i] = t.guess_b[i]; }
@@ -341,6 +441,7 @@ SBX_API sbx_status sbx_plan_create(const sbx_config *cfg, sbx_plan **out_plan)
     SBX_TRY(upload(&p->d_window, p->h_window.data(), p->n * sizeof(float)));
     SBX_TRY(upload(&p->d_wtw, t.wtw.data(), t.wtw.size() * sizeof(float)));
     SBX_TRY(upload(&p->d_twp, t.twp.data(), t.twp.size() * sizeof(float)));
+    SBX_TRY(upload(&p->d_twp_block, t.twp_block.data(), t.twp_block.size() * sizeof(float)));
     SBX_TRY(upload(&p->d_rowmap, p->h_rowmap.data(), p->rows * sizeof(sbx::RowMap)));
     SBX_TRY(upload(&p->d_chunks, t.chunks.data(), t.chunks.size() * sizeof(sbx::RowChunk)));
     SBX_TRY(upload(&p->d_samp, t.samp.data(), t.samp.size() * sizeof(uint32_t)));

@@ -9,7 +9,7 @@
 #include <vector>
 
 #include "../../include/sbx.h"
-#include "stft_kernels.cuh"
+#include "stft_large.cuh"
 
 namespace sbx {
 namespace tables {
@@ -88,6 +88,8 @@ struct HostTables {
     std::vector<float> window;          // [N]
     std::vector<float> wtw;             // [(P-1) N] x (re, im): window[n] * W_M^(n q0)
     std::vector<float> twp;             // per-pass twiddle planes x (re, im), see KernelArgs::twp
+    std::vector<float> twp_block;       // large path: planes of the 4096-point block transform
+    bool large = false;                 // M > 16384: the multi-kernel path of stft_large.cuh
     std::vector<RowMap> rowmap;         // [H]
     std::vector<RowChunk> chunks;       // rows grouped so that a chunk's samples fit the kernel's scratch area
     std::vector<uint32_t> samp;         // per (row, sample): {floor(x), weight bits}, see KernelArgs::samp
@@ -134,16 +136,27 @@ inline void build(const sbx_config &cfg, HostTables &t)
     // per-pass twiddle planes: plane j of pass p holds W_(S_p R_p)^(2^j lo), lo < S_p
     int log2n = 0;
     while ((1u << log2n) < t.n) ++log2n;
+    t.large = t.m > 16384;
+    auto planes = [](const RadixPlan &rp, int first_pass, int last_pass, std::vector<float> &dst) {
+        dst.clear();
+        for (int p = first_pass; p < last_pass; ++p) {
+            const uint32_t s = 1u << rp.log2stride(p), span = s << rp.log2r(p);
+            for (int j = 0; j < TW_PLANES; ++j)
+                for (uint32_t lo = 0; lo < s; ++lo) {
+                    const double ang = -2.0 * M_PI * (double)(((uint64_t)lo << j) % span) / (double)span;
+                    dst.push_back((float)std::cos(ang));
+                    dst.push_back((float)std::sin(ang));
+                }
+        }
+    };
     const RadixPlan rp(log2n);
-    t.twp.clear();
-    for (int p = 0; p + 1 < rp.npass; ++p) {
-        const uint32_t s = 1u << rp.log2stride(p), span = s << rp.log2r(p);
-        for (int j = 0; j < TW_PLANES; ++j)
-            for (uint32_t lo = 0; lo < s; ++lo) {
-                const double ang = -2.0 * M_PI * (double)(((uint64_t)lo << j) % span) / (double)span;
-                t.twp.push_back((float)std::cos(ang));
-                t.twp.push_back((float)std::sin(ang));
-            }
+    if (t.large) {
+        planes(rp, 0, 1, t.twp);                               // the global radix-R0 pass: W_N^(2^j lo), lo < 4096
+        const RadixPlan rb(LARGE_LOG2_BLOCK);
+        planes(rb, 0, rb.npass - 1, t.twp_block);              // the 4096-point block transform
+    } else {
+        planes(rp, 0, rp.npass - 1, t.twp);
+        t.twp_block.clear();
     }
 
     t.rowmap.resize(t.rows);
@@ -185,7 +198,7 @@ inline void build(const sbx_config &cfg, HostTables &t)
         }
     }
     // row chunks: greedy, a chunk's samples must fit the kernel's scratch area ((M/2) * 16/17 slots)
-    const uint32_t cap = (uint32_t)((((uint64_t)t.m / 2) * 16) / 17);
+    const uint32_t cap = t.large ? (uint32_t)LARGE_SCRATCH : (uint32_t)((((uint64_t)t.m / 2) * 16) / 17);
     t.chunks.clear();
     t.ok = true;
     RowChunk ck = {0, 0, 0, 0};

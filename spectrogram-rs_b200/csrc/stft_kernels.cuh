@@ -263,9 +263,10 @@ template <int LOG2N_, int LOG2PAD_, int CH_> struct Geom {
     static __host__ __device__ constexpr int zkey(int i)
     {
         int k = (i >> 4) & 7;
-        if (key_ext_src(0) >= 0) k ^= (i >> key_ext_src(0)) & 1;
-        if (key_ext_src(1) >= 0) k ^= ((i >> key_ext_src(1)) & 1) << 1;
-        if (key_ext_src(2) >= 0) k ^= ((i >> key_ext_src(2)) & 1) << 2;
+        constexpr int e0 = key_ext_src(0), e1 = key_ext_src(1), e2 = key_ext_src(2);
+        if (e0 >= 0) k ^= (i >> (e0 >= 0 ? e0 : 0)) & 1;
+        if (e1 >= 0) k ^= ((i >> (e1 >= 0 ? e1 : 0)) & 1) << 1;
+        if (e2 >= 0) k ^= ((i >> (e2 >= 0 ? e2 : 0)) & 1) << 2;
         return k;
     }
     // element index -> physical float2 slot: permutes the eight 16-byte chunks of every 128-byte row.

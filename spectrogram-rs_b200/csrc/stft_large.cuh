@@ -1,0 +1,185 @@
+// stft_large.cuh -- transforms too long for one SM's shared memory (M = P*N > 16384, N = 8192 .. 65536).
+//
+// Same algorithm as stft_kernels.cuh -- P premultiplied sub-transforms of length N, in-place radix
+// (R0,16,16,16) DIF with R0 = N/4096, digit-reversed output, conjugate-symmetry split, host-tabulated
+// resample, threshold dB step -- but the first radix-R0 pass works global -> global, after which every
+// 4096-point block is an independent transform that fits shared memory:
+//
+//   large_first   : PCM -> window -> W_M^(n q0) premultiply -> radix-R0 butterfly -> W_N^(lo q) -> Y   (global)
+//   large_block   : one 4096-point block of Y: three radix-16 passes in shared memory, in place      (global)
+//   large_split   : bins kk = 1..M/2-1 from Z[pos(kk)], Z[pos(M-kk)] -> (L,R) magnitudes             (global)
+//   large_colour  : resample (lane per sample, taps read through L1/L2) + dB step + LUT -> RGBA
+//
+// Scratch per frame pair (mono) or frame (stereo): M float2 for Y/Z plus M/2 float2 of magnitudes.
+#pragma once
+#include "stft_kernels.cuh"
+
+namespace sbx {
+
+constexpr int LARGE_LOG2_BLOCK = 12;                       // 4096-point blocks
+constexpr int LARGE_BLOCK = 1 << LARGE_LOG2_BLOCK;
+constexpr int LARGE_THREADS = 256;
+constexpr int LARGE_SCRATCH = (LARGE_BLOCK * 16) / 17;     // resample scratch slots of large_colour (32 KB)
+
+using G12 = Geom<LARGE_LOG2_BLOCK, 0, 2>;                  // the block transform: 4096 = 16 x 16 x 16
+
+struct LargeArgs {
+    KernelArgs k;               // tables as in the fused kernel; k.twp = planes of the FIRST (radix-R0) pass
+    const float2 *twp_block;    // twiddle planes of the 4096-point block transform (G12 layout)
+    float2 *zbuf;               // [units][M] transform scratch
+    float2 *magbuf;             // [units][M/2] magnitudes by bin kk (index 0 unused)
+    unsigned long long frame_base;   // first frame of this launch (chunked batches)
+    uint32_t units;             // frame pairs (mono) or frames (stereo) in this launch
+    uint32_t log2n, log2pad;
+};
+
+template <int LOG2N, int LOG2PAD> struct GeomL {
+    static constexpr int N = 1 << LOG2N, PAD = 1 << LOG2PAD, LOG2M = LOG2N + LOG2PAD, M = 1 << LOG2M;
+    static constexpr int LOG2R0 = LOG2N - LARGE_LOG2_BLOCK, R0 = 1 << LOG2R0;
+    static_assert(LOG2R0 >= 1 && LOG2R0 <= 4, "first-pass radix 2..16");
+    // bin kk = PAD*k + q0, k = d0 + R0*k_local  ->  position q0*N + d0*4096 + digitrev_4096(k_local)
+    static __host__ __device__ constexpr int pos_of_bin(int kk)
+    {
+        const int q0 = kk & (PAD - 1), k = kk >> LOG2PAD;
+        const int d0 = k & (R0 - 1), kl = k >> LOG2R0;
+        return (q0 << LOG2N) + (d0 << LARGE_LOG2_BLOCK) + G12::pos_of_bin(kl);
+    }
+};
+
+// ---- pass 0: global PCM -> global Y --------------------------------------------------------------
+// one thread per (unit, q0, lo): R0 inputs n = lo + 4096 r
+template <int LOG2N, int LOG2PAD, int CH>
+__device__ __forceinline__ void large_first(const LargeArgs &la, unsigned int block_id)
+{
+    using GL = GeomL<LOG2N, LOG2PAD>;
+    constexpr int R = GL::R0;
+    const KernelArgs &a = la.k;
+    constexpr int TILES = LARGE_BLOCK / LARGE_THREADS;                 // thread tiles per (unit, q0)
+    const unsigned int tile = block_id % TILES, q0 = (block_id / TILES) % GL::PAD, unit = block_id / (TILES * GL::PAD);
+    const int lo = tile * LARGE_THREADS + threadIdx.x;
+    const unsigned long long frame0 = la.frame_base + (unsigned long long)unit * (CH == 1 ? 2 : 1);
+    const bool second_valid = CH == 1 && frame0 + 1 < a.n_frames;
+    const float *pa = a.pcm + frame0 * (unsigned long long)a.hop * CH;
+    const float *pb = pa + a.hop;
+    float2 v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int n = lo + r * LARGE_BLOCK;
+        float2 s;
+        if constexpr (CH == 2) {
+            s = __ldg(reinterpret_cast<const float2 *>(pa) + n);
+        } else {
+            s.x = __ldg(pa + n);
+            s.y = second_valid ? __ldg(pb + n) : 0.0f;
+        }
+        if (q0 == 0) {
+            const float wn = __ldg(a.window + n);
+            s.x *= wn;  s.y *= wn;
+        } else {
+            s = cmul(s, __ldg(a.wtw + (size_t)(q0 - 1) * GL::N + n));
+        }
+        v[r] = s;
+    }
+    Butterfly<R>::run(v);
+    apply_twiddles<R>(v, a.twp + lo, LARGE_BLOCK);                     // W_N^(lo q)
+    float2 *y = la.zbuf + (size_t)unit * GL::M + ((size_t)q0 << LOG2N) + lo;
+#pragma unroll
+    for (int q = 0; q < R; ++q) y[(size_t)q * LARGE_BLOCK] = v[q];
+}
+
+// ---- passes 1..3: one 4096-point block in shared memory -------------------------------------------
+// phase 0: load + first radix-16 pass; phases 1,2: pass_inplace<G12,1|2>; phase 3: write back
+__device__ __forceinline__ void large_block_load(float2 *z, const float2 *src, const float2 *twp_block)
+{
+    constexpr int S = 256;
+    for (int w = threadIdx.x; w < LARGE_BLOCK / 16; w += LARGE_THREADS) {
+        float2 v[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = src[w + r * S];
+        Butterfly<16>::run(v);
+        apply_twiddles<16>(v, twp_block + w, S);
+        const int bx = G12::zsw(w);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) z[SBX_ZAT(G12, bx, q * S)] = v[q];
+    }
+}
+__device__ __forceinline__ void large_block_store(const float2 *z, float2 *dst)
+{
+    for (int i = threadIdx.x; i < LARGE_BLOCK; i += LARGE_THREADS) dst[i] = z[G12::zsw(i)];
+}
+
+// ---- split: global Z -> global magnitudes -----------------------------------------------------------
+template <int LOG2N, int LOG2PAD, int CH>
+__device__ __forceinline__ void large_split(const LargeArgs &la, unsigned int block_id)
+{
+    using GL = GeomL<LOG2N, LOG2PAD>;
+    const KernelArgs &a = la.k;
+    constexpr unsigned int PER_UNIT = (GL::M / 2) / LARGE_THREADS;
+    const unsigned int unit = block_id / PER_UNIT;
+    const int kk = (block_id % PER_UNIT) * LARGE_THREADS + threadIdx.x;
+    if (kk == 0) return;                                                       // DC is dropped (fft.rs:81)
+    const float2 *zu = la.zbuf + (size_t)unit * GL::M;
+    const float2 m = split_pair(zu[GL::pos_of_bin(kk)], zu[GL::pos_of_bin(GL::M - kk)], a.scale);
+    la.magbuf[(size_t)unit * (GL::M / 2) + kk] = m;
+    if (a.mags_out != nullptr) {
+        const unsigned long long frame0 = la.frame_base + (unsigned long long)unit * (CH == 1 ? 2 : 1);
+        float2 *out = reinterpret_cast<float2 *>(a.mags_out) + frame0 * a.k_out + (kk - 1);
+        if constexpr (CH == 1) {
+            out[0] = make_float2(m.x, m.x);
+            if (frame0 + 1 < a.n_frames) out[a.k_out] = make_float2(m.y, m.y);
+        } else {
+            out[0] = m;
+        }
+    }
+}
+
+#ifndef SBX_EMU
+template <int LOG2N, int LOG2PAD, int CH>
+__global__ void __launch_bounds__(LARGE_THREADS) large_first_kernel(const LargeArgs la)
+{
+    large_first<LOG2N, LOG2PAD, CH>(la, blockIdx.x);
+}
+
+// grid = units * (M / 4096)
+static __global__ void __launch_bounds__(LARGE_THREADS) large_block_kernel(const LargeArgs la)
+{
+    __shared__ __align__(16) float2 z[LARGE_BLOCK];
+    float2 *blk = la.zbuf + (size_t)blockIdx.x * LARGE_BLOCK;
+    KernelArgs a = la.k;
+    a.twp = la.twp_block;
+    large_block_load(z, blk, la.twp_block);
+    __syncthreads();
+    pass_inplace<G12, 1>(z, a);
+    __syncthreads();
+    pass_inplace<G12, 2>(z, a);
+    __syncthreads();
+    large_block_store(z, blk);
+}
+
+template <int LOG2N, int LOG2PAD, int CH>
+__global__ void __launch_bounds__(LARGE_THREADS) large_split_kernel(const LargeArgs la)
+{
+    large_split<LOG2N, LOG2PAD, CH>(la, blockIdx.x);
+}
+
+// grid = units; mags by bin kk from global memory (magbuf, or a caller's K x (L,R) array shifted by one)
+template <bool PAIR>
+__global__ void __launch_bounds__(LARGE_THREADS) large_colour_kernel(const LargeArgs la, const float2 *mags_base, size_t mags_stride)
+{
+    __shared__ __align__(16) float2 scratch[LARGE_BLOCK];
+    const KernelArgs &a = la.k;
+    const float2 *mags = mags_base + (size_t)blockIdx.x * mags_stride;
+    const unsigned long long frame0 = la.frame_base + (unsigned long long)blockIdx.x * (PAIR ? 2 : 1);
+    const bool second_valid = PAIR && frame0 + 1 < a.n_frames;
+    for (uint32_t c = 0; c < a.n_chunks; ++c) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.chunks) + c);
+        const RowChunk ck = {raw.x, raw.y, raw.z, raw.w};
+        if (c != 0) __syncthreads();
+        resample_samples<LARGE_THREADS>(mags, scratch, a, ck);
+        __syncthreads();
+        colour_rows<PAIR, LARGE_THREADS>(scratch, a.thr, a.lut, a, ck, frame0, second_valid);
+    }
+}
+#endif  // SBX_EMU
+
+}  // namespace sbx

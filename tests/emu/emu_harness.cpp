@@ -2,7 +2,7 @@
 // the host by calling each barrier-delimited phase of stft_kernels.cuh for every thread id in
 // turn, with the product's own host tables (sbx_tables.h).
 #define SBX_EMU 1
-#include "../../spectrogram-rs_b200/csrc/stft_kernels.cuh"
+#include "../../spectrogram-rs_b200/csrc/stft_large.cuh"
 #include "../../spectrogram-rs_b200/csrc/sbx_tables.h"
 
 #include <vector>
@@ -71,6 +71,66 @@ int emu_dispatch_pad(int lp, int ch, const sbx::KernelArgs &a, unsigned long lon
     return -2;
 }
 
+// ---- large path: the four kernels of stft_large.cuh, one block at a time ------------------------------
+template <int LOG2N, int LOG2PAD, int CH>
+int emu_large(sbx::LargeArgs la, float *mags_out, uint8_t *rgba)
+{
+    using GL = sbx::GeomL<LOG2N, LOG2PAD>;
+    const uint32_t per = CH == 1 ? 2 : 1;
+    const unsigned long long units = (la.k.n_frames + per - 1) / per;
+    std::vector<float2> zbuf(GL::M), magbuf(GL::M / 2);
+    la.zbuf = zbuf.data();
+    la.magbuf = magbuf.data();
+    la.k.mags_out = mags_out;
+    la.k.rgba = rgba;
+    la.units = 1;
+    for (unsigned long long u = 0; u < units; ++u) {
+        la.frame_base = u * per;
+        for (unsigned b = 0; b < GL::PAD * (sbx::LARGE_BLOCK / sbx::LARGE_THREADS); ++b)
+            for (int t = 0; t < sbx::LARGE_THREADS; ++t) { threadIdx.x = t; sbx::large_first<LOG2N, LOG2PAD, CH>(la, b); }
+        for (unsigned b = 0; b < GL::M / sbx::LARGE_BLOCK; ++b) {
+            std::vector<float2> z(sbx::LARGE_BLOCK);
+            float2 *blk = la.zbuf + (size_t)b * sbx::LARGE_BLOCK;
+            sbx::KernelArgs a = la.k;
+            a.twp = la.twp_block;
+            for (int t = 0; t < sbx::LARGE_THREADS; ++t) { threadIdx.x = t; sbx::large_block_load(z.data(), blk, la.twp_block); }
+            for (int t = 0; t < sbx::LARGE_THREADS; ++t) { threadIdx.x = t; sbx::pass_inplace<sbx::G12, 1>(z.data(), a); }
+            for (int t = 0; t < sbx::LARGE_THREADS; ++t) { threadIdx.x = t; sbx::pass_inplace<sbx::G12, 2>(z.data(), a); }
+            for (int t = 0; t < sbx::LARGE_THREADS; ++t) { threadIdx.x = t; sbx::large_block_store(z.data(), blk); }
+        }
+        for (unsigned b = 0; b < (GL::M / 2) / sbx::LARGE_THREADS; ++b)
+            for (int t = 0; t < sbx::LARGE_THREADS; ++t) { threadIdx.x = t; sbx::large_split<LOG2N, LOG2PAD, CH>(la, b); }
+        if (rgba) {
+            std::vector<float2> scratch(sbx::LARGE_BLOCK);
+            const unsigned long long frame0 = la.frame_base;
+            const bool second_valid = CH == 1 && frame0 + 1 < la.k.n_frames;
+            for (uint32_t c = 0; c < la.k.n_chunks; ++c) {
+                const sbx::RowChunk ck = la.k.chunks[c];
+                for (int t = 0; t < sbx::LARGE_THREADS; ++t) { threadIdx.x = t; sbx::resample_samples<sbx::LARGE_THREADS>(la.magbuf, scratch.data(), la.k, ck); }
+                for (int t = 0; t < sbx::LARGE_THREADS; ++t) { threadIdx.x = t; sbx::colour_rows<CH == 1, sbx::LARGE_THREADS>(scratch.data(), la.k.thr, la.k.lut, la.k, ck, frame0, second_valid); }
+            }
+        }
+    }
+    return 0;
+}
+
+template <int LOG2N, int LOG2PAD>
+int emu_large_ch(int ch, const sbx::LargeArgs &la, float *mags, uint8_t *rgba)
+{
+    if constexpr (LOG2N + LOG2PAD <= 14 || LOG2N + LOG2PAD > 18) return -2;
+    else return ch == 1 ? emu_large<LOG2N, LOG2PAD, 1>(la, mags, rgba) : emu_large<LOG2N, LOG2PAD, 2>(la, mags, rgba);
+}
+template <int LOG2N>
+int emu_large_pad(int lp, int ch, const sbx::LargeArgs &la, float *mags, uint8_t *rgba)
+{
+    switch (lp) {
+        case 0: return emu_large_ch<LOG2N, 0>(ch, la, mags, rgba);
+        case 1: return emu_large_ch<LOG2N, 1>(ch, la, mags, rgba);
+        case 2: return emu_large_ch<LOG2N, 2>(ch, la, mags, rgba);
+    }
+    return -2;
+}
+
 int ilog2(uint32_t v) { int l = 0; while ((1u << l) < v) ++l; return (1u << l) == v ? l : -1; }
 
 }  // namespace
@@ -106,6 +166,20 @@ long long emu_batch(const sbx_config *cfg, const float *pcm, unsigned long long 
     for (int i = 0; i < 2; ++i) { a.guess_a[i] = t.guess_a[i]; a.guess_b[i] = t.guess_b[i]; }
     a.interp = (int)cfg->interp; a.scheme = (int)cfg->scheme;
     const int ln = ilog2(t.n), lp = ilog2(t.pad), ch = (int)cfg->channels;
+    if (t.large) {
+        sbx::LargeArgs la{};
+        la.k = a;
+        la.twp_block = reinterpret_cast<const float2 *>(t.twp_block.data());
+        int st;
+        switch (ln) {
+            case 13: st = emu_large_pad<13>(lp, ch, la, mags_lr, rgba); break;
+            case 14: st = emu_large_pad<14>(lp, ch, la, mags_lr, rgba); break;
+            case 15: st = emu_large_pad<15>(lp, ch, la, mags_lr, rgba); break;
+            case 16: st = emu_large_pad<16>(lp, ch, la, mags_lr, rgba); break;
+            default: st = -2;
+        }
+        return st != 0 ? st : (long long)frames;
+    }
     if (ln < 8 || ln > 13 || lp < 0) return -2;
     const int per = ch == 1 ? 2 : 1;
     for (unsigned long long f0 = 0; f0 < frames; f0 += per) {

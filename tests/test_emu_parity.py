@@ -28,6 +28,11 @@ CASES = [
     (2048, 1, 2, 512, 512, 0),
     (256, 1, 1, 100, 77, 0),
     (1024, 2, 1, 1, 33, 0),
+    # M > 16384: the multi-kernel path of stft_large.cuh (cfg5's N >= 8192 at P = 4)
+    (8192, 4, 1, 1024, 2048, 0),
+    (16384, 2, 2, 2048, 512, 1),
+    (32768, 1, 1, 4096, 256, 0),
+    (65536, 4, 1, 8192, 2048, 0),
 ]
 
 
@@ -112,3 +117,23 @@ def test_colour_thresholds_reproduce_the_db_chain(magma, db):
         tt = L.orc_db_chain(float(pv), db_min, db_max, eps)
         want[i] = L.orc_gradient_index(tt)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("n,pad,ch,hop,rows,interp", [(1024, 2, 2, 256, 256, 0), (1024, 2, 1, 256, 256, 0),
+                                                      (4096, 2, 2, 512, 1024, 1), (16384, 2, 2, 2048, 512, 0)])
+def test_stereo_pan_scheme(viridis, n, pad, ch, hop, rows, interp):
+    """ColorScheme::new_stereo (colorscheme.rs:63-66): colour = gradient(l / (|l| + |r|)), alpha = normalised dB."""
+    ns = n + hop * 3
+    if ch == 2:
+        pcm = signals.stereo_loopback(ns)
+        pcm[:, 1] *= np.linspace(0, 2, ns).astype(np.float32)         # sweep the pan
+    else:
+        pcm = signals.white_noise(ns)
+    cfg = emu.make_config(viridis, window_n=n, pad_factor=pad, hop=hop, rows_h=rows, channels=ch, interp=interp, scheme=1)
+    mags, rgba = emu.batch(cfg, pcm)
+    p = oracle.params(window_n=n, pad_factor=pad, hop=hop, rows_h=rows, interp=interp, stereo_scheme=1)
+    rec = np.stack([oracle.column_from_magnitudes(p, mags[f], viridis) for f in range(mags.shape[0])])
+    assert np.array_equal(rec, rgba)
+    assert rgba[..., 3].min() < 64 and rgba[..., 3].max() > 128        # alpha really varies
+    if ch == 1:
+        assert np.all((rgba[..., :3] == viridis[128]).all(axis=2) | (rgba[..., :3] == viridis[0]).all(axis=2))

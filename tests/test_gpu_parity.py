@@ -50,6 +50,13 @@ CASES = [
     (4096, 4, 1, 512, 2048, 0),        # cfg5 geometry (N = 4096)
     (2048, 1, 2, 512, 512, 0),
     (256, 1, 1, 100, 77, 0),           # ragged hop / odd H
+    # M > 16384: the multi-kernel path (cfg5's larger sizes)
+    (8192, 4, 1, 1024, 2048, 0),
+    (16384, 2, 2, 2048, 512, 1),
+    (32768, 1, 1, 4096, 256, 0),
+    (16384, 4, 1, 2048, 2048, 0),
+    (32768, 4, 2, 4096, 1024, 0),
+    (65536, 4, 1, 8192, 2048, 0),      # cfg5's largest: M = 262144
 ]
 
 
@@ -200,7 +207,9 @@ def test_errors_do_not_abort(sbx, magma):
         sbx.Plan(window_n=2400, lut=magma)                          # the live app's size: not yet supported
     assert e.value.status == -2
     with pytest.raises(sbx.SbxError):
-        sbx.Plan(window_n=8192, pad_factor=4, lut=magma)
+        sbx.Plan(window_n=131072, pad_factor=2, lut=magma)
+    with pytest.raises(sbx.SbxError):
+        sbx.Plan(window_n=4096, pad_factor=8, lut=magma)
     with pytest.raises(sbx.SbxError):
         sbx.Plan(window_n=1024, hop=0, lut=magma)
     with sbx.Plan(window_n=1024, lut=magma) as plan:
@@ -222,4 +231,20 @@ def test_cpp_host_mirror_runs(tmp_path):
     m = re.search(r"frames=(\d+) k=(\d+) peak_bin=(\d+) peak=([\d.]+) column=1 alpha=255", out.stdout)
     assert m, out.stdout
     assert int(m.group(1)) == 5 and int(m.group(2)) == 2047
-    assert abs(int(m.group(3)) + 1 - 1000.0 * 4096 / 48000.0) <= 1 and 0.4 < float(m.group(4)) <= 0.5
+    assert abs(int(m.group(3)) + 1 - 1000.0 * 4096 / 48000.0) <= 1 and 0.2 < float(m.group(4)) <= 0.25   # A/2 for a sine of amplitude A = 0.5
+
+
+@pytest.mark.parametrize("n,pad,ch,hop,rows", [(1024, 2, 2, 256, 256), (4096, 2, 1, 512, 1024), (16384, 2, 2, 2048, 512)])
+def test_stereo_pan_scheme(sbx, viridis, n, pad, ch, hop, rows):
+    """SBX_SCHEME_STEREO (colorscheme.rs:63-66): bit-exact with the oracle given identical magnitudes."""
+    ns = n + hop * 4
+    pcm = signals.stereo_loopback(ns) if ch == 2 else signals.white_noise(ns)
+    if ch == 2:
+        pcm[:, 1] *= np.linspace(0, 2, ns).astype(np.float32)
+    p = oracle.params(window_n=n, pad_factor=pad, hop=hop, rows_h=rows, stereo_scheme=1)
+    with sbx.Plan(window_n=n, pad_factor=pad, hop=hop, rows_h=rows, channels=ch, lut=viridis, scheme=1) as plan:
+        g = plan.process_batch(pcm)
+        o_rgba, o_mags = oracle.batch(p, pcm, ch, viridis, want_mags=True)
+        assert np.array_equal(plan.colorize_magnitudes(o_mags), o_rgba)
+        assert (g != o_rgba).any(axis=2).mean() <= 2e-3 and np.abs(g.astype(int) - o_rgba.astype(int))[..., 3].max() <= 1
+        assert g[..., 3].min() < 64 and g[..., 3].max() > 128

@@ -20,8 +20,11 @@ ap.add_argument("--cfg", type=int, default=1)
 ap.add_argument("--frames", type=int, default=32768)
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--mags", action="store_true", help="magnitude output instead of RGBA")
+ap.add_argument("--n", type=int, default=0, help="cfg5 sweep: window N with P = 4, hop = N/8, H = 2048")
 a = ap.parse_args()
-kw = CFG[a.cfg]
+kw = dict(CFG[a.cfg])
+if a.n:
+    kw.update(window_n=a.n, pad_factor=4, hop=a.n // 8, rows_h=2048, channels=1)
 plan = sbx.Plan(**kw)
 s = torch.cuda.Stream()
 torch.cuda.set_stream(s)
@@ -45,4 +48,4 @@ for _ in range(a.iters):
 e1.record(s)
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.iters
-print(f"cfg{a.cfg} frames={a.frames} {ms:.4f} ms/launch  {a.frames / ms / 1e3:.3f} Mframes/s")
+print(f"cfg{a.cfg} N={kw['window_n']} P={kw['pad_factor']} hop={kw['hop']} frames={a.frames} {ms:.4f} ms/launch  {a.frames / ms / 1e3:.3f} Mframes/s")
