@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsbx_b200.so")
 SOURCES = ["sbx_plan.cu", "sbx_live.cu"]
-DEPS = SOURCES + ["stft_kernels.cuh", "stft_large.cuh", "sbx_internal.h", "sbx_tables.h", "luts.inc", os.path.join("..", "..", "include", "sbx.h")]
+DEPS = SOURCES + ["stft_kernels.cuh", "stft_large.cuh", "stft_generic.cuh", "sbx_internal.h", "sbx_tables.h", "luts.inc", os.path.join("..", "..", "include", "sbx.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

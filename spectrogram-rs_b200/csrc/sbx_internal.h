@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "../../include/sbx.h"
+#include "stft_generic.cuh"
 #include "stft_large.cuh"
 
 struct sbx_plan {
@@ -29,6 +30,12 @@ struct sbx_plan {
     sbx::RowChunk *d_chunks = nullptr;
     uint2 *d_samp = nullptr;
     int taps_clamped = 0;
+
+    // generic path (window not a power of two): run-time radix list, full twiddle table, bin -> position table
+    bool generic = false;
+    float2 *d_twm = nullptr;
+    uint32_t *d_pos_tab = nullptr;
+    std::vector<uint32_t> radix, stride;
 
     // large path (M > 16384): block-transform twiddles and per-launch scratch
     bool large = false;
@@ -73,6 +80,8 @@ namespace sbx {
 // launches the fused kernel for `channels`-layout PCM on `stream`
 sbx_status launch_fused(sbx_plan *p, int channels, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba,
                         float *d_mags, cudaStream_t stream);
+sbx_status launch_generic(sbx_plan *p, int channels, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba,
+                          float *d_mags, cudaStream_t stream);
 sbx_status launch_large(sbx_plan *p, int channels, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba,
                         float *d_mags, cudaStream_t stream);
 sbx_status launch_colourise(sbx_plan *p, const float *d_mags, uint64_t n_frames, uint8_t *d_rgba, cudaStream_t stream);

@@ -93,6 +93,7 @@ cudaError_t launch_pad(int log2pad, int channels, const KernelArgs &args, uint64
 sbx_status launch_fused(sbx_plan *p, int channels, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba,
                         float *d_mags, cudaStream_t stream)
 {
+    if (p->generic) return launch_generic(p, channels, d_pcm, n_frames, d_rgba, d_mags, stream);
     if (p->large) return launch_large(p, channels, d_pcm, n_frames, d_rgba, d_mags, stream);
     KernelArgs a = p->base_args();
     a.pcm = d_pcm;
@@ -111,6 +112,40 @@ sbx_status launch_fused(sbx_plan *p, int channels, const float *d_pcm, uint64_t 
     }
     if (e != cudaSuccess) return cuda_fail(p, e, "fused_frames_kernel launch");
     if (n_frames) p->launches += 1;
+    return SBX_OK;
+}
+
+// ---- generic path (window not a power of two) -----------------------------------------------------
+constexpr size_t kMaxSmemOptIn = 227 * 1024;
+
+sbx_status launch_generic(sbx_plan *p, int channels, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba,
+                          float *d_mags, cudaStream_t stream)
+{
+    if (n_frames == 0) return SBX_OK;
+    GenericArgs g{};
+    g.k = p->base_args();
+    g.k.pcm = d_pcm;
+    g.k.rgba = d_rgba;
+    g.k.mags_out = d_mags;
+    g.k.n_frames = n_frames;
+    g.twm = p->d_twm;
+    g.pos_tab = p->d_pos_tab;
+    g.n = p->n; g.pad = p->pad; g.m = p->m;
+    g.npass = (uint32_t)p->radix.size();
+    for (size_t i = 0; i < p->radix.size(); ++i) { g.radix[i] = p->radix[i]; g.stride[i] = p->stride[i]; }
+    const size_t smem = (size_t)p->m * 12;                      // transform [M] + magnitudes [M/2], float2
+    const uint64_t ctas = channels == 1 ? (n_frames + 1) / 2 : n_frames;
+    if (ctas > 0x7fffffffull) return fail(p, SBX_ERR_INVALID_ARGUMENT, "too many frames in one launch");
+    cudaError_t e;
+    if (channels == 1) {
+        e = cudaFuncSetAttribute(generic_frames_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) { generic_frames_kernel<1><<<(unsigned)ctas, GENERIC_THREADS, smem, stream>>>(g); e = cudaGetLastError(); }
+    } else {
+        e = cudaFuncSetAttribute(generic_frames_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) { generic_frames_kernel<2><<<(unsigned)ctas, GENERIC_THREADS, smem, stream>>>(g); e = cudaGetLastError(); }
+    }
+    if (e != cudaSuccess) return cuda_fail(p, e, "generic_frames_kernel launch");
+    p->launches += 1;
     return SBX_OK;
 }
 
@@ -212,6 +247,21 @@ template <int LOG2M> cudaError_t launch_colourise_one(const KernelArgs &a, uint6
 
 sbx_status launch_colourise(sbx_plan *p, const float *d_mags, uint64_t n_frames, uint8_t *d_rgba, cudaStream_t stream)
 {
+    if (p->generic) {
+        if (n_frames == 0) return SBX_OK;
+        if (n_frames > 0x7fffffffull) return fail(p, SBX_ERR_INVALID_ARGUMENT, "too many frames");
+        KernelArgs a = p->base_args();
+        a.mags_in = d_mags;
+        a.rgba = d_rgba;
+        a.n_frames = n_frames;
+        const uint32_t slots = p->m / 2 + 16;
+        const size_t smem = (size_t)slots * sizeof(float2);
+        cudaError_t eg = cudaFuncSetAttribute(generic_colour_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (eg == cudaSuccess) { generic_colour_kernel<<<(unsigned)n_frames, GENERIC_THREADS, smem, stream>>>(a, slots); eg = cudaGetLastError(); }
+        if (eg != cudaSuccess) return cuda_fail(p, eg, "generic_colour_kernel launch");
+        p->launches += 1;
+        return SBX_OK;
+    }
     if (p->large) {
         if (n_frames == 0) return SBX_OK;
         if (n_frames > 0x7fffffffull) return fail(p, SBX_ERR_INVALID_ARGUMENT, "too many frames");
@@ -351,7 +401,7 @@ SBX_API void sbx_plan_destroy(sbx_plan *p)
         cudaFree(s.d_rgba);
     }
     cudaFree(p->d_window); cudaFree(p->d_wtw); cudaFree(p->d_twp); cudaFree(p->d_rowmap); cudaFree(p->d_chunks);
-    cudaFree(p->d_samp); cudaFree(p->d_twp_block); cudaFree(p->d_zbuf); cudaFree(p->d_magbuf);
+    cudaFree(p->d_samp); cudaFree(p->d_twm); cudaFree(p->d_pos_tab); cudaFree(p->d_twp_block); cudaFree(p->d_zbuf); cudaFree(p->d_magbuf);
     cudaFree(p->d_thr); cudaFree(p->d_lut); cudaFree(p->d_frame); cudaFree(p->d_mags1); cudaFree(p->d_col);
     if (p->h_frame) cudaFreeHost(p->h_frame);
     if (p->h_col) cudaFreeHost(p->h_col);
@@ -365,17 +415,29 @@ SBX_API sbx_status sbx_plan_create(const sbx_config *cfg, sbx_plan **out_plan)
     if (!cfg || !out_plan) return fail(nullptr, SBX_ERR_INVALID_ARGUMENT, "cfg and out_plan must not be NULL");
     if (cfg->struct_size != sizeof(sbx_config) || cfg->abi_version != SBX_ABI_VERSION)
         return fail(nullptr, SBX_ERR_INVALID_ARGUMENT, "sbx_config size/version mismatch (call sbx_config_default first)");
-    const int log2n = ilog2_exact(cfg->window_n), log2pad = ilog2_exact(cfg->pad_factor);
-    if (cfg->window_n < 2) return fail(nullptr, SBX_ERR_INVALID_ARGUMENT, "window_n must be >= 2");
-    if (log2n < 0)
-        return fail(nullptr, SBX_ERR_UNSUPPORTED, "window_n must be a power of two (mixed-radix sizes such as the live app's 2400 are not implemented yet)");
-    if (log2n < (int)kMinLog2N || log2n > (int)kMaxLog2NLarge)
-        return fail(nullptr, SBX_ERR_UNSUPPORTED, "window_n must be in [256, 65536]");
+    int log2n = ilog2_exact(cfg->window_n);
+    const int log2pad = ilog2_exact(cfg->pad_factor);
+    if (cfg->window_n < 4) return fail(nullptr, SBX_ERR_INVALID_ARGUMENT, "window_n must be >= 4");
     if (log2pad < 0 || log2pad > 2) return fail(nullptr, SBX_ERR_UNSUPPORTED, "pad_factor must be 1, 2 or 4");
-    if (log2n + log2pad > (int)kMaxLog2MLarge)
-        return fail(nullptr, SBX_ERR_UNSUPPORTED, "window_n * pad_factor must be <= 262144");
-    if (log2n + log2pad > (int)kMaxLog2M && log2n < 13)
-        return fail(nullptr, SBX_ERR_UNSUPPORTED, "transforms longer than 16384 need window_n >= 8192");
+    const bool generic = log2n < (int)kMinLog2N;                  // not a power of two, or a tiny one
+    if (generic) {
+        log2n = -1;
+        if ((uint64_t)cfg->window_n * cfg->pad_factor * 12 > sbx::kMaxSmemOptIn)
+            return fail(nullptr, SBX_ERR_UNSUPPORTED, "non-power-of-two windows need window_n * pad_factor <= 19370 (one SM's shared memory)");
+        if (((cfg->window_n * cfg->pad_factor) & 1u) != 0)
+            return fail(nullptr, SBX_ERR_UNSUPPORTED, "window_n * pad_factor must be even");
+        uint32_t rest = cfg->window_n;
+        for (uint32_t f : {2u, 3u, 5u, 7u})
+            while (rest % f == 0) rest /= f;
+        if (rest != 1)
+            return fail(nullptr, SBX_ERR_UNSUPPORTED, "window_n has a prime factor larger than 7 (supported radices: 2, 3, 4, 5, 7, 8, 16)");
+    } else {
+        if (log2n > (int)kMaxLog2NLarge) return fail(nullptr, SBX_ERR_UNSUPPORTED, "window_n must be <= 65536");
+        if (log2n + log2pad > (int)kMaxLog2MLarge)
+            return fail(nullptr, SBX_ERR_UNSUPPORTED, "window_n * pad_factor must be <= 262144");
+        if (log2n + log2pad > (int)kMaxLog2M && log2n < 13)
+            return fail(nullptr, SBX_ERR_UNSUPPORTED, "transforms longer than 16384 need window_n >= 8192");
+    }
     if (cfg->channels != 1 && cfg->channels != 2) return fail(nullptr, SBX_ERR_INVALID_ARGUMENT, "channels must be 1 or 2");
     if (cfg->hop == 0) return fail(nullptr, SBX_ERR_INVALID_ARGUMENT, "hop must be >= 1");
     if (cfg->rows_h == 0 || cfg->rows_h > (1u << 20)) return fail(nullptr, SBX_ERR_INVALID_ARGUMENT, "rows_h must be in [1, 2^20]");
@@ -417,8 +479,13 @@ SBX_API sbx_status sbx_plan_create(const sbx_config *cfg, sbx_plan **out_plan)
     p->scale = t.scale;
     if (!t.ok) {
         delete p;
-        return fail(nullptr, SBX_ERR_UNSUPPORTED, "a row of the bin map averages more samples than the shared-memory scratch holds");
+        return fail(nullptr, SBX_ERR_UNSUPPORTED, t.generic && t.radix.empty()
+                        ? "window_n has a prime factor larger than 7 (supported radices: 2, 3, 4, 5, 7, 8, 16)"
+                        : "window_n cannot be factored into supported radices, or a row of the bin map averages more samples than the shared-memory scratch holds");
     }
+    p->generic = t.generic;
+    p->radix = t.radix;
+    p->stride = t.stride;
     p->h_window = t.window;
     p->h_rowmap = t.rowmap;
     p->h_thr_raw = t.thr_raw;
@@ -441,6 +508,8 @@ SBX_API sbx_status sbx_plan_create(const sbx_config *cfg, sbx_plan **out_plan)
     SBX_TRY(upload(&p->d_window, p->h_window.data(), p->n * sizeof(float)));
     SBX_TRY(upload(&p->d_wtw, t.wtw.data(), t.wtw.size() * sizeof(float)));
     SBX_TRY(upload(&p->d_twp, t.twp.data(), t.twp.size() * sizeof(float)));
+    SBX_TRY(upload(&p->d_twm, t.twm.data(), t.twm.size() * sizeof(float)));
+    SBX_TRY(upload(&p->d_pos_tab, t.pos_tab.data(), t.pos_tab.size() * sizeof(uint32_t)));
     SBX_TRY(upload(&p->d_twp_block, t.twp_block.data(), t.twp_block.size() * sizeof(float)));
     SBX_TRY(upload(&p->d_rowmap, p->h_rowmap.data(), p->rows * sizeof(sbx::RowMap)));
     SBX_TRY(upload(&p->d_chunks, t.chunks.data(), t.chunks.size() * sizeof(sbx::RowChunk)));

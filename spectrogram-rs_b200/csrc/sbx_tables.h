@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/sbx.h"
+#include "stft_generic.cuh"
 #include "stft_large.cuh"
 
 namespace sbx {
@@ -90,6 +91,10 @@ struct HostTables {
     std::vector<float> twp;             // per-pass twiddle planes x (re, im), see KernelArgs::twp
     std::vector<float> twp_block;       // large path: planes of the 4096-point block transform
     bool large = false;                 // M > 16384: the multi-kernel path of stft_large.cuh
+    bool generic = false;               // N not a power of two: the run-time mixed-radix path of stft_generic.cuh
+    std::vector<float> twm;             // generic: [M] x (re, im) full twiddle table W_M^t
+    std::vector<uint32_t> pos_tab;      // generic: [M] position of bin kk
+    std::vector<uint32_t> radix, stride;// generic: per-pass radix and butterfly stride
     std::vector<RowMap> rowmap;         // [H]
     std::vector<RowChunk> chunks;       // rows grouped so that a chunk's samples fit the kernel's scratch area
     std::vector<uint32_t> samp;         // per (row, sample): {floor(x), weight bits}, see KernelArgs::samp
@@ -111,6 +116,7 @@ struct RadixPlan {
 
 inline void build(const sbx_config &cfg, HostTables &t)
 {
+    t.ok = true;
     t.n = cfg.window_n;
     t.pad = cfg.pad_factor;
     t.m = t.n * t.pad;
@@ -123,9 +129,14 @@ inline void build(const sbx_config &cfg, HostTables &t)
     t.window.resize(t.n);
     for (uint32_t i = 0; i < t.n; ++i) t.window[i] = hann_f32(i, t.n);
 
-    // sub-transform premultiply: window[n] * W_M^(n q0), q0 = 1..P-1 (f64 product of the f32 window)
-    t.wtw.assign((size_t)(t.pad - 1) * t.n * 2, 0.0f);
-    for (uint32_t q0 = 1; q0 < t.pad; ++q0)
+    t.generic = (t.n & (t.n - 1)) != 0 || t.n < 256;
+    t.large = !t.generic && t.m > 16384;
+
+    // sub-transform premultiply: window[n] * W_M^(n q0), q0 = 1..P-1 (f64 product of the f32 window);
+    // the generic path multiplies by W_M^(n q0) from its full table instead
+    t.wtw.clear();
+    if (!t.generic) t.wtw.assign((size_t)(t.pad - 1) * t.n * 2, 0.0f);
+    for (uint32_t q0 = 1; q0 < t.pad && !t.generic; ++q0)
         for (uint32_t i = 0; i < t.n; ++i) {
             const double ang = -2.0 * M_PI * (double)(((uint64_t)i * q0) % t.m) / (double)t.m;
             const size_t o = ((size_t)(q0 - 1) * t.n + i) * 2;
@@ -133,10 +144,34 @@ inline void build(const sbx_config &cfg, HostTables &t)
             t.wtw[o + 1] = (float)((double)t.window[i] * std::sin(ang));
         }
 
+    // ---- transform tables ----------------------------------------------------------------------
+    t.twm.clear(); t.pos_tab.clear(); t.radix.clear(); t.stride.clear();
+    if (t.generic) {
+        // radix list from {16, 8, 4, 2, 3, 5, 7}; a left-over factor means a prime > 7: unsupported
+        uint32_t rest = t.n;
+        const uint32_t cand[] = {16, 8, 4, 2, 3, 5, 7};
+        for (uint32_t r : cand)
+            while (rest % r == 0 && rest > 1) { t.radix.push_back(r); rest /= r; }
+        if (rest != 1 || t.radix.size() > (size_t)GENERIC_MAX_PASSES || (t.m & 1u) || t.m < 8) { t.radix.clear(); t.ok = false; return; }
+        uint32_t s = t.n;
+        for (uint32_t r : t.radix) { s /= r; t.stride.push_back(s); }
+        t.twm.resize((size_t)t.m * 2);
+        for (uint32_t k = 0; k < t.m; ++k) {
+            const double ang = -2.0 * M_PI * (double)k / (double)t.m;
+            t.twm[2 * (size_t)k] = (float)std::cos(ang);
+            t.twm[2 * (size_t)k + 1] = (float)std::sin(ang);
+        }
+        // bin kk = P k + q0, k = sum d_p (R_0 .. R_(p-1))  ->  position q0 N + sum d_p S_p
+        t.pos_tab.resize(t.m);
+        for (uint32_t kk = 0; kk < t.m; ++kk) {
+            uint32_t k = kk / t.pad, pos = (kk % t.pad) * t.n;
+            for (size_t p = 0; p < t.radix.size(); ++p) { pos += (k % t.radix[p]) * t.stride[p]; k /= t.radix[p]; }
+            t.pos_tab[kk] = pos;
+        }
+    }
     // per-pass twiddle planes: plane j of pass p holds W_(S_p R_p)^(2^j lo), lo < S_p
     int log2n = 0;
     while ((1u << log2n) < t.n) ++log2n;
-    t.large = t.m > 16384;
     auto planes = [](const RadixPlan &rp, int first_pass, int last_pass, std::vector<float> &dst) {
         dst.clear();
         for (int p = first_pass; p < last_pass; ++p) {
@@ -150,7 +185,10 @@ inline void build(const sbx_config &cfg, HostTables &t)
         }
     };
     const RadixPlan rp(log2n);
-    if (t.large) {
+    if (t.generic) {
+        t.twp.clear();
+        t.twp_block.clear();
+    } else if (t.large) {
         planes(rp, 0, 1, t.twp);                               // the global radix-R0 pass: W_N^(2^j lo), lo < 4096
         const RadixPlan rb(LARGE_LOG2_BLOCK);
         planes(rb, 0, rb.npass - 1, t.twp_block);              // the 4096-point block transform
@@ -200,7 +238,6 @@ inline void build(const sbx_config &cfg, HostTables &t)
     // row chunks: greedy, a chunk's samples must fit the kernel's scratch area ((M/2) * 16/17 slots)
     const uint32_t cap = t.large ? (uint32_t)LARGE_SCRATCH : (uint32_t)((((uint64_t)t.m / 2) * 16) / 17);
     t.chunks.clear();
-    t.ok = true;
     RowChunk ck = {0, 0, 0, 0};
     for (uint32_t py = 0; py < t.rows; ++py) {
         const RowMap &rm = t.rowmap[py];

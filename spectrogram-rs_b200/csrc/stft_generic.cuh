@@ -1,0 +1,185 @@
+// stft_generic.cuh -- windows that are not a power of two (the live app's N = (0.05 s * sr) as usize:
+// 2400 @ 48 kHz, 2205 @ 44.1 kHz; src/widgets/gpu_spectrogram.rs:323, src/fourier/fft.rs:19-21).
+//
+// Same structure as the fused kernel -- P premultiplied sub-transforms of length N, in-place DIF,
+// digit-reversed output, conjugate-symmetry split, tabulated resample, threshold dB step -- with the
+// radix list chosen at run time from {16, 8, 4, 2, 3, 5, 7}: N = 2400 = 16*2*3*5*5, 2205 = 3*3*5*7*7.
+// This is the low-rate live path (819 frames/s in the reference), so it trades the fused kernel's
+// swizzles and compile-time index math for generality: bin -> position comes from a host table, twiddles
+// from the full W_M table.  One CTA per frame (stereo) or frame pair (mono); the transform (M float2)
+// and the magnitudes (M/2 float2) live in shared memory: M <= 16384.
+#pragma once
+#include "stft_kernels.cuh"
+
+namespace sbx {
+
+constexpr int GENERIC_THREADS = 256;
+constexpr int GENERIC_MAX_PASSES = 12;
+
+struct GenericArgs {
+    KernelArgs k;                 // window, rowmap, chunks, samp, thr, lut, rgba, mags_out, pcm ... (wtw/twp unused)
+    const float2 *twm;            // [M] W_M^t, f64-computed, rounded once
+    const uint32_t *pos_tab;      // [M] position of bin kk in the transform buffer
+    uint32_t n, pad, m, npass;
+    uint32_t radix[GENERIC_MAX_PASSES];
+    uint32_t stride[GENERIC_MAX_PASSES];   // butterfly stride of each pass: N / (R_0 ... R_p)
+};
+
+// R-point DFT, natural order in and out.  Powers of two reuse the fused kernel's butterflies; 3, 5 and 7
+// are evaluated directly from the table (w[j] = W_R^j).
+template <int R> struct SmallDft {
+    static __device__ __forceinline__ void run(float2 (&v)[R], const float2 *twm, uint32_t m)
+    {
+        if constexpr (R == 2 || R == 4 || R == 8 || R == 16) {
+            (void)twm; (void)m;
+            Butterfly<R>::run(v);
+        } else {
+            float2 w[R];
+#pragma unroll
+            for (int j = 0; j < R; ++j) w[j] = __ldg(twm + (size_t)j * (m / R));
+            float2 y[R];
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                float2 acc = v[0];
+#pragma unroll
+                for (int r = 1; r < R; ++r) {
+                    const float2 t = cmul(v[r], w[(r * q) % R]);
+                    acc.x += t.x;  acc.y += t.y;
+                }
+                y[q] = acc;
+            }
+#pragma unroll
+            for (int q = 0; q < R; ++q) v[q] = y[q];
+        }
+    }
+};
+
+// phase 0: PCM -> window -> W_M^(n q0) premultiply -> shared memory, natural order per sub-transform
+template <int CH>
+__device__ __forceinline__ void generic_load(float2 *z, const GenericArgs &g, unsigned long long frame0, bool second_valid)
+{
+    const KernelArgs &a = g.k;
+    const float *pa = a.pcm + frame0 * (unsigned long long)a.hop * CH;
+    const float *pb = pa + a.hop;
+    for (uint32_t i = threadIdx.x; i < g.m; i += GENERIC_THREADS) {
+        const uint32_t q0 = i / g.n, n = i - q0 * g.n;
+        float2 s;
+        if constexpr (CH == 2) {
+            s = __ldg(reinterpret_cast<const float2 *>(pa) + n);
+        } else {
+            s.x = __ldg(pa + n);
+            s.y = second_valid ? __ldg(pb + n) : 0.0f;
+        }
+        const float wn = __ldg(a.window + n);
+        s.x *= wn;  s.y *= wn;                                            // fft.rs:57-63
+        if (q0 != 0) s = cmul(s, __ldg(g.twm + ((size_t)n * q0) % g.m));
+        z[i] = s;
+    }
+}
+
+// one in-place DIF pass of radix R at stride S over all P sub-transforms
+template <int R>
+__device__ __forceinline__ void generic_pass(float2 *z, const GenericArgs &g, uint32_t S, bool last)
+{
+    const uint32_t per_sub = g.n / R, count = g.pad * per_sub;
+    const uint32_t tstep = g.m / (S * R);                                 // W_(S R)^(lo q) = W_M^(lo q tstep)
+    for (uint32_t u = threadIdx.x; u < count; u += GENERIC_THREADS) {
+        const uint32_t sub = u / per_sub, uu = u - sub * per_sub;
+        const uint32_t hi = uu / S, lo = uu - hi * S;
+        float2 *b = z + (size_t)sub * g.n + (size_t)hi * S * R + lo;
+        float2 v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = b[(size_t)r * S];
+        SmallDft<R>::run(v, g.twm, g.m);
+        b[0] = v[0];
+#pragma unroll
+        for (int q = 1; q < R; ++q)
+            b[(size_t)q * S] = last ? v[q] : cmul(v[q], __ldg(g.twm + (size_t)lo * q * tstep));
+    }
+}
+
+__device__ __forceinline__ void generic_pass_dispatch(float2 *z, const GenericArgs &g, uint32_t p)
+{
+    const uint32_t S = g.stride[p];
+    const bool last = p + 1 == g.npass;
+    switch (g.radix[p]) {
+        case 2: generic_pass<2>(z, g, S, last); break;
+        case 3: generic_pass<3>(z, g, S, last); break;
+        case 4: generic_pass<4>(z, g, S, last); break;
+        case 5: generic_pass<5>(z, g, S, last); break;
+        case 7: generic_pass<7>(z, g, S, last); break;
+        case 8: generic_pass<8>(z, g, S, last); break;
+        case 16: generic_pass<16>(z, g, S, last); break;
+        default: break;
+    }
+}
+
+// L/R split (fft.rs:81-95) into a separate magnitude array indexed by bin kk
+__device__ __forceinline__ void generic_split(const float2 *z, float2 *mags, const GenericArgs &g)
+{
+    for (uint32_t kk = 1 + threadIdx.x; kk < g.m / 2; kk += GENERIC_THREADS)
+        mags[kk] = split_pair(z[__ldg(g.pos_tab + kk)], z[__ldg(g.pos_tab + (g.m - kk))], g.k.scale);
+}
+
+#ifndef SBX_EMU
+template <int CH>
+__global__ void __launch_bounds__(GENERIC_THREADS) generic_frames_kernel(const GenericArgs g)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *z = reinterpret_cast<float2 *>(smem_raw);                    // [M]; reused as resample scratch
+    float2 *mags = z + g.m;                                               // [M/2]
+    const KernelArgs &a = g.k;
+    const unsigned long long frame0 = (unsigned long long)blockIdx.x * (CH == 1 ? 2 : 1);
+    const bool second_valid = CH == 1 && frame0 + 1 < a.n_frames;
+    generic_load<CH>(z, g, frame0, second_valid);
+    for (uint32_t p = 0; p < g.npass; ++p) {
+        __syncthreads();
+        generic_pass_dispatch(z, g, p);
+    }
+    __syncthreads();
+    generic_split(z, mags, g);
+    __syncthreads();
+    if (a.mags_out != nullptr) {
+        float2 *out = reinterpret_cast<float2 *>(a.mags_out) + frame0 * a.k_out;
+        for (uint32_t j = threadIdx.x; j < a.k_out; j += GENERIC_THREADS) {
+            const float2 m = mags[j + 1];
+            if constexpr (CH == 1) {
+                out[j] = make_float2(m.x, m.x);
+                if (second_valid) out[a.k_out + j] = make_float2(m.y, m.y);
+            } else {
+                out[j] = m;
+            }
+        }
+    }
+    if (a.rgba != nullptr) {
+        for (uint32_t c = 0; c < a.n_chunks; ++c) {
+            const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.chunks) + c);
+            const RowChunk ck = {raw.x, raw.y, raw.z, raw.w};
+            if (c != 0) __syncthreads();
+            resample_samples<GENERIC_THREADS>(mags, z, a, ck);
+            __syncthreads();
+            colour_rows<CH == 1, GENERIC_THREADS>(z, a.thr, a.lut, a, ck, frame0, second_valid);
+        }
+    }
+}
+
+// colourise-only for generic plans: magnitudes from global memory, scratch in shared memory
+__global__ void __launch_bounds__(GENERIC_THREADS) static generic_colour_kernel(const KernelArgs a, uint32_t scratch_slots)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *scratch = reinterpret_cast<float2 *>(smem_raw);
+    (void)scratch_slots;
+    const unsigned long long frame = blockIdx.x;
+    const float2 *mags = reinterpret_cast<const float2 *>(a.mags_in) + frame * a.k_out - 1;   // bin kk = j + 1
+    for (uint32_t c = 0; c < a.n_chunks; ++c) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.chunks) + c);
+        const RowChunk ck = {raw.x, raw.y, raw.z, raw.w};
+        if (c != 0) __syncthreads();
+        resample_samples<GENERIC_THREADS>(mags, scratch, a, ck);
+        __syncthreads();
+        colour_rows<false, GENERIC_THREADS>(scratch, a.thr, a.lut, a, ck, frame, false);
+    }
+}
+#endif  // SBX_EMU
+
+}  // namespace sbx

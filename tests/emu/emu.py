@@ -25,7 +25,7 @@ binding = _binding()
 
 def build(force=False):
     deps = [os.path.join(HERE, f) for f in ("emu_harness.cpp", "emu_shim.h")] + \
-           [os.path.join(CSRC, f) for f in ("stft_kernels.cuh", "stft_large.cuh", "sbx_tables.h")]
+           [os.path.join(CSRC, f) for f in ("stft_kernels.cuh", "stft_large.cuh", "stft_generic.cuh", "sbx_tables.h")]
     if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps):
         subprocess.run(["g++", "-O1", "-std=c++17", "-I", HERE, "-ffp-contract=off", "-fPIC", "-shared",
                         "-fvisibility=hidden", "-o", LIB_PATH, os.path.join(HERE, "emu_harness.cpp")],

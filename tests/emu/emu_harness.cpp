@@ -131,6 +131,41 @@ int emu_large_pad(int lp, int ch, const sbx::LargeArgs &la, float *mags, uint8_t
     return -2;
 }
 
+// ---- generic (mixed-radix) path: stft_generic.cuh, one CTA ------------------------------------------
+template <int CH>
+int emu_generic(const sbx::GenericArgs &g0, unsigned long long frames, float *mags_out, uint8_t *rgba)
+{
+    sbx::GenericArgs g = g0;
+    g.k.rgba = rgba;
+    const int per = CH == 1 ? 2 : 1;
+    for (unsigned long long frame0 = 0; frame0 < frames; frame0 += per) {
+        std::vector<float2> z(g.m), mags(g.m / 2);
+        const bool second_valid = CH == 1 && frame0 + 1 < frames;
+        for (int t = 0; t < sbx::GENERIC_THREADS; ++t) { threadIdx.x = t; sbx::generic_load<CH>(z.data(), g, frame0, second_valid); }
+        for (uint32_t p = 0; p < g.npass; ++p)
+            for (int t = 0; t < sbx::GENERIC_THREADS; ++t) { threadIdx.x = t; sbx::generic_pass_dispatch(z.data(), g, p); }
+        for (int t = 0; t < sbx::GENERIC_THREADS; ++t) { threadIdx.x = t; sbx::generic_split(z.data(), mags.data(), g); }
+        if (mags_out) {
+            float *o = mags_out + (size_t)frame0 * g.k.k_out * 2;
+            for (uint32_t j = 0; j < g.k.k_out; ++j) {
+                const float2 m = mags[j + 1];
+                if (CH == 1) {
+                    o[2 * j] = m.x; o[2 * j + 1] = m.x;
+                    if (second_valid) { o[2 * (g.k.k_out + j)] = m.y; o[2 * (g.k.k_out + j) + 1] = m.y; }
+                } else { o[2 * j] = m.x; o[2 * j + 1] = m.y; }
+            }
+        }
+        if (rgba) {
+            for (uint32_t c = 0; c < g.k.n_chunks; ++c) {
+                const sbx::RowChunk ck = g.k.chunks[c];
+                for (int t = 0; t < sbx::GENERIC_THREADS; ++t) { threadIdx.x = t; sbx::resample_samples<sbx::GENERIC_THREADS>(mags.data(), z.data(), g.k, ck); }
+                for (int t = 0; t < sbx::GENERIC_THREADS; ++t) { threadIdx.x = t; sbx::colour_rows<CH == 1, sbx::GENERIC_THREADS>(z.data(), g.k.thr, g.k.lut, g.k, ck, frame0, second_valid); }
+            }
+        }
+    }
+    return 0;
+}
+
 int ilog2(uint32_t v) { int l = 0; while ((1u << l) < v) ++l; return (1u << l) == v ? l : -1; }
 
 }  // namespace
@@ -166,6 +201,16 @@ long long emu_batch(const sbx_config *cfg, const float *pcm, unsigned long long 
     for (int i = 0; i < 2; ++i) { a.guess_a[i] = t.guess_a[i]; a.guess_b[i] = t.guess_b[i]; }
     a.interp = (int)cfg->interp; a.scheme = (int)cfg->scheme;
     const int ln = ilog2(t.n), lp = ilog2(t.pad), ch = (int)cfg->channels;
+    if (t.generic) {
+        sbx::GenericArgs g{};
+        g.k = a;
+        g.twm = reinterpret_cast<const float2 *>(t.twm.data());
+        g.pos_tab = t.pos_tab.data();
+        g.n = t.n; g.pad = t.pad; g.m = t.m; g.npass = (uint32_t)t.radix.size();
+        for (size_t i = 0; i < t.radix.size(); ++i) { g.radix[i] = t.radix[i]; g.stride[i] = t.stride[i]; }
+        const int st = ch == 1 ? emu_generic<1>(g, frames, mags_lr, rgba) : emu_generic<2>(g, frames, mags_lr, rgba);
+        return st != 0 ? st : (long long)frames;
+    }
     if (t.large) {
         sbx::LargeArgs la{};
         la.k = a;

@@ -28,6 +28,12 @@ CASES = [
     (2048, 1, 2, 512, 512, 0),
     (256, 1, 1, 100, 77, 0),
     (1024, 2, 1, 1, 33, 0),
+    # not a power of two: stft_generic.cuh (the live app's 2400 @ 48 kHz / 2205 @ 44.1 kHz windows)
+    (2400, 2, 2, 58, 1024, 0),
+    (2205, 2, 2, 86, 1024, 0),
+    (2400, 2, 1, 93, 512, 1),
+    (1600, 4, 1, 200, 256, 0),
+    (100, 2, 2, 10, 64, 0),
     # M > 16384: the multi-kernel path of stft_large.cuh (cfg5's N >= 8192 at P = 4)
     (8192, 4, 1, 1024, 2048, 0),
     (16384, 2, 2, 2048, 512, 1),

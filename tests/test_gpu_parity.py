@@ -50,6 +50,13 @@ CASES = [
     (4096, 4, 1, 512, 2048, 0),        # cfg5 geometry (N = 4096)
     (2048, 1, 2, 512, 512, 0),
     (256, 1, 1, 100, 77, 0),           # ragged hop / odd H
+    # windows that are not a power of two: the live app's (0.05 s * sr) as usize, run-time mixed radix
+    (2400, 2, 2, 58, 1024, 0),         # 48 kHz, hop = (2.5/2048 * 48000) as usize  (gpu_spectrogram.rs:21-23,323)
+    (2205, 2, 2, 86, 1024, 0),         # 44.1 kHz
+    (2400, 2, 1, 93, 512, 1),
+    (1600, 4, 1, 200, 256, 0),
+    (100, 2, 2, 10, 64, 0),            # the dummy transform the widgets start with (gpu_spectrogram.rs:80)
+    (4800, 2, 2, 512, 1024, 0),        # 96 kHz
     # M > 16384: the multi-kernel path (cfg5's larger sizes)
     (8192, 4, 1, 1024, 2048, 0),
     (16384, 2, 2, 2048, 512, 1),
@@ -204,7 +211,7 @@ def test_live_ring_semantics(sbx, magma):
 
 def test_errors_do_not_abort(sbx, magma):
     with pytest.raises(sbx.SbxError) as e:
-        sbx.Plan(window_n=2400, lut=magma)                          # the live app's size: not yet supported
+        sbx.Plan(window_n=2402, lut=magma)                          # 2 * 1201: prime factor > 7
     assert e.value.status == -2
     with pytest.raises(sbx.SbxError):
         sbx.Plan(window_n=131072, pad_factor=2, lut=magma)
