@@ -254,7 +254,7 @@ sbx_status launch_colourise(sbx_plan *p, const float *d_mags, uint64_t n_frames,
         a.mags_in = d_mags;
         a.rgba = d_rgba;
         a.n_frames = n_frames;
-        const uint32_t slots = p->m / 2 + 16;
+        const uint32_t slots = p->m / 2;
         const size_t smem = (size_t)slots * sizeof(float2);
         cudaError_t eg = cudaFuncSetAttribute(generic_colour_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (eg == cudaSuccess) { generic_colour_kernel<<<(unsigned)n_frames, GENERIC_THREADS, smem, stream>>>(a, slots); eg = cudaGetLastError(); }

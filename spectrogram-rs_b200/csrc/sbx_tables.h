@@ -198,6 +198,7 @@ inline void build(const sbx_config &cfg, HostTables &t)
     }
 
     t.rowmap.resize(t.rows);
+    std::vector<uint32_t> samp_first(t.rows);                 // first entry of each row in the per-sample table
     uint64_t total_samples = 0;
     for (uint32_t py = 0; py < t.rows; ++py) {
         const float f0 = row_edge_hz(cfg.f_min, cfg.f_max, py, t.rows);
@@ -209,15 +210,43 @@ inline void build(const sbx_config &cfg, HostTables &t)
         rm.f0 = f0;
         rm.step = (f1 - f0) / (float)n;                                                // lin_space step
         rm.n = n;
-        rm.aux = (uint32_t)total_samples;
+        rm.aux = 0;                                                                    // scratch slot, set below
+        samp_first[py] = (uint32_t)total_samples;
         total_samples += n;
         t.rowmap[py] = rm;
     }
-    // per-sample positions x = index_of(lin_space(f0..f1, n)[s])  (ifs.rs:67-69, :24-31), stored as
-    // floor(x) and the interpolation weight: mu = x - floor(x) (cubic, ifs.rs:90) or
-    // (1 - cos((x - low) * PI)) / 2 (cosine, ifs.rs:82-83; f32, host libm)
+    // Row chunks and scratch slots.  A chunk is a run of rows whose interpolated samples fit the kernel's
+    // scratch area; row py's samples occupy slots aux .. aux+n-1 of its chunk, and rows with an even n >= 4 get
+    // one slot of padding so that the per-row stride is odd: the threads of colour_rows (one per row) then read
+    // different shared-memory banks at every step of their sequential sums (n = 2 is left at a 2-way conflict
+    // so that cfg1's 3893 samples still fit one chunk of M/2 = 4096 slots).
+    const uint32_t cap = t.large ? (uint32_t)LARGE_BLOCK : t.m / 2;
+    t.chunks.clear();
+    RowChunk ck = {0, 0, 0, 0};
+    uint32_t slot = 0;
+    for (uint32_t py = 0; py < t.rows; ++py) {
+        RowMap &rm = t.rowmap[py];
+        const uint32_t need = rm.n + (((rm.n & 1u) == 0 && rm.n >= 4) ? 1u : 0u);
+        if (need > cap || need >= (1u << 15)) t.ok = false;
+        if (slot + need > cap && ck.row_end > ck.row_begin) {
+            t.chunks.push_back(ck);
+            ck.row_begin = py; ck.samp_begin = samp_first[py];
+            slot = 0;
+        }
+        rm.aux = slot;
+        slot += need;
+        ck.row_end = py + 1;
+        ck.samp_end = samp_first[py] + rm.n;
+    }
+    t.chunks.push_back(ck);
+
+    // per-sample table: x = index_of(lin_space(f0..f1, n)[s])  (ifs.rs:67-69, :24-31), stored as
+    //   word 0: floor(x) in bits 0..16, the sample's scratch slot in bits 17..31
+    //   word 1: the interpolation weight: mu = x - floor(x) (cubic, ifs.rs:90) or
+    //           (1 - cos((x - low) * PI)) / 2 (cosine, ifs.rs:82-83; f32, host libm)
     t.samp.resize(total_samples * 2);
     t.taps_clamped = false;
+    if (t.k_out >= (1u << 17)) t.ok = false;
     const float pi = 3.14159265358979323846f;
     for (uint32_t py = 0; py < t.rows; ++py) {
         const RowMap &rm = t.rowmap[py];
@@ -231,25 +260,10 @@ inline void build(const sbx_config &cfg, HostTables &t)
             if (x1 < 1 || x1 + 2 > t.k_out - 1) t.taps_clamped = true;
             uint32_t wbits;
             std::memcpy(&wbits, &w, 4);
-            t.samp[2 * (size_t)(rm.aux + s)] = x1;
-            t.samp[2 * (size_t)(rm.aux + s) + 1] = wbits;
+            t.samp[2 * (size_t)(samp_first[py] + s)] = x1 | ((rm.aux + s) << 17);
+            t.samp[2 * (size_t)(samp_first[py] + s) + 1] = wbits;
         }
     }
-    // row chunks: greedy, a chunk's samples must fit the kernel's scratch area ((M/2) * 16/17 slots)
-    const uint32_t cap = t.large ? (uint32_t)LARGE_SCRATCH : (uint32_t)((((uint64_t)t.m / 2) * 16) / 17);
-    t.chunks.clear();
-    RowChunk ck = {0, 0, 0, 0};
-    for (uint32_t py = 0; py < t.rows; ++py) {
-        const RowMap &rm = t.rowmap[py];
-        if (rm.n > cap) t.ok = false;
-        if (ck.samp_end - ck.samp_begin + rm.n > cap && ck.row_end > ck.row_begin) {
-            t.chunks.push_back(ck);
-            ck.row_begin = py; ck.samp_begin = rm.aux;
-        }
-        ck.row_end = py + 1;
-        ck.samp_end = rm.aux + rm.n;
-    }
-    t.chunks.push_back(ck);
 
     t.thr_raw.resize(512);
     const sbx_config c = cfg;

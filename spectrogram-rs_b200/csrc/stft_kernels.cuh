@@ -33,7 +33,7 @@ struct RowMap {            // one output row py (0 = lowest frequency) of the lo
     float f0;              // first sample frequency            (lin_space start)
     float step;            // (f1 - f0) / n                     (lin_space step)
     uint32_t n;            // samples averaged for this row
-    uint32_t aux;          // offset of this row's first entry in the cosine-weight table
+    uint32_t aux;          // first scratch slot of this row's samples within its chunk
 };
 
 struct RowChunk {          // consecutive rows whose interpolated samples fit the shared scratch area
@@ -51,8 +51,9 @@ struct KernelArgs {
     const float2 *twp;           // per DIF pass p: TW_PLANES planes of S_p entries, plane j = W_(S_p R_p)^(2^j lo)
     const RowMap *rowmap;        // [H]
     const RowChunk *chunks;      // [n_chunks]
-    const uint2 *samp;           // per (row, sample): {floor(x) as int, weight as f32 bits}, x = index_of(f0 + s*step);
-                                 //   weight = x - floor(x) (CUBIC) or (1 - cos(frac*pi))/2 (COSINE, host libm)
+    const uint2 *samp;           // per (row, sample): {floor(x) | scratch slot << 17, weight as f32 bits},
+                                 //   x = index_of(f0 + s*step); weight = x - floor(x) (CUBIC) or
+                                 //   (1 - cos(frac*pi))/2 (COSINE, host libm)
     const float *thr;            // [2][264] step thresholds with sentinels: colour index, alpha
     const uint32_t *lut;         // [256] packed r | g<<8 | b<<16 | 255<<24
     unsigned long long n_frames;
@@ -216,7 +217,7 @@ template <int LOG2N_, int LOG2PAD_, int CH_> struct Geom {
         return o;
     }
     static constexpr int TW_TOTAL = tw_offset(NPASS - 1);                      // the last pass has no twiddles
-    static constexpr int SCRATCH = ((M / 2) * 16) / 17;                        // resample scratch slots (padded 17/16)
+    static constexpr int SCRATCH = M / 2;                                      // resample scratch slots (upper half of the buffer)
 
     // bin kk = PAD*k + q0 lives at position q0*N + digitrev(k): a pure bit permutation of kk
     static __host__ __device__ constexpr int pos_of_bin(int kk)
@@ -514,8 +515,6 @@ __device__ __forceinline__ int step_index(const float *ts, float p, float eps, f
     return idx;
 }
 
-__device__ __forceinline__ int scratch_slot(int g) { return g + (g >> 4); }   // 17/16 padding
-
 // One interpolated sample (both channels) -- magnitude_at (ifs.rs:46-48).  mags is indexed by bin
 // kk = j + 1; x1 = floor(x), w = the interpolation weight, both precomputed by the plan.
 template <bool CLAMP>
@@ -565,7 +564,7 @@ __device__ __forceinline__ void resample_samples_impl(const float2 *mags, float2
         for (int i = 0; i < 4; ++i) {
             const uint32_t g = g0 + i * THREADS;
             if (g < count)
-                scratch[scratch_slot((int)g)] = interp_sample<CLAMP>(mags, a, (int)sp[i].x, __uint_as_float(sp[i].y), k_last);
+                scratch[sp[i].x >> 17] = interp_sample<CLAMP>(mags, a, (int)(sp[i].x & 0x1ffffu), __uint_as_float(sp[i].y), k_last);
         }
     }
 }
@@ -577,55 +576,69 @@ __device__ __forceinline__ void resample_samples(const float2 *mags, float2 *scr
 }
 
 // Phase B: one thread per row: sequential mean of its samples (the reference's summation order,
-// ifs.rs:71-73), dB step, LUT, packed RGBA store
+// ifs.rs:71-73), dB step, LUT, packed RGBA store.  Two rows per thread are kept in flight (their
+// loads and the dependent chains of the two colour look-ups overlap).
+template <bool PAIR>
+__device__ __forceinline__ void colour_one_row(float ax, float ay, uint32_t n, uint32_t py, const float *thr, const uint32_t *lut,
+                                               const KernelArgs &a, uint32_t *outA, uint32_t *outB, bool second_valid)
+{
+    if (n > 1) {                                                             // x / 1.0f == x exactly
+        const float nf = (float)n;
+        ax = __fdiv_rn(ax, nf);
+        ay = __fdiv_rn(ay, nf);
+    }
+    const uint32_t row = a.rows - 1u - py;                                   // simple_spectrogram.rs:150
+    const float *thr_a = thr + THR_STRIDE;
+    if constexpr (PAIR) {
+        // mono: (ax, ay) are the L(=R) magnitudes of frames A and B
+        const float pA = __fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ax, ax));
+        const float pB = __fadd_rn(__fmul_rn(ay, ay), __fmul_rn(ay, ay));
+        if (a.scheme == 0) {
+            const int iA = step_index(thr, pA, a.db_eps, a.guess_a[0], a.guess_b[0]);
+            const int iB = step_index(thr, pB, a.db_eps, a.guess_a[0], a.guess_b[0]);
+            outA[row] = __ldg(lut + iA);
+            if (second_valid) outB[row] = __ldg(lut + iB);
+        } else {
+            // l == r: pan = l / (|l| + |r|) = 0.5 for finite l > 0, else NaN or negative -> index 0
+            const uint32_t panA = (ax > 0.0f && ax < 3.0e38f) ? 128u : 0u, panB = (ay > 0.0f && ay < 3.0e38f) ? 128u : 0u;
+            outA[row] = (__ldg(lut + panA) & 0x00ffffffu) | ((uint32_t)step_index(thr_a, pA, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
+            if (second_valid)
+                outB[row] = (__ldg(lut + panB) & 0x00ffffffu) | ((uint32_t)step_index(thr_a, pB, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
+        }
+    } else {
+        const float p = __fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay));    // norm_sqr
+        if (a.scheme == 0) {
+            outA[row] = __ldg(lut + step_index(thr, p, a.db_eps, a.guess_a[0], a.guess_b[0]));
+        } else {
+            const double pan = (double)ax / (double)__fadd_rn(fabsf(ax), fabsf(ay));
+            const double v = floor(pan * 256.0);
+            const uint32_t idx = !(v >= 0.0) ? 0u : (v > 255.0 ? 255u : (uint32_t)v);
+            outA[row] = (__ldg(lut + idx) & 0x00ffffffu) | ((uint32_t)step_index(thr_a, p, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
+        }
+    }
+}
+
 template <bool PAIR, int THREADS>
 __device__ __forceinline__ void colour_rows(const float2 *scratch, const float *thr, const uint32_t *lut,
                                             const KernelArgs &a, const RowChunk ck, unsigned long long frame0, bool second_valid)
 {
     uint32_t *outA = reinterpret_cast<uint32_t *>(a.rgba) + frame0 * a.rows;
     uint32_t *outB = outA + a.rows;
-    for (uint32_t py = ck.row_begin + threadIdx.x; py < ck.row_end; py += THREADS) {
-        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.rowmap) + py);
-        const uint32_t n = raw.z;
-        const int first = (int)(raw.w - ck.samp_begin);
-        float ax = 0.0f, ay = 0.0f;
-        for (uint32_t s = 0; s < n; ++s) {
-            const float2 v = scratch[scratch_slot(first + (int)s)];
-            ax = __fadd_rn(ax, v.x);
-            ay = __fadd_rn(ay, v.y);
+    for (uint32_t py0 = ck.row_begin + threadIdx.x; py0 < ck.row_end; py0 += 2 * THREADS) {
+        const uint32_t py1 = py0 + THREADS;
+        const bool has1 = py1 < ck.row_end;
+        const uint4 r0 = __ldg(reinterpret_cast<const uint4 *>(a.rowmap) + py0);
+        const uint4 r1 = has1 ? __ldg(reinterpret_cast<const uint4 *>(a.rowmap) + py1) : make_uint4(0u, 0u, 0u, 0u);
+        const uint32_t n0 = r0.z, n1 = r1.z;                                 // n1 == 0 when the second row is absent
+        const float2 *m0 = scratch + r0.w, *m1 = scratch + r1.w;             // odd stride between rows
+        float ax0 = 0.0f, ay0 = 0.0f, ax1 = 0.0f, ay1 = 0.0f;
+        const uint32_t nmax = n0 > n1 ? n0 : n1;
+        for (uint32_t s = 0; s < nmax; ++s) {
+            if (s < n0) { const float2 v = m0[s]; ax0 = __fadd_rn(ax0, v.x); ay0 = __fadd_rn(ay0, v.y); }
+            if (s < n1) { const float2 v = m1[s]; ax1 = __fadd_rn(ax1, v.x); ay1 = __fadd_rn(ay1, v.y); }
         }
-        if (n > 1) {                                                             // x / 1.0f == x exactly
-            const float nf = (float)n;
-            ax = __fdiv_rn(ax, nf);
-            ay = __fdiv_rn(ay, nf);
-        }
-        const uint32_t row = a.rows - 1u - py;                                   // simple_spectrogram.rs:150
-        const float *thr_a = thr + THR_STRIDE;
-        if constexpr (PAIR) {
-            // mono: (ax, ay) are the L(=R) magnitudes of frames A and B
-            const float pA = __fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ax, ax));
-            const float pB = __fadd_rn(__fmul_rn(ay, ay), __fmul_rn(ay, ay));
-            if (a.scheme == 0) {
-                outA[row] = __ldg(lut + step_index(thr, pA, a.db_eps, a.guess_a[0], a.guess_b[0]));
-                if (second_valid) outB[row] = __ldg(lut + step_index(thr, pB, a.db_eps, a.guess_a[0], a.guess_b[0]));
-            } else {
-                // l == r: pan = l / (|l| + |r|) = 0.5 for finite l > 0, else NaN or negative -> index 0
-                const uint32_t panA = (ax > 0.0f && ax < 3.0e38f) ? 128u : 0u, panB = (ay > 0.0f && ay < 3.0e38f) ? 128u : 0u;
-                outA[row] = (__ldg(lut + panA) & 0x00ffffffu) | ((uint32_t)step_index(thr_a, pA, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
-                if (second_valid)
-                    outB[row] = (__ldg(lut + panB) & 0x00ffffffu) | ((uint32_t)step_index(thr_a, pB, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
-            }
-        } else {
-            const float p = __fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay));    // norm_sqr
-            if (a.scheme == 0) {
-                outA[row] = __ldg(lut + step_index(thr, p, a.db_eps, a.guess_a[0], a.guess_b[0]));
-            } else {
-                const double pan = (double)ax / (double)__fadd_rn(fabsf(ax), fabsf(ay));
-                const double v = floor(pan * 256.0);
-                const uint32_t idx = !(v >= 0.0) ? 0u : (v > 255.0 ? 255u : (uint32_t)v);
-                outA[row] = (__ldg(lut + idx) & 0x00ffffffu) | ((uint32_t)step_index(thr_a, p, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
-            }
-        }
+        colour_one_row<PAIR>(ax0, ay0, n0, py0, thr, lut, a, outA, outB, second_valid);
+        if (has1) colour_one_row<PAIR>(ax1, ay1, n1, py1, thr, lut, a, outA, outB, second_valid);
     }
 }
 

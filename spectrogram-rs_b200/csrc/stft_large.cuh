@@ -19,7 +19,6 @@ namespace sbx {
 constexpr int LARGE_LOG2_BLOCK = 12;                       // 4096-point blocks
 constexpr int LARGE_BLOCK = 1 << LARGE_LOG2_BLOCK;
 constexpr int LARGE_THREADS = 256;
-constexpr int LARGE_SCRATCH = (LARGE_BLOCK * 16) / 17;     // resample scratch slots of large_colour (32 KB)
 
 using G12 = Geom<LARGE_LOG2_BLOCK, 0, 2>;                  // the block transform: 4096 = 16 x 16 x 16
 
