@@ -337,22 +337,87 @@ def extras(sbx, signals, torch):
                     device=torch.cuda.current_device())
     live = plan.live(4096)
     lr = signals.stereo_loopback(2048 * 64)
-    col = np.empty((1024, 4), np.uint8)
-    lat = []
-    for i in range(11000):
-        blk = lr[(i % 64) * 2048:(i % 64 + 1) * 2048]
-        t0 = time.perf_counter_ns()
-        live.push(blk)
-        live.pop_column(col)
-        t1 = time.perf_counter_ns()
-        if i >= 1000:
-            lat.append((t1 - t0) * 1e-3)
-    lat = np.array(lat)
+    live.measure(lr[:2048], 1000)                                        # warm-up
+    lat = np.concatenate([live.measure(lr[(i % 64) * 2048:(i % 64 + 1) * 2048], 100) for i in range(100)])
     res["cfg2_live_latency_us"] = {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
                                    "mean": float(lat.mean()), "samples": int(lat.size),
-                                   "what": "push 2048 stereo samples into the pinned ring + pop one RGBA column (CUDA graph H2D->kernel->D2H + sync), timed on the host through ctypes"}
+                                   "what": "host CLOCK_MONOTONIC around: push 2048 stereo samples into the pinned ring + pop one RGBA column (one CUDA graph: H2D 16 KB -> fused kernel -> D2H 4 KB, then stream sync); native loop sbx_live_measure"}
+    # the same frame, kernel only (device-resident input and output, CUDA events on the launching stream)
+    d_lr = torch.from_numpy(lr[:2048]).cuda()
+    d_col = torch.empty((1, 1024, 4), dtype=torch.uint8, device="cuda")
+    plan.set_stream(stream.cuda_stream)
+    for _ in range(20):
+        plan.process_batch_device(d_lr, 2048, d_col, 1)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record(stream)
+    for _ in range(200):
+        plan.process_batch_device(d_lr, 2048, d_col, 1)
+    b.record(stream)
+    torch.cuda.synchronize()
+    res["cfg2_kernel_only_us"] = a.elapsed_time(b) * 1e3 / 200
+    # the reference application's own live geometry: N = (0.05 s * 48 kHz) = 2400, hop 58 (mixed-radix path)
+    plan_l = sbx.Plan(sample_rate=48000.0, window_n=2400, pad_factor=2, hop=58, rows_h=1024, channels=2, lut="magma",
+                      device=torch.cuda.current_device())
+    live_l = plan_l.live(4096)
+    live_l.push(lr[:2400])
+    live_l.measure(lr[:58], 500)
+    lat = live_l.measure(lr[58:116], 5000)
+    res["app_live_n2400_latency_us"] = {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
+                                        "what": "reference app geometry: N 2400, M 4800, hop 58 samples (819 frames/s needed)"}
+    live_l.close(); plan_l.close()
     live.close()
     plan.close()
+
+    # cfg4: 64 independent 48 kHz channels x 60 s (5618 frames each), one launch per channel, 1 GPU
+    n4, hop4, ch4, ns4 = 4096, 512, 64, 48000 * 60
+    plan = sbx.Plan(sample_rate=48000.0, window_n=n4, pad_factor=2, hop=hop4, rows_h=1024, channels=1, lut="magma",
+                    device=torch.cuda.current_device())
+    plan.set_stream(stream.cuda_stream)
+    F4 = plan.num_frames(ns4)
+    x4 = torch.from_numpy(np.stack([signals.channel_tone(c, ns4) for c in range(8)])).cuda().repeat(8, 1).contiguous()
+    out4 = torch.empty((ch4, F4, 1024, 4), dtype=torch.uint8, device="cuda")
+
+    def run4():
+        for c in range(ch4):
+            plan.process_batch_device(x4[c], ns4, out4[c], F4)
+    run4()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record(stream)
+    for _ in range(3):
+        run4()
+    b.record(stream)
+    torch.cuda.synchronize()
+    res["cfg4_frames_per_s"] = 3 * ch4 * F4 / (a.elapsed_time(b) * 1e-3)
+    res["cfg4_workload"] = "64 channels x 60 s @ 48 kHz (5618 frames each), N=4096 -> M=8192, hop 512, one launch per channel on 1 GPU; channels shard 64/G per GPU with no halo"
+    plan.close()
+    del x4, out4
+
+    # cfg5: FFT-size sweep, P = 4, hop = N/8, H = 2048, white noise; N <= 4096 fused kernel, N >= 8192 four-kernel path
+    sweep = {}
+    for n5 in (512, 1024, 2048, 4096, 8192, 16384, 32768, 65536):
+        F5 = max(256, (1 << 25) // n5)
+        plan = sbx.Plan(sample_rate=48000.0, window_n=n5, pad_factor=4, hop=n5 // 8, rows_h=2048, channels=1, lut="magma",
+                        device=torch.cuda.current_device())
+        plan.set_stream(stream.cuda_stream)
+        ns5 = (F5 - 1) * (n5 // 8) + n5
+        x5 = torch.from_numpy(signals.white_noise(ns5)).cuda()
+        out5 = torch.empty((F5, 2048, 4), dtype=torch.uint8, device="cuda")
+        for _ in range(2):
+            plan.process_batch_device(x5, ns5, out5, F5)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record(stream)
+        for _ in range(3):
+            plan.process_batch_device(x5, ns5, out5, F5)
+        b.record(stream)
+        torch.cuda.synchronize()
+        fps = 3 * F5 / (a.elapsed_time(b) * 1e-3)
+        sweep[str(n5)] = {"frames_per_s": fps, "hbm_frac": fps * ((n5 // 8) * 4 + 2048 * 4) / 1e9 / measured_peaks()[0]["hbm_gbs"]}
+        plan.close()
+        del x5, out5
+    res["cfg5_sweep_1gpu"] = sweep
     return res
 
 

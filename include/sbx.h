@@ -187,6 +187,12 @@ SBX_API uint32_t   sbx_live_push(sbx_live *live, const float *samples, uint32_t 
 SBX_API sbx_status sbx_live_pop_column(sbx_live *live, uint8_t *rgba);
 SBX_API sbx_status sbx_live_pop_magnitudes(sbx_live *live, float *out_lr);
 SBX_API uint32_t   sbx_live_buffered(const sbx_live *live);
+/* Measurement helper for the live path (no reference counterpart): `iters` times, push `n_samples` frames of
+ * `channels` floats from `samples` and pop one column, timing each push+pop pair on the host with
+ * CLOCK_MONOTONIC; latencies_us[i] receives the i-th latency in microseconds.  Returns SBX_OK, or the first
+ * failing status (SBX_NOT_ENOUGH_SAMPLES if a pop found fewer than N buffered samples). */
+SBX_API sbx_status sbx_live_measure(sbx_live *live, const float *samples, uint32_t n_samples, uint32_t channels,
+                                    uint32_t iters, float *latencies_us);
 
 /* ---- pinned host memory helpers (for callers without a CUDA binding) --------------------- */
 SBX_API void *sbx_host_alloc(size_t bytes);

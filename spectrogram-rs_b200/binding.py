@@ -58,6 +58,7 @@ SYMBOLS = {
     "sbx_live_pop_column": (C.c_int32, [_vp, _vp]),
     "sbx_live_pop_magnitudes": (C.c_int32, [_vp, _vp]),
     "sbx_live_buffered": (C.c_uint32, [_vp]),
+    "sbx_live_measure": (C.c_int32, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp]),
     "sbx_host_alloc": (_vp, [C.c_size_t]),
     "sbx_host_free": (None, [_vp]),
     "sbx_abi_version": (C.c_uint32, []),

