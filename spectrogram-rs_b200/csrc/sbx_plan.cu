@@ -49,14 +49,22 @@ sbx_status cuda_fail(const sbx_plan *p, cudaError_t e, const char *what)
 }
 
 // ---- kernel dispatch ---------------------------------------------------------------------------
+constexpr size_t kMaxSmemOptIn = 227 * 1024;           // opt-in dynamic shared memory per CTA on sm_100
+
+// Per-device launch geometry of the persistent kernel: resident CTAs per SM x SM count.
+struct PersistentGeom { bool ready = false; int ctas = 0, occ = 0; size_t smem = 0; };
+
 template <int LOG2N, int LOG2PAD, int CH>
 cudaError_t launch_one(const KernelArgs &args, uint64_t n_frames, cudaStream_t stream)
 {
     using G = Geom<LOG2N, LOG2PAD, CH>;
     static bool configured[64] = {};
+    static PersistentGeom pgeom[64];
+    static uint32_t pgeom_hop[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !configured[dev]) {
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(fused_frames_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         configured[dev] = true;
@@ -64,6 +72,43 @@ cudaError_t launch_one(const KernelArgs &args, uint64_t n_frames, cudaStream_t s
     const uint64_t ctas = (n_frames + G::FRAMES_PER_CTA - 1) / G::FRAMES_PER_CTA;
     if (ctas == 0) return cudaSuccess;
     if (ctas > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+
+    // Persistent, TMA-staged variant: grid = SMs x resident CTAs, the next unit's PCM span prefetched into shared
+    // memory by cp.async.bulk while the current unit is transformed.  Used where only ONE CTA fits an SM
+    // (M = 16384: 128 KB of transform buffer), i.e. where no second CTA hides the load latency of pass 0:
+    // measured on a B200, cfg3 19.9 -> 21.8 M frames/s.  With two or more resident CTAs the one-CTA-per-unit
+    // grid is faster (cfg1: 51.3 vs 47.7 M frames/s): the hardware staggers CTA start times, so co-resident
+    // CTAs sit in different phases, whereas persistent CTAs run in lock-step and contend for the same pipe.
+    // Needs 16-byte aligned sample spans and enough units to fill the machine.
+    constexpr uint32_t FPC = G::FRAMES_PER_CTA;
+    const uint32_t unit_stride_bytes = FPC * args.hop * CH * 4u;
+    const uint32_t span_bytes = (G::N + (FPC - 1) * args.hop) * CH * 4u;
+    static const bool disabled = std::getenv("SBX_NO_PERSISTENT") != nullptr;
+    const bool aligned = (unit_stride_bytes % 16u) == 0 && (span_bytes % 16u) == 0 &&
+                         (reinterpret_cast<uintptr_t>(args.pcm) % 16u) == 0;
+    const size_t smem_p = (size_t)G::SMEM_BYTES + span_bytes;
+    if (!disabled && aligned && smem_p <= kMaxSmemOptIn) {
+        PersistentGeom &pg = pgeom[dev];
+        if (!pg.ready || pgeom_hop[dev] != args.hop) {
+            cudaError_t e = cudaFuncSetAttribute(fused_frames_persistent_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
+            if (e != cudaSuccess) return e;
+            int occ = 0, sms = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused_frames_persistent_kernel<G>, G::THREADS, smem_p);
+            if (e != cudaSuccess) return e;
+            e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (e != cudaSuccess) return e;
+            pg.ctas = occ * sms;
+            pg.occ = occ;
+            pg.smem = smem_p;
+            pg.ready = true;
+            pgeom_hop[dev] = args.hop;
+        }
+        static const bool forced = std::getenv("SBX_FORCE_PERSISTENT") != nullptr;
+        if (pg.ctas > 0 && ctas >= (uint64_t)pg.ctas * 2 && (pg.occ == 1 || forced)) {
+            fused_frames_persistent_kernel<G><<<(unsigned)pg.ctas, G::THREADS, pg.smem, stream>>>(args, (uint32_t)ctas);
+            return cudaGetLastError();
+        }
+    }
     fused_frames_kernel<G><<<(unsigned)ctas, G::THREADS, G::SMEM_BYTES, stream>>>(args);
     return cudaGetLastError();
 }
@@ -116,8 +161,6 @@ sbx_status launch_fused(sbx_plan *p, int channels, const float *d_pcm, uint64_t 
 }
 
 // ---- generic path (window not a power of two) -----------------------------------------------------
-constexpr size_t kMaxSmemOptIn = 227 * 1024;
-
 sbx_status launch_generic(sbx_plan *p, int channels, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba,
                           float *d_mags, cudaStream_t stream)
 {

@@ -318,13 +318,15 @@ __device__ __forceinline__ void apply_twiddles(float2 (&v)[R], const float2 *pla
 // DIF passes
 // ----------------------------------------------------------------------------------------------
 
-// Pass 0: global PCM -> window -> sub-transform premultiply -> radix butterfly -> twiddle -> smem
-template <class G>
-__device__ __forceinline__ void pass_first(float2 *z, const KernelArgs &a, unsigned long long frame0, bool second_valid)
+// Pass 0: PCM -> window -> sub-transform premultiply -> radix butterfly -> twiddle -> smem.
+// STAGED = false: PCM is read from global memory (pa = this unit's first sample).
+// STAGED = true : `pa` points at the unit's sample span in SHARED memory, put there by a bulk async
+//                 copy (the persistent kernel); frame B of a mono pair is the same span shifted by hop.
+template <class G, bool STAGED = false>
+__device__ __forceinline__ void pass_first(float2 *z, const KernelArgs &a, const float *pa, bool second_valid)
 {
     constexpr int LR = G::log2r(0), R = 1 << LR, LS = G::log2stride(0), S = 1 << LS;
     constexpr int PER_SUB = G::N / R, COUNT = G::PAD * PER_SUB;
-    const float *pa = a.pcm + frame0 * (unsigned long long)a.hop * G::CH;
     const float *pb = pa + a.hop;                                    // mono: the next frame
     for (int w = threadIdx.x; w < COUNT; w += G::THREADS) {
         const int q0 = w / PER_SUB, lo = w % PER_SUB;                // q0 is warp-uniform (PER_SUB % 32 == 0)
@@ -333,7 +335,14 @@ __device__ __forceinline__ void pass_first(float2 *z, const KernelArgs &a, unsig
         for (int r = 0; r < R; ++r) {
             const int n = lo + r * S;
             float2 s;
-            if constexpr (G::CH == 2) {
+            if constexpr (STAGED) {
+                if constexpr (G::CH == 2) {
+                    s = reinterpret_cast<const float2 *>(pa)[n];
+                } else {
+                    s.x = pa[n];
+                    s.y = second_valid ? pb[n] : 0.0f;
+                }
+            } else if constexpr (G::CH == 2) {
                 s = __ldg(reinterpret_cast<const float2 *>(pa) + n);
             } else {
                 s.x = __ldg(pa + n);
@@ -662,17 +671,10 @@ __device__ __forceinline__ void resample_colour(float2 *z, const KernelArgs &a, 
     }
 }
 
+// everything after pass 0: remaining passes, L/R split, optional magnitude store, resample + colour
 template <class G>
-__global__ void __launch_bounds__(G::THREADS) fused_frames_kernel(const KernelArgs a)
+__device__ __forceinline__ void frame_tail(float2 *z, const KernelArgs &a, unsigned long long frame0, bool second_valid)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2 *z = reinterpret_cast<float2 *>(smem_raw);
-
-    const unsigned long long frame0 = (unsigned long long)blockIdx.x * G::FRAMES_PER_CTA;
-    const bool second_valid = G::CH == 1 && frame0 + 1 < a.n_frames;
-
-    pass_first<G>(z, a, frame0, second_valid);
-    __syncthreads();
     RunPasses<G, 1>::run(z, a);
     {
         SplitRegs<G> regs;
@@ -681,7 +683,6 @@ __global__ void __launch_bounds__(G::THREADS) fused_frames_kernel(const KernelAr
         split_write<G>(z, regs);
     }
     __syncthreads();
-
     if (a.mags_out != nullptr) {
         float2 *out = reinterpret_cast<float2 *>(a.mags_out) + frame0 * a.k_out;
         for (uint32_t j = threadIdx.x; j < a.k_out; j += G::THREADS) {
@@ -696,6 +697,89 @@ __global__ void __launch_bounds__(G::THREADS) fused_frames_kernel(const KernelAr
     }
     if (a.rgba != nullptr)
         resample_colour<G::LOG2M, G::CH == 1, G::THREADS>(z, a, frame0, second_valid);
+}
+
+template <class G>
+__global__ void __launch_bounds__(G::THREADS) fused_frames_kernel(const KernelArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *z = reinterpret_cast<float2 *>(smem_raw);
+
+    const unsigned long long frame0 = (unsigned long long)blockIdx.x * G::FRAMES_PER_CTA;
+    const bool second_valid = G::CH == 1 && frame0 + 1 < a.n_frames;
+
+    pass_first<G, false>(z, a, a.pcm + frame0 * (unsigned long long)a.hop * G::CH, second_valid);
+    __syncthreads();
+    frame_tail<G>(z, a, frame0, second_valid);
+}
+
+// ---- persistent variant: grid = SMs x resident CTAs, PCM staged through shared memory by bulk async copies ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// cp.async.bulk (the TMA engine's 1-D form): global -> shared, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+    uint32_t done = 0, spins = 0;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (!done && ++spins > (1u << 24)) __trap();      // a lost copy must fault, never hang the GPU
+    } while (!done);
+}
+
+// Unit u = one frame (stereo) or one frame pair (mono).  The sample span of unit u+grid is copied into the
+// stage buffer by one elected thread as soon as pass 0 of unit u has consumed it, so the copy overlaps
+// passes 1.., the split and the resample of unit u.  Requires 16-byte aligned spans (checked by the host).
+template <class G>
+__global__ void __launch_bounds__(G::THREADS) fused_frames_persistent_kernel(const KernelArgs a, uint32_t n_units)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *z = reinterpret_cast<float2 *>(smem_raw);
+    float *stage = reinterpret_cast<float *>(smem_raw + (size_t)G::M * 8);
+    __shared__ __align__(8) unsigned long long bar;
+
+    constexpr uint32_t FPC = G::FRAMES_PER_CTA;
+    const uint32_t full_bytes = (G::N + (FPC - 1) * a.hop) * G::CH * 4u;      // both frames of a pair
+    const uint32_t one_bytes = G::N * G::CH * 4u;                               // a trailing half-filled pair
+    auto unit_bytes = [&](uint32_t u) { return (unsigned long long)u * FPC + FPC <= a.n_frames ? full_bytes : one_bytes; };
+    auto unit_src = [&](uint32_t u) { return a.pcm + (unsigned long long)u * FPC * a.hop * G::CH; };
+
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    uint32_t u = blockIdx.x;
+    if (threadIdx.x == 0 && u < n_units) {
+        mbar_expect_tx(&bar, unit_bytes(u));
+        bulk_copy_g2s(stage, unit_src(u), unit_bytes(u), &bar);
+    }
+    uint32_t parity = 0;
+    for (; u < n_units; u += gridDim.x) {
+        const unsigned long long frame0 = (unsigned long long)u * FPC;
+        const bool second_valid = G::CH == 1 && frame0 + 1 < a.n_frames;
+        mbar_wait(&bar, parity);
+        parity ^= 1u;
+        pass_first<G, true>(z, a, stage, second_valid);
+        __syncthreads();                                    // stage consumed, pass 0 stored
+        const uint32_t next = u + gridDim.x;
+        if (threadIdx.x == 0 && next < n_units) {
+            mbar_expect_tx(&bar, unit_bytes(next));
+            bulk_copy_g2s(stage, unit_src(next), unit_bytes(next), &bar);
+        }
+        frame_tail<G>(z, a, frame0, second_valid);
+        __syncthreads();                                    // the next unit's pass 0 overwrites z
+    }
 }
 
 // magnitudes (frames x K x (L,R), device) -> RGBA columns: the resample/colour stage alone

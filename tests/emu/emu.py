@@ -62,7 +62,9 @@ def make_config(lut_rgb, sample_rate=48000.0, window_n=4096, pad_factor=2, hop=5
     return cfg
 
 
-def batch(cfg, pcm, want_mags=True, want_rgba=True):
+def batch(cfg, pcm, want_mags=True, want_rgba=True, staged=False):
+    """staged=True emulates the persistent kernel's pass 0 (PCM span in a stage buffer)."""
+    lib().emu_set_staged(1 if staged else 0)
     pcm = np.ascontiguousarray(pcm, dtype=np.float32)
     n_samples = pcm.shape[0]
     n, hop = cfg.window_n, cfg.hop

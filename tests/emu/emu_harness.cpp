@@ -9,6 +9,8 @@
 
 namespace {
 
+bool g_emu_staged = false;
+
 template <class G, int P> struct EmuPasses {
     static void run(float2 *z, const sbx::KernelArgs &a)
     {
@@ -25,7 +27,16 @@ int emu_cta(const sbx::KernelArgs &a, unsigned long long frame0, float *mags_out
 {
     std::vector<float2> z(G::M);
     const bool second_valid = G::CH == 1 && frame0 + 1 < a.n_frames;
-    for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::pass_first<G>(z.data(), a, frame0, second_valid); }
+    const float *src = a.pcm + frame0 * (unsigned long long)a.hop * G::CH;
+    if (g_emu_staged) {
+        // the persistent kernel's path: the unit's sample span sits in a (shared-memory) stage buffer
+        const size_t span = ((size_t)G::N + (second_valid ? a.hop : 0)) * G::CH;
+        std::vector<float> stage(((size_t)G::N + a.hop) * G::CH, 0.0f);
+        std::copy(src, src + span, stage.begin());
+        for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::pass_first<G, true>(z.data(), a, stage.data(), second_valid); }
+    } else {
+        for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::pass_first<G, false>(z.data(), a, src, second_valid); }
+    }
     EmuPasses<G, 1>::run(z.data(), a);
     std::vector<sbx::SplitRegs<G>> regs(G::THREADS);
     for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::split_read<G>(z.data(), a, regs[t]); }
@@ -242,6 +253,9 @@ long long emu_batch(const sbx_config *cfg, const float *pcm, unsigned long long 
     }
     return (long long)frames;
 }
+
+__attribute__((visibility("default")))
+void emu_set_staged(int staged) { g_emu_staged = staged != 0; }
 
 // host tables of the product, exposed so CPU tests can compare them with the oracle bit for bit
 __attribute__((visibility("default")))

@@ -255,3 +255,31 @@ def test_stereo_pan_scheme(sbx, viridis, n, pad, ch, hop, rows):
         assert np.array_equal(plan.colorize_magnitudes(o_mags), o_rgba)
         assert (g != o_rgba).any(axis=2).mean() <= 2e-3 and np.abs(g.astype(int) - o_rgba.astype(int))[..., 3].max() <= 1
         assert g[..., 3].min() < 64 and g[..., 3].max() > 128
+
+
+@pytest.mark.parametrize("n,pad,ch,hop,frames", [(8192, 2, 1, 256, 701), (4096, 4, 2, 512, 330)])
+def test_persistent_tma_staged_kernel(sbx, viridis, n, pad, ch, hop, frames):
+    """Enough units to take the persistent kernel (grid = SMs x resident CTAs, PCM staged into shared memory by
+    cp.async.bulk): one CTA per SM at M = 16384.  Odd frame count: the trailing half-filled mono pair copies a
+    shorter span.  Compared with the oracle and with the one-CTA-per-unit kernel (a short batch of the same data)."""
+    ns = n + hop * (frames - 1)
+    pcm = signals.sweeps_plus_noise(ns, 96000.0) if ch == 1 else signals.stereo_loopback(ns)
+    p = oracle.params(sample_rate=96000.0, window_n=n, pad_factor=pad, hop=hop, rows_h=512)
+    o_rgba, o_mags = oracle.batch(p, pcm, ch, viridis, want_mags=True, threads=8)
+    with sbx.Plan(sample_rate=96000.0, window_n=n, pad_factor=pad, hop=hop, rows_h=512, channels=ch, lut=viridis) as plan:
+        import torch
+        d_pcm = torch.from_numpy(pcm).cuda()
+        d_mags = torch.zeros((frames, plan.k, 2), dtype=torch.float32, device="cuda")
+        launches = plan.launch_count
+        assert plan.magnitudes_batch_device(d_pcm, ns, d_mags, frames) == frames
+        g_rgba = plan.process_batch(pcm)
+        plan.synchronize()
+        g_mags = d_mags.cpu().numpy()
+        assert plan.launch_count > launches
+        peak = np.abs(o_mags).max(axis=(1, 2), keepdims=True)
+        assert (np.abs(g_mags - o_mags) / peak).max() <= MAG_TOL
+        assert (g_rgba != o_rgba).any(axis=2).mean() <= 1e-3
+        assert np.array_equal(plan.colorize_magnitudes(g_mags[:8]), g_rgba[:8])
+        # the same leading frames through a short batch (one CTA per unit, global loads)
+        short = plan.process_batch(pcm[: n + hop * 9])
+        assert np.array_equal(short, g_rgba[:10])
