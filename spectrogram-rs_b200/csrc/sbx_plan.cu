@@ -77,8 +77,9 @@ cudaError_t launch_one(const KernelArgs &args, uint64_t n_frames, cudaStream_t s
     // memory by cp.async.bulk while the current unit is transformed.  Used where only ONE CTA fits an SM
     // (M = 16384: 128 KB of transform buffer), i.e. where no second CTA hides the load latency of pass 0:
     // measured on a B200, cfg3 19.9 -> 21.8 M frames/s.  With two or more resident CTAs the one-CTA-per-unit
-    // grid is faster (cfg1: 51.3 vs 47.7 M frames/s): the hardware staggers CTA start times, so co-resident
-    // CTAs sit in different phases, whereas persistent CTAs run in lock-step and contend for the same pipe.
+    // grid is faster (cfg1: 51.3 vs 47.7 M frames/s; staggering the start of co-resident persistent CTAs by
+    // 3-12 k cycles changed nothing, so it is not a lock-step effect -- the extra 18 KB of staging per CTA
+    // leaves less L1 for the plan tables, and there is one more barrier per unit).
     // Needs 16-byte aligned sample spans and enough units to fill the machine.
     constexpr uint32_t FPC = G::FRAMES_PER_CTA;
     const uint32_t unit_stride_bytes = FPC * args.hop * CH * 4u;
