@@ -27,6 +27,7 @@ struct sbx_plan {
     float2 *d_wtw = nullptr;
     float2 *d_twp = nullptr;
     sbx::RowMap *d_rowmap = nullptr;
+    uint32_t *d_rowinfo = nullptr;
     sbx::RowChunk *d_chunks = nullptr;
     uint2 *d_samp = nullptr;
     int taps_clamped = 0;

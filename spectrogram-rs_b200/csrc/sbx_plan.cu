@@ -351,6 +351,7 @@ sbx::KernelArgs sbx_plan::base_args() const
     a.wtw = d_wtw;
     a.twp = d_twp;
     a.rowmap = d_rowmap;
+    a.rowinfo = d_rowinfo;
     a.chunks = d_chunks;
     a.n_chunks = n_chunks;
     a.samp = d_samp;
@@ -444,7 +445,7 @@ SBX_API void sbx_plan_destroy(sbx_plan *p)
         cudaFree(s.d_pcm);
         cudaFree(s.d_rgba);
     }
-    cudaFree(p->d_window); cudaFree(p->d_wtw); cudaFree(p->d_twp); cudaFree(p->d_rowmap); cudaFree(p->d_chunks);
+    cudaFree(p->d_window); cudaFree(p->d_wtw); cudaFree(p->d_twp); cudaFree(p->d_rowmap); cudaFree(p->d_rowinfo); cudaFree(p->d_chunks);
     cudaFree(p->d_samp); cudaFree(p->d_twm); cudaFree(p->d_pos_tab); cudaFree(p->d_twp_block); cudaFree(p->d_zbuf); cudaFree(p->d_magbuf);
     cudaFree(p->d_thr); cudaFree(p->d_lut); cudaFree(p->d_frame); cudaFree(p->d_mags1); cudaFree(p->d_col);
     if (p->h_frame) cudaFreeHost(p->h_frame);
@@ -556,6 +557,7 @@ SBX_API sbx_status sbx_plan_create(const sbx_config *cfg, sbx_plan **out_plan)
     SBX_TRY(upload(&p->d_pos_tab, t.pos_tab.data(), t.pos_tab.size() * sizeof(uint32_t)));
     SBX_TRY(upload(&p->d_twp_block, t.twp_block.data(), t.twp_block.size() * sizeof(float)));
     SBX_TRY(upload(&p->d_rowmap, p->h_rowmap.data(), p->rows * sizeof(sbx::RowMap)));
+    SBX_TRY(upload(&p->d_rowinfo, t.rowinfo.data(), t.rowinfo.size() * sizeof(uint32_t)));
     SBX_TRY(upload(&p->d_chunks, t.chunks.data(), t.chunks.size() * sizeof(sbx::RowChunk)));
     SBX_TRY(upload(&p->d_samp, t.samp.data(), t.samp.size() * sizeof(uint32_t)));
     SBX_TRY(upload(&p->d_thr, t.thr.data(), t.thr.size() * sizeof(float)));

@@ -96,6 +96,7 @@ struct HostTables {
     std::vector<uint32_t> pos_tab;      // generic: [M] position of bin kk
     std::vector<uint32_t> radix, stride;// generic: per-pass radix and butterfly stride
     std::vector<RowMap> rowmap;         // [H]
+    std::vector<uint32_t> rowinfo;      // [H] n | first scratch slot << 16 (what the kernels read)
     std::vector<RowChunk> chunks;       // rows grouped so that a chunk's samples fit the kernel's scratch area
     std::vector<uint32_t> samp;         // per (row, sample): {floor(x), weight bits}, see KernelArgs::samp
     bool taps_clamped = false;          // some cubic tap falls outside [0, K-1]
@@ -227,7 +228,7 @@ inline void build(const sbx_config &cfg, HostTables &t)
     for (uint32_t py = 0; py < t.rows; ++py) {
         RowMap &rm = t.rowmap[py];
         const uint32_t need = rm.n + (((rm.n & 1u) == 0 && rm.n >= 4) ? 1u : 0u);
-        if (need > cap || need >= (1u << 15)) t.ok = false;
+        if (need > cap || need >= (1u << 15) || cap > (1u << 16)) t.ok = false;
         if (slot + need > cap && ck.row_end > ck.row_begin) {
             t.chunks.push_back(ck);
             ck.row_begin = py; ck.samp_begin = samp_first[py];
@@ -239,6 +240,8 @@ inline void build(const sbx_config &cfg, HostTables &t)
         ck.samp_end = samp_first[py] + rm.n;
     }
     t.chunks.push_back(ck);
+    t.rowinfo.resize(t.rows);
+    for (uint32_t py = 0; py < t.rows; ++py) t.rowinfo[py] = t.rowmap[py].n | (t.rowmap[py].aux << 16);
 
     // per-sample table: x = index_of(lin_space(f0..f1, n)[s])  (ifs.rs:67-69, :24-31), stored as
     //   word 0: floor(x) in bits 0..16, the sample's scratch slot in bits 17..31

@@ -49,7 +49,8 @@ struct KernelArgs {
     const float *window;         // [N] periodic Hann, f32, host-computed (fft.rs:59-63)
     const float2 *wtw;           // [(P-1) N] window[n] * W_M^(n q0), q0 = 1..P-1 (sub-transform premultiply)
     const float2 *twp;           // per DIF pass p: TW_PLANES planes of S_p entries, plane j = W_(S_p R_p)^(2^j lo)
-    const RowMap *rowmap;        // [H]
+    const RowMap *rowmap;        // [H] (host-side description; the kernels read rowinfo)
+    const uint32_t *rowinfo;     // [H] n | first scratch slot << 16
     const RowChunk *chunks;      // [n_chunks]
     const uint2 *samp;           // per (row, sample): {floor(x) | scratch slot << 17, weight as f32 bits},
                                  //   x = index_of(f0 + s*step); weight = x - floor(x) (CUBIC) or
@@ -192,6 +193,70 @@ template <> struct Butterfly<16> {
     }
 };
 
+// ---- cache-policy loads ------------------------------------------------------------------------
+// PCM streams through once per CTA while ~100 KB of plan tables (window, twiddles, sample table, thresholds)
+// are re-read by every CTA, so tables are loaded with L1::evict_last.  Measured on a B200 (cfg1, M frames/s):
+// default/default 52.0, PCM evict_first 52.2, tables evict_last 52.9, PCM no_allocate + tables evict_last 52.5
+// -- within noise: the kernel is issue- and shared-memory-bound, not L1-capacity-bound.
+#ifndef SBX_PCM_POLICY
+#define SBX_PCM_POLICY 0        // 0: default, 1: L1::evict_first, 2: L1::no_allocate
+#endif
+#ifndef SBX_TABLE_KEEP
+#define SBX_TABLE_KEEP 1        // 1: tables with L1::evict_last
+#endif
+__device__ __forceinline__ float ldg_pcm(const float *p)
+{
+#if defined(SBX_EMU) || SBX_PCM_POLICY == 0
+    return __ldg(p);
+#elif SBX_PCM_POLICY == 1
+    float v; asm volatile("ld.global.nc.L1::evict_first.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v;
+#else
+    float v; asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v;
+#endif
+}
+__device__ __forceinline__ float2 ldg_pcm2(const float2 *p)
+{
+#if defined(SBX_EMU) || SBX_PCM_POLICY == 0
+    return __ldg(p);
+#elif SBX_PCM_POLICY == 1
+    float2 v; asm volatile("ld.global.nc.L1::evict_first.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p)); return v;
+#else
+    float2 v; asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p)); return v;
+#endif
+}
+__device__ __forceinline__ float ldg_tab(const float *p)
+{
+#if defined(SBX_EMU) || SBX_TABLE_KEEP == 0
+    return __ldg(p);
+#else
+    float v; asm volatile("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v;
+#endif
+}
+__device__ __forceinline__ float2 ldg_tab(const float2 *p)
+{
+#if defined(SBX_EMU) || SBX_TABLE_KEEP == 0
+    return __ldg(p);
+#else
+    float2 v; asm volatile("ld.global.nc.L1::evict_last.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p)); return v;
+#endif
+}
+__device__ __forceinline__ uint2 ldg_tab(const uint2 *p)
+{
+#if defined(SBX_EMU) || SBX_TABLE_KEEP == 0
+    return __ldg(p);
+#else
+    uint2 v; asm volatile("ld.global.nc.L1::evict_last.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p)); return v;
+#endif
+}
+__device__ __forceinline__ uint32_t ldg_tab(const uint32_t *p)
+{
+#if defined(SBX_EMU) || SBX_TABLE_KEEP == 0
+    return __ldg(p);
+#else
+    uint32_t v; asm volatile("ld.global.nc.L1::evict_last.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
+#endif
+}
+
 // ----------------------------------------------------------------------------------------------
 // compile-time geometry
 // ----------------------------------------------------------------------------------------------
@@ -285,22 +350,22 @@ template <int LOG2N_, int LOG2PAD_, int CH_> struct Geom {
 template <int R>
 __device__ __forceinline__ void apply_twiddles(float2 (&v)[R], const float2 *plane, int plane_stride)
 {
-    const float2 w1 = __ldg(plane);
+    const float2 w1 = ldg_tab(plane);
     v[1] = cmul(v[1], w1);
     if constexpr (R >= 4) {
-        const float2 w2 = SBX_TW_LOADS >= 4 ? __ldg(plane + plane_stride) : csqr(w1);
+        const float2 w2 = SBX_TW_LOADS >= 4 ? ldg_tab(plane + plane_stride) : csqr(w1);
         const float2 w3 = cmul(w2, w1);
         v[2] = cmul(v[2], w2);
         v[3] = cmul(v[3], w3);
         if constexpr (R >= 8) {
-            const float2 w4 = SBX_TW_LOADS >= 2 ? __ldg(plane + 2 * plane_stride) : csqr(w2);
+            const float2 w4 = SBX_TW_LOADS >= 2 ? ldg_tab(plane + 2 * plane_stride) : csqr(w2);
             const float2 w5 = cmul(w4, w1), w6 = cmul(w4, w2), w7 = cmul(w4, w3);
             v[4] = cmul(v[4], w4);
             v[5] = cmul(v[5], w5);
             v[6] = cmul(v[6], w6);
             v[7] = cmul(v[7], w7);
             if constexpr (R >= 16) {
-                const float2 w8 = SBX_TW_LOADS >= 4 ? __ldg(plane + 3 * plane_stride) : csqr(w4);
+                const float2 w8 = SBX_TW_LOADS >= 4 ? ldg_tab(plane + 3 * plane_stride) : csqr(w4);
                 v[8] = cmul(v[8], w8);
                 v[9] = cmul(v[9], cmul(w8, w1));
                 v[10] = cmul(v[10], cmul(w8, w2));
@@ -343,16 +408,16 @@ __device__ __forceinline__ void pass_first(float2 *z, const KernelArgs &a, const
                     s.y = second_valid ? pb[n] : 0.0f;
                 }
             } else if constexpr (G::CH == 2) {
-                s = __ldg(reinterpret_cast<const float2 *>(pa) + n);
+                s = ldg_pcm2(reinterpret_cast<const float2 *>(pa) + n);
             } else {
-                s.x = __ldg(pa + n);
-                s.y = second_valid ? __ldg(pb + n) : 0.0f;
+                s.x = ldg_pcm(pa + n);
+                s.y = second_valid ? ldg_pcm(pb + n) : 0.0f;
             }
             if (q0 == 0) {
-                const float wn = __ldg(a.window + n);
+                const float wn = ldg_tab(a.window + n);
                 s.x *= wn;  s.y *= wn;                               // fft.rs:57-63 (complex * f32)
             } else {
-                s = cmul(s, __ldg(a.wtw + (q0 - 1) * G::N + n));     // window and W_M^(n q0) in one factor
+                s = cmul(s, ldg_tab(a.wtw + (q0 - 1) * G::N + n));   // window and W_M^(n q0) in one factor
             }
             v[r] = s;
         }
@@ -514,12 +579,12 @@ __device__ __forceinline__ int step_index(const float *ts, float p, float eps, f
 {
     const float t = fast_log2(p + eps) * ga + gb;
     int idx = (int)fminf(fmaxf(t, 0.0f), 255.0f);           // NaN -> 0
-    const float lo = __ldg(ts + idx), hi = __ldg(ts + idx + 1);   // ts[0] = -inf, ts[256] = +inf
+    const float lo = ldg_tab(ts + idx), hi = ldg_tab(ts + idx + 1);   // ts[0] = -inf, ts[256] = +inf
     if (p >= hi) {
-        do { ++idx; } while (idx < 255 && p >= __ldg(ts + idx + 1));
+        do { ++idx; } while (idx < 255 && p >= ldg_tab(ts + idx + 1));
         if (idx > 255) idx = 255;
     } else if (p < lo) {
-        do { --idx; } while (idx > 0 && p < __ldg(ts + idx));
+        do { --idx; } while (idx > 0 && p < ldg_tab(ts + idx));
     }
     return idx;
 }
@@ -567,7 +632,7 @@ __device__ __forceinline__ void resample_samples_impl(const float2 *mags, float2
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const uint32_t g = g0 + i * THREADS;
-            sp[i] = g < count ? __ldg(tab + g) : make_uint2(0u, 0u);
+            sp[i] = g < count ? ldg_tab(tab + g) : make_uint2(0u, 0u);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -605,24 +670,24 @@ __device__ __forceinline__ void colour_one_row(float ax, float ay, uint32_t n, u
         if (a.scheme == 0) {
             const int iA = step_index(thr, pA, a.db_eps, a.guess_a[0], a.guess_b[0]);
             const int iB = step_index(thr, pB, a.db_eps, a.guess_a[0], a.guess_b[0]);
-            outA[row] = __ldg(lut + iA);
-            if (second_valid) outB[row] = __ldg(lut + iB);
+            outA[row] = ldg_tab(lut + iA);
+            if (second_valid) outB[row] = ldg_tab(lut + iB);
         } else {
             // l == r: pan = l / (|l| + |r|) = 0.5 for finite l > 0, else NaN or negative -> index 0
             const uint32_t panA = (ax > 0.0f && ax < 3.0e38f) ? 128u : 0u, panB = (ay > 0.0f && ay < 3.0e38f) ? 128u : 0u;
-            outA[row] = (__ldg(lut + panA) & 0x00ffffffu) | ((uint32_t)step_index(thr_a, pA, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
+            outA[row] = (ldg_tab(lut + panA) & 0x00ffffffu) | ((uint32_t)step_index(thr_a, pA, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
             if (second_valid)
-                outB[row] = (__ldg(lut + panB) & 0x00ffffffu) | ((uint32_t)step_index(thr_a, pB, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
+                outB[row] = (ldg_tab(lut + panB) & 0x00ffffffu) | ((uint32_t)step_index(thr_a, pB, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
         }
     } else {
         const float p = __fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay));    // norm_sqr
         if (a.scheme == 0) {
-            outA[row] = __ldg(lut + step_index(thr, p, a.db_eps, a.guess_a[0], a.guess_b[0]));
+            outA[row] = ldg_tab(lut + step_index(thr, p, a.db_eps, a.guess_a[0], a.guess_b[0]));
         } else {
             const double pan = (double)ax / (double)__fadd_rn(fabsf(ax), fabsf(ay));
             const double v = floor(pan * 256.0);
             const uint32_t idx = !(v >= 0.0) ? 0u : (v > 255.0 ? 255u : (uint32_t)v);
-            outA[row] = (__ldg(lut + idx) & 0x00ffffffu) | ((uint32_t)step_index(thr_a, p, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
+            outA[row] = (ldg_tab(lut + idx) & 0x00ffffffu) | ((uint32_t)step_index(thr_a, p, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
         }
     }
 }
@@ -636,10 +701,9 @@ __device__ __forceinline__ void colour_rows(const float2 *scratch, const float *
     for (uint32_t py0 = ck.row_begin + threadIdx.x; py0 < ck.row_end; py0 += 2 * THREADS) {
         const uint32_t py1 = py0 + THREADS;
         const bool has1 = py1 < ck.row_end;
-        const uint4 r0 = __ldg(reinterpret_cast<const uint4 *>(a.rowmap) + py0);
-        const uint4 r1 = has1 ? __ldg(reinterpret_cast<const uint4 *>(a.rowmap) + py1) : make_uint4(0u, 0u, 0u, 0u);
-        const uint32_t n0 = r0.z, n1 = r1.z;                                 // n1 == 0 when the second row is absent
-        const float2 *m0 = scratch + r0.w, *m1 = scratch + r1.w;             // odd stride between rows
+        const uint32_t r0 = ldg_tab(a.rowinfo + py0), r1 = has1 ? ldg_tab(a.rowinfo + py1) : 0u;
+        const uint32_t n0 = r0 & 0xffffu, n1 = r1 & 0xffffu;                 // n1 == 0 when the second row is absent
+        const float2 *m0 = scratch + (r0 >> 16), *m1 = scratch + (r1 >> 16); // odd stride between rows
         float ax0 = 0.0f, ay0 = 0.0f, ax1 = 0.0f, ay1 = 0.0f;
         const uint32_t nmax = n0 > n1 ? n0 : n1;
         for (uint32_t s = 0; s < nmax; ++s) {

@@ -200,6 +200,7 @@ long long emu_batch(const sbx_config *cfg, const float *pcm, unsigned long long 
     a.wtw = reinterpret_cast<const float2 *>(t.wtw.data());
     a.twp = reinterpret_cast<const float2 *>(t.twp.data());
     a.rowmap = t.rowmap.data();
+    a.rowinfo = t.rowinfo.data();
     a.chunks = t.chunks.data();
     a.n_chunks = (uint32_t)t.chunks.size();
     a.samp = reinterpret_cast<const uint2 *>(t.samp.data());
