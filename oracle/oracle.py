@@ -77,6 +77,8 @@ def lib():
         L.orc_batch.restype = C.c_int64
         L.orc_batch.argtypes = [C.POINTER(OrcParams), f32p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64,
                                 u8p, u8p, f32p, C.c_int]
+        L.orc_colour_batch.restype = C.c_int
+        L.orc_colour_batch.argtypes = [C.POINTER(OrcParams), f32p, C.c_uint64, u8p, u8p, C.c_int]
         L.orc_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -199,3 +201,34 @@ def batch(p, pcm, channels, lut_rgb, want_rgba=True, want_mags=False, frame_lo=0
 
 def max_threads():
     return int(lib().orc_max_threads())
+
+
+def batch_pocketfft(p, pcm, channels, lut_rgb, threads=1, chunk_frames=2048):
+    """The same path with the FFT stage done by pocketfft (scipy.fft, complex64, `workers=threads`) instead of the
+    oracle's own radix-2 FFT: the stand-in for the reference's FFTW call in the timed CPU baseline (FFTW is not
+    in this image).  Window/pack, L/R split and scale are numpy restatements of fft.rs:57-63 and :81-95; the
+    resample + colour stage is the C oracle, threaded over frames.  Returns rgba (frames, H, 4)."""
+    import scipy.fft
+    pcm = np.ascontiguousarray(pcm, dtype=np.float32)
+    n, pad, hop = p.window_n, p.pad_factor, p.hop
+    m, k = n * pad, num_output_frequencies(n, pad)
+    total = num_frames(pcm.shape[0], n, hop)
+    w = hann(n)
+    scale = np.float32(2.0) / np.float32(n)
+    lut_rgb = np.ascontiguousarray(lut_rgb, dtype=np.uint8)
+    rgba = np.empty((total, p.rows_h, 4), np.uint8)
+    for f0 in range(0, total, chunk_frames):
+        f1 = min(total, f0 + chunk_frames)
+        idx = (np.arange(f0, f1) * hop)[:, None] + np.arange(n)[None, :]
+        if channels == 1:
+            s = pcm[idx] * w
+            z = s + 1j * s                                   # (s, s) duplication, audio_input_list_model.rs:67
+        else:
+            z = pcm[idx, 0] * w + 1j * (pcm[idx, 1] * w)
+        zf = scipy.fft.fft(z.astype(np.complex64), n=m, axis=1, workers=threads)
+        a, b = zf[:, 1:k + 1], np.conj(zf[:, m - 1:m - 1 - k:-1])
+        mags = np.empty((f1 - f0, k, 2), np.float32)
+        mags[..., 0] = np.abs(a + b) / np.float32(2.0) * scale
+        mags[..., 1] = np.abs(a - b) / np.float32(2.0) * scale
+        lib().orc_colour_batch(C.byref(p), _f32(mags), f1 - f0, _u8(lut_rgb), _u8(rgba[f0:f1]), threads)
+    return rgba

@@ -511,6 +511,38 @@ ORC_API int64_t orc_batch(const orc_params *p, const float *pcm, uint64_t n_samp
     return err ? -1 : (int64_t)count;
 }
 
+/* resample + colour stage alone over a batch of spectra (threads over frames): lets the timed CPU baseline
+ * use a faster FFT library for the FFT stage (pocketfft via scipy; FFTW itself is not in this image) */
+typedef struct { const orc_params *p; const float *mags; const uint8_t *lut; uint8_t *rgba; uint64_t lo, hi; } orc_cjob;
+static void *orc_colour_worker(void *arg)
+{
+    orc_cjob *j = (orc_cjob *)arg;
+    uint32_t k_out = orc_num_output_frequencies(j->p->window_n, j->p->pad_factor);
+    for (uint64_t f = j->lo; f < j->hi; ++f)
+        orc_column_from_magnitudes(j->p, j->mags + (size_t)f * 2 * k_out, j->lut, j->rgba + (size_t)f * 4 * j->p->rows_h);
+    return NULL;
+}
+ORC_API int orc_colour_batch(const orc_params *p, const float *mags_lr, uint64_t n_frames, const uint8_t *lut_rgb,
+                             uint8_t *rgba, int threads)
+{
+    if (threads < 1) threads = 1;
+    if ((uint64_t)threads > n_frames) threads = (int)(n_frames ? n_frames : 1);
+    orc_cjob *jobs = (orc_cjob *)calloc((size_t)threads, sizeof(orc_cjob));
+    pthread_t *tid = (pthread_t *)calloc((size_t)threads, sizeof(pthread_t));
+    char *started = (char *)calloc((size_t)threads, 1);
+    if (!jobs || !tid || !started) { free(jobs); free(tid); free(started); return -1; }
+    for (int t = 0; t < threads; ++t) {
+        jobs[t].p = p; jobs[t].mags = mags_lr; jobs[t].lut = lut_rgb; jobs[t].rgba = rgba;
+        jobs[t].lo = n_frames * (uint64_t)t / (uint64_t)threads;
+        jobs[t].hi = n_frames * (uint64_t)(t + 1) / (uint64_t)threads;
+        if (threads > 1 && pthread_create(&tid[t], NULL, orc_colour_worker, &jobs[t]) == 0) started[t] = 1;
+        else orc_colour_worker(&jobs[t]);
+    }
+    for (int t = 0; t < threads; ++t) if (started[t]) pthread_join(tid[t], NULL);
+    free(jobs); free(tid); free(started);
+    return 0;
+}
+
 ORC_API int orc_max_threads(void)
 {
     long n = sysconf(_SC_NPROCESSORS_ONLN);
