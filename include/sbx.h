@@ -152,6 +152,21 @@ SBX_API sbx_status sbx_process_batch_device(sbx_plan *plan, const float *d_pcm, 
 SBX_API sbx_status sbx_magnitudes_batch_device(sbx_plan *plan, const float *d_pcm, uint64_t n_samples,
                                                float *d_mags_lr, uint64_t capacity_frames, uint64_t *frames_out);
 
+/* ---- feed formats of the GL widget (GPUSpectrogram) -------------------------------------------- */
+
+/* Batched FastFourierTransform::process with the rows packed as IEEE binary16 pairs: the texel format of
+ * GPUSpectrogram's F16F16 ring texture (src/widgets/gpu_spectrogram.rs:218-227,255-275), so the rows can be
+ * uploaded without a CPU-side Vec<(f32,f32)>.  d_mags_f16 = frames x K x (L,R) uint16 (binary16 bits,
+ * round-to-nearest-even).  DEVICE pointers, asynchronous on the plan's stream. */
+SBX_API sbx_status sbx_magnitudes_batch_device_f16(sbx_plan *plan, const float *d_pcm, uint64_t n_samples,
+                                                   uint16_t *d_mags_f16, uint64_t capacity_frames, uint64_t *frames_out);
+
+/* ColorScheme::lookup_table(resolution) (src/colorscheme.rs:73-92): the resolution x resolution x (r,g,b,a) f32
+ * palette GPUSpectrogram uploads as a texture (gpu_spectrogram.rs:232-239).  table[i][j]: magnitude =
+ * i/(res-1), pan = 1 - j/(res-1); mono schemes: colour = gradient(magnitude)/256, alpha 1; stereo schemes:
+ * colour = gradient(pan)/256, alpha = magnitude.  Host memory, out has resolution*resolution*4 floats. */
+SBX_API sbx_status sbx_palette_table(const sbx_plan *plan, uint32_t resolution, float *out_rgba);
+
 /* ---- streams ------------------------------------------------------------------------------ */
 /* Use the caller's CUDA stream (a cudaStream_t passed as void*; NULL restores the plan's own). */
 SBX_API sbx_status sbx_set_stream(sbx_plan *plan, void *cuda_stream);

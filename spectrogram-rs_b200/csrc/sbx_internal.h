@@ -54,6 +54,8 @@ struct sbx_plan {
     float *d_mags1 = nullptr;           // K x 2
     uint8_t *d_col = nullptr;           // H x 4
 
+    float *d_f16_scratch = nullptr;     // f32 rows of one chunk, packed to binary16 by sbx_magnitudes_batch_device_f16
+
     // batch pipeline slots (host-pointer batch entry point)
     static constexpr int kSlots = 3;
     struct Slot {

@@ -1,6 +1,8 @@
 // sbx_plan.cu -- plan construction (host-computed tables), kernel dispatch and the C ABI of
 // include/sbx.h.  No CPU compute fallback exists: every transform entry point launches the sm_100a
 // kernels of stft_kernels.cuh or fails with SBX_ERR_CUDA / SBX_ERR_UNSUPPORTED.
+#include <cuda_fp16.h>
+
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -344,6 +346,15 @@ sbx_status launch_colourise(sbx_plan *p, const float *d_mags, uint64_t n_frames,
 
 }  // namespace sbx
 
+namespace sbx {
+// f32 (L,R) rows -> binary16 pairs (round-to-nearest-even), the texel format of the GL widget's F16F16 texture
+__global__ void __launch_bounds__(256) pack_f16_kernel(const float2 *__restrict__ in, __half2 *__restrict__ out, size_t count)
+{
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < count; i += (size_t)gridDim.x * 256)
+        out[i] = __float22half2_rn(in[i]);
+}
+}  // namespace sbx
+
 sbx::KernelArgs sbx_plan::base_args() const
 {
     sbx::KernelArgs a{};
@@ -446,7 +457,7 @@ SBX_API void sbx_plan_destroy(sbx_plan *p)
         cudaFree(s.d_rgba);
     }
     cudaFree(p->d_window); cudaFree(p->d_wtw); cudaFree(p->d_twp); cudaFree(p->d_rowmap); cudaFree(p->d_rowinfo); cudaFree(p->d_chunks);
-    cudaFree(p->d_samp); cudaFree(p->d_twm); cudaFree(p->d_pos_tab); cudaFree(p->d_twp_block); cudaFree(p->d_zbuf); cudaFree(p->d_magbuf);
+    cudaFree(p->d_samp); cudaFree(p->d_f16_scratch); cudaFree(p->d_twm); cudaFree(p->d_pos_tab); cudaFree(p->d_twp_block); cudaFree(p->d_zbuf); cudaFree(p->d_magbuf);
     cudaFree(p->d_thr); cudaFree(p->d_lut); cudaFree(p->d_frame); cudaFree(p->d_mags1); cudaFree(p->d_col);
     if (p->h_frame) cudaFreeHost(p->h_frame);
     if (p->h_col) cudaFreeHost(p->h_col);
@@ -691,6 +702,59 @@ SBX_API sbx_status sbx_magnitudes_batch_device(sbx_plan *p, const float *d_pcm, 
 {
     if (p && !d_mags_lr && sbx_num_frames(p, n_samples)) return fail(p, SBX_ERR_INVALID_ARGUMENT, "d_mags_lr is NULL");
     return batch_device(p, d_pcm, n_samples, nullptr, d_mags_lr, capacity_frames, frames_out);
+}
+
+SBX_API sbx_status sbx_magnitudes_batch_device_f16(sbx_plan *p, const float *d_pcm, uint64_t n_samples, uint16_t *d_mags_f16,
+                                                   uint64_t capacity_frames, uint64_t *frames_out)
+{
+    if (frames_out) *frames_out = 0;
+    if (!p) return SBX_ERR_INVALID_ARGUMENT;
+    const uint64_t frames = sbx_num_frames(p, n_samples);
+    if (frames == 0) return SBX_OK;
+    if (!d_pcm || !d_mags_f16) return fail(p, SBX_ERR_INVALID_ARGUMENT, "NULL device buffer");
+    if (frames > capacity_frames) return fail(p, SBX_ERR_BUFFER_TOO_SMALL, "output capacity is smaller than the frame count");
+    if ((reinterpret_cast<uintptr_t>(d_pcm) & 15u) != 0) return fail(p, SBX_ERR_INVALID_ARGUMENT, "d_pcm must be 16-byte aligned");
+    SBX_CUDA(p, cudaSetDevice(p->cfg.device));
+    // f32 rows go through a chunk-sized scratch (even frame count: mono pairs), then are packed
+    uint64_t chunk = ((uint64_t)64 << 20) / ((uint64_t)p->k_out * 8);
+    chunk = chunk < 2 ? 2 : (chunk & ~1ull);
+    if (!p->d_f16_scratch) {
+        SBX_CUDA(p, cudaMalloc(&p->d_f16_scratch, (size_t)chunk * p->k_out * 8));
+    }
+    for (uint64_t f0 = 0; f0 < frames; f0 += chunk) {
+        const uint64_t nf = frames - f0 < chunk ? frames - f0 : chunk;
+        sbx_status st = sbx::launch_fused(p, (int)p->channels, d_pcm + (size_t)f0 * p->hop * p->channels, nf, nullptr,
+                                          p->d_f16_scratch, p->stream);
+        if (st != SBX_OK) return st;
+        const size_t count = (size_t)nf * p->k_out;
+        const unsigned blocks = (unsigned)((count + 255) / 256 > 148 * 16 ? 148 * 16 : (count + 255) / 256);
+        sbx::pack_f16_kernel<<<blocks, 256, 0, p->stream>>>(reinterpret_cast<const float2 *>(p->d_f16_scratch),
+                                                           reinterpret_cast<__half2 *>(d_mags_f16) + (size_t)f0 * p->k_out, count);
+        SBX_CUDA(p, cudaGetLastError());
+        p->launches += 1;
+    }
+    if (frames_out) *frames_out = frames;
+    return SBX_OK;
+}
+
+SBX_API sbx_status sbx_palette_table(const sbx_plan *p, uint32_t resolution, float *out)
+{
+    if (!p || !out || resolution < 2) return SBX_ERR_INVALID_ARGUMENT;
+    // gradient.eval_continuous(t) for the 256-entry ramps: lut[clamp(floor(t * 256), 0, 255)]
+    auto eval = [p](double t, float rgb[3]) {
+        const double v = std::floor(t * 256.0);
+        const int idx = !(v >= 0.0) ? 0 : (v > 255.0 ? 255 : (int)v);
+        for (int c = 0; c < 3; ++c) rgb[c] = (float)p->cfg.lut_rgb[3 * idx + c] / 256.0f;      // colorscheme.rs:83,86
+    };
+    for (uint32_t i = 0; i < resolution; ++i)
+        for (uint32_t j = 0; j < resolution; ++j) {
+            const float magnitude = (float)i / (float)(resolution - 1);                          // :79
+            const float pan = 1.0f - ((float)j / (float)(resolution - 1));                       // :80
+            float *o = out + ((size_t)i * resolution + j) * 4;
+            if (p->cfg.scheme == SBX_SCHEME_STEREO) { eval((double)pan, o); o[3] = magnitude; }
+            else { eval((double)magnitude, o); o[3] = 1.0f; }
+        }
+    return SBX_OK;
 }
 
 // ---- batch, host buffers: chunked, H2D / kernel / D2H overlapped over kSlots streams -------------

@@ -153,6 +153,18 @@ class Plan:
         self._check(self._lib.sbx_magnitudes_batch_device(self._h, _ptr(d_pcm), n_samples, _ptr(d_mags), capacity_frames, C.byref(got)))
         return int(got.value)
 
+    def magnitudes_batch_device_f16(self, d_pcm, n_samples, d_mags_f16, capacity_frames):
+        """Rows as binary16 (L,R) pairs: the GL widget's F16F16 texel format (gpu_spectrogram.rs:218-227)."""
+        got = C.c_uint64()
+        self._check(self._lib.sbx_magnitudes_batch_device_f16(self._h, _ptr(d_pcm), n_samples, _ptr(d_mags_f16), capacity_frames, C.byref(got)))
+        return int(got.value)
+
+    def palette_table(self, resolution=32):
+        """ColorScheme::lookup_table(resolution) (colorscheme.rs:73-92): (res, res, 4) float32."""
+        out = np.empty((resolution, resolution, 4), np.float32)
+        self._check(self._lib.sbx_palette_table(self._h, resolution, out.ctypes.data))
+        return out
+
     def set_stream(self, cuda_stream):
         self._check(self._lib.sbx_set_stream(self._h, cuda_stream))
 

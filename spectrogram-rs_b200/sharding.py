@@ -28,12 +28,18 @@ class TimeBlock:
         return max(0, self.sample_hi - self.sample_lo)
 
 
-def time_blocks(n_samples, window_n, hop, world):
-    """Rank g of `world` owns frames [F*g/world, F*(g+1)/world) of the F frames of the recording."""
+def time_blocks(n_samples, window_n, hop, world, frame_align=1):
+    """Rank g of `world` owns frames [F*g/world, F*(g+1)/world) of the F frames of the recording.
+
+    `frame_align`: block boundaries are rounded down to a multiple of it.  Mono plans transform frames in pairs
+    (frame 2c and 2c+1 share one complex FFT), so use frame_align=2 there: a shard that started on an odd frame
+    would put every frame in the other slot of its pair, which is the same column only up to the last bit of
+    the FFT.  With aligned boundaries shard == unsharded byte for byte."""
     total = num_frames(n_samples, window_n, hop)
     blocks = []
     for g in range(world):
-        lo, hi = total * g // world, total * (g + 1) // world
+        lo = (total * g // world) // frame_align * frame_align
+        hi = total if g == world - 1 else (total * (g + 1) // world) // frame_align * frame_align
         s_lo = lo * hop
         s_hi = (hi - 1) * hop + window_n if hi > lo else s_lo
         blocks.append(TimeBlock(g, lo, hi, s_lo, s_hi))

@@ -179,9 +179,8 @@ def test_time_block_sharding_is_exact(sbx, magma):
         whole = plan.process_batch(x)
         total = whole.shape[0]
         parts = []
-        for g in range(3):
-            lo, hi = total * g // 3, total * (g + 1) // 3
-            parts.append(plan.process_batch(x[lo * hop:(hi - 1) * hop + n]))
+        for b in sbx.sharding.time_blocks(ns, n, hop, 3, frame_align=2):      # mono: pair-aligned boundaries
+            parts.append(plan.process_batch(x[b.sample_lo:b.sample_hi]))
         assert np.array_equal(np.concatenate(parts), whole)
 
 
@@ -283,3 +282,31 @@ def test_persistent_tma_staged_kernel(sbx, viridis, n, pad, ch, hop, frames):
         # the same leading frames through a short batch (one CTA per unit, global loads)
         short = plan.process_batch(pcm[: n + hop * 9])
         assert np.array_equal(short, g_rgba[:10])
+
+
+def test_gl_widget_feed_formats(sbx, magma):
+    """next-4: F16F16 rows (bit-exact round-to-nearest-even of the f32 rows) and the 32x32 palette table of
+    ColorScheme::lookup_table (colorscheme.rs:73-92)."""
+    import torch
+    n, hop, frames = 2048, 512, 9
+    ns = n + hop * (frames - 1)
+    pcm = signals.stereo_loopback(ns)
+    with sbx.Plan(window_n=n, hop=hop, rows_h=256, channels=2, lut=magma) as plan:
+        d_pcm = torch.from_numpy(pcm).cuda()
+        d32 = torch.zeros((frames, plan.k, 2), dtype=torch.float32, device="cuda")
+        d16 = torch.zeros((frames, plan.k, 2), dtype=torch.float16, device="cuda")
+        assert plan.magnitudes_batch_device(d_pcm, ns, d32, frames) == frames
+        assert plan.magnitudes_batch_device_f16(d_pcm, ns, d16, frames) == frames
+        plan.synchronize()
+        assert np.array_equal(d16.cpu().numpy().view(np.uint16), d32.cpu().numpy().astype(np.float16).view(np.uint16))
+        tab = plan.palette_table(32)
+        assert tab.shape == (32, 32, 4) and np.all(tab[..., 3] == 1.0)
+        for i in (0, 7, 31):
+            t = np.float32(i) / np.float32(31)
+            idx = min(255, int(np.floor(float(t) * 256.0)))
+            assert np.allclose(tab[i, :, :3], magma[idx] / 256.0)
+    with sbx.Plan(window_n=n, hop=hop, rows_h=256, channels=2, lut=magma, scheme=1) as plan:
+        tab = plan.palette_table(32)
+        assert np.allclose(tab[:, 5, 3], np.arange(32, dtype=np.float32) / 31)            # alpha = magnitude
+        pan = np.float32(1.0) - np.float32(5) / np.float32(31)
+        assert np.allclose(tab[3, 5, :3], magma[min(255, int(np.floor(float(pan) * 256.0)))] / 256.0)

@@ -104,6 +104,10 @@ def test_time_blocks_partition_frames_exactly(sbx):
                 if b.frames:
                     assert b.sample_lo == b.frame_lo * hop and b.sample_hi == (b.frame_hi - 1) * hop + n <= S
                     assert sh.num_frames(b.samples, n, hop) == b.frames          # halo = N - hop samples
+    for world in (2, 3, 8):                                             # mono plans: pair-aligned boundaries
+        blocks = sh.time_blocks(2880000, 4096, 512, world, frame_align=2)
+        assert all(b.frame_lo % 2 == 0 for b in blocks) and blocks[-1].frame_hi == 5618
+        assert sum(b.frames for b in blocks) == 5618
     assert sh.channel_blocks(64, 8) == [(8 * g, 8 * g + 8) for g in range(8)]
     assert sh.channel_blocks(3, 2) == [(0, 1), (1, 3)]
 
