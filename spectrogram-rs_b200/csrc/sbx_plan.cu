@@ -204,7 +204,8 @@ cudaError_t launch_large_one(const LargeArgs &la, bool want_rgba, cudaStream_t s
     large_first_kernel<LOG2N, LOG2PAD, CH><<<units * GL::PAD * (LARGE_BLOCK / LARGE_THREADS), LARGE_THREADS, 0, stream>>>(la);
     large_block_kernel<<<units * (GL::M / LARGE_BLOCK), LARGE_THREADS, 0, stream>>>(la);
     large_split_kernel<LOG2N, LOG2PAD, CH><<<units * ((GL::M / 2) / LARGE_THREADS), LARGE_THREADS, 0, stream>>>(la);
-    if (want_rgba) large_colour_kernel<CH == 1><<<units, LARGE_THREADS, 0, stream>>>(la, la.magbuf, (size_t)GL::M / 2);
+    if (want_rgba)
+        large_colour_kernel<CH == 1><<<dim3(units, la.k.n_chunks), LARGE_THREADS, 0, stream>>>(la, la.magbuf, (size_t)GL::M / 2);
     return cudaGetLastError();
 }
 
@@ -235,9 +236,13 @@ sbx_status launch_large(sbx_plan *p, int channels, const float *d_pcm, uint64_t 
 {
     if (n_frames == 0) return SBX_OK;
     if (p->large_units == 0) {
-        // scratch: (M + M/2) float2 per unit, about 512 MiB in total, at least one unit
+        // scratch: (M + M/2) float2 per unit, SBX_LARGE_SCRATCH_MB (default 512) MiB per chunk of units.  Measured
+        // on a B200 (cfg5, N = 65536): 512 MiB 0.68 M frames/s, 96 MiB (L2-resident) 0.57, 48 MiB 0.53 -- bigger
+        // grids beat L2 residency of the hand-off between the four kernels.
         const size_t per_unit = (size_t)p->m * 12;
-        uint64_t units = ((uint64_t)512 << 20) / per_unit;
+        const char *env = std::getenv("SBX_LARGE_SCRATCH_MB");
+        const uint64_t budget_mb = env && std::atoi(env) > 0 ? (uint64_t)std::atoi(env) : 512u;
+        uint64_t units = (budget_mb << 20) / per_unit;
         units = units < 1 ? 1 : (units > 8192 ? 8192 : units);
         cudaError_t e = cudaMalloc(&p->d_zbuf, units * (size_t)p->m * sizeof(float2));
         if (e == cudaSuccess) e = cudaMalloc(&p->d_magbuf, units * (size_t)(p->m / 2) * sizeof(float2));
@@ -317,7 +322,8 @@ sbx_status launch_colourise(sbx_plan *p, const float *d_mags, uint64_t n_frames,
         la.k.n_frames = n_frames;
         la.units = (uint32_t)n_frames;
         // magnitudes are indexed by bin kk = j + 1: shift the caller's K x (L,R) rows by one entry
-        large_colour_kernel<false><<<(unsigned)n_frames, LARGE_THREADS, 0, stream>>>(
+        if (la.k.n_chunks > 65535u) return fail(p, SBX_ERR_UNSUPPORTED, "too many row chunks");
+        large_colour_kernel<false><<<dim3((unsigned)n_frames, la.k.n_chunks), LARGE_THREADS, 0, stream>>>(
             la, reinterpret_cast<const float2 *>(d_mags) - 1, (size_t)p->k_out);
         cudaError_t el = cudaGetLastError();
         if (el != cudaSuccess) return cuda_fail(p, el, "large_colour_kernel launch");

@@ -161,7 +161,8 @@ __global__ void __launch_bounds__(LARGE_THREADS) large_split_kernel(const LargeA
     large_split<LOG2N, LOG2PAD, CH>(la, blockIdx.x);
 }
 
-// grid = units; mags by bin kk from global memory (magbuf, or a caller's K x (L,R) array shifted by one)
+// grid = (units, row chunks): row chunks are independent, so each CTA resamples and colours one chunk of one
+// unit; mags by bin kk from global memory (magbuf, or a caller's K x (L,R) array shifted by one)
 template <bool PAIR>
 __global__ void __launch_bounds__(LARGE_THREADS) large_colour_kernel(const LargeArgs la, const float2 *mags_base, size_t mags_stride)
 {
@@ -170,14 +171,11 @@ __global__ void __launch_bounds__(LARGE_THREADS) large_colour_kernel(const Large
     const float2 *mags = mags_base + (size_t)blockIdx.x * mags_stride;
     const unsigned long long frame0 = la.frame_base + (unsigned long long)blockIdx.x * (PAIR ? 2 : 1);
     const bool second_valid = PAIR && frame0 + 1 < a.n_frames;
-    for (uint32_t c = 0; c < a.n_chunks; ++c) {
-        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.chunks) + c);
-        const RowChunk ck = {raw.x, raw.y, raw.z, raw.w};
-        if (c != 0) __syncthreads();
-        resample_samples<LARGE_THREADS>(mags, scratch, a, ck);
-        __syncthreads();
-        colour_rows<PAIR, LARGE_THREADS>(scratch, a.thr, a.lut, a, ck, frame0, second_valid);
-    }
+    const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.chunks) + blockIdx.y);
+    const RowChunk ck = {raw.x, raw.y, raw.z, raw.w};
+    resample_samples<LARGE_THREADS>(mags, scratch, a, ck);
+    __syncthreads();
+    colour_rows<PAIR, LARGE_THREADS>(scratch, a.thr, a.lut, a, ck, frame0, second_valid);
 }
 #endif  // SBX_EMU
 
