@@ -42,6 +42,29 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Libraries print to stdout on their own (NCCL's "NCCL version ..." banner, for one).  The contract is ONE
+    JSON line on stdout, so everything written to fd 1 from here on goes to stderr and only emit() writes to
+    the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -160,7 +183,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def main():
@@ -179,6 +202,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    claim_stdout()
 
     if args.impl == "reference":
         run_reference(args, rank, world)
@@ -312,7 +336,7 @@ def main():
         rate, cores, sample = cpu_reference_rate()
         out["cpu_baseline"] = {"value": rate, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
