@@ -310,3 +310,80 @@ def test_gl_widget_feed_formats(sbx, magma):
         assert np.allclose(tab[:, 5, 3], np.arange(32, dtype=np.float32) / 31)            # alpha = magnitude
         pan = np.float32(1.0) - np.float32(5) / np.float32(31)
         assert np.allclose(tab[3, 5, :3], magma[min(255, int(np.floor(float(pan) * 256.0)))] / 256.0)
+
+
+def test_reference_interface_mirror(sbx, magma):
+    """The reference's own call pattern through the Python mirror: FastFourierTransform::new(sr, 0.05) (N = 2400,
+    the mixed-radix path), AudioStreamTransform over a HeapRb ring with stride 2.5 s / 2048, and the column
+    loop of SimpleSpectrogram::snapshot with its scrolling offset."""
+    sr = 48000.0
+    fft = sbx.FastFourierTransform(sr, 0.05)                        # gpu_spectrogram.rs:321-324
+    assert fft.num_input_samples() == 2400 and fft.num_output_frequencies() == 2399 and fft.sample_rate() == sr
+    lr = signals.stereo_loopback(4000, sr)
+    assert fft.process(lr[:2399]) is None                           # fft.rs:72
+    m = fft.process(lr)
+    o = oracle.frame_magnitudes(lr, 2400, 2)
+    assert m.shape == (2399, 2) and np.abs(m - o).max() <= MAG_TOL * np.abs(o).max()
+    m_iter = fft.process((float(a), float(b)) for a, b in lr[:2400])          # any iterable of (l, r)
+    assert np.array_equal(m_iter, m)
+
+    ring = sbx.HeapRb(4096)                                         # audio_input_list_model.rs:30
+    assert ring.push_iter(map(tuple, lr)) == 4000
+    stream = sbx.AudioStreamTransform(ring, fft, 2.5 / 2048.0)      # gpu_spectrogram.rs:21-23 -> hop 58
+    outs = list(stream.process())
+    assert len(outs) == oracle.num_frames(4000, 2400, 58) == 28
+    assert np.array_equal(outs[3], fft.process(lr[3 * 58:3 * 58 + 2400]))
+    assert len(ring) == 4000 - 29 * 58                              # 28 frames + the failing attempt
+
+    ring2 = sbx.HeapRb(4096)
+    ring2.push_mono(signals.white_noise(3000))                      # mono device: (s, s) duplication
+    cols = sbx.SpectrogramColumns(ring2, sample_rate=sr, width=16, height=128)   # period 0.05 s, stride 2/1024 s -> hop 93
+    assert cols.plan.n == 2400 and cols.plan.hop == 93
+    drawn = cols.snapshot()
+    assert drawn == oracle.num_frames(3000, 2400, 93) == 7 and cols.offset == 7
+    assert cols.buffer[:, :7, 3].min() == 255 and cols.buffer[:, 7:, 3].max() == 0
+    first = cols.plan.process_column(np.stack([signals.white_noise(3000)[:2400]] * 2, 1))
+    assert np.array_equal(cols.buffer[:, 0, :], first)
+    cols.set_sample_rate(44100)                                     # re-plan: N = (0.05 * 44100) as usize = 2205
+    assert cols.plan.n == 2205
+
+
+def test_live_mono_push_and_wraparound(sbx, magma):
+    """Mono pushes are duplicated to (s, s); the ring wraps; windows straddling the wrap are linearised."""
+    n, hop = 1024, 256
+    x = signals.white_noise(n + hop * 40)
+    with sbx.Plan(window_n=n, hop=hop, rows_h=256, channels=2, lut=magma) as plan:
+        live = plan.live(1500)                                      # not a multiple of anything
+        want = plan.process_batch(np.stack([x, x], 1))
+        # model of the reference cursor (audio_transform.rs:37-41): transform the first N buffered samples without
+        # consuming them, then skip(hop) -- also after the failing attempt, which discards up to hop samples
+        model, n_cols = [], 0
+        for pos in range(0, len(x), 700):                           # a callback delivering 700 samples at a time
+            chunk = x[pos:pos + 700]
+            room = 1500 - len(model)
+            assert live.push(chunk, channels=1) == min(len(chunk), room)
+            model.extend(chunk[:room].tolist())
+            for _ in range(64):                                     # bounded drain; a failing pop ends the tick
+                col = live.pop_column()
+                window = np.asarray(model[:n], np.float32)
+                del model[:min(hop, len(model))]
+                if col is None:
+                    assert len(window) < n
+                    break
+                assert len(window) == n
+                assert np.array_equal(col, plan.process_column(np.stack([window, window], 1)))
+                n_cols += 1
+            assert live.buffered() == len(model)
+        assert n_cols >= 10, n_cols
+        live.close()
+    # a stream that always has a full window never skips and reproduces the batch exactly
+    with sbx.Plan(window_n=n, hop=hop, rows_h=256, channels=2, lut=magma) as plan:
+        live = plan.live(1500)
+        want = plan.process_batch(np.stack([x, x], 1))
+        live.push(x[:n], channels=1)
+        pos = n
+        for f in range(want.shape[0]):
+            col = live.pop_column()
+            assert col is not None and np.array_equal(col, want[f]), f
+            pos += live.push(x[pos:pos + hop], channels=1)
+        live.close()
