@@ -322,7 +322,9 @@ def main():
                      "fp32_tflops_5MlogM": value / world * FLOPS_FRAME / 1e12,
                      "note": "path is FP32/shared-memory bound at this hop (44-87 flop/B vs a 12 flop/B ridge, SURVEY.md D6)"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": ns_e * 4, "d2h_bytes_per_step": Fe * ROWS * 4,
-                "frames_per_gpu_per_step": Fe, "steps": e2e_steps, "api": "sbx_process_batch (host pointers, pinned)"},
+                "frames_per_gpu_per_step": Fe, "steps": e2e_steps, "api": "sbx_process_batch (host pointers, pinned)",
+                "d2h_gbs_per_gpu": e2e_value / world * ROWS * 4 / 1e9, "h2d_gbs_per_gpu": e2e_value / world * HOP * 4 / 1e9,
+                "note": "bound by the PCIe D2H of the RGBA output (4 KB per frame): chunked, three streams, H2D/kernel/D2H overlapped"},
         "gpu_launches": launches * world,
         "clocks": clocks,
     }
