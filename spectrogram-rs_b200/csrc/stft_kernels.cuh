@@ -70,6 +70,9 @@ struct KernelArgs {
 #ifndef SBX_EPT_LOG2
 #define SBX_EPT_LOG2 4           // log2 of the transform points each thread owns per pass (4: M/16 threads, 5: M/32)
 #endif
+#ifndef SBX_MIN_CTAS_256
+#define SBX_MIN_CTAS_256 5       // resident-CTA target of the 256-thread kernels (M = 4096): 5 -> 48 registers, no spills; measured cfg2 53.7 / 55.3 / 50.7 M frames/s at 4 / 5 / 6
+#endif
 #ifndef SBX_MAX_THREADS
 #define SBX_MAX_THREADS 1024     // CTA size cap: M = 16384 runs one 1024-thread CTA per SM (measured +7..12 % over 512)
 #endif
@@ -269,6 +272,10 @@ template <int LOG2N_, int LOG2PAD_, int CH_> struct Geom {
     static constexpr int REM = LOG2N & 3;                  // first pass radix 2^REM when REM != 0
     static constexpr int NPASS = LOG2N / 4 + (REM ? 1 : 0);
     static constexpr int THREADS = (M >> SBX_EPT_LOG2) < 64 ? 64 : ((M >> SBX_EPT_LOG2) > SBX_MAX_THREADS ? SBX_MAX_THREADS : (M >> SBX_EPT_LOG2));
+    // register budget: 64 per thread (THREADS * MIN_CTAS = 1024).  Without the second launch bound ptxas aims
+    // for three resident 512-thread CTAs at cfg1, caps the kernel at 40 registers and spills (measured: 49 vs
+    // 52.5 M frames/s); the kernel needs 79 unconstrained and fits 64 without spilling.
+    static constexpr int MIN_CTAS = THREADS >= 1024 ? 1 : (THREADS == 256 ? SBX_MIN_CTAS_256 : 1024 / THREADS);
     static constexpr int FRAMES_PER_CTA = CH == 1 ? 2 : 1;
     static constexpr int SMEM_BYTES = M * 8;
     static __host__ __device__ constexpr int log2r(int p) { return (REM != 0 && p == 0) ? REM : 4; }
@@ -390,40 +397,55 @@ __device__ __forceinline__ void apply_twiddles(float2 (&v)[R], const float2 *pla
 // STAGED = false: PCM is read from global memory (pa = this unit's first sample).
 // STAGED = true : `pa` points at the unit's sample span in SHARED memory, put there by a bulk async
 //                 copy (the persistent kernel); frame B of a mono pair is the same span shifted by hop.
+// The R inputs of a butterfly are S samples apart: all addresses are one base pointer plus compile-time
+// offsets.  Q0ZERO selects the window-only (q0 = 0) or window * W_M^(n q0) (q0 > 0) factor; q0 is
+// warp-uniform, so the caller branches once per butterfly instead of predicating every load.
+template <class G, bool STAGED, bool Q0ZERO>
+__device__ __forceinline__ void first_inputs(float2 (&v)[1 << G::log2r(0)], const KernelArgs &a, const float *pa_lo,
+                                             const float *pb_lo, bool second_valid, int q0, int lo)
+{
+    constexpr int R = 1 << G::log2r(0), S = 1 << G::log2stride(0);
+    const float *win_lo = a.window + lo;
+    const float2 *wtw_lo = a.wtw + (Q0ZERO ? 0 : (q0 - 1) * G::N) + lo;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        float2 s;
+        if constexpr (STAGED) {
+            if constexpr (G::CH == 2) {
+                s = reinterpret_cast<const float2 *>(pa_lo)[r * S];
+            } else {
+                s.x = pa_lo[r * S];
+                s.y = second_valid ? pb_lo[r * S] : 0.0f;
+            }
+        } else if constexpr (G::CH == 2) {
+            s = ldg_pcm2(reinterpret_cast<const float2 *>(pa_lo) + r * S);
+        } else {
+            s.x = ldg_pcm(pa_lo + r * S);
+            s.y = second_valid ? ldg_pcm(pb_lo + r * S) : 0.0f;
+        }
+        if constexpr (Q0ZERO) {
+            const float wn = ldg_tab(win_lo + r * S);
+            s.x *= wn;  s.y *= wn;                                   // fft.rs:57-63 (complex * f32)
+        } else {
+            s = cmul(s, ldg_tab(wtw_lo + r * S));                    // window and W_M^(n q0) in one factor
+        }
+        v[r] = s;
+    }
+}
+
 template <class G, bool STAGED = false>
 __device__ __forceinline__ void pass_first(float2 *z, const KernelArgs &a, const float *pa, bool second_valid)
 {
     constexpr int LR = G::log2r(0), R = 1 << LR, LS = G::log2stride(0), S = 1 << LS;
     constexpr int PER_SUB = G::N / R, COUNT = G::PAD * PER_SUB;
-    const float *pb = pa + a.hop;                                    // mono: the next frame
     for (int w = threadIdx.x; w < COUNT; w += G::THREADS) {
         const int q0 = w / PER_SUB, lo = w % PER_SUB;                // q0 is warp-uniform (PER_SUB % 32 == 0)
+        // CH == 2: pa addresses interleaved (l,r) pairs; frame B of a mono pair starts hop samples later
+        const float *pa_lo = pa + (size_t)lo * G::CH;
+        const float *pb_lo = pa_lo + a.hop;
         float2 v[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int n = lo + r * S;
-            float2 s;
-            if constexpr (STAGED) {
-                if constexpr (G::CH == 2) {
-                    s = reinterpret_cast<const float2 *>(pa)[n];
-                } else {
-                    s.x = pa[n];
-                    s.y = second_valid ? pb[n] : 0.0f;
-                }
-            } else if constexpr (G::CH == 2) {
-                s = ldg_pcm2(reinterpret_cast<const float2 *>(pa) + n);
-            } else {
-                s.x = ldg_pcm(pa + n);
-                s.y = second_valid ? ldg_pcm(pb + n) : 0.0f;
-            }
-            if (q0 == 0) {
-                const float wn = ldg_tab(a.window + n);
-                s.x *= wn;  s.y *= wn;                               // fft.rs:57-63 (complex * f32)
-            } else {
-                s = cmul(s, ldg_tab(a.wtw + (q0 - 1) * G::N + n));   // window and W_M^(n q0) in one factor
-            }
-            v[r] = s;
-        }
+        if (q0 == 0) first_inputs<G, STAGED, true>(v, a, pa_lo, pb_lo, second_valid, q0, lo);
+        else first_inputs<G, STAGED, false>(v, a, pa_lo, pb_lo, second_valid, q0, lo);
         Butterfly<R>::run(v);
         if constexpr (G::NPASS > 1) apply_twiddles<R>(v, a.twp + lo, S);   // W_N^(lo q)
         const int bx = G::zsw((q0 << G::LOG2N) + lo);
@@ -767,7 +789,7 @@ __device__ __forceinline__ void frame_tail(float2 *z, const KernelArgs &a, unsig
 }
 
 template <class G>
-__global__ void __launch_bounds__(G::THREADS) fused_frames_kernel(const KernelArgs a)
+__global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) fused_frames_kernel(const KernelArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *z = reinterpret_cast<float2 *>(smem_raw);
@@ -811,7 +833,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
 // stage buffer by one elected thread as soon as pass 0 of unit u has consumed it, so the copy overlaps
 // passes 1.., the split and the resample of unit u.  Requires 16-byte aligned spans (checked by the host).
 template <class G>
-__global__ void __launch_bounds__(G::THREADS) fused_frames_persistent_kernel(const KernelArgs a, uint32_t n_units)
+__global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) fused_frames_persistent_kernel(const KernelArgs a, uint32_t n_units)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *z = reinterpret_cast<float2 *>(smem_raw);
