@@ -100,7 +100,7 @@ struct HostTables {
     std::vector<RowChunk> chunks;       // rows grouped so that a chunk's samples fit the kernel's scratch area
     std::vector<uint32_t> samp;         // per (row, sample): {floor(x), weight bits}, see KernelArgs::samp
     bool taps_clamped = false;          // some cubic tap falls outside [0, K-1]
-    std::vector<float> thr;             // [2][THR_STRIDE] with sentinels
+    std::vector<float> thr;             // [2][256] pairs (ts[i], ts[i+1]), see step_index
     std::vector<float> thr_raw;         // [2][256] the bare thresholds (introspection)
     float guess_a[2], guess_b[2];
     uint32_t lut[256];
@@ -272,12 +272,15 @@ inline void build(const sbx_config &cfg, HostTables &t)
     const sbx_config c = cfg;
     step_thresholds([&c](float pw) { return colour_step(pw, c); }, t.thr_raw.data());
     step_thresholds([&c](float pw) { return alpha_step(pw, c); }, t.thr_raw.data() + 256);
-    // device layout per set: [-inf, thr[0..254], +inf, pad...]
+    // device layout per set: 256 pairs (ts[i], ts[i+1]) of ts = [-inf, thr[0..254], +inf]
     t.thr.assign(2 * THR_STRIDE, std::numeric_limits<float>::infinity());
     for (int set = 0; set < 2; ++set) {
+        float ts[257];
+        ts[0] = -std::numeric_limits<float>::infinity();
+        for (int i = 0; i < 255; ++i) ts[1 + i] = t.thr_raw[set * 256 + i];
+        ts[256] = std::numeric_limits<float>::infinity();
         float *dst = t.thr.data() + set * THR_STRIDE;
-        dst[0] = -std::numeric_limits<float>::infinity();
-        for (int i = 0; i < 255; ++i) dst[1 + i] = t.thr_raw[set * 256 + i];
+        for (int i = 0; i < 256; ++i) { dst[2 * i] = ts[i]; dst[2 * i + 1] = ts[i + 1]; }
     }
     // guess of the step: t = (10 log10(x) - db_min) / (db_max - db_min) * levels = log2(x) * a + b
     const double range = (double)cfg.db_max - (double)cfg.db_min;

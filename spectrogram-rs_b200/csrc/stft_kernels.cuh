@@ -55,7 +55,7 @@ struct KernelArgs {
     const uint2 *samp;           // per (row, sample): {floor(x) | scratch slot << 17, weight as f32 bits},
                                  //   x = index_of(f0 + s*step); weight = x - floor(x) (CUBIC) or
                                  //   (1 - cos(frac*pi))/2 (COSINE, host libm)
-    const float *thr;            // [2][264] step thresholds with sentinels: colour index, alpha
+    const float *thr;            // [2][256] pairs (ts[i], ts[i+1]) of step thresholds with sentinels: colour index, alpha
     const uint32_t *lut;         // [256] packed r | g<<8 | b<<16 | 255<<24
     unsigned long long n_frames;
     uint32_t hop, rows, k_out, n_chunks;
@@ -80,7 +80,7 @@ constexpr int TW_PLANES = 4;     // twiddle planes stored per pass: W^(1,2,4,8 *
 #ifndef SBX_TW_LOADS
 #define SBX_TW_LOADS 2           // planes actually loaded per butterfly (1: W^lo; 2: + W^4lo; 4: all); rest by products
 #endif
-constexpr int THR_STRIDE = 264;  // floats per threshold set: [-inf, thr[0..254], +inf, pad]
+constexpr int THR_STRIDE = 512;  // floats per threshold set: 256 pairs (ts[i], ts[i+1]), ts = [-inf, thr[0..254], +inf]
 
 // ----------------------------------------------------------------------------------------------
 // complex helpers and small DFT butterflies (forward, exp(-i...))
@@ -597,19 +597,21 @@ __device__ __forceinline__ float cubic1(float y0, float y1, float y2, float y3, 
     return __fadd_rn(__fadd_rn(__fmul_rn(a0, mu3), __fmul_rn(a1, mu2)), __fadd_rn(__fmul_rn(a2, mu), y1));
 }
 
-// Step function of p: the number of thresholds <= p.  ts = [-inf, thr[0..254], +inf]; the guess
-// log2(p + eps) * ga + gb is the same dB chain evaluated with the fast log, and is corrected against
-// the exact host-computed thresholds, so the result is exact whatever the error of the guess.
+// Step function of p: the number of thresholds <= p.  ts = [-inf, thr[0..254], +inf], stored as the pairs
+// tp[i] = (ts[i], ts[i+1]) so that one 8-byte load brackets the guess.  The guess log2(p + eps) * ga + gb is the
+// same dB chain evaluated with the fast log, and is corrected against the exact host-computed thresholds, so
+// the result is exact whatever the error of the guess.
 __device__ __forceinline__ int step_index(const float *ts, float p, float eps, float ga, float gb)
 {
+    const float2 *tp = reinterpret_cast<const float2 *>(ts);
     const float t = fast_log2(p + eps) * ga + gb;
     int idx = (int)fminf(fmaxf(t, 0.0f), 255.0f);           // NaN -> 0
-    const float lo = ldg_tab(ts + idx), hi = ldg_tab(ts + idx + 1);   // ts[0] = -inf, ts[256] = +inf
-    if (p >= hi) {
-        do { ++idx; } while (idx < 255 && p >= ldg_tab(ts + idx + 1));
+    const float2 lh = ldg_tab(tp + idx);                     // ts[idx] <= p < ts[idx+1]  <=>  step == idx
+    if (p >= lh.y) {
+        do { ++idx; } while (idx < 255 && p >= ldg_tab(tp + idx).y);
         if (idx > 255) idx = 255;
-    } else if (p < lo) {
-        do { --idx; } while (idx > 0 && p < ldg_tab(ts + idx));
+    } else if (p < lh.x) {
+        do { --idx; } while (idx > 0 && p < ldg_tab(tp + idx).x);
     }
     return idx;
 }
