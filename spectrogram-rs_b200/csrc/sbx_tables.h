@@ -228,7 +228,18 @@ inline void build(const sbx_config &cfg, HostTables &t)
     for (uint32_t py = 0; py < t.rows; ++py) {
         RowMap &rm = t.rowmap[py];
         const uint32_t need = rm.n + (((rm.n & 1u) == 0 && rm.n >= 4) ? 1u : 0u);
-        if (need > cap || need >= (1u << 15) || cap > (1u << 16)) t.ok = false;
+        if (cap > (1u << 15)) t.ok = false;                               // slots travel in 15 bits
+        if (need > cap) {
+            // a row too long for the scratch area (large path only: few rows over a very long transform) gets a
+            // chunk of its own, recognisable by samp_end - samp_begin > cap; the kernel resamples it in parts
+            if (!t.large) t.ok = false;
+            if (ck.row_end > ck.row_begin) t.chunks.push_back(ck);
+            rm.aux = 0;
+            t.chunks.push_back(RowChunk{py, py + 1, samp_first[py], samp_first[py] + rm.n});
+            ck = RowChunk{py + 1, py + 1, samp_first[py] + rm.n, samp_first[py] + rm.n};
+            slot = 0;
+            continue;
+        }
         if (slot + need > cap && ck.row_end > ck.row_begin) {
             t.chunks.push_back(ck);
             ck.row_begin = py; ck.samp_begin = samp_first[py];
@@ -239,7 +250,7 @@ inline void build(const sbx_config &cfg, HostTables &t)
         ck.row_end = py + 1;
         ck.samp_end = samp_first[py] + rm.n;
     }
-    t.chunks.push_back(ck);
+    if (ck.row_end > ck.row_begin) t.chunks.push_back(ck);
     t.rowinfo.resize(t.rows);
     for (uint32_t py = 0; py < t.rows; ++py) t.rowinfo[py] = t.rowmap[py].n | (t.rowmap[py].aux << 16);
 
@@ -263,7 +274,7 @@ inline void build(const sbx_config &cfg, HostTables &t)
             if (x1 < 1 || x1 + 2 > t.k_out - 1) t.taps_clamped = true;
             uint32_t wbits;
             std::memcpy(&wbits, &w, 4);
-            t.samp[2 * (size_t)(samp_first[py] + s)] = x1 | ((rm.aux + s) << 17);
+            t.samp[2 * (size_t)(samp_first[py] + s)] = x1 | (((rm.aux + s) & 0x7fffu) << 17);   // big rows ignore the slot
             t.samp[2 * (size_t)(samp_first[py] + s) + 1] = wbits;
         }
     }

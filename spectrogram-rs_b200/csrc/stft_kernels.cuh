@@ -742,6 +742,44 @@ __device__ __forceinline__ void colour_rows(const float2 *scratch, const float *
     }
 }
 
+// A row that averages more samples than the scratch area holds (only possible on the large path: few rows over a
+// very long transform).  The row is resampled in parts of `cap` samples; between parts one thread continues
+// the row's sequential sum, so the summation order is still the reference's.  Phase functions for the emulation:
+// big_row_part_samples (all threads) / big_row_part_sum (thread 0), then big_row_finish (thread 0).
+template <int THREADS, bool CLAMP>
+__device__ __forceinline__ void big_row_part_samples_impl(const float2 *mags, float2 *scratch, const KernelArgs &a,
+                                                          uint32_t samp_lo, uint32_t samp_hi)
+{
+    const int k_last = (int)a.k_out - 1;
+    for (uint32_t g = samp_lo + threadIdx.x; g < samp_hi; g += THREADS) {
+        const uint2 sp = ldg_tab(a.samp + g);
+        scratch[g - samp_lo] = interp_sample<CLAMP>(mags, a, (int)(sp.x & 0x1ffffu), __uint_as_float(sp.y), k_last);
+    }
+}
+template <int THREADS>
+__device__ __forceinline__ void big_row_part_samples(const float2 *mags, float2 *scratch, const KernelArgs &a,
+                                                     uint32_t samp_lo, uint32_t samp_hi)
+{
+    if (a.taps_clamped) big_row_part_samples_impl<THREADS, true>(mags, scratch, a, samp_lo, samp_hi);
+    else big_row_part_samples_impl<THREADS, false>(mags, scratch, a, samp_lo, samp_hi);
+}
+__device__ __forceinline__ void big_row_part_sum(const float2 *scratch, uint32_t count, float2 &acc)
+{
+    if (threadIdx.x != 0) return;
+    for (uint32_t s = 0; s < count; ++s) {
+        acc.x = __fadd_rn(acc.x, scratch[s].x);
+        acc.y = __fadd_rn(acc.y, scratch[s].y);
+    }
+}
+template <bool PAIR>
+__device__ __forceinline__ void big_row_finish(float2 acc, uint32_t n, uint32_t py, const KernelArgs &a,
+                                               unsigned long long frame0, bool second_valid)
+{
+    if (threadIdx.x != 0) return;
+    uint32_t *outA = reinterpret_cast<uint32_t *>(a.rgba) + frame0 * a.rows;
+    colour_one_row<PAIR>(acc.x, acc.y, n, py, a.thr, a.lut, a, outA, outA + a.rows, second_valid);
+}
+
 // ----------------------------------------------------------------------------------------------
 // kernels
 // ----------------------------------------------------------------------------------------------

@@ -173,6 +173,19 @@ __global__ void __launch_bounds__(LARGE_THREADS) large_colour_kernel(const Large
     const bool second_valid = PAIR && frame0 + 1 < a.n_frames;
     const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.chunks) + blockIdx.y);
     const RowChunk ck = {raw.x, raw.y, raw.z, raw.w};
+    if (ck.samp_end - ck.samp_begin > (uint32_t)LARGE_BLOCK) {
+        // one row with more samples than the scratch holds: resample it in parts, one thread carries the sum
+        float2 acc = make_float2(0.0f, 0.0f);
+        for (uint32_t lo = ck.samp_begin; lo < ck.samp_end; lo += LARGE_BLOCK) {
+            const uint32_t hi = lo + LARGE_BLOCK < ck.samp_end ? lo + LARGE_BLOCK : ck.samp_end;
+            big_row_part_samples<LARGE_THREADS>(mags, scratch, a, lo, hi);
+            __syncthreads();
+            big_row_part_sum(scratch, hi - lo, acc);
+            __syncthreads();
+        }
+        big_row_finish<PAIR>(acc, ck.samp_end - ck.samp_begin, ck.row_begin, a, frame0, second_valid);
+        return;
+    }
     resample_samples<LARGE_THREADS>(mags, scratch, a, ck);
     __syncthreads();
     colour_rows<PAIR, LARGE_THREADS>(scratch, a.thr, a.lut, a, ck, frame0, second_valid);

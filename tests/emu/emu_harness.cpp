@@ -117,6 +117,18 @@ int emu_large(sbx::LargeArgs la, float *mags_out, uint8_t *rgba)
             const bool second_valid = CH == 1 && frame0 + 1 < la.k.n_frames;
             for (uint32_t c = 0; c < la.k.n_chunks; ++c) {
                 const sbx::RowChunk ck = la.k.chunks[c];
+                if (ck.samp_end - ck.samp_begin > (uint32_t)sbx::LARGE_BLOCK) {
+                    float2 acc = make_float2(0.0f, 0.0f);
+                    for (uint32_t lo = ck.samp_begin; lo < ck.samp_end; lo += sbx::LARGE_BLOCK) {
+                        const uint32_t hi = std::min(lo + (uint32_t)sbx::LARGE_BLOCK, ck.samp_end);
+                        for (int t = 0; t < sbx::LARGE_THREADS; ++t) { threadIdx.x = t; sbx::big_row_part_samples<sbx::LARGE_THREADS>(la.magbuf, scratch.data(), la.k, lo, hi); }
+                        threadIdx.x = 0;
+                        sbx::big_row_part_sum(scratch.data(), hi - lo, acc);
+                    }
+                    threadIdx.x = 0;
+                    sbx::big_row_finish<CH == 1>(acc, ck.samp_end - ck.samp_begin, ck.row_begin, la.k, frame0, second_valid);
+                    continue;
+                }
                 for (int t = 0; t < sbx::LARGE_THREADS; ++t) { threadIdx.x = t; sbx::resample_samples<sbx::LARGE_THREADS>(la.magbuf, scratch.data(), la.k, ck); }
                 for (int t = 0; t < sbx::LARGE_THREADS; ++t) { threadIdx.x = t; sbx::colour_rows<CH == 1, sbx::LARGE_THREADS>(scratch.data(), la.k.thr, la.k.lut, la.k, ck, frame0, second_valid); }
             }

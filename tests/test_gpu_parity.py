@@ -64,6 +64,7 @@ CASES = [
     (16384, 4, 1, 2048, 2048, 0),
     (32768, 4, 2, 4096, 1024, 0),
     (65536, 4, 1, 8192, 2048, 0),      # cfg5's largest: M = 262144
+    (8192, 4, 1, 4096, 16, 0),         # 16 rows over 16383 bins: rows longer than the resample scratch area
 ]
 
 
