@@ -388,3 +388,46 @@ def test_live_mono_push_and_wraparound(sbx, magma):
             assert col is not None and np.array_equal(col, want[f]), f
             pos += live.push(x[pos:pos + hop], channels=1)
         live.close()
+
+
+def test_seeded_random_configurations(sbx, magma):
+    """24 seeded random geometries (odd hops, hop > N, tiny / huge frequency ranges, one-row images, both
+    interpolators and schemes, all three kernel families) through the C ABI against the oracle."""
+    import torch
+    rng = np.random.Generator(np.random.PCG64(2026))
+    sizes = [256, 512, 1024, 2048, 4096, 100, 300, 441, 1470, 2205, 2400, 8192]
+    for case in range(24):
+        n = int(rng.choice(sizes))
+        if n == 8192:
+            pad = 4
+        elif n & (n - 1):
+            pad = int(rng.choice([2, 4]))
+        else:
+            pad = int(rng.choice([1, 2, 4]))
+            if n * pad > 16384:
+                pad = 2
+        sr = float(rng.choice([8000.0, 22050.0, 44100.0, 48000.0, 96000.0]))
+        hop = int(rng.choice([1, 3, n // 8, n // 2, n, n + 17, int(rng.integers(1, 2 * n))]))
+        rows = int(rng.choice([1, 2, 7, 33, 100, 257])) if n != 8192 else int(rng.choice([16, 64]))
+        f_min = float(rng.choice([1.0, 20.0, 32.0, 500.0]))
+        f_max = float(rng.choice([f_min * 1.5, 4000.0, sr / 2, 22030.0, sr]))
+        f_max = f_max if f_max > f_min else f_min * 2
+        interp, scheme, ch, frames = int(rng.integers(0, 2)), int(rng.integers(0, 2)), int(rng.integers(1, 3)), int(rng.integers(1, 5))
+        ns = n + max(1, hop) * (frames - 1)
+        amp = 10.0 ** rng.uniform(-4, 0.3)
+        x = (amp * rng.standard_normal(ns)).astype(np.float32)
+        pcm = x if ch == 1 else np.stack([x, (0.3 * amp * rng.standard_normal(ns)).astype(np.float32)], 1)
+        kw = dict(sample_rate=sr, window_n=n, pad_factor=pad, hop=max(1, hop), rows_h=rows, f_min=f_min, f_max=f_max, interp=interp)
+        p = oracle.params(stereo_scheme=scheme, **kw)
+        o_rgba, o_mags = oracle.batch(p, pcm, ch, magma, want_mags=True)
+        with sbx.Plan(channels=ch, scheme=scheme, lut=magma, **kw) as plan:
+            g_rgba = plan.process_batch(pcm)
+            d = torch.zeros((frames, plan.k, 2), dtype=torch.float32, device="cuda")
+            plan.magnitudes_batch_device(torch.from_numpy(pcm).cuda(), ns, d, frames)
+            plan.synchronize()
+            g_mags = d.cpu().numpy()
+            peak = np.maximum(np.abs(o_mags).max(axis=(1, 2), keepdims=True), 1e-30)
+            assert (np.abs(g_mags - o_mags) / peak).max() <= MAG_TOL, (case, kw)
+            rec = np.stack([oracle.column_from_magnitudes(p, g_mags[f], magma) for f in range(frames)])
+            assert np.array_equal(plan.colorize_magnitudes(g_mags), rec), (case, kw)
+            assert np.array_equal(g_rgba, rec), (case, kw)
