@@ -400,17 +400,28 @@ __device__ __forceinline__ void apply_twiddles(float2 (&v)[R], const float2 *pla
 // The R inputs of a butterfly are S samples apart: all addresses are one base pointer plus compile-time
 // offsets.  Q0ZERO selects the window-only (q0 = 0) or window * W_M^(n q0) (q0 > 0) factor; q0 is
 // warp-uniform, so the caller branches once per butterfly instead of predicating every load.
-template <class G, bool STAGED, bool Q0ZERO>
+// SHIFT > 0 (mono pairs, global loads only): hop == SHIFT * S, so frame B's input r is frame A's input r + SHIFT
+// and the pair needs R + SHIFT loads instead of 2 R.
+template <class G, bool STAGED, bool Q0ZERO, int SHIFT = 0>
 __device__ __forceinline__ void first_inputs(float2 (&v)[1 << G::log2r(0)], const KernelArgs &a, const float *pa_lo,
                                              const float *pb_lo, bool second_valid, int q0, int lo)
 {
     constexpr int R = 1 << G::log2r(0), S = 1 << G::log2stride(0);
     const float *win_lo = a.window + lo;
     const float2 *wtw_lo = a.wtw + (Q0ZERO ? 0 : (q0 - 1) * G::N) + lo;
+    float xs[SHIFT > 0 ? R + SHIFT : 1];
+    if constexpr (SHIFT > 0) {
+#pragma unroll
+        for (int r = 0; r < R + SHIFT; ++r)
+            xs[r] = (r < R || second_valid) ? ldg_pcm(pa_lo + r * S) : 0.0f;   // r >= R lies in frame B only
+    }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         float2 s;
-        if constexpr (STAGED) {
+        if constexpr (SHIFT > 0) {
+            s.x = xs[r];
+            s.y = second_valid ? xs[r + SHIFT] : 0.0f;
+        } else if constexpr (STAGED) {
             if constexpr (G::CH == 2) {
                 s = reinterpret_cast<const float2 *>(pa_lo)[r * S];
             } else {
@@ -444,8 +455,23 @@ __device__ __forceinline__ void pass_first(float2 *z, const KernelArgs &a, const
         const float *pa_lo = pa + (size_t)lo * G::CH;
         const float *pb_lo = pa_lo + a.hop;
         float2 v[R];
-        if (q0 == 0) first_inputs<G, STAGED, true>(v, a, pa_lo, pb_lo, second_valid, q0, lo);
-        else first_inputs<G, STAGED, false>(v, a, pa_lo, pb_lo, second_valid, q0, lo);
+        if constexpr (G::CH == 1 && !STAGED && R >= 8) {
+            // the common overlaps: hop = S or 2 S (cfg1, cfg4: hop 512 = 2 * 256)
+            const uint32_t hop = a.hop;
+            if (hop == 2u * S) {
+                if (q0 == 0) first_inputs<G, STAGED, true, 2>(v, a, pa_lo, pb_lo, second_valid, q0, lo);
+                else first_inputs<G, STAGED, false, 2>(v, a, pa_lo, pb_lo, second_valid, q0, lo);
+            } else if (hop == 1u * S) {
+                if (q0 == 0) first_inputs<G, STAGED, true, 1>(v, a, pa_lo, pb_lo, second_valid, q0, lo);
+                else first_inputs<G, STAGED, false, 1>(v, a, pa_lo, pb_lo, second_valid, q0, lo);
+            } else {
+                if (q0 == 0) first_inputs<G, STAGED, true>(v, a, pa_lo, pb_lo, second_valid, q0, lo);
+                else first_inputs<G, STAGED, false>(v, a, pa_lo, pb_lo, second_valid, q0, lo);
+            }
+        } else {
+            if (q0 == 0) first_inputs<G, STAGED, true>(v, a, pa_lo, pb_lo, second_valid, q0, lo);
+            else first_inputs<G, STAGED, false>(v, a, pa_lo, pb_lo, second_valid, q0, lo);
+        }
         Butterfly<R>::run(v);
         if constexpr (G::NPASS > 1) apply_twiddles<R>(v, a.twp + lo, S);   // W_N^(lo q)
         const int bx = G::zsw((q0 << G::LOG2N) + lo);
