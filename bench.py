@@ -334,6 +334,10 @@ def main():
             out["extra"] = extras(sbx, signals, torch)
         except Exception as exc:                            # extras must never lose the headline line
             out["extra"] = {"error": repr(exc)}
+        if isinstance(out["extra"].get("cfg2_live_latency_us"), dict):
+            # the second half of BASELINE.json's metric ("p50 live-frame latency"), surfaced at the top level
+            lat = out["extra"]["cfg2_live_latency_us"]
+            out["live_latency_us"] = {"p50": lat["p50"], "p99": lat["p99"], "workload": "cfg2: 48 kHz stereo, 2048-pt frames, one at a time from the pinned ring, 1 GPU"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, cores, sample = cpu_reference_rate()
         out["cpu_baseline"] = {"value": rate, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
