@@ -203,7 +203,15 @@ cudaError_t launch_large_one(const LargeArgs &la, bool want_rgba, cudaStream_t s
     const unsigned units = la.units;
     large_first_kernel<LOG2N, LOG2PAD, CH><<<units * GL::PAD * (LARGE_BLOCK / LARGE_THREADS), LARGE_THREADS, 0, stream>>>(la);
     large_block_kernel<<<units * (GL::M / LARGE_BLOCK), LARGE_THREADS, 0, stream>>>(la);
-    large_split_kernel<LOG2N, LOG2PAD, CH><<<units * ((GL::M / 2) / LARGE_THREADS), LARGE_THREADS, 0, stream>>>(la);
+    static bool split_configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !split_configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(large_split_kernel<LOG2N, LOG2PAD, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, GL::SPLIT_SMEM);
+        if (e != cudaSuccess) return e;
+        split_configured[dev] = true;
+    }
+    large_split_kernel<LOG2N, LOG2PAD, CH><<<units * (GL::Q / 2), LARGE_THREADS, GL::SPLIT_SMEM, stream>>>(la);
     if (want_rgba)
         large_colour_kernel<CH == 1><<<dim3(units, la.k.n_chunks), LARGE_THREADS, 0, stream>>>(la, la.magbuf, (size_t)GL::M / 2);
     return cudaGetLastError();

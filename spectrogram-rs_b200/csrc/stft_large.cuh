@@ -6,8 +6,11 @@
 // 4096-point block is an independent transform that fits shared memory:
 //
 //   large_first   : PCM -> window -> W_M^(n q0) premultiply -> radix-R0 butterfly -> W_N^(lo q) -> Y   (global)
-//   large_block   : one 4096-point block of Y: three radix-16 passes in shared memory, in place      (global)
-//   large_split   : bins kk = 1..M/2-1 from Z[pos(kk)], Z[pos(M-kk)] -> (L,R) magnitudes             (global)
+//   large_block   : one 4096-point block of Y: three radix-16 passes in shared memory, written back in
+//                   natural order of the block's own bin index k (digit reversal undone in shared memory)
+//   large_split   : bins kk = 1..M/2-1 from Z[kk], Z[M-kk] -> (L,R) magnitudes.  Bin kk = k*Q + c lives in
+//                   block c at index k (Q = M/4096 blocks), i.e. Z is the transpose of the bin order: the kernel
+//                   is a tiled transpose through shared memory, 512-byte runs on both the read and the write side
 //   large_colour  : resample (lane per sample, taps read through L1/L2) + dB step + LUT -> RGBA
 //
 // Scratch per frame pair (mono) or frame (stereo): M float2 for Y/Z plus M/2 float2 of magnitudes.
@@ -43,6 +46,12 @@ template <int LOG2N, int LOG2PAD> struct GeomL {
         const int d0 = k & (R0 - 1), kl = k >> LOG2R0;
         return (q0 << LOG2N) + (d0 << LARGE_LOG2_BLOCK) + G12::pos_of_bin(kl);
     }
+    // After large_block every 4096-point block holds its bins in natural order of the block-local index k, and
+    // bin kk = k*Q + c sits in the block with "column" c = d0*PAD + q0, which is block number q0*R0 + d0.
+    static constexpr int LOG2Q = LOG2M - LARGE_LOG2_BLOCK, Q = 1 << LOG2Q;   // blocks per unit
+    static constexpr int TK = LARGE_BLOCK / Q;                                // k values per split tile (tile = 4096 bins)
+    static constexpr int SPLIT_SMEM = 2 * TK * (Q + 1) * 8;                   // own + partner tiles, padded rows
+    static __host__ __device__ constexpr int block_of_column(int c) { return ((c & (PAD - 1)) << LOG2R0) + (c >> LOG2PAD); }
 };
 
 // ---- pass 0: global PCM -> global Y --------------------------------------------------------------
@@ -102,32 +111,57 @@ __device__ __forceinline__ void large_block_load(float2 *z, const float2 *src, c
         for (int q = 0; q < 16; ++q) z[SBX_ZAT(G12, bx, q * S)] = v[q];
     }
 }
+// write-back in natural order of the block-local bin index k (digit reversal undone here, in shared memory)
 __device__ __forceinline__ void large_block_store(const float2 *z, float2 *dst)
 {
-    for (int i = threadIdx.x; i < LARGE_BLOCK; i += LARGE_THREADS) dst[i] = z[G12::zsw(i)];
+    for (int k = threadIdx.x; k < LARGE_BLOCK; k += LARGE_THREADS) dst[k] = z[G12::zsw(G12::pos_of_bin(k))];
 }
 
-// ---- split: global Z -> global magnitudes -----------------------------------------------------------
+// ---- split: global Z -> global magnitudes (tiled transpose) -------------------------------------------
+// One CTA = one tile of 4096 consecutive bins kk in [k0*Q, (k0+TK)*Q), k0 = tile*TK < 2048.
+// phase 1 (large_split_load): for every column c, TK consecutive elements of block c (own) and the mirrored run
+//   of block Q-c (partner, M-kk = (4095-k)*Q + (Q-c); column 0 mirrors onto itself at 4096-k) -> shared memory;
+// phase 2 (large_split_emit): consecutive threads take consecutive kk.
+template <int LOG2N, int LOG2PAD>
+__device__ __forceinline__ void large_split_load(const LargeArgs &la, unsigned int block_id, float2 *own, float2 *par)
+{
+    using GL = GeomL<LOG2N, LOG2PAD>;
+    const unsigned int unit = block_id / (GL::Q / 2), tile = block_id % (GL::Q / 2);
+    const int k0 = tile * GL::TK;
+    const float2 *zu = la.zbuf + (size_t)unit * GL::M;
+#pragma unroll 8
+    for (int i = threadIdx.x; i < LARGE_BLOCK; i += LARGE_THREADS) {
+        const int c = i / GL::TK, j = i % GL::TK, k = k0 + j;
+        own[j * (GL::Q + 1) + c] = zu[((size_t)GL::block_of_column(c) << LARGE_LOG2_BLOCK) + k];
+        const int cp = (GL::Q - c) & (GL::Q - 1);
+        const int kp = c != 0 ? LARGE_BLOCK - 1 - k : LARGE_BLOCK - k;          // k = 0, c = 0 is DC: no partner
+        par[j * (GL::Q + 1) + c] = kp < LARGE_BLOCK ? zu[((size_t)GL::block_of_column(cp) << LARGE_LOG2_BLOCK) + kp]
+                                                    : make_float2(0.0f, 0.0f);
+    }
+}
+
 template <int LOG2N, int LOG2PAD, int CH>
-__device__ __forceinline__ void large_split(const LargeArgs &la, unsigned int block_id)
+__device__ __forceinline__ void large_split_emit(const LargeArgs &la, unsigned int block_id, const float2 *own, const float2 *par)
 {
     using GL = GeomL<LOG2N, LOG2PAD>;
     const KernelArgs &a = la.k;
-    constexpr unsigned int PER_UNIT = (GL::M / 2) / LARGE_THREADS;
-    const unsigned int unit = block_id / PER_UNIT;
-    const int kk = (block_id % PER_UNIT) * LARGE_THREADS + threadIdx.x;
-    if (kk == 0) return;                                                       // DC is dropped (fft.rs:81)
-    const float2 *zu = la.zbuf + (size_t)unit * GL::M;
-    const float2 m = split_pair(zu[GL::pos_of_bin(kk)], zu[GL::pos_of_bin(GL::M - kk)], a.scale);
-    la.magbuf[(size_t)unit * (GL::M / 2) + kk] = m;
-    if (a.mags_out != nullptr) {
-        const unsigned long long frame0 = la.frame_base + (unsigned long long)unit * (CH == 1 ? 2 : 1);
-        float2 *out = reinterpret_cast<float2 *>(a.mags_out) + frame0 * a.k_out + (kk - 1);
-        if constexpr (CH == 1) {
-            out[0] = make_float2(m.x, m.x);
-            if (frame0 + 1 < a.n_frames) out[a.k_out] = make_float2(m.y, m.y);
-        } else {
-            out[0] = m;
+    const unsigned int unit = block_id / (GL::Q / 2), tile = block_id % (GL::Q / 2);
+    const int kk0 = tile * LARGE_BLOCK;                                        // = k0 * Q
+    const unsigned long long frame0 = la.frame_base + (unsigned long long)unit * (CH == 1 ? 2 : 1);
+    for (int i = threadIdx.x; i < LARGE_BLOCK; i += LARGE_THREADS) {
+        const int kk = kk0 + i;
+        if (kk == 0) continue;                                                 // DC is dropped (fft.rs:81)
+        const int j = i >> GL::LOG2Q, c = i & (GL::Q - 1);
+        const float2 m = split_pair(own[j * (GL::Q + 1) + c], par[j * (GL::Q + 1) + c], a.scale);
+        la.magbuf[(size_t)unit * (GL::M / 2) + kk] = m;
+        if (a.mags_out != nullptr) {
+            float2 *out = reinterpret_cast<float2 *>(a.mags_out) + frame0 * a.k_out + (kk - 1);
+            if constexpr (CH == 1) {
+                out[0] = make_float2(m.x, m.x);
+                if (frame0 + 1 < a.n_frames) out[a.k_out] = make_float2(m.y, m.y);
+            } else {
+                out[0] = m;
+            }
         }
     }
 }
@@ -155,10 +189,17 @@ static __global__ void __launch_bounds__(LARGE_THREADS) large_block_kernel(const
     large_block_store(z, blk);
 }
 
+// grid = units * Q/2, dynamic shared memory = GeomL::SPLIT_SMEM
 template <int LOG2N, int LOG2PAD, int CH>
 __global__ void __launch_bounds__(LARGE_THREADS) large_split_kernel(const LargeArgs la)
 {
-    large_split<LOG2N, LOG2PAD, CH>(la, blockIdx.x);
+    using GL = GeomL<LOG2N, LOG2PAD>;
+    extern __shared__ __align__(16) unsigned char split_smem[];
+    float2 *own = reinterpret_cast<float2 *>(split_smem);
+    float2 *par = own + GL::TK * (GL::Q + 1);
+    large_split_load<LOG2N, LOG2PAD>(la, blockIdx.x, own, par);
+    __syncthreads();
+    large_split_emit<LOG2N, LOG2PAD, CH>(la, blockIdx.x, own, par);
 }
 
 // grid = (units, row chunks): row chunks are independent, so each CTA resamples and colours one chunk of one

@@ -109,8 +109,11 @@ int emu_large(sbx::LargeArgs la, float *mags_out, uint8_t *rgba)
             for (int t = 0; t < sbx::LARGE_THREADS; ++t) { threadIdx.x = t; sbx::pass_inplace<sbx::G12, 2>(z.data(), a); }
             for (int t = 0; t < sbx::LARGE_THREADS; ++t) { threadIdx.x = t; sbx::large_block_store(z.data(), blk); }
         }
-        for (unsigned b = 0; b < (GL::M / 2) / sbx::LARGE_THREADS; ++b)
-            for (int t = 0; t < sbx::LARGE_THREADS; ++t) { threadIdx.x = t; sbx::large_split<LOG2N, LOG2PAD, CH>(la, b); }
+        for (unsigned b = 0; b < (unsigned)GL::Q / 2; ++b) {
+            std::vector<float2> own(GL::TK * (GL::Q + 1)), par(GL::TK * (GL::Q + 1));
+            for (int t = 0; t < sbx::LARGE_THREADS; ++t) { threadIdx.x = t; sbx::large_split_load<LOG2N, LOG2PAD>(la, b, own.data(), par.data()); }
+            for (int t = 0; t < sbx::LARGE_THREADS; ++t) { threadIdx.x = t; sbx::large_split_emit<LOG2N, LOG2PAD, CH>(la, b, own.data(), par.data()); }
+        }
         if (rgba) {
             std::vector<float2> scratch(sbx::LARGE_BLOCK);
             const unsigned long long frame0 = la.frame_base;
