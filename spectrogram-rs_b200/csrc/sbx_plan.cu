@@ -784,8 +784,11 @@ SBX_API sbx_status sbx_process_batch(sbx_plan *p, const float *pcm, uint64_t n_s
     SBX_CUDA(p, cudaSetDevice(p->cfg.device));
 
     if (p->chunk_frames == 0) {
-        // at most ~32 MiB of RGBA and ~64 MiB of PCM per chunk, even frame count (mono pairs), at least 2 frames
-        uint64_t cf = ((uint64_t)32 << 20) / ((uint64_t)p->rows * 4);
+        // at most ~32 MiB of RGBA (SBX_BATCH_CHUNK_MB) and ~64 MiB of PCM per chunk, even frame count (mono pairs),
+        // at least 2 frames
+        const char *env = std::getenv("SBX_BATCH_CHUNK_MB");
+        const uint64_t chunk_mb = env && std::atoi(env) > 0 ? (uint64_t)std::atoi(env) : 32u;
+        uint64_t cf = (chunk_mb << 20) / ((uint64_t)p->rows * 4);
         const uint64_t cf_pcm = ((uint64_t)64 << 20) / ((uint64_t)p->hop * p->channels * sizeof(float));
         cf = cf < cf_pcm ? cf : cf_pcm;
         cf = cf < 2 ? 2 : (cf & ~1ull);
