@@ -518,13 +518,14 @@ __device__ __forceinline__ void pass_inplace(float2 *z, const KernelArgs &a)
     }
 }
 
-template <class G, int P> struct RunPasses {
+// passes P .. END-1, each followed by a barrier
+template <class G, int P, int END = G::NPASS> struct RunPasses {
     static __device__ __forceinline__ void run(float2 *z, const KernelArgs &a)
     {
-        if constexpr (P < G::NPASS) {
+        if constexpr (P < END) {
             pass_inplace<G, P>(z, a);
             __syncthreads();
-            RunPasses<G, P + 1>::run(z, a);
+            RunPasses<G, P + 1, END>::run(z, a);
         }
     }
 };
@@ -607,6 +608,57 @@ __device__ __forceinline__ void split_write(float2 *z, const SplitRegs<G> &r)
 #pragma unroll
     for (int p = 0; p < SplitRegs<G>::PER_THREAD; ++p)
         if (p != 0 || tid != 0) z[tid | (p << SplitConst<G>::LT)] = r.mag[p];      // kk = 0 (DC) is dropped
+}
+
+// ---- last pass fused with the split (THREADS == M/16, i.e. one row per thread) -----------------------
+// The stride-1 pass works on whole rows and any thread may take any row, so thread t takes the row that holds
+// ITS split bins: row pos_of_bin(t) >> 4, whose elements 0..7 are the bins t | p << log2 T (p = 0..7).  Those stay
+// in registers; only elements 8..15 -- the partners some other thread needs -- go back to shared memory.
+// Saves the write of the lower half rows and the split's read of them (one of five 64 KB round trips).
+template <class G> struct LastSplit {
+    static constexpr bool ENABLED = G::THREADS * 16 == G::M && G::NPASS >= 2 && SplitRegs<G>::PER_THREAD == 8 &&
+                                    SplitConst<G>::B0 == 0;
+};
+
+template <class G>
+__device__ __forceinline__ void last_pass_keep_own(float2 *z, SplitRegs<G> &r)
+{
+    const int w = G::pos_of_bin(threadIdx.x) >> 4;                            // my row
+    float4 *row = reinterpret_cast<float4 *>(z) + (w << 3);
+    const int key = G::zkey(w << 4);
+    float2 v[16];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float4 t = row[c ^ key];
+        v[2 * c] = make_float2(t.x, t.y);
+        v[2 * c + 1] = make_float2(t.z, t.w);
+    }
+    Butterfly<16>::run(v);
+#pragma unroll
+    for (int p = 0; p < 8; ++p) r.mag[p] = v[p];                              // own bins, kept in registers
+#pragma unroll
+    for (int c = 4; c < 8; ++c)                                               // elements 8..15: somebody's partners
+        row[c ^ key] = make_float4(v[2 * c].x, v[2 * c].y, v[2 * c + 1].x, v[2 * c + 1].y);
+}
+
+// after the barrier: r.mag[p] (own Z values) -> (L,R) magnitudes, partners read 16 bytes at a time
+template <class G>
+__device__ __forceinline__ void split_with_own(const float2 *z, const KernelArgs &a, SplitRegs<G> &r)
+{
+    using C = SplitConst<G>;
+    const int tid = threadIdx.x;
+    const int par = G::zsw(G::pos_of_bin((G::THREADS - tid) & (G::THREADS - 1)));
+#pragma unroll
+    for (int pa = 0; pa < 8; pa += 2) {
+        const int pb = pa + 1;
+        float4 y = *reinterpret_cast<const float4 *>(z + (par ^ C::partner(pb)));     // .xy: partner of pb, .zw: of pa
+        if (tid == 0) {
+            const float2 ya = z[C::partner_t0(pa)], yb = z[C::partner_t0(pb)];
+            y = make_float4(yb.x, yb.y, ya.x, ya.y);
+        }
+        r.mag[pa] = split_pair(r.mag[pa], make_float2(y.z, y.w), a.scale);
+        r.mag[pb] = split_pair(r.mag[pb], make_float2(y.x, y.y), a.scale);
+    }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -830,8 +882,16 @@ __device__ __forceinline__ void resample_colour(float2 *z, const KernelArgs &a, 
 template <class G>
 __device__ __forceinline__ void frame_tail(float2 *z, const KernelArgs &a, unsigned long long frame0, bool second_valid)
 {
-    RunPasses<G, 1>::run(z, a);
-    {
+    if constexpr (LastSplit<G>::ENABLED) {
+        RunPasses<G, 1, G::NPASS - 1>::run(z, a);
+        SplitRegs<G> regs;
+        last_pass_keep_own<G>(z, regs);
+        __syncthreads();
+        split_with_own<G>(z, a, regs);
+        __syncthreads();
+        split_write<G>(z, regs);
+    } else {
+        RunPasses<G, 1>::run(z, a);
         SplitRegs<G> regs;
         split_read<G>(z, a, regs);
         __syncthreads();

@@ -11,12 +11,12 @@ namespace {
 
 bool g_emu_staged = false;
 
-template <class G, int P> struct EmuPasses {
+template <class G, int P, int END = G::NPASS> struct EmuPasses {
     static void run(float2 *z, const sbx::KernelArgs &a)
     {
-        if constexpr (P < G::NPASS) {
+        if constexpr (P < END) {
             for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::pass_inplace<G, P>(z, a); }
-            EmuPasses<G, P + 1>::run(z, a);
+            EmuPasses<G, P + 1, END>::run(z, a);
         }
     }
 };
@@ -37,9 +37,15 @@ int emu_cta(const sbx::KernelArgs &a, unsigned long long frame0, float *mags_out
     } else {
         for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::pass_first<G, false>(z.data(), a, src, second_valid); }
     }
-    EmuPasses<G, 1>::run(z.data(), a);
     std::vector<sbx::SplitRegs<G>> regs(G::THREADS);
-    for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::split_read<G>(z.data(), a, regs[t]); }
+    if constexpr (sbx::LastSplit<G>::ENABLED) {
+        EmuPasses<G, 1, G::NPASS - 1>::run(z.data(), a);
+        for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::last_pass_keep_own<G>(z.data(), regs[t]); }
+        for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::split_with_own<G>(z.data(), a, regs[t]); }
+    } else {
+        EmuPasses<G, 1>::run(z.data(), a);
+        for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::split_read<G>(z.data(), a, regs[t]); }
+    }
     for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::split_write<G>(z.data(), regs[t]); }
     if (mags_out) {
         for (uint32_t j = 0; j < a.k_out; ++j) {
