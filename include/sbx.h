@@ -191,6 +191,7 @@ SBX_API sbx_status sbx_get_window(const sbx_plan *plan, float *w);
  * src/devices/audio_input_list_model.rs:30) with AudioStreamTransform's cursor semantics
  * (src/fourier/audio_transform.rs:34-42) and one captured CUDA graph
  * (H2D -> fused kernel -> D2H) per frame. */
+/* The live stream borrows the plan: destroy it (sbx_live_destroy) before sbx_plan_destroy(plan). */
 SBX_API sbx_status sbx_live_create(sbx_plan *plan, uint32_t ring_capacity_samples, sbx_live **out_live);
 SBX_API void       sbx_live_destroy(sbx_live *live);
 /* Producer side (the cpal callback, src/devices/audio_input_list_model.rs:66-72): pushes up to
