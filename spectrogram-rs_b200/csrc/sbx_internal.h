@@ -46,6 +46,7 @@ struct sbx_plan {
     uint32_t large_units = 0;           // scratch capacity in units (frame pairs / frames)
     float *d_thr = nullptr;
     uint32_t *d_lut = nullptr;
+    uint4 *d_ctab = nullptr;
 
     // single-frame staging (host pinned + device)
     float *h_frame = nullptr;           // max(N, K) x 2 floats: N x 2 in, reused for K x 2 out

@@ -383,6 +383,7 @@ sbx::KernelArgs sbx_plan::base_args() const
     a.taps_clamped = taps_clamped;
     a.thr = d_thr;
     a.lut = d_lut;
+    a.ctab = d_ctab;
     a.hop = hop;
     a.rows = rows;
     a.k_out = k_out;
@@ -472,7 +473,7 @@ SBX_API void sbx_plan_destroy(sbx_plan *p)
     }
     cudaFree(p->d_window); cudaFree(p->d_wtw); cudaFree(p->d_twp); cudaFree(p->d_rowmap); cudaFree(p->d_rowinfo); cudaFree(p->d_chunks);
     cudaFree(p->d_samp); cudaFree(p->d_f16_scratch); cudaFree(p->d_twm); cudaFree(p->d_pos_tab); cudaFree(p->d_twp_block); cudaFree(p->d_zbuf); cudaFree(p->d_magbuf);
-    cudaFree(p->d_thr); cudaFree(p->d_lut); cudaFree(p->d_frame); cudaFree(p->d_mags1); cudaFree(p->d_col);
+    cudaFree(p->d_thr); cudaFree(p->d_lut); cudaFree(p->d_ctab); cudaFree(p->d_frame); cudaFree(p->d_mags1); cudaFree(p->d_col);
     if (p->h_frame) cudaFreeHost(p->h_frame);
     if (p->h_col) cudaFreeHost(p->h_col);
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
@@ -587,6 +588,7 @@ SBX_API sbx_status sbx_plan_create(const sbx_config *cfg, sbx_plan **out_plan)
     SBX_TRY(upload(&p->d_samp, t.samp.data(), t.samp.size() * sizeof(uint32_t)));
     SBX_TRY(upload(&p->d_thr, t.thr.data(), t.thr.size() * sizeof(float)));
     SBX_TRY(upload(&p->d_lut, t.lut, sizeof(t.lut)));
+    SBX_TRY(upload(&p->d_ctab, t.ctab, sizeof(t.ctab)));
     SBX_TRY(cudaMalloc(&p->d_frame, (size_t)p->n * 2 * sizeof(float)));
     SBX_TRY(cudaMalloc(&p->d_mags1, (size_t)p->k_out * 2 * sizeof(float)));
     SBX_TRY(cudaMalloc(&p->d_col, (size_t)p->rows * 4));

@@ -104,6 +104,7 @@ struct HostTables {
     std::vector<float> thr_raw;         // [2][256] the bare thresholds (introspection)
     float guess_a[2], guess_b[2];
     uint32_t lut[256];
+    uint32_t ctab[1024];                // [256] {ts[i], ts[i+1], lut[i], 0} (colour step bracket + colour)
     bool ok = true;                     // false: a row has more samples than the scratch area holds
 };
 
@@ -304,6 +305,11 @@ inline void build(const sbx_config &cfg, HostTables &t)
     for (int i = 0; i < 256; ++i)
         t.lut[i] = (uint32_t)cfg.lut_rgb[3 * i] | ((uint32_t)cfg.lut_rgb[3 * i + 1] << 8) |
                    ((uint32_t)cfg.lut_rgb[3 * i + 2] << 16) | (255u << 24);
+    for (int i = 0; i < 256; ++i) {
+        std::memcpy(&t.ctab[4 * i], &t.thr[2 * i], 8);                 // (ts[i], ts[i+1]) of the colour set
+        t.ctab[4 * i + 2] = t.lut[i];
+        t.ctab[4 * i + 3] = 0;
+    }
 }
 
 }  // namespace tables

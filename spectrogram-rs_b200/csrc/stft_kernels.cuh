@@ -57,6 +57,7 @@ struct KernelArgs {
                                  //   (1 - cos(frac*pi))/2 (COSINE, host libm)
     const float *thr;            // [2][256] pairs (ts[i], ts[i+1]) of step thresholds with sentinels: colour index, alpha
     const uint32_t *lut;         // [256] packed r | g<<8 | b<<16 | 255<<24
+    const uint4 *ctab;           // [256] {ts[i], ts[i+1], lut[i], 0}: the colour step and its colour in one 16-byte load
     unsigned long long n_frames;
     uint32_t hop, rows, k_out, n_chunks;
     float scale;                 // 2 / N     (fft.rs:92)
@@ -252,6 +253,16 @@ __device__ __forceinline__ uint2 ldg_tab(const uint2 *p)
     return __ldg(p);
 #else
     uint2 v; asm volatile("ld.global.nc.L1::evict_last.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p)); return v;
+#endif
+}
+__device__ __forceinline__ uint4 ldg_tab(const uint4 *p)
+{
+#if defined(SBX_EMU) || SBX_TABLE_KEEP == 0
+    return __ldg(p);
+#else
+    uint4 v;
+    asm volatile("ld.global.nc.L1::evict_last.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
 #endif
 }
 __device__ __forceinline__ uint32_t ldg_tab(const uint32_t *p)
@@ -694,6 +705,18 @@ __device__ __forceinline__ int step_index(const float *ts, float p, float eps, f
     return idx;
 }
 
+// Mono schemes: the packed RGBA of power p.  One 16-byte load brings the bracket of the guessed step and its
+// colour; only a wrong guess (p within a rounding error of a threshold) takes the exact search.
+__device__ __forceinline__ uint32_t step_colour(const KernelArgs &a, float p)
+{
+    const float t = fast_log2(p + a.db_eps) * a.guess_a[0] + a.guess_b[0];
+    const int idx = (int)fminf(fmaxf(t, 0.0f), 255.0f);      // NaN -> 0
+    const uint4 e = ldg_tab(a.ctab + idx);
+    if (p >= __uint_as_float(e.y) || p < __uint_as_float(e.x))
+        return ldg_tab(a.lut + step_index(a.thr, p, a.db_eps, a.guess_a[0], a.guess_b[0]));
+    return e.z;
+}
+
 // One interpolated sample (both channels) -- magnitude_at (ifs.rs:46-48).  mags is indexed by bin
 // kk = j + 1; x1 = floor(x), w = the interpolation weight, both precomputed by the plan.
 template <bool CLAMP>
@@ -773,10 +796,9 @@ __device__ __forceinline__ void colour_one_row(float ax, float ay, uint32_t n, u
         const float pA = __fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ax, ax));
         const float pB = __fadd_rn(__fmul_rn(ay, ay), __fmul_rn(ay, ay));
         if (a.scheme == 0) {
-            const int iA = step_index(thr, pA, a.db_eps, a.guess_a[0], a.guess_b[0]);
-            const int iB = step_index(thr, pB, a.db_eps, a.guess_a[0], a.guess_b[0]);
-            outA[row] = ldg_tab(lut + iA);
-            if (second_valid) outB[row] = ldg_tab(lut + iB);
+            const uint32_t cA = step_colour(a, pA), cB = step_colour(a, pB);
+            outA[row] = cA;
+            if (second_valid) outB[row] = cB;
         } else {
             // l == r: pan = l / (|l| + |r|) = 0.5 for finite l > 0, else NaN or negative -> index 0
             const uint32_t panA = (ax > 0.0f && ax < 3.0e38f) ? 128u : 0u, panB = (ay > 0.0f && ay < 3.0e38f) ? 128u : 0u;
@@ -787,7 +809,7 @@ __device__ __forceinline__ void colour_one_row(float ax, float ay, uint32_t n, u
     } else {
         const float p = __fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay));    // norm_sqr
         if (a.scheme == 0) {
-            outA[row] = ldg_tab(lut + step_index(thr, p, a.db_eps, a.guess_a[0], a.guess_b[0]));
+            outA[row] = step_colour(a, p);
         } else {
             const double pan = (double)ax / (double)__fadd_rn(fabsf(ax), fabsf(ay));
             const double v = floor(pan * 256.0);

@@ -228,6 +228,7 @@ long long emu_batch(const sbx_config *cfg, const float *pcm, unsigned long long 
     a.taps_clamped = t.taps_clamped ? 1 : 0;
     a.thr = t.thr.data();
     a.lut = t.lut;
+    a.ctab = reinterpret_cast<const uint4 *>(t.ctab);
     a.n_frames = frames;
     a.hop = cfg->hop; a.rows = t.rows; a.k_out = t.k_out;
     a.scale = t.scale; a.db_eps = cfg->db_eps;
