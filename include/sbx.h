@@ -173,6 +173,11 @@ SBX_API sbx_status sbx_set_stream(sbx_plan *plan, void *cuda_stream);
 SBX_API sbx_status sbx_synchronize(sbx_plan *plan);
 /* Kernel launches issued by this plan since creation (bench.py's gpu_launches evidence). */
 SBX_API uint64_t   sbx_launch_count(const sbx_plan *plan);
+/* Which kernel family the plan's batch entry points run for its channel layout (evidence for bench.py and the
+ * tests; static string): "fused-pair" (two mono frames per CTA), "fused-real" (one mono frame per CTA as the
+ * even/odd packed half-length sequence; needs an even hop, else "fused-pair" / "large" runs), "fused-stereo",
+ * "large" (four kernels, M > 16384) or "generic" (window not a power of two). */
+SBX_API const char *sbx_kernel_path(const sbx_plan *plan);
 
 /* ---- introspection for the bit-exactness tests ------------------------------------------- */
 /* The log-frequency bin map the plan computed on the host: per row py (0 = lowest frequency)

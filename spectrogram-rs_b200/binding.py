@@ -51,6 +51,7 @@ SYMBOLS = {
     "sbx_set_stream": (C.c_int32, [_vp, _vp]),
     "sbx_synchronize": (C.c_int32, [_vp]),
     "sbx_launch_count": (C.c_uint64, [_vp]),
+    "sbx_kernel_path": (C.c_char_p, [_vp]),
     "sbx_get_bin_map": (C.c_int32, [_vp, _f32p, _f32p, _u32p, _f32p]),
     "sbx_get_color_thresholds": (C.c_int32, [_vp, _f32p]),
     "sbx_get_window": (C.c_int32, [_vp, _f32p]),

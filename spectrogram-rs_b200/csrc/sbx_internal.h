@@ -38,6 +38,13 @@ struct sbx_plan {
     uint32_t *d_pos_tab = nullptr;
     std::vector<uint32_t> radix, stride;
 
+    // REAL geometry (mono batches of long windows, one frame per CTA): tables of the half-length packed transform
+    bool real_ok = false;               // tables exist
+    bool use_real = false;              // mono batches take it (plan-time choice, see choose_real)
+    float2 *d_twp_real = nullptr;
+    float4 *d_wtw4 = nullptr;
+    float2 *d_rtw = nullptr;
+
     // large path (M > 16384): block-transform twiddles and per-launch scratch
     bool large = false;
     float2 *d_twp_block = nullptr;
@@ -63,14 +70,11 @@ struct sbx_plan {
         cudaStream_t stream = nullptr;
         float *d_pcm = nullptr;
         uint8_t *d_rgba = nullptr;
-        float *h_pcm = nullptr;         // pinned bounce buffers (used when the caller's memory is pageable)
-        uint8_t *h_rgba = nullptr;
-        cudaEvent_t done = nullptr;
-        // pending pageable copy-out
-        uint8_t *pending_dst = nullptr;
-        size_t pending_bytes = 0;
     } slots[kSlots];
     uint64_t chunk_frames = 0;
+
+    // launch geometry of the persistent kernel for this plan's hop, per channel layout (index CH - 1; 2 = REAL)
+    struct PersistentGeom { bool ready = false; int ctas = 0, occ = 0; size_t smem = 0; } pgeom[3];
 
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;      // current stream (own or caller's)

@@ -3,6 +3,7 @@
 // kernels of stft_kernels.cuh or fails with SBX_ERR_CUDA / SBX_ERR_UNSUPPORTED.
 #include <cuda_fp16.h>
 
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -18,7 +19,7 @@ namespace {
 
 thread_local std::string g_create_error;
 
-constexpr uint32_t kMinLog2N = 8, kMaxLog2M = 14;                      // fused (single-SM) kernel: N <= 8192, M <= 16384
+constexpr uint32_t kMinLog2N = 8, kMaxLog2M = 14;                      // fused (single-SM) kernel: M <= 16384
 constexpr uint32_t kMaxLog2NLarge = 16, kMaxLog2MLarge = 18;             // multi-kernel path of stft_large.cuh
 
 int ilog2_exact(uint32_t v)
@@ -53,24 +54,29 @@ sbx_status cuda_fail(const sbx_plan *p, cudaError_t e, const char *what)
 // ---- kernel dispatch ---------------------------------------------------------------------------
 constexpr size_t kMaxSmemOptIn = 227 * 1024;           // opt-in dynamic shared memory per CTA on sm_100
 
-// Per-device launch geometry of the persistent kernel: resident CTAs per SM x SM count.
-struct PersistentGeom { bool ready = false; int ctas = 0, occ = 0; size_t smem = 0; };
-
-template <int LOG2N, int LOG2PAD, int CH>
-cudaError_t launch_one(const KernelArgs &args, uint64_t n_frames, cudaStream_t stream)
+// Opt a kernel in to `bytes` of dynamic shared memory, once per device.  `done` is the kernel's own flag array
+// (one static per template instance); the attribute call is idempotent, so two host threads racing on the first
+// launch only repeat it.
+constexpr int kMaxDevices = 64;
+template <class Kernel> cudaError_t allow_smem(Kernel kernel, size_t bytes, std::atomic<bool> (&done)[kMaxDevices])
 {
-    using G = Geom<LOG2N, LOG2PAD, CH>;
-    static bool configured[64] = {};
-    static PersistentGeom pgeom[64];
-    static uint32_t pgeom_hop[64] = {};
     int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-    if (!configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(fused_frames_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        configured[dev] = true;
-    }
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+    if (done[dev].load(std::memory_order_acquire)) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) done[dev].store(true, std::memory_order_release);
+    return e;
+}
+
+template <class G>
+cudaError_t launch_geom(sbx_plan *p, const KernelArgs &args, uint64_t n_frames, cudaStream_t stream)
+{
+    constexpr int CH = G::CH;
+    static std::atomic<bool> configured[kMaxDevices], configured_p[kMaxDevices];
+    cudaError_t e = allow_smem(fused_frames_kernel<G>, G::SMEM_BYTES, configured);
+    if (e != cudaSuccess) return e;
     const uint64_t ctas = (n_frames + G::FRAMES_PER_CTA - 1) / G::FRAMES_PER_CTA;
     if (ctas == 0) return cudaSuccess;
     if (ctas > 0x7fffffffull) return cudaErrorInvalidConfiguration;
@@ -90,21 +96,23 @@ cudaError_t launch_one(const KernelArgs &args, uint64_t n_frames, cudaStream_t s
     const bool aligned = (unit_stride_bytes % 16u) == 0 && (span_bytes % 16u) == 0 &&
                          (reinterpret_cast<uintptr_t>(args.pcm) % 16u) == 0;
     const size_t smem_p = (size_t)G::SMEM_BYTES + span_bytes;
-    if (!disabled && aligned && smem_p <= kMaxSmemOptIn) {
-        PersistentGeom &pg = pgeom[dev];
-        if (!pg.ready || pgeom_hop[dev] != args.hop) {
-            cudaError_t e = cudaFuncSetAttribute(fused_frames_persistent_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
-            if (e != cudaSuccess) return e;
+    constexpr size_t kPersistentDynMax = kMaxSmemOptIn - 64;     // the kernel also has a static mbarrier
+    if (!disabled && aligned && smem_p <= kPersistentDynMax) {
+        // the opt-in is the device maximum (the staging span depends on the plan's hop); occupancy and grid are
+        // per plan and channel layout
+        e = allow_smem(fused_frames_persistent_kernel<G>, kPersistentDynMax, configured_p);
+        if (e != cudaSuccess) return e;
+        sbx_plan::PersistentGeom &pg = p->pgeom[G::REAL ? 2 : CH - 1];
+        if (!pg.ready) {
             int occ = 0, sms = 0;
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused_frames_persistent_kernel<G>, G::THREADS, smem_p);
             if (e != cudaSuccess) return e;
-            e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->cfg.device);
             if (e != cudaSuccess) return e;
             pg.ctas = occ * sms;
             pg.occ = occ;
             pg.smem = smem_p;
             pg.ready = true;
-            pgeom_hop[dev] = args.hop;
         }
         static const bool forced = std::getenv("SBX_FORCE_PERSISTENT") != nullptr;
         if (pg.ctas > 0 && ctas >= (uint64_t)pg.ctas * 2 && (pg.occ == 1 || forced)) {
@@ -117,30 +125,86 @@ cudaError_t launch_one(const KernelArgs &args, uint64_t n_frames, cudaStream_t s
 }
 
 template <int LOG2N, int LOG2PAD>
-cudaError_t launch_ch(int channels, const KernelArgs &args, uint64_t n_frames, cudaStream_t stream)
+cudaError_t launch_ch(sbx_plan *p, int channels, const KernelArgs &args, uint64_t n_frames, cudaStream_t stream)
 {
     if constexpr (LOG2N + LOG2PAD > (int)kMaxLog2M) {
         return cudaErrorInvalidConfiguration;
     } else {
-        return channels == 1 ? launch_one<LOG2N, LOG2PAD, 1>(args, n_frames, stream)
-                             : launch_one<LOG2N, LOG2PAD, 2>(args, n_frames, stream);
+        return channels == 1 ? launch_geom<Geom<LOG2N, LOG2PAD, 1>>(p, args, n_frames, stream)
+                             : launch_geom<Geom<LOG2N, LOG2PAD, 2>>(p, args, n_frames, stream);
     }
 }
 
 template <int LOG2N>
-cudaError_t launch_pad(int log2pad, int channels, const KernelArgs &args, uint64_t n_frames, cudaStream_t stream)
+cudaError_t launch_pad(sbx_plan *p, int channels, const KernelArgs &args, uint64_t n_frames, cudaStream_t stream)
 {
-    switch (log2pad) {
-        case 0: return launch_ch<LOG2N, 0>(channels, args, n_frames, stream);
-        case 1: return launch_ch<LOG2N, 1>(channels, args, n_frames, stream);
-        case 2: return launch_ch<LOG2N, 2>(channels, args, n_frames, stream);
+    switch (p->log2pad) {
+        case 0: return launch_ch<LOG2N, 0>(p, channels, args, n_frames, stream);
+        case 1: return launch_ch<LOG2N, 1>(p, channels, args, n_frames, stream);
+        case 2: return launch_ch<LOG2N, 2>(p, channels, args, n_frames, stream);
         default: return cudaErrorInvalidConfiguration;
     }
+}
+
+// REAL geometry: one mono frame per CTA, transformed as the packed sequence of N/2 sample pairs (M/2 points).
+// Wins where a frame PAIR no longer fits two CTAs per SM (M >= 16384) and makes M = 32768 a single-kernel path.
+template <int LOG2NC, int LOG2PAD>
+cudaError_t launch_real_one(sbx_plan *p, const KernelArgs &a, uint64_t n_frames, cudaStream_t stream)
+{
+    return launch_geom<Geom<LOG2NC, LOG2PAD, 2, true>>(p, a, n_frames, stream);
+}
+
+bool real_path_wanted(const sbx_plan *p, int channels, const float *d_pcm)
+{
+    return channels == 1 && p->use_real && (p->hop & 1u) == 0 && (reinterpret_cast<uintptr_t>(d_pcm) & 7u) == 0;
+}
+
+// SBX_REAL=0 / 1 overrides the plan-time default (tables::HostTables::real_auto): 1 = wherever the tables exist.
+bool choose_real(bool real_ok, bool real_auto)
+{
+    const char *env = std::getenv("SBX_REAL");
+    if (env && env[0] == '0') return false;
+    if (env && env[0] == '1') return real_ok;
+    return real_auto;
+}
+
+sbx_status launch_real(sbx_plan *p, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba, float *d_mags, cudaStream_t stream)
+{
+    KernelArgs a = p->base_args();
+    a.pcm = d_pcm;
+    a.rgba = d_rgba;
+    a.mags_out = d_mags;
+    a.n_frames = n_frames;
+    a.twp = p->d_twp_real;
+    a.hop = p->hop / 2;                                    // in sample pairs
+    cudaError_t e = cudaErrorInvalidConfiguration;
+    switch (p->log2n + p->log2pad) {
+        case 13:
+            if (p->log2pad == 0) e = launch_real_one<12, 0>(p, a, n_frames, stream);
+            else if (p->log2pad == 1) e = launch_real_one<11, 1>(p, a, n_frames, stream);
+            else if (p->log2pad == 2) e = launch_real_one<10, 2>(p, a, n_frames, stream);
+            break;
+        case 14:
+            if (p->log2pad == 0) e = launch_real_one<13, 0>(p, a, n_frames, stream);
+            else if (p->log2pad == 1) e = launch_real_one<12, 1>(p, a, n_frames, stream);
+            else if (p->log2pad == 2) e = launch_real_one<11, 2>(p, a, n_frames, stream);
+            break;
+        case 15:
+            if (p->log2pad == 0) e = launch_real_one<14, 0>(p, a, n_frames, stream);
+            else if (p->log2pad == 1) e = launch_real_one<13, 1>(p, a, n_frames, stream);
+            else if (p->log2pad == 2) e = launch_real_one<12, 2>(p, a, n_frames, stream);
+            break;
+        default: break;
+    }
+    if (e != cudaSuccess) return cuda_fail(p, e, "fused_frames_kernel (real-sequence geometry) launch");
+    if (n_frames) p->launches += 1;
+    return SBX_OK;
 }
 
 sbx_status launch_fused(sbx_plan *p, int channels, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba,
                         float *d_mags, cudaStream_t stream)
 {
+    if (real_path_wanted(p, channels, d_pcm)) return launch_real(p, d_pcm, n_frames, d_rgba, d_mags, stream);
     if (p->generic) return launch_generic(p, channels, d_pcm, n_frames, d_rgba, d_mags, stream);
     if (p->large) return launch_large(p, channels, d_pcm, n_frames, d_rgba, d_mags, stream);
     KernelArgs a = p->base_args();
@@ -150,12 +214,13 @@ sbx_status launch_fused(sbx_plan *p, int channels, const float *d_pcm, uint64_t 
     a.n_frames = n_frames;
     cudaError_t e;
     switch (p->log2n) {
-        case 8: e = launch_pad<8>(p->log2pad, channels, a, n_frames, stream); break;
-        case 9: e = launch_pad<9>(p->log2pad, channels, a, n_frames, stream); break;
-        case 10: e = launch_pad<10>(p->log2pad, channels, a, n_frames, stream); break;
-        case 11: e = launch_pad<11>(p->log2pad, channels, a, n_frames, stream); break;
-        case 12: e = launch_pad<12>(p->log2pad, channels, a, n_frames, stream); break;
-        case 13: e = launch_pad<13>(p->log2pad, channels, a, n_frames, stream); break;
+        case 8: e = launch_pad<8>(p, channels, a, n_frames, stream); break;
+        case 9: e = launch_pad<9>(p, channels, a, n_frames, stream); break;
+        case 10: e = launch_pad<10>(p, channels, a, n_frames, stream); break;
+        case 11: e = launch_pad<11>(p, channels, a, n_frames, stream); break;
+        case 12: e = launch_pad<12>(p, channels, a, n_frames, stream); break;
+        case 13: e = launch_pad<13>(p, channels, a, n_frames, stream); break;
+        case 14: e = launch_pad<14>(p, channels, a, n_frames, stream); break;      // P = 1 only (M <= 16384)
         default: e = cudaErrorInvalidConfiguration; break;
     }
     if (e != cudaSuccess) return cuda_fail(p, e, "fused_frames_kernel launch");
@@ -182,12 +247,13 @@ sbx_status launch_generic(sbx_plan *p, int channels, const float *d_pcm, uint64_
     const size_t smem = (size_t)p->m * 12;                      // transform [M] + magnitudes [M/2], float2
     const uint64_t ctas = channels == 1 ? (n_frames + 1) / 2 : n_frames;
     if (ctas > 0x7fffffffull) return fail(p, SBX_ERR_INVALID_ARGUMENT, "too many frames in one launch");
+    static std::atomic<bool> configured1[kMaxDevices], configured2[kMaxDevices];
     cudaError_t e;
     if (channels == 1) {
-        e = cudaFuncSetAttribute(generic_frames_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = allow_smem(generic_frames_kernel<1>, kMaxSmemOptIn, configured1);
         if (e == cudaSuccess) { generic_frames_kernel<1><<<(unsigned)ctas, GENERIC_THREADS, smem, stream>>>(g); e = cudaGetLastError(); }
     } else {
-        e = cudaFuncSetAttribute(generic_frames_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = allow_smem(generic_frames_kernel<2>, kMaxSmemOptIn, configured2);
         if (e == cudaSuccess) { generic_frames_kernel<2><<<(unsigned)ctas, GENERIC_THREADS, smem, stream>>>(g); e = cudaGetLastError(); }
     }
     if (e != cudaSuccess) return cuda_fail(p, e, "generic_frames_kernel launch");
@@ -203,14 +269,9 @@ cudaError_t launch_large_one(const LargeArgs &la, bool want_rgba, cudaStream_t s
     const unsigned units = la.units;
     large_first_kernel<LOG2N, LOG2PAD, CH><<<units * GL::PAD * (LARGE_BLOCK / LARGE_THREADS), LARGE_THREADS, 0, stream>>>(la);
     large_block_kernel<<<units * (GL::M / LARGE_BLOCK), LARGE_THREADS, 0, stream>>>(la);
-    static bool split_configured[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !split_configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(large_split_kernel<LOG2N, LOG2PAD, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, GL::SPLIT_SMEM);
-        if (e != cudaSuccess) return e;
-        split_configured[dev] = true;
-    }
+    static std::atomic<bool> split_configured[kMaxDevices];
+    cudaError_t e = allow_smem(large_split_kernel<LOG2N, LOG2PAD, CH>, GL::SPLIT_SMEM, split_configured);
+    if (e != cudaSuccess) return e;
     large_split_kernel<LOG2N, LOG2PAD, CH><<<units * (GL::Q / 2), LARGE_THREADS, GL::SPLIT_SMEM, stream>>>(la);
     if (want_rgba)
         large_colour_kernel<CH == 1><<<dim3(units, la.k.n_chunks), LARGE_THREADS, 0, stream>>>(la, la.magbuf, (size_t)GL::M / 2);
@@ -289,15 +350,10 @@ sbx_status launch_large(sbx_plan *p, int channels, const float *d_pcm, uint64_t 
 
 template <int LOG2M> cudaError_t launch_colourise_one(const KernelArgs &a, uint64_t n_frames, cudaStream_t stream)
 {
-    static bool configured[64] = {};
+    static std::atomic<bool> configured[kMaxDevices];
     const int smem = 8 << LOG2M;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(colourise_kernel<LOG2M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        configured[dev] = true;
-    }
+    cudaError_t e = allow_smem(colourise_kernel<LOG2M>, smem, configured);
+    if (e != cudaSuccess) return e;
     if (n_frames == 0) return cudaSuccess;
     if (n_frames > 0x7fffffffull) return cudaErrorInvalidConfiguration;
     colourise_kernel<LOG2M><<<(unsigned)n_frames, 256, smem, stream>>>(a);
@@ -315,7 +371,8 @@ sbx_status launch_colourise(sbx_plan *p, const float *d_mags, uint64_t n_frames,
         a.n_frames = n_frames;
         const uint32_t slots = p->m / 2;
         const size_t smem = (size_t)slots * sizeof(float2);
-        cudaError_t eg = cudaFuncSetAttribute(generic_colour_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        static std::atomic<bool> configured[kMaxDevices];
+        cudaError_t eg = allow_smem(generic_colour_kernel, kMaxSmemOptIn, configured);
         if (eg == cudaSuccess) { generic_colour_kernel<<<(unsigned)n_frames, GENERIC_THREADS, smem, stream>>>(a, slots); eg = cudaGetLastError(); }
         if (eg != cudaSuccess) return cuda_fail(p, eg, "generic_colour_kernel launch");
         p->launches += 1;
@@ -375,6 +432,8 @@ sbx::KernelArgs sbx_plan::base_args() const
     a.window = d_window;
     a.wtw = d_wtw;
     a.twp = d_twp;
+    a.wtw4 = d_wtw4;
+    a.rtw = d_rtw;
     a.rowmap = d_rowmap;
     a.rowinfo = d_rowinfo;
     a.chunks = d_chunks;
@@ -467,13 +526,12 @@ SBX_API void sbx_plan_destroy(sbx_plan *p)
     if (p->own_stream) cudaStreamSynchronize(p->own_stream);
     for (auto &s : p->slots) {
         if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
-        if (s.done) cudaEventDestroy(s.done);
         cudaFree(s.d_pcm);
         cudaFree(s.d_rgba);
     }
     cudaFree(p->d_window); cudaFree(p->d_wtw); cudaFree(p->d_twp); cudaFree(p->d_rowmap); cudaFree(p->d_rowinfo); cudaFree(p->d_chunks);
     cudaFree(p->d_samp); cudaFree(p->d_f16_scratch); cudaFree(p->d_twm); cudaFree(p->d_pos_tab); cudaFree(p->d_twp_block); cudaFree(p->d_zbuf); cudaFree(p->d_magbuf);
-    cudaFree(p->d_thr); cudaFree(p->d_lut); cudaFree(p->d_ctab); cudaFree(p->d_frame); cudaFree(p->d_mags1); cudaFree(p->d_col);
+    cudaFree(p->d_thr); cudaFree(p->d_lut); cudaFree(p->d_ctab); cudaFree(p->d_twp_real); cudaFree(p->d_wtw4); cudaFree(p->d_rtw); cudaFree(p->d_frame); cudaFree(p->d_mags1); cudaFree(p->d_col);
     if (p->h_frame) cudaFreeHost(p->h_frame);
     if (p->h_col) cudaFreeHost(p->h_col);
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
@@ -561,6 +619,8 @@ SBX_API sbx_status sbx_plan_create(const sbx_config *cfg, sbx_plan **out_plan)
     p->h_rowmap = t.rowmap;
     p->h_thr_raw = t.thr_raw;
     p->large = t.large;
+    p->real_ok = t.real_ok;
+    p->use_real = sbx::choose_real(t.real_ok, t.real_auto);
     p->n_chunks = (uint32_t)t.chunks.size();
     p->taps_clamped = t.taps_clamped ? 1 : 0;
     for (int i = 0; i < 2; ++i) { p->guess_a[i] = t.guess_a[i]; p->guess_b[i] = t.guess_b[i]; }
@@ -579,6 +639,9 @@ SBX_API sbx_status sbx_plan_create(const sbx_config *cfg, sbx_plan **out_plan)
     SBX_TRY(upload(&p->d_window, p->h_window.data(), p->n * sizeof(float)));
     SBX_TRY(upload(&p->d_wtw, t.wtw.data(), t.wtw.size() * sizeof(float)));
     SBX_TRY(upload(&p->d_twp, t.twp.data(), t.twp.size() * sizeof(float)));
+    SBX_TRY(upload(&p->d_twp_real, t.twp_real.data(), t.twp_real.size() * sizeof(float)));
+    SBX_TRY(upload(&p->d_wtw4, t.wtw4.data(), t.wtw4.size() * sizeof(float)));
+    SBX_TRY(upload(&p->d_rtw, t.rtw.data(), t.rtw.size() * sizeof(float)));
     SBX_TRY(upload(&p->d_twm, t.twm.data(), t.twm.size() * sizeof(float)));
     SBX_TRY(upload(&p->d_pos_tab, t.pos_tab.data(), t.pos_tab.size() * sizeof(uint32_t)));
     SBX_TRY(upload(&p->d_twp_block, t.twp_block.data(), t.twp_block.size() * sizeof(float)));
@@ -609,6 +672,15 @@ SBX_API uint32_t sbx_rows(const sbx_plan *p) { return p ? p->rows : 0; }
 SBX_API uint32_t sbx_hop(const sbx_plan *p) { return p ? p->hop : 0; }
 SBX_API uint32_t sbx_channels(const sbx_plan *p) { return p ? p->channels : 0; }
 SBX_API uint64_t sbx_launch_count(const sbx_plan *p) { return p ? p->launches : 0; }
+
+SBX_API const char *sbx_kernel_path(const sbx_plan *p)
+{
+    if (!p) return "";
+    if (p->generic) return "generic";
+    if (p->channels == 1 && p->use_real && (p->hop & 1u) == 0) return "fused-real";
+    if (p->large) return "large";
+    return p->channels == 1 ? "fused-pair" : "fused-stereo";
+}
 
 SBX_API uint64_t sbx_num_frames(const sbx_plan *p, uint64_t n_samples)
 {
@@ -795,11 +867,20 @@ SBX_API sbx_status sbx_process_batch(sbx_plan *p, const float *pcm, uint64_t n_s
         cf = cf < cf_pcm ? cf : cf_pcm;
         cf = cf < 2 ? 2 : (cf & ~1ull);
         const size_t pcm_bytes = ((size_t)(cf - 1) * p->hop + p->n) * p->channels * sizeof(float);
+        cudaError_t e = cudaSuccess;
         for (auto &s : p->slots) {
-            SBX_CUDA(p, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-            SBX_CUDA(p, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
-            SBX_CUDA(p, cudaMalloc(&s.d_pcm, pcm_bytes));
-            SBX_CUDA(p, cudaMalloc(&s.d_rgba, (size_t)cf * p->rows * 4));
+            if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaMalloc(&s.d_pcm, pcm_bytes);
+            if (e == cudaSuccess) e = cudaMalloc(&s.d_rgba, (size_t)cf * p->rows * 4);
+        }
+        if (e != cudaSuccess) {                                      // leave no half-built pipeline behind
+            for (auto &s : p->slots) {
+                if (s.stream) cudaStreamDestroy(s.stream);
+                cudaFree(s.d_pcm);
+                cudaFree(s.d_rgba);
+                s = sbx_plan::Slot{};
+            }
+            return cuda_fail(p, e, "batch pipeline allocation");
         }
         p->chunk_frames = cf;
     }
@@ -807,18 +888,26 @@ SBX_API sbx_status sbx_process_batch(sbx_plan *p, const float *pcm, uint64_t n_s
     SBX_CUDA(p, cudaStreamSynchronize(p->stream));
     const uint64_t cf = p->chunk_frames;
     uint64_t chunk = 0;
-    for (uint64_t f0 = 0; f0 < frames; f0 += cf, ++chunk) {
+    sbx_status st = SBX_OK;
+    for (uint64_t f0 = 0; f0 < frames && st == SBX_OK; f0 += cf, ++chunk) {
         sbx_plan::Slot &s = p->slots[chunk % sbx_plan::kSlots];
         const uint64_t nf = frames - f0 < cf ? frames - f0 : cf;
         const size_t samples = (size_t)(nf - 1) * p->hop + p->n;
-        SBX_CUDA(p, cudaMemcpyAsync(s.d_pcm, pcm + (size_t)f0 * p->hop * p->channels,
-                                    samples * p->channels * sizeof(float), cudaMemcpyHostToDevice, s.stream));
-        sbx_status st = sbx::launch_fused(p, (int)p->channels, s.d_pcm, nf, s.d_rgba, nullptr, s.stream);
-        if (st != SBX_OK) return st;
-        SBX_CUDA(p, cudaMemcpyAsync(rgba + (size_t)f0 * p->rows * 4, s.d_rgba, (size_t)nf * p->rows * 4,
-                                    cudaMemcpyDeviceToHost, s.stream));
+        cudaError_t e = cudaMemcpyAsync(s.d_pcm, pcm + (size_t)f0 * p->hop * p->channels,
+                                        samples * p->channels * sizeof(float), cudaMemcpyHostToDevice, s.stream);
+        if (e != cudaSuccess) { st = cuda_fail(p, e, "batch H2D copy"); break; }
+        st = sbx::launch_fused(p, (int)p->channels, s.d_pcm, nf, s.d_rgba, nullptr, s.stream);
+        if (st != SBX_OK) break;
+        e = cudaMemcpyAsync(rgba + (size_t)f0 * p->rows * 4, s.d_rgba, (size_t)nf * p->rows * 4,
+                            cudaMemcpyDeviceToHost, s.stream);
+        if (e != cudaSuccess) st = cuda_fail(p, e, "batch D2H copy");
     }
-    for (auto &s : p->slots) SBX_CUDA(p, cudaStreamSynchronize(s.stream));
+    // always drain: no copy into the caller's buffers may still be in flight when this returns, error or not
+    for (auto &s : p->slots) {
+        const cudaError_t e = cudaStreamSynchronize(s.stream);
+        if (e != cudaSuccess && st == SBX_OK) st = cuda_fail(p, e, "batch stream synchronize");
+    }
+    if (st != SBX_OK) return st;
     if (frames_out) *frames_out = frames;
     return SBX_OK;
 }

@@ -90,6 +90,12 @@ struct HostTables {
     std::vector<float> wtw;             // [(P-1) N] x (re, im): window[n] * W_M^(n q0)
     std::vector<float> twp;             // per-pass twiddle planes x (re, im), see KernelArgs::twp
     std::vector<float> twp_block;       // large path: planes of the 4096-point block transform
+    // REAL geometry (one mono frame per CTA as the even/odd packed sequence of N/2 pairs, M in {16384, 32768})
+    bool real_ok = false;               // the tables below exist
+    bool real_auto = false;             // ... and mono batches take the geometry by default (see build)
+    std::vector<float> twp_real;        // per-pass planes of the N/2-point sub-transform
+    std::vector<float> wtw4;            // [(P-1) N/2] x {w[2n] c, w[2n+1] s, w[2n] s, w[2n+1] c}, (c, s) = W_(M/2)^(n q0)
+    std::vector<float> rtw;             // [M/32] x (re, im): W_M^t, recombination twiddle of bin t
     bool large = false;                 // M > 16384: the multi-kernel path of stft_large.cuh
     bool generic = false;               // N not a power of two: the run-time mixed-radix path of stft_generic.cuh
     std::vector<float> twm;             // generic: [M] x (re, im) full twiddle table W_M^t
@@ -199,6 +205,30 @@ inline void build(const sbx_config &cfg, HostTables &t)
         t.twp_block.clear();
     }
 
+    // REAL geometry: transform of the packed sequence z[n] = x[2n] + i x[2n+1], length M/2 with N/2 non-zero pairs
+    t.real_ok = !t.generic && t.m >= REAL_MIN_M && t.m <= REAL_MAX_M && t.n >= 512;
+    t.twp_real.clear(); t.wtw4.clear(); t.rtw.clear();
+    if (t.real_ok) {
+        const RadixPlan rr(log2n - 1);
+        planes(rr, 0, rr.npass - 1, t.twp_real);
+        const uint32_t nc = t.n / 2, mc = t.m / 2;
+        t.wtw4.assign((size_t)(t.pad - 1) * nc * 4, 0.0f);
+        for (uint32_t q0 = 1; q0 < t.pad; ++q0)
+            for (uint32_t i = 0; i < nc; ++i) {
+                const double ang = -2.0 * M_PI * (double)(((uint64_t)i * q0) % mc) / (double)mc;
+                const double c = std::cos(ang), sn = std::sin(ang);
+                const double w0 = (double)t.window[2 * i], w1 = (double)t.window[2 * i + 1];
+                float *o = t.wtw4.data() + ((size_t)(q0 - 1) * nc + i) * 4;
+                o[0] = (float)(w0 * c); o[1] = (float)(w1 * sn); o[2] = (float)(w0 * sn); o[3] = (float)(w1 * c);
+            }
+        t.rtw.resize((size_t)(t.m / 32) * 2);
+        for (uint32_t k = 0; k < t.m / 32; ++k) {
+            const double ang = -2.0 * M_PI * (double)k / (double)t.m;
+            t.rtw[2 * (size_t)k] = (float)std::cos(ang);
+            t.rtw[2 * (size_t)k + 1] = (float)std::sin(ang);
+        }
+    }
+
     t.rowmap.resize(t.rows);
     std::vector<uint32_t> samp_first(t.rows);                 // first entry of each row in the per-sample table
     uint64_t total_samples = 0;
@@ -252,6 +282,14 @@ inline void build(const sbx_config &cfg, HostTables &t)
         ck.samp_end = samp_first[py] + rm.n;
     }
     if (ck.row_end > ck.row_begin) t.chunks.push_back(ck);
+    for (const RowChunk &c : t.chunks)
+        if (c.samp_end - c.samp_begin > cap) t.real_ok = false;            // rows resampled in parts: large path only
+    // Default choice between the frame-pair kernel and the real-sequence geometry for mono batches.  Measured on a
+    // B200 (M frames/s, pair vs real): cfg3 N 8192 P 2: 22.6 vs 29.3; N 8192 P 4 (M 32768, pair = the four-kernel
+    // large path): 5.7 vs 9.0; but cfg1 N 4096 P 2: 59.0 vs 52.7; N 4096 P 4: 25.2 vs 23.6; N 2048 P 4: 49.2 vs 45.1.
+    // The half-length transform wins exactly where it needs one shared-memory pass fewer (N/2 = 16^k) or where the
+    // pair no longer fits one SM at all.
+    t.real_auto = t.real_ok && (t.large || RadixPlan(log2n - 1).npass < RadixPlan(log2n).npass);
     t.rowinfo.resize(t.rows);
     for (uint32_t py = 0; py < t.rows; ++py) t.rowinfo[py] = t.rowmap[py].n | (t.rowmap[py].aux << 16);
 

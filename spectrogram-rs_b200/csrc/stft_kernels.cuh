@@ -8,7 +8,9 @@
 //   mono PCM   : a = frame 2c, b = frame 2c+1           (two frames share one transform; the
 //                reference's (s,s) duplication gives L == R == |S[k]|*2/N)
 // and the same conjugate-symmetry split (src/fourier/fft.rs:81-89) separates the two real
-// sequences afterwards.
+// sequences afterwards.  Long mono windows (real length >= 16384, Geom<.., REAL = true>) instead give
+// every frame its own CTA: z[n] = x[2n] + i x[2n+1] halves the transform (the even/odd split of a real
+// sequence), so the buffer is 64 KB instead of 128 KB per unit and two CTAs fit an SM.
 //
 // FFT structure (see tools/fft_model.py for the numpy model of the index math):
 //   * the zero padding is never materialised: the radix-P DIF step over a sequence whose last
@@ -49,6 +51,8 @@ struct KernelArgs {
     const float *window;         // [N] periodic Hann, f32, host-computed (fft.rs:59-63)
     const float2 *wtw;           // [(P-1) N] window[n] * W_M^(n q0), q0 = 1..P-1 (sub-transform premultiply)
     const float2 *twp;           // per DIF pass p: TW_PLANES planes of S_p entries, plane j = W_(S_p R_p)^(2^j lo)
+    const float4 *wtw4;          // REAL: [(P-1) N/2] {w0 c, w1 s, w0 s, w1 c}: (w[2n], w[2n+1]) and (c, s) = W_(M/2)^(n q0)
+    const float2 *rtw;           // REAL: [M/32] W_M^t, the even/odd recombination twiddle of bin t (M = real length)
     const RowMap *rowmap;        // [H] (host-side description; the kernels read rowinfo)
     const uint32_t *rowinfo;     // [H] n | first scratch slot << 16
     const RowChunk *chunks;      // [n_chunks]
@@ -81,6 +85,7 @@ constexpr int TW_PLANES = 4;     // twiddle planes stored per pass: W^(1,2,4,8 *
 #ifndef SBX_TW_LOADS
 #define SBX_TW_LOADS 2           // planes actually loaded per butterfly (1: W^lo; 2: + W^4lo; 4: all); rest by products
 #endif
+constexpr uint32_t REAL_MIN_M = 8192, REAL_MAX_M = 32768;   // real transform lengths the REAL geometry is built for
 constexpr int THR_STRIDE = 512;  // floats per threshold set: 256 pairs (ts[i], ts[i+1]), ts = [-inf, thr[0..254], +inf]
 
 // ----------------------------------------------------------------------------------------------
@@ -247,6 +252,16 @@ __device__ __forceinline__ float2 ldg_tab(const float2 *p)
     float2 v; asm volatile("ld.global.nc.L1::evict_last.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p)); return v;
 #endif
 }
+__device__ __forceinline__ float4 ldg_tab(const float4 *p)
+{
+#if defined(SBX_EMU) || SBX_TABLE_KEEP == 0
+    return __ldg(p);
+#else
+    float4 v;
+    asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+#endif
+}
 __device__ __forceinline__ uint2 ldg_tab(const uint2 *p)
 {
 #if defined(SBX_EMU) || SBX_TABLE_KEEP == 0
@@ -277,8 +292,12 @@ __device__ __forceinline__ uint32_t ldg_tab(const uint32_t *p)
 // ----------------------------------------------------------------------------------------------
 // compile-time geometry
 // ----------------------------------------------------------------------------------------------
-template <int LOG2N_, int LOG2PAD_, int CH_> struct Geom {
+// REAL_: the complex sequence is the even/odd packing z[n] = x[2n] + i x[2n+1] of ONE real (mono) frame of 2 N
+// samples, zero-padded to 2 M; addressed like stereo PCM (CH_ = 2) with hop/2 pairs between frames.
+template <int LOG2N_, int LOG2PAD_, int CH_, bool REAL_ = false> struct Geom {
     static constexpr int LOG2N = LOG2N_, LOG2PAD = LOG2PAD_, CH = CH_;
+    static constexpr bool REAL = REAL_;
+    static_assert(!REAL_ || CH_ == 2, "the real-sequence packing reads sample pairs");
     static constexpr int N = 1 << LOG2N, PAD = 1 << LOG2PAD, LOG2M = LOG2N + LOG2PAD, M = 1 << LOG2M;
     static constexpr int REM = LOG2N & 3;                  // first pass radix 2^REM when REM != 0
     static constexpr int NPASS = LOG2N / 4 + (REM ? 1 : 0);
@@ -445,7 +464,15 @@ __device__ __forceinline__ void first_inputs(float2 (&v)[1 << G::log2r(0)], cons
             s.x = ldg_pcm(pa_lo + r * S);
             s.y = second_valid ? ldg_pcm(pb_lo + r * S) : 0.0f;
         }
-        if constexpr (Q0ZERO) {
+        if constexpr (G::REAL) {
+            if constexpr (Q0ZERO) {
+                const float2 wn = ldg_tab(reinterpret_cast<const float2 *>(a.window) + lo + r * S);
+                s.x *= wn.x;  s.y *= wn.y;                           // even and odd sample, each with its own window value
+            } else {
+                const float4 f = ldg_tab(a.wtw4 + (q0 - 1) * G::N + lo + r * S);
+                s = make_float2(s.x * f.x - s.y * f.y, s.x * f.z + s.y * f.w);
+            }
+        } else if constexpr (Q0ZERO) {
             const float wn = ldg_tab(win_lo + r * S);
             s.x *= wn;  s.y *= wn;                                   // fft.rs:57-63 (complex * f32)
         } else {
@@ -562,7 +589,12 @@ template <class G> struct SplitConst {
     static constexpr int PMASK = (G::M >> LT) - 1;
     static __host__ __device__ constexpr int own(int p) { return G::zsw(G::pos_of_bin(p << LT)); }
     static __host__ __device__ constexpr int partner(int p) { return G::zsw(G::pos_of_bin(((~p) & PMASK) << LT)); }
-    static __host__ __device__ constexpr int partner_t0(int p) { return p == 0 ? 0 : G::zsw(G::pos_of_bin(G::M - (p << LT))); }
+    // thread 0: M - kk carries into the p field; its kk = 0 slot (DC, dropped) pairs with itself, or -- REAL -- is
+    // used for bin M/2, the one bin that is its own partner
+    static __host__ __device__ constexpr int partner_t0(int p)
+    {
+        return p == 0 ? (G::REAL ? G::zsw(G::pos_of_bin(G::M / 2)) : 0) : G::zsw(G::pos_of_bin(G::M - (p << LT)));
+    }
     // the bit of p that maps to position bit 0: p and p | (1 << B0) sit in one 16-byte chunk
     static __host__ __device__ constexpr int pair_bit()
     {
@@ -581,6 +613,26 @@ __device__ __forceinline__ float2 split_pair(float2 x, float2 y, float scale)
     const float rr = fast_sqrt(rx * rx + ry * ry) * 0.5f;
     return make_float2(l * scale, rr * scale);
 }
+
+// REAL: a = Z[kk], b = Z[M-kk] of the packed sequence, w = W_(2M)^kk.  With E, O the spectra of the even and odd
+// samples, a + conj b = 2 E and a - conj b = 2i O, and the real sequence's spectrum is X[kk] = E + w O,
+// X[M-kk] = conj(E - w O).  Returns (|X[kk]|, |X[M-kk]|) * scale  (L == R == |X| * 2/N for (s,s) input).
+__device__ __forceinline__ float2 split_pair_real(float2 x, float2 y, float2 w, float scale)
+{
+    const float sx = x.x + y.x, sy = x.y - y.y;   // a + conj b
+    const float dx = x.x - y.x, dy = x.y + y.y;   // a - conj b
+    const float tx = w.x * dy + w.y * dx;         // w * (-i d)
+    const float ty = w.y * dy - w.x * dx;
+    const float ox = sx + tx, oy = sy + ty, px = sx - tx, py = sy - ty;
+    return make_float2(fast_sqrt(ox * ox + oy * oy) * 0.5f * scale, fast_sqrt(px * px + py * py) * 0.5f * scale);
+}
+// W_32^p = exp(-i pi p / 16), p = 0..7: the part of the recombination twiddle that depends on the bin's p field
+__host__ __device__ constexpr float w32_cos(int p)
+{
+    return p == 0 ? 1.0f : p == 1 ? 0.98078528040323044913f : p == 2 ? 0.92387953251128675613f : p == 3 ? 0.83146961230254523708f
+         : p == 4 ? 0.70710678118654752440f : p == 5 ? 0.55557023301960222474f : p == 6 ? 0.38268343236508977173f : 0.19509032201612826785f;
+}
+__host__ __device__ constexpr float w32_sin(int p) { return p == 0 ? 0.0f : w32_cos(8 - p); }
 
 template <class G>
 __device__ __forceinline__ void split_read(const float2 *z, const KernelArgs &a, SplitRegs<G> &r)
@@ -616,9 +668,20 @@ template <class G>
 __device__ __forceinline__ void split_write(float2 *z, const SplitRegs<G> &r)
 {
     const int tid = threadIdx.x;
+    if constexpr (G::REAL) {
+        // one magnitude per bin kk = 1 .. M-1 of the real spectrum, natural order, over the lower half of the buffer
+        float *zf = reinterpret_cast<float *>(z);
 #pragma unroll
-    for (int p = 0; p < SplitRegs<G>::PER_THREAD; ++p)
-        if (p != 0 || tid != 0) z[tid | (p << SplitConst<G>::LT)] = r.mag[p];      // kk = 0 (DC) is dropped
+        for (int p = 0; p < SplitRegs<G>::PER_THREAD; ++p) {
+            const int kk = tid | (p << SplitConst<G>::LT);
+            if (kk != 0) { zf[kk] = r.mag[p].x; zf[G::M - kk] = r.mag[p].y; }
+            else zf[G::M / 2] = r.mag[p].x;                                        // thread 0's DC slot carries bin M/2
+        }
+    } else {
+#pragma unroll
+        for (int p = 0; p < SplitRegs<G>::PER_THREAD; ++p)
+            if (p != 0 || tid != 0) z[tid | (p << SplitConst<G>::LT)] = r.mag[p];  // kk = 0 (DC) is dropped
+    }
 }
 
 // ---- last pass fused with the split (THREADS == M/16, i.e. one row per thread) -----------------------
@@ -659,6 +722,8 @@ __device__ __forceinline__ void split_with_own(const float2 *z, const KernelArgs
     using C = SplitConst<G>;
     const int tid = threadIdx.x;
     const int par = G::zsw(G::pos_of_bin((G::THREADS - tid) & (G::THREADS - 1)));
+    float2 wt = make_float2(1.0f, 0.0f);
+    if constexpr (G::REAL) wt = ldg_tab(a.rtw + tid);                                 // W_(2M)^tid
 #pragma unroll
     for (int pa = 0; pa < 8; pa += 2) {
         const int pb = pa + 1;
@@ -667,8 +732,19 @@ __device__ __forceinline__ void split_with_own(const float2 *z, const KernelArgs
             const float2 ya = z[C::partner_t0(pa)], yb = z[C::partner_t0(pb)];
             y = make_float4(yb.x, yb.y, ya.x, ya.y);
         }
-        r.mag[pa] = split_pair(r.mag[pa], make_float2(y.z, y.w), a.scale);
-        r.mag[pb] = split_pair(r.mag[pb], make_float2(y.x, y.y), a.scale);
+        if constexpr (G::REAL) {
+            // W_(2M)^kk, kk = tid | p << log2 T:  W_(2M)^tid * W_32^p
+            const float2 wa = pa == 0 ? wt : cmul(wt, make_float2(w32_cos(pa), -w32_sin(pa)));
+            const float2 wb = cmul(wt, make_float2(w32_cos(pb), -w32_sin(pb)));
+            if (pa == 0 && tid == 0)                                                  // y.zw = Z[M/2]: |X[M/2]| = |Z[M/2]|
+                r.mag[0] = make_float2(fast_sqrt(y.z * y.z + y.w * y.w) * a.scale, 0.0f);
+            else
+                r.mag[pa] = split_pair_real(r.mag[pa], make_float2(y.z, y.w), wa, a.scale);
+            r.mag[pb] = split_pair_real(r.mag[pb], make_float2(y.x, y.y), wb, a.scale);
+        } else {
+            r.mag[pa] = split_pair(r.mag[pa], make_float2(y.z, y.w), a.scale);
+            r.mag[pb] = split_pair(r.mag[pb], make_float2(y.x, y.y), a.scale);
+        }
     }
 }
 
@@ -717,40 +793,51 @@ __device__ __forceinline__ uint32_t step_colour(const KernelArgs &a, float p)
     return e.z;
 }
 
-// One interpolated sample (both channels) -- magnitude_at (ifs.rs:46-48).  mags is indexed by bin
-// kk = j + 1; x1 = floor(x), w = the interpolation weight, both precomputed by the plan.
-template <bool CLAMP>
-__device__ __forceinline__ float2 interp_sample(const float2 *mags, const KernelArgs &a, int x1, float w, int k_last)
+// One interpolated sample -- magnitude_at (ifs.rs:46-48).  mags is indexed by bin kk = j + 1; x1 = floor(x),
+// w = the interpolation weight, both precomputed by the plan.  T = float2: both channels (or both frames of a
+// mono pair); T = float: the single frame of the REAL geometry.
+__device__ __forceinline__ float cubicv(float y0, float y1, float y2, float y3, float mu, float mu2, float mu3)
 {
-    float2 v;
+    return cubic1(y0, y1, y2, y3, mu, mu2, mu3);
+}
+__device__ __forceinline__ float2 cubicv(float2 y0, float2 y1, float2 y2, float2 y3, float mu, float mu2, float mu3)
+{
+    return make_float2(cubic1(y0.x, y1.x, y2.x, y3.x, mu, mu2, mu3), cubic1(y0.y, y1.y, y2.y, y3.y, mu, mu2, mu3));
+}
+__device__ __forceinline__ float mixv(float yl, float yh, float omt, float w) { return __fadd_rn(__fmul_rn(yl, omt), __fmul_rn(yh, w)); }
+__device__ __forceinline__ float2 mixv(float2 yl, float2 yh, float omt, float w)
+{
+    return make_float2(mixv(yl.x, yh.x, omt, w), mixv(yl.y, yh.y, omt, w));
+}
+
+template <bool CLAMP, class T>
+__device__ __forceinline__ T interp_sample(const T *mags, const KernelArgs &a, int x1, float w, int k_last)
+{
     if (a.interp == 0) {                                                     // cubic_interpolate, ifs.rs:88-105
         const float mu = w;
         const float mu2 = __fmul_rn(mu, mu), mu3 = __fmul_rn(mu, mu2);
-        float2 y0, y1, y2, y3;
+        T y0, y1, y2, y3;
         if constexpr (CLAMP) {
             y0 = mags[(x1 > 0 ? x1 - 1 : 0) + 1];
             y1 = mags[x1 + 1];
             y2 = mags[min(x1 + 1, k_last) + 1];
             y3 = mags[min(x1 + 2, k_last) + 1];
         } else {
-            const float2 *m = mags + x1;
+            const T *m = mags + x1;
             y0 = m[0]; y1 = m[1]; y2 = m[2]; y3 = m[3];
         }
-        v.x = cubic1(y0.x, y1.x, y2.x, y3.x, mu, mu2, mu3);
-        v.y = cubic1(y0.y, y1.y, y2.y, y3.y, mu, mu2, mu3);
+        return cubicv(y0, y1, y2, y3, mu, mu2, mu3);
     } else {                                                                 // cosine_interpolate, ifs.rs:78-86
         const float omt = __fsub_rn(1.0f, w);
-        const float2 yl = mags[x1 + 1], yh = mags[min(x1 + 1, k_last) + 1];  // high = clamp(ceil x, low+1, K-1)
-        v.x = __fadd_rn(__fmul_rn(yl.x, omt), __fmul_rn(yh.x, w));
-        v.y = __fadd_rn(__fmul_rn(yl.y, omt), __fmul_rn(yh.y, w));
+        const T yl = mags[x1 + 1], yh = mags[min(x1 + 1, k_last) + 1];       // high = clamp(ceil x, low+1, K-1)
+        return mixv(yl, yh, omt, w);
     }
-    return v;
 }
 
 // Phase A of a row chunk: one lane per (row, sample); consecutive lanes read consecutive bins.
 // The sample-table loads of four iterations are issued together (latency hiding).
-template <int THREADS, bool CLAMP>
-__device__ __forceinline__ void resample_samples_impl(const float2 *mags, float2 *scratch, const KernelArgs &a, const RowChunk ck)
+template <int THREADS, bool CLAMP, class T>
+__device__ __forceinline__ void resample_samples_impl(const T *mags, T *scratch, const KernelArgs &a, const RowChunk ck)
 {
     const int k_last = (int)a.k_out - 1;
     const uint32_t count = ck.samp_end - ck.samp_begin;
@@ -770,8 +857,8 @@ __device__ __forceinline__ void resample_samples_impl(const float2 *mags, float2
         }
     }
 }
-template <int THREADS>
-__device__ __forceinline__ void resample_samples(const float2 *mags, float2 *scratch, const KernelArgs &a, const RowChunk ck)
+template <int THREADS, class T>
+__device__ __forceinline__ void resample_samples(const T *mags, T *scratch, const KernelArgs &a, const RowChunk ck)
 {
     if (a.taps_clamped) resample_samples_impl<THREADS, true>(mags, scratch, a, ck);
     else resample_samples_impl<THREADS, false>(mags, scratch, a, ck);
@@ -816,6 +903,42 @@ __device__ __forceinline__ void colour_one_row(float ax, float ay, uint32_t n, u
             const uint32_t idx = !(v >= 0.0) ? 0u : (v > 255.0 ? 255u : (uint32_t)v);
             outA[row] = (ldg_tab(lut + idx) & 0x00ffffffu) | ((uint32_t)step_index(thr_a, p, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
         }
+    }
+}
+
+// REAL geometry: one mono frame, ax = the row's summed L (== R) magnitude
+__device__ __forceinline__ void colour_one_row_single(float ax, uint32_t n, uint32_t py, const KernelArgs &a, uint32_t *out)
+{
+    if (n > 1) ax = __fdiv_rn(ax, (float)n);
+    const uint32_t row = a.rows - 1u - py;                                   // simple_spectrogram.rs:150
+    const float p = __fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ax, ax));        // norm_sqr of (l, l)
+    if (a.scheme == 0) {
+        out[row] = step_colour(a, p);
+    } else {
+        const uint32_t pan = (ax > 0.0f && ax < 3.0e38f) ? 128u : 0u;        // l / (|l| + |l|), see colour_one_row
+        out[row] = (ldg_tab(a.lut + pan) & 0x00ffffffu) |
+                   ((uint32_t)step_index(a.thr + THR_STRIDE, p, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
+    }
+}
+
+template <int THREADS>
+__device__ __forceinline__ void colour_rows_single(const float *scratch, const KernelArgs &a, const RowChunk ck, unsigned long long frame)
+{
+    uint32_t *out = reinterpret_cast<uint32_t *>(a.rgba) + frame * a.rows;
+    for (uint32_t py0 = ck.row_begin + threadIdx.x; py0 < ck.row_end; py0 += 2 * THREADS) {
+        const uint32_t py1 = py0 + THREADS;
+        const bool has1 = py1 < ck.row_end;
+        const uint32_t r0 = ldg_tab(a.rowinfo + py0), r1 = has1 ? ldg_tab(a.rowinfo + py1) : 0u;
+        const uint32_t n0 = r0 & 0xffffu, n1 = r1 & 0xffffu;
+        const float *m0 = scratch + (r0 >> 16), *m1 = scratch + (r1 >> 16);
+        float a0 = 0.0f, a1 = 0.0f;
+        const uint32_t nmax = n0 > n1 ? n0 : n1;
+        for (uint32_t s = 0; s < nmax; ++s) {
+            if (s < n0) a0 = __fadd_rn(a0, m0[s]);
+            if (s < n1) a1 = __fadd_rn(a1, m1[s]);
+        }
+        colour_one_row_single(a0, n0, py0, a, out);
+        if (has1) colour_one_row_single(a1, n1, py1, a, out);
     }
 }
 
@@ -900,6 +1023,21 @@ __device__ __forceinline__ void resample_colour(float2 *z, const KernelArgs &a, 
     }
 }
 
+template <int LOG2M, int THREADS>
+__device__ __forceinline__ void resample_colour_single(float2 *z, const KernelArgs &a, unsigned long long frame)
+{
+    const float *mags = reinterpret_cast<const float *>(z);   // M floats: the lower half of the buffer
+    float *scratch = reinterpret_cast<float *>(z) + (1 << LOG2M);
+    for (uint32_t c = 0; c < a.n_chunks; ++c) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.chunks) + c);
+        const RowChunk ck = {raw.x, raw.y, raw.z, raw.w};
+        if (c != 0) __syncthreads();
+        resample_samples<THREADS>(mags, scratch, a, ck);
+        __syncthreads();
+        colour_rows_single<THREADS>(scratch, a, ck, frame);
+    }
+}
+
 // everything after pass 0: remaining passes, L/R split, optional magnitude store, resample + colour
 template <class G>
 __device__ __forceinline__ void frame_tail(float2 *z, const KernelArgs &a, unsigned long long frame0, bool second_valid)
@@ -920,20 +1058,30 @@ __device__ __forceinline__ void frame_tail(float2 *z, const KernelArgs &a, unsig
         split_write<G>(z, regs);
     }
     __syncthreads();
-    if (a.mags_out != nullptr) {
-        float2 *out = reinterpret_cast<float2 *>(a.mags_out) + frame0 * a.k_out;
-        for (uint32_t j = threadIdx.x; j < a.k_out; j += G::THREADS) {
-            const float2 m = z[j + 1];
-            if constexpr (G::CH == 1) {
-                out[j] = make_float2(m.x, m.x);
-                if (second_valid) out[a.k_out + j] = make_float2(m.y, m.y);
-            } else {
-                out[j] = m;
+    if constexpr (G::REAL) {
+        static_assert(LastSplit<G>::ENABLED, "the real-sequence split lives in the fused last pass");
+        if (a.mags_out != nullptr) {
+            float2 *out = reinterpret_cast<float2 *>(a.mags_out) + frame0 * a.k_out;
+            const float *zf = reinterpret_cast<const float *>(z);
+            for (uint32_t j = threadIdx.x; j < a.k_out; j += G::THREADS) out[j] = make_float2(zf[j + 1], zf[j + 1]);
+        }
+        if (a.rgba != nullptr) resample_colour_single<G::LOG2M, G::THREADS>(z, a, frame0);
+    } else {
+        if (a.mags_out != nullptr) {
+            float2 *out = reinterpret_cast<float2 *>(a.mags_out) + frame0 * a.k_out;
+            for (uint32_t j = threadIdx.x; j < a.k_out; j += G::THREADS) {
+                const float2 m = z[j + 1];
+                if constexpr (G::CH == 1) {
+                    out[j] = make_float2(m.x, m.x);
+                    if (second_valid) out[a.k_out + j] = make_float2(m.y, m.y);
+                } else {
+                    out[j] = m;
+                }
             }
         }
+        if (a.rgba != nullptr)
+            resample_colour<G::LOG2M, G::CH == 1, G::THREADS>(z, a, frame0, second_valid);
     }
-    if (a.rgba != nullptr)
-        resample_colour<G::LOG2M, G::CH == 1, G::THREADS>(z, a, frame0, second_valid);
 }
 
 template <class G>

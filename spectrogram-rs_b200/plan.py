@@ -175,6 +175,11 @@ class Plan:
     def launch_count(self):
         return int(self._lib.sbx_launch_count(self._h))
 
+    @property
+    def kernel_path(self):
+        """'fused-pair' | 'fused-real' | 'fused-stereo' | 'large' | 'generic' (sbx_kernel_path)."""
+        return self._lib.sbx_kernel_path(self._h).decode()
+
     # -- introspection -----------------------------------------------------------------------
     def bin_map(self):
         f0, step = np.empty(self.rows, np.float32), np.empty(self.rows, np.float32)

@@ -10,6 +10,7 @@
 namespace {
 
 bool g_emu_staged = false;
+int g_emu_real = 2;                     // mono batches on the REAL geometry: 0 never, 1 wherever its tables exist, 2 the product's default
 
 template <class G, int P, int END = G::NPASS> struct EmuPasses {
     static void run(float2 *z, const sbx::KernelArgs &a)
@@ -47,6 +48,24 @@ int emu_cta(const sbx::KernelArgs &a, unsigned long long frame0, float *mags_out
         for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::split_read<G>(z.data(), a, regs[t]); }
     }
     for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::split_write<G>(z.data(), regs[t]); }
+    if constexpr (G::REAL) {
+        const float *zf = reinterpret_cast<const float *>(z.data());
+        if (mags_out) {
+            float *o = mags_out + (size_t)frame0 * a.k_out * 2;
+            for (uint32_t j = 0; j < a.k_out; ++j) { o[2 * j] = zf[j + 1]; o[2 * j + 1] = zf[j + 1]; }
+        }
+        if (rgba) {
+            sbx::KernelArgs b = a;
+            b.rgba = rgba;
+            float *scratch = reinterpret_cast<float *>(z.data()) + G::M;
+            for (uint32_t c = 0; c < a.n_chunks; ++c) {
+                const sbx::RowChunk ck = a.chunks[c];
+                for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::resample_samples<G::THREADS>(zf, scratch, b, ck); }
+                for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::colour_rows_single<G::THREADS>(scratch, b, ck, frame0); }
+            }
+        }
+        return 0;
+    }
     if (mags_out) {
         for (uint32_t j = 0; j < a.k_out; ++j) {
             const float2 m = z[j + 1];
@@ -86,6 +105,16 @@ int emu_dispatch_pad(int lp, int ch, const sbx::KernelArgs &a, unsigned long lon
         case 2: return emu_dispatch_ch<LOG2N, 2>(ch, a, f0, mags, rgba);
     }
     return -2;
+}
+
+template <int LOG2NC, int LOG2PAD>
+int emu_real(const sbx::KernelArgs &a, unsigned long long frames, float *mags, uint8_t *rgba)
+{
+    for (unsigned long long f = 0; f < frames; ++f) {
+        const int st = emu_cta<sbx::Geom<LOG2NC, LOG2PAD, 2, true>>(a, f, mags, rgba);
+        if (st != 0) return st;
+    }
+    return 0;
 }
 
 // ---- large path: the four kernels of stft_large.cuh, one block at a time ------------------------------
@@ -235,6 +264,27 @@ long long emu_batch(const sbx_config *cfg, const float *pcm, unsigned long long 
     for (int i = 0; i < 2; ++i) { a.guess_a[i] = t.guess_a[i]; a.guess_b[i] = t.guess_b[i]; }
     a.interp = (int)cfg->interp; a.scheme = (int)cfg->scheme;
     const int ln = ilog2(t.n), lp = ilog2(t.pad), ch = (int)cfg->channels;
+    const bool use_real = g_emu_real == 0 ? false : (g_emu_real == 1 ? t.real_ok : t.real_auto);
+    if (ch == 1 && use_real && (cfg->hop & 1u) == 0) {
+        sbx::KernelArgs r = a;
+        r.twp = reinterpret_cast<const float2 *>(t.twp_real.data());
+        r.wtw4 = reinterpret_cast<const float4 *>(t.wtw4.data());
+        r.rtw = reinterpret_cast<const float2 *>(t.rtw.data());
+        r.hop = cfg->hop / 2;
+        int st = -2;
+        switch ((ln + lp) * 4 + lp) {
+            case 13 * 4 + 0: st = emu_real<12, 0>(r, frames, mags_lr, rgba); break;
+            case 13 * 4 + 1: st = emu_real<11, 1>(r, frames, mags_lr, rgba); break;
+            case 13 * 4 + 2: st = emu_real<10, 2>(r, frames, mags_lr, rgba); break;
+            case 14 * 4 + 0: st = emu_real<13, 0>(r, frames, mags_lr, rgba); break;
+            case 14 * 4 + 1: st = emu_real<12, 1>(r, frames, mags_lr, rgba); break;
+            case 14 * 4 + 2: st = emu_real<11, 2>(r, frames, mags_lr, rgba); break;
+            case 15 * 4 + 0: st = emu_real<14, 0>(r, frames, mags_lr, rgba); break;
+            case 15 * 4 + 1: st = emu_real<13, 1>(r, frames, mags_lr, rgba); break;
+            case 15 * 4 + 2: st = emu_real<12, 2>(r, frames, mags_lr, rgba); break;
+        }
+        return st != 0 ? st : (long long)frames;
+    }
     if (t.generic) {
         sbx::GenericArgs g{};
         g.k = a;
@@ -259,7 +309,7 @@ long long emu_batch(const sbx_config *cfg, const float *pcm, unsigned long long 
         }
         return st != 0 ? st : (long long)frames;
     }
-    if (ln < 8 || ln > 13 || lp < 0) return -2;
+    if (ln < 8 || ln > 14 || lp < 0) return -2;
     const int per = ch == 1 ? 2 : 1;
     for (unsigned long long f0 = 0; f0 < frames; f0 += per) {
         int st;
@@ -270,6 +320,7 @@ long long emu_batch(const sbx_config *cfg, const float *pcm, unsigned long long 
             case 11: st = emu_dispatch_pad<11>(lp, ch, a, f0, mags_lr, rgba); break;
             case 12: st = emu_dispatch_pad<12>(lp, ch, a, f0, mags_lr, rgba); break;
             case 13: st = emu_dispatch_pad<13>(lp, ch, a, f0, mags_lr, rgba); break;
+            case 14: st = emu_dispatch_pad<14>(lp, ch, a, f0, mags_lr, rgba); break;
             default: st = -2;
         }
         if (st != 0) return st;
@@ -279,6 +330,9 @@ long long emu_batch(const sbx_config *cfg, const float *pcm, unsigned long long 
 
 __attribute__((visibility("default")))
 void emu_set_staged(int staged) { g_emu_staged = staged != 0; }
+
+__attribute__((visibility("default")))
+void emu_set_real(int mode) { g_emu_real = mode; }
 
 // host tables of the product, exposed so CPU tests can compare them with the oracle bit for bit
 __attribute__((visibility("default")))

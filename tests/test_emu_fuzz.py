@@ -16,22 +16,25 @@ generic_n = st.sampled_from([100, 120, 300, 441, 600, 1000, 1470, 2205, 2400])
 
 @st.composite
 def configs(draw):
-    kind = draw(st.sampled_from(["fused", "fused", "generic", "large"]))
+    kind = draw(st.sampled_from(["fused", "fused", "generic", "large", "real"]))
     if kind == "fused":
         n, pad = draw(pow2_small), draw(st.sampled_from([1, 2, 4]))
+    elif kind == "real":                 # mono, real transform length 8192 .. 32768: one frame per CTA (even hops)
+        n, pad = draw(st.sampled_from([(2048, 4), (4096, 2), (8192, 1), (8192, 2), (4096, 4)]))
     elif kind == "generic":
         n, pad = draw(generic_n), draw(st.sampled_from([2, 4]))
     else:
         n, pad = 8192, 4
     sr = draw(st.sampled_from([8000.0, 22050.0, 44100.0, 48000.0, 96000.0]))
     hop = draw(st.one_of(st.integers(1, 2 * n), st.sampled_from([n // 8, n // 2, n])))
-    rows = draw(st.sampled_from([1, 2, 7, 33, 64, 100, 257] if kind != "large" else [16, 64]))
+    rows = draw(st.sampled_from([1, 2, 7, 33, 64, 100, 257] if kind not in ("large", "real") else [16, 64]))
     f_min = draw(st.sampled_from([1.0, 20.0, 32.0, 500.0]))
     f_max = draw(st.sampled_from([f_min * 1.5, 4000.0, sr / 2, 22030.0, sr]))
     if f_max <= f_min:
         f_max = f_min * 2
     return dict(kind=kind, sample_rate=sr, window_n=n, pad_factor=pad, hop=max(1, hop), rows_h=rows, f_min=f_min, f_max=f_max,
-                interp=draw(st.integers(0, 1)), scheme=draw(st.integers(0, 1)), channels=draw(st.integers(1, 2)),
+                interp=draw(st.integers(0, 1)), scheme=draw(st.integers(0, 1)),
+                channels=1 if kind == "real" else draw(st.integers(1, 2)),
                 db=draw(st.sampled_from([(-70.0, -10.0, 1e-7), (-100.0, 0.0, 1e-10), (-30.0, -5.0, 1e-7)])),
                 seed=draw(st.integers(0, 2 ** 16)), frames=draw(st.integers(1, 3)))
 
@@ -51,7 +54,7 @@ def test_random_configurations(c):
     kw = dict(sample_rate=c["sample_rate"], window_n=n, pad_factor=c["pad_factor"], hop=hop, rows_h=c["rows_h"],
               f_min=c["f_min"], f_max=c["f_max"], db_min=db_min, db_max=db_max, db_eps=eps, interp=c["interp"])
     cfg = emu.make_config(LUT, channels=ch, scheme=c["scheme"], **kw)
-    mags, rgba = emu.batch(cfg, pcm)
+    mags, rgba = emu.batch(cfg, pcm, real=True if c["kind"] == "real" else None)
     p = oracle.params(stereo_scheme=c["scheme"], **kw)
     o_rgba, o_mags = oracle.batch(p, pcm, ch, LUT, want_mags=True)
     assert mags.shape == o_mags.shape and rgba.shape == o_rgba.shape

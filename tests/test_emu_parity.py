@@ -26,6 +26,7 @@ CASES = [
     (8192, 2, 1, 256, 1024, 0),
     (4096, 4, 1, 512, 2048, 0),
     (2048, 1, 2, 512, 512, 0),
+    (16384, 1, 2, 2048, 128, 0),
     (256, 1, 1, 100, 77, 0),
     (1024, 2, 1, 1, 33, 0),
     # not a power of two: stft_generic.cuh (the live app's 2400 @ 48 kHz / 2205 @ 44.1 kHz windows)
@@ -65,6 +66,50 @@ def test_emulated_kernel_matches_oracle(magma, n, pad, ch, hop, rows, interp):
     rec = np.stack([oracle.column_from_magnitudes(p, mags[f], magma) for f in range(frames)])
     assert np.array_equal(rec, rgba)
     assert ((rgba != o_rgba).any(axis=2)).mean() <= 2e-3
+
+
+REAL_CASES = [
+    # (N, P, hop, H, interp, scheme): mono; real transform lengths 8192, 16384 and 32768, every pad factor
+    (4096, 2, 512, 1024, 0, 0),
+    (2048, 4, 256, 512, 0, 0),
+    (8192, 1, 1024, 256, 1, 0),
+    (8192, 2, 256, 1024, 0, 0),          # cfg3
+    (4096, 4, 512, 2048, 0, 1),
+    (16384, 1, 2048, 512, 0, 0),
+    (8192, 4, 1024, 2048, 0, 0),         # cfg5, N = 8192
+    (16384, 2, 2048, 1024, 1, 0),
+    (32768, 1, 4096, 512, 0, 1),
+]
+
+
+@pytest.mark.parametrize("n,pad,hop,rows,interp,scheme", REAL_CASES)
+@pytest.mark.parametrize("real", [True, False])
+def test_real_sequence_geometry_matches_oracle(magma, n, pad, hop, rows, interp, scheme, real):
+    """Mono batches have two kernels: a frame PAIR packed into one complex transform, and ONE frame as the even/odd
+    packed sequence of half the length (Geom<.., REAL>).  Both must reproduce the oracle, whichever the plan picks."""
+    ns = n + hop * 2 + 2
+    pcm = _pcm(1, ns, seed=n + pad)
+    frames = oracle.num_frames(ns, n, hop)
+    cfg = emu.make_config(magma, window_n=n, pad_factor=pad, hop=hop, rows_h=rows, channels=1, interp=interp, scheme=scheme)
+    mags, rgba = emu.batch(cfg, pcm, real=real, staged=(n == 8192))
+    p = oracle.params(window_n=n, pad_factor=pad, hop=hop, rows_h=rows, interp=interp, stereo_scheme=scheme)
+    o_rgba, o_mags = oracle.batch(p, pcm, 1, magma, want_mags=True)
+    peak = np.abs(o_mags).max(axis=(1, 2), keepdims=True)
+    assert (np.abs(mags - o_mags) / peak).max() <= MAG_TOL
+    assert np.array_equal(mags[..., 0], mags[..., 1])                   # (s, s) input: L == R
+    rec = np.stack([oracle.column_from_magnitudes(p, mags[f], magma) for f in range(frames)])
+    assert np.array_equal(rec, rgba)
+    assert ((rgba != o_rgba).any(axis=2)).mean() <= 2e-3
+
+
+def test_real_sequence_geometry_needs_an_even_hop(magma):
+    """hop odd: frames start on odd samples, the pair loads would be misaligned -> the frame-pair kernel runs."""
+    n, pad, hop, rows = 8192, 2, 255, 256
+    pcm = _pcm(1, n + 3 * hop)
+    cfg = emu.make_config(magma, window_n=n, pad_factor=pad, hop=hop, rows_h=rows, channels=1)
+    m_auto, c_auto = emu.batch(cfg, pcm, real=True)
+    m_pair, c_pair = emu.batch(cfg, pcm, real=False)
+    assert np.array_equal(m_auto, m_pair) and np.array_equal(c_auto, c_pair)
 
 
 @pytest.mark.parametrize("name,kw,ch,lut", [

@@ -49,6 +49,7 @@ CASES = [
     (8192, 2, 1, 256, 1024, 0),        # cfg3 geometry
     (4096, 4, 1, 512, 2048, 0),        # cfg5 geometry (N = 4096)
     (2048, 1, 2, 512, 512, 0),
+    (16384, 1, 2, 2048, 512, 0),       # the longest single-SM transform without padding
     (256, 1, 1, 100, 77, 0),           # ragged hop / odd H
     # windows that are not a power of two: the live app's (0.05 s * sr) as usize, run-time mixed radix
     (2400, 2, 2, 58, 1024, 0),         # 48 kHz, hop = (2.5/2048 * 48000) as usize  (gpu_spectrogram.rs:21-23,323)
@@ -282,6 +283,65 @@ def test_persistent_tma_staged_kernel(sbx, viridis, n, pad, ch, hop, frames):
         assert np.array_equal(plan.colorize_magnitudes(g_mags[:8]), g_rgba[:8])
         # the same leading frames through a short batch (one CTA per unit, global loads)
         short = plan.process_batch(pcm[: n + hop * 9])
+        assert np.array_equal(short, g_rgba[:10])
+
+
+@pytest.mark.parametrize("n,pad,hop,rows,interp,scheme", [
+    (4096, 2, 512, 1024, 0, 0), (2048, 4, 256, 512, 0, 0), (8192, 1, 1024, 256, 1, 0), (8192, 2, 256, 1024, 0, 0),
+    (4096, 4, 512, 2048, 0, 1), (16384, 1, 2048, 512, 0, 0), (8192, 4, 1024, 2048, 0, 0), (16384, 2, 2048, 1024, 1, 0),
+    (32768, 1, 4096, 512, 0, 1)])
+def test_real_sequence_geometry(sbx, magma, monkeypatch, n, pad, hop, rows, interp, scheme):
+    """Mono batches: the frame-pair kernel (SBX_REAL=0; the four-kernel path beyond M = 16384) and the one-frame
+    real-sequence geometry (SBX_REAL=1) against the oracle and against each other, on an odd frame count."""
+    import torch
+    frames = 9
+    ns = n + hop * (frames - 1) + 3
+    pcm = _pcm(1, ns, seed=n + pad)
+    p = oracle.params(window_n=n, pad_factor=pad, hop=hop, rows_h=rows, interp=interp, stereo_scheme=scheme)
+    o_rgba, o_mags = oracle.batch(p, pcm, 1, magma, want_mags=True, threads=4)
+    peak = np.abs(o_mags).max(axis=(1, 2), keepdims=True)
+    got = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("SBX_REAL", mode)
+        with sbx.Plan(window_n=n, pad_factor=pad, hop=hop, rows_h=rows, channels=1, interp=interp, scheme=scheme, lut=magma) as plan:
+            assert (plan.kernel_path == "fused-real") == (mode == "1")
+            d_pcm = torch.from_numpy(pcm).cuda()
+            d_mags = torch.zeros((frames, plan.k, 2), dtype=torch.float32, device="cuda")
+            assert plan.magnitudes_batch_device(d_pcm, ns, d_mags, frames) == frames
+            g_rgba = plan.process_batch(pcm)
+            plan.synchronize()
+            g_mags = d_mags.cpu().numpy()
+            assert (np.abs(g_mags - o_mags) / peak).max() <= MAG_TOL
+            assert np.array_equal(g_mags[..., 0], g_mags[..., 1])
+            rec = np.stack([oracle.column_from_magnitudes(p, g_mags[f], magma) for f in range(frames)])
+            assert np.array_equal(g_rgba, rec)
+            assert (g_rgba != o_rgba).any(axis=2).mean() <= 2e-3
+            got[mode] = g_rgba
+    assert (got["0"] != got["1"]).any(axis=2).mean() <= 2e-3
+    monkeypatch.delenv("SBX_REAL")
+    with sbx.Plan(window_n=n, pad_factor=pad, hop=hop + 1, rows_h=rows, channels=1, lut=magma) as plan:
+        assert plan.kernel_path != "fused-real"                      # odd hop: sample pairs would be misaligned
+
+
+def test_real_sequence_geometry_persistent(sbx, viridis):
+    """M = 32768 mono: one 1024-thread CTA per SM, persistent grid with cp.async.bulk staging; enough frames to take it."""
+    import torch
+    n, pad, hop, rows, frames = 8192, 4, 1024, 256, 2 * 148 + 37
+    ns = n + hop * (frames - 1)
+    pcm = signals.sweeps_plus_noise(ns, 48000.0)
+    p = oracle.params(window_n=n, pad_factor=pad, hop=hop, rows_h=rows)
+    o_rgba, o_mags = oracle.batch(p, pcm, 1, viridis, want_mags=True, threads=8)
+    with sbx.Plan(window_n=n, pad_factor=pad, hop=hop, rows_h=rows, channels=1, lut=viridis) as plan:
+        assert plan.kernel_path == "fused-real"
+        d_mags = torch.zeros((frames, plan.k, 2), dtype=torch.float32, device="cuda")
+        assert plan.magnitudes_batch_device(torch.from_numpy(pcm).cuda(), ns, d_mags, frames) == frames
+        g_rgba = plan.process_batch(pcm)
+        plan.synchronize()
+        g_mags = d_mags.cpu().numpy()
+        peak = np.abs(o_mags).max(axis=(1, 2), keepdims=True)
+        assert (np.abs(g_mags - o_mags) / peak).max() <= MAG_TOL
+        assert (g_rgba != o_rgba).any(axis=2).mean() <= 1e-3
+        short = plan.process_batch(pcm[: n + hop * 9])               # one CTA per frame, global loads
         assert np.array_equal(short, g_rgba[:10])
 
 
