@@ -259,10 +259,13 @@ def test_stereo_pan_scheme(sbx, viridis, n, pad, ch, hop, rows):
 
 
 @pytest.mark.parametrize("n,pad,ch,hop,frames", [(8192, 2, 1, 256, 701), (4096, 4, 2, 512, 330)])
-def test_persistent_tma_staged_kernel(sbx, viridis, n, pad, ch, hop, frames):
+def test_persistent_tma_staged_kernel(sbx, viridis, monkeypatch, n, pad, ch, hop, frames):
     """Enough units to take the persistent kernel (grid = SMs x resident CTAs, PCM staged into shared memory by
     cp.async.bulk): one CTA per SM at M = 16384.  Odd frame count: the trailing half-filled mono pair copies a
-    shorter span.  Compared with the oracle and with the one-CTA-per-unit kernel (a short batch of the same data)."""
+    shorter span.  Compared with the oracle and with the one-CTA-per-unit kernel (a short batch of the same data).
+    SBX_REAL=0 keeps the mono case on the frame-pair kernel (the default there is the real-sequence geometry,
+    test_real_sequence_geometry*)."""
+    monkeypatch.setenv("SBX_REAL", "0")
     ns = n + hop * (frames - 1)
     pcm = signals.sweeps_plus_noise(ns, 96000.0) if ch == 1 else signals.stereo_loopback(ns)
     p = oracle.params(sample_rate=96000.0, window_n=n, pad_factor=pad, hop=hop, rows_h=512)
