@@ -375,8 +375,25 @@ def extras(sbx, signals, torch):
     res["cfg3_frames_per_s"] = F3 / (ms * 1e-3)
     res["cfg3_workload"] = "96 kHz mono, N=8192 -> M=16384, hop 256, H=1024, Viridis, %d frames/step" % F3
     res["cfg3_hbm_frac"] = res["cfg3_frames_per_s"] * (hop3 * 4 + 4096) / 1e9 / measured_peaks()[0]["hbm_gbs"]
+    res["cfg3_kernel_path"] = plan.kernel_path
+    # the column store: cfg3's columns blitted into a 65536-column row-major image (256 MiB), a pure
+    # HBM-streaming transpose: bytes = columns read + image written
+    W = 1 << 16
+    img = torch.empty((1024, W, 4), dtype=torch.uint8, device="cuda")
+    for _ in range(2):
+        plan.blit_columns_device(out, W, img, W, W * 4, 0)
+    torch.cuda.synchronize()
+    a.record(stream)
+    for _ in range(5):
+        plan.blit_columns_device(out, W, img, W, W * 4, 0)
+    b.record(stream)
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 5
+    res["column_store_blit"] = {"gbs": 2 * W * 4096 / (ms * 1e-3) / 1e9,
+                                "hbm_frac": 2 * W * 4096 / (ms * 1e-3) / 1e9 / measured_peaks()[0]["hbm_gbs"],
+                                "what": "sbx_blit_columns_device: 65536 columns x 1024 rows -> row-major RGBA image (tiled transpose)"}
     plan.close()
-    del x, out
+    del x, out, img
 
     # cfg2: live single stream, 48 kHz stereo, 2048-pt frames pushed one at a time through the pinned ring
     plan = sbx.Plan(sample_rate=48000.0, window_n=2048, pad_factor=2, hop=2048, rows_h=1024, channels=2, lut="magma",

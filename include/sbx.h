@@ -167,6 +167,18 @@ SBX_API sbx_status sbx_magnitudes_batch_device_f16(sbx_plan *plan, const float *
  * colour = gradient(pan)/256, alpha = magnitude.  Host memory, out has resolution*resolution*4 floats. */
 SBX_API sbx_status sbx_palette_table(const sbx_plan *plan, uint32_t resolution, float *out_rgba);
 
+/* The column store of SimpleSpectrogram (src/widgets/simple_spectrogram.rs:89-94 pixbuf, :141-164 column loop):
+ * a width x rows RGBA8 image, row-major with rowstride_bytes per row (the GdkPixbuf layout, in which a column is
+ * strided).  Column f of d_columns (n_frames x rows x 4, row 0 = top, as the batch entry points write them) lands
+ * in image column (first_column + f) mod width -- `self.offset = (self.offset + 1) % width`, :164 -- so the store
+ * scrolls by wrapping around; when n_frames > width only the last `width` columns are drawn.  *next_column_out
+ * (may be NULL) receives (first_column + n_frames) mod width, the cursor for the next call.  DEVICE pointers,
+ * asynchronous on the plan's stream; a tiled transpose, both sides coalesced.  rowstride_bytes must be a multiple
+ * of 4 and >= 4 * width, d_image 4-byte aligned. */
+SBX_API sbx_status sbx_blit_columns_device(sbx_plan *plan, const uint8_t *d_columns, uint64_t n_frames, uint8_t *d_image,
+                                           uint32_t width, uint32_t rowstride_bytes, uint32_t first_column,
+                                           uint32_t *next_column_out);
+
 /* ---- streams ------------------------------------------------------------------------------ */
 /* Use the caller's CUDA stream (a cudaStream_t passed as void*; NULL restores the plan's own). */
 SBX_API sbx_status sbx_set_stream(sbx_plan *plan, void *cuda_stream);

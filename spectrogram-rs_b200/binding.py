@@ -48,6 +48,7 @@ SYMBOLS = {
     "sbx_magnitudes_batch_device": (C.c_int32, [_vp, _vp, C.c_uint64, _vp, C.c_uint64, _u64p]),
     "sbx_magnitudes_batch_device_f16": (C.c_int32, [_vp, _vp, C.c_uint64, _vp, C.c_uint64, _u64p]),
     "sbx_palette_table": (C.c_int32, [_vp, C.c_uint32, _vp]),
+    "sbx_blit_columns_device": (C.c_int32, [_vp, _vp, C.c_uint64, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _u32p]),
     "sbx_set_stream": (C.c_int32, [_vp, _vp]),
     "sbx_synchronize": (C.c_int32, [_vp]),
     "sbx_launch_count": (C.c_uint64, [_vp]),

@@ -426,6 +426,33 @@ __global__ void __launch_bounds__(256) pack_f16_kernel(const float2 *__restrict_
 }
 }  // namespace sbx
 
+namespace sbx {
+// columns (frames x rows, one packed pixel each) -> row-major image: a 32 x 32 tiled transpose through shared memory.
+// Reads run along a column (consecutive rows), writes along an image row (consecutive frames); the image column
+// wraps modulo `width`.  frames <= width (the host drops columns that would be overwritten).
+__global__ void __launch_bounds__(256) blit_columns_kernel(const uint32_t *__restrict__ cols, uint32_t frames, uint32_t rows,
+                                                            uint32_t *__restrict__ image, uint32_t width, uint32_t stride_px,
+                                                            uint32_t first_column)
+{
+    __shared__ uint32_t tile[32][33];
+    const uint32_t f0 = blockIdx.x * 32u, r0 = blockIdx.y * 32u;
+    const uint32_t tx = threadIdx.x & 31u, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (uint32_t i = ty; i < 32u; i += 8u) {
+        const uint32_t f = f0 + i, r = r0 + tx;
+        if (f < frames && r < rows) tile[i][tx] = cols[(size_t)f * rows + r];
+    }
+    __syncthreads();
+#pragma unroll
+    for (uint32_t i = ty; i < 32u; i += 8u) {
+        const uint32_t f = f0 + tx, r = r0 + i;
+        uint32_t x = first_column + f;                      // both < width
+        if (x >= width) x -= width;
+        if (f < frames && r < rows) image[(size_t)r * stride_px + x] = tile[tx][i];
+    }
+}
+}  // namespace sbx
+
 sbx::KernelArgs sbx_plan::base_args() const
 {
     sbx::KernelArgs a{};
@@ -842,6 +869,33 @@ SBX_API sbx_status sbx_palette_table(const sbx_plan *p, uint32_t resolution, flo
             if (p->cfg.scheme == SBX_SCHEME_STEREO) { eval((double)pan, o); o[3] = magnitude; }
             else { eval((double)magnitude, o); o[3] = 1.0f; }
         }
+    return SBX_OK;
+}
+
+SBX_API sbx_status sbx_blit_columns_device(sbx_plan *p, const uint8_t *d_columns, uint64_t n_frames, uint8_t *d_image,
+                                           uint32_t width, uint32_t rowstride_bytes, uint32_t first_column, uint32_t *next_column_out)
+{
+    if (!p) return SBX_ERR_INVALID_ARGUMENT;
+    if (width == 0 || first_column >= width) return fail(p, SBX_ERR_INVALID_ARGUMENT, "need width >= 1 and first_column < width");
+    if ((rowstride_bytes & 3u) != 0 || (uint64_t)rowstride_bytes < 4ull * width)
+        return fail(p, SBX_ERR_INVALID_ARGUMENT, "rowstride_bytes must be a multiple of 4 and >= 4 * width");
+    if (next_column_out) *next_column_out = (uint32_t)((first_column + n_frames) % width);
+    if (n_frames == 0) return SBX_OK;
+    if (!d_columns || !d_image) return fail(p, SBX_ERR_INVALID_ARGUMENT, "NULL device buffer");
+    if (((reinterpret_cast<uintptr_t>(d_columns) | reinterpret_cast<uintptr_t>(d_image)) & 3u) != 0)
+        return fail(p, SBX_ERR_INVALID_ARGUMENT, "buffers must be 4-byte aligned");
+    // columns older than one image width are overwritten by later ones: draw only the last `width`
+    const uint64_t skip = n_frames > width ? n_frames - width : 0;
+    const uint32_t frames = (uint32_t)(n_frames - skip);
+    const uint32_t first = (uint32_t)((first_column + skip) % width);
+    SBX_CUDA(p, cudaSetDevice(p->cfg.device));
+    const dim3 grid((frames + 31) / 32, (p->rows + 31) / 32);
+    if (grid.y > 65535u) return fail(p, SBX_ERR_UNSUPPORTED, "rows_h too large for the blit grid");
+    sbx::blit_columns_kernel<<<grid, 256, 0, p->stream>>>(reinterpret_cast<const uint32_t *>(d_columns) + (size_t)skip * p->rows, frames,
+                                                         p->rows, reinterpret_cast<uint32_t *>(d_image), width, rowstride_bytes / 4,
+                                                         first);
+    SBX_CUDA(p, cudaGetLastError());
+    p->launches += 1;
     return SBX_OK;
 }
 

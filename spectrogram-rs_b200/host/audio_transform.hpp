@@ -8,6 +8,7 @@
 #pragma once
 #include <atomic>
 #include <cstdint>
+#include <cstring>
 #include <optional>
 #include <stdexcept>
 #include <string>
@@ -157,6 +158,23 @@ template <class T> struct AudioStreamTransform {
             sink(std::move(*out));
             ++frames;
         }
+    }
+};
+
+// The pixbuf of SimpleSpectrogram (simple_spectrogram.rs:89-94) and its column cursor (:150-164): a row-major
+// RGBA8 image whose column `offset` receives each new frame, then advances modulo the width.  Host side, for the
+// live path's one-column-at-a-time flow; batches blit on the device with sbx_blit_columns_device.
+struct ColumnStore {
+    size_t width, height, rowstride, offset = 0;
+    std::vector<uint8_t> pixels;
+
+    ColumnStore(size_t w, size_t h) : width(w), height(h), rowstride(w * 4), pixels(w * h * 4, 0) {}
+
+    // column: height x (r,g,b,a), row 0 = top (what process_column / sbx_live_pop_column produce)
+    void put_column(const uint8_t *column)
+    {
+        for (size_t y = 0; y < height; ++y) std::memcpy(&pixels[y * rowstride + offset * 4], column + y * 4, 4);
+        offset = (offset + 1) % width;                                              // :164
     }
 };
 

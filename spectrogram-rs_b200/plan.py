@@ -165,6 +165,15 @@ class Plan:
         self._check(self._lib.sbx_palette_table(self._h, resolution, out.ctypes.data))
         return out
 
+    def blit_columns_device(self, d_columns, n_frames, d_image, width, rowstride_bytes, first_column=0):
+        """The column store of SimpleSpectrogram (simple_spectrogram.rs:141-164) on the device: column f of
+        d_columns (frames x rows x 4) -> image column (first_column + f) % width of a row-major RGBA8 image.
+        Returns the next column cursor.  Asynchronous on the plan's stream."""
+        nxt = C.c_uint32(0)
+        self._check(self._lib.sbx_blit_columns_device(self._h, _ptr(d_columns), n_frames, _ptr(d_image), width,
+                                                      rowstride_bytes, first_column, C.byref(nxt)))
+        return int(nxt.value)
+
     def set_stream(self, cuda_stream):
         self._check(self._lib.sbx_set_stream(self._h, cuda_stream))
 

@@ -348,6 +348,37 @@ def test_real_sequence_geometry_persistent(sbx, viridis):
         assert np.array_equal(short, g_rgba[:10])
 
 
+def test_column_store_blit(sbx, magma):
+    """a-9: the scrolling column store of SimpleSpectrogram (simple_spectrogram.rs:141-164) on the device: columns
+    land in a row-major image at (cursor + f) % width; wrap-around, padded row stride, more frames than columns."""
+    import torch
+    n, hop, rows, width, pad_px = 1024, 256, 77, 50, 3
+    with sbx.Plan(window_n=n, pad_factor=2, hop=hop, rows_h=rows, channels=1, lut=magma) as plan:
+        stride = (width + pad_px) * 4
+        img = torch.full((rows, width + pad_px, 4), 7, dtype=torch.uint8, device="cuda")
+        ref = np.full((rows, width + pad_px, 4), 7, np.uint8)
+        cursor, ref_cursor = 0, 0
+        rng = np.random.Generator(np.random.PCG64(9))
+        for frames in (1, 33, 50, 0, 64, 131, 2):
+            ns = n + hop * (frames - 1) if frames else n - 1
+            pcm = (0.3 * rng.standard_normal(ns)).astype(np.float32)
+            cols = torch.zeros((max(frames, 1), rows, 4), dtype=torch.uint8, device="cuda")
+            assert plan.process_batch_device(torch.from_numpy(pcm).cuda(), ns, cols, max(frames, 1)) == frames
+            cursor = plan.blit_columns_device(cols, frames, img, width, stride, cursor)
+            plan.synchronize()
+            h = cols.cpu().numpy()
+            for f in range(frames):                                    # the reference's loop, one column at a time
+                ref[:, ref_cursor, :] = h[f]
+                ref_cursor = (ref_cursor + 1) % width
+            assert cursor == ref_cursor
+            assert np.array_equal(img.cpu().numpy(), ref)
+        assert (ref[:, width:, :] == 7).all()                          # the row padding is never written
+        with pytest.raises(sbx.SbxError):
+            plan.blit_columns_device(cols, 1, img, width, width * 4 - 4, 0)
+        with pytest.raises(sbx.SbxError):
+            plan.blit_columns_device(cols, 1, img, width, stride, width)
+
+
 def test_gl_widget_feed_formats(sbx, magma):
     """next-4: F16F16 rows (bit-exact round-to-nearest-even of the f32 rows) and the 32x32 palette table of
     ColorScheme::lookup_table (colorscheme.rs:73-92)."""
