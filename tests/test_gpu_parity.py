@@ -348,6 +348,33 @@ def test_real_sequence_geometry_persistent(sbx, viridis):
         assert np.array_equal(short, g_rgba[:10])
 
 
+@pytest.mark.parametrize("n,pad,ch,hop,rows", [
+    (4096, 2, 1, 512, 1024), (2048, 2, 2, 2048, 1024), (8192, 2, 1, 256, 1024), (8192, 2, 1, 255, 333), (8192, 4, 1, 1024, 2048),
+    (16384, 1, 2, 2048, 100), (16384, 4, 1, 2048, 512), (2400, 2, 2, 58, 1024), (512, 4, 1, 64, 2048)])
+def test_outputs_stay_inside_their_buffers(sbx, magma, n, pad, ch, hop, rows):
+    """Every kernel family writes exactly frames x rows x 4 bytes (and frames x K x 2 floats): canary frames before
+    and after the output region of an odd-length batch must survive, and no output byte may keep its canary."""
+    import torch
+    frames, guard = 5, 3
+    ns = n + hop * (frames - 1)
+    pcm = _pcm(ch, ns, seed=3)
+    with sbx.Plan(window_n=n, pad_factor=pad, hop=hop, rows_h=rows, channels=ch, lut=magma) as plan:
+        d_pcm = torch.from_numpy(pcm).cuda()
+        rgba = torch.full((frames + 2 * guard, rows, 4), 0x5A, dtype=torch.uint8, device="cuda")
+        mags = torch.full((frames + 2 * guard, plan.k, 2), -123.0, dtype=torch.float32, device="cuda")
+        f16 = torch.full((frames + 2 * guard, plan.k, 2), 0x7E7E, dtype=torch.int16, device="cuda")
+        assert plan.process_batch_device(d_pcm, ns, rgba[guard:], frames) == frames
+        assert plan.magnitudes_batch_device(d_pcm, ns, mags[guard:], frames) == frames
+        assert plan.magnitudes_batch_device_f16(d_pcm, ns, f16[guard:], frames) == frames
+        plan.synchronize()
+        r, m, h = rgba.cpu().numpy(), mags.cpu().numpy(), f16.cpu().numpy()
+        for arr, canary in ((r, 0x5A), (m, -123.0), (h, 0x7E7E)):
+            assert (arr[:guard] == canary).all() and (arr[guard + frames:] == canary).all()
+        assert (r[guard:guard + frames, :, 3] == 255).all()            # every pixel written (alpha 255 != 0x5A)
+        assert (m[guard:guard + frames] >= 0).all()                    # every magnitude written
+        assert (h[guard:guard + frames] != 0x7E7E).any(axis=(1, 2)).all()
+
+
 def test_column_store_blit(sbx, magma):
     """a-9: the scrolling column store of SimpleSpectrogram (simple_spectrogram.rs:141-164) on the device: columns
     land in a row-major image at (cursor + f) % width; wrap-around, padded row stride, more frames than columns."""
