@@ -93,7 +93,14 @@ SBX_API sbx_status sbx_builtin_lut(const char *name, uint8_t lut_rgb[768]);
 SBX_API uint32_t sbx_samples_from_seconds(float seconds, float sample_rate);
 
 /* ---- plan lifetime: replaces FastFourierTransform::new (src/fourier/fft.rs:18-31), which
- * re-plans FFTW on every sample-rate change (src/widgets/simple_spectrogram.rs:214-219). ---- */
+ * re-plans FFTW on every sample-rate change (src/widgets/simple_spectrogram.rs:214-219). ----
+ * Supported geometry (anything else: SBX_ERR_UNSUPPORTED, never a silent fallback):
+ *   - N a power of two, 256 .. 65536, P in {1, 2, 4}, M = P*N <= 262144 (M > 16384 needs N >= 8192);
+ *   - N = 2^a 3^b 5^c 7^d otherwise (the application's 2400 / 2205 / 4800 / 9600, the widgets' N = 100),
+ *     P in {1, 2, 4} with M even and 12*M bytes within one SM's shared memory (M <= 19370);
+ *   - any hop >= 1, H in [1, 2^20], channels 1 or 2, both interpolators, both scheme kinds.
+ * Plan creation computes every table on the host (window, twiddles, bin map, per-sample positions and weights,
+ * dB-step thresholds) and uploads them; the kernels never evaluate exp / log / cos. */
 SBX_API sbx_status sbx_plan_create(const sbx_config *cfg, sbx_plan **out_plan);
 SBX_API void       sbx_plan_destroy(sbx_plan *plan);
 

@@ -59,7 +59,7 @@ for case in range(a.cases):
     try:
         plan = sbx.Plan(channels=ch, scheme=scheme, lut=lut, **kw)
     except sbx.SbxError as e:
-        if e.status == -4:                                    # SBX_ERR_UNSUPPORTED (e.g. a row longer than the scratch area)
+        if e.status == -2:                                    # SBX_ERR_UNSUPPORTED (e.g. a row longer than the scratch area)
             continue
         raise
     with plan:
