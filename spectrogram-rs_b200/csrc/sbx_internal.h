@@ -92,6 +92,9 @@ sbx_status launch_generic(sbx_plan *p, int channels, const float *d_pcm, uint64_
                           float *d_mags, cudaStream_t stream);
 sbx_status launch_large(sbx_plan *p, int channels, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba,
                         float *d_mags, cudaStream_t stream);
+sbx_status launch_real(sbx_plan *p, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba, float *d_mags, cudaStream_t stream);
+cudaError_t launch_fused_small(sbx_plan *p, int channels, const KernelArgs &a, uint64_t n_frames, cudaStream_t stream);   // N <= 1024
+cudaError_t launch_fused_big(sbx_plan *p, int channels, const KernelArgs &a, uint64_t n_frames, cudaStream_t stream);     // N >= 2048
 sbx_status launch_colourise(sbx_plan *p, const float *d_mags, uint64_t n_frames, uint8_t *d_rgba, cudaStream_t stream);
 sbx_status fail(const sbx_plan *p, sbx_status st, const std::string &msg);
 sbx_status cuda_fail(const sbx_plan *p, cudaError_t e, const char *what);

@@ -1,4 +1,4 @@
-// sbx_plan.cu -- plan construction (host-computed tables), kernel dispatch and the C ABI of
+// sbx_plan.cu -- plan construction (host-computed tables), path selection, the colourise / pack / blit kernels and the C ABI of
 // include/sbx.h.  No CPU compute fallback exists: every transform entry point launches the sm_100a
 // kernels of stft_kernels.cuh or fails with SBX_ERR_CUDA / SBX_ERR_UNSUPPORTED.
 #include <cuda_fp16.h>
@@ -12,15 +12,12 @@
 #include <new>
 
 #include "luts.inc"
-#include "sbx_internal.h"
+#include "sbx_launch.h"
 #include "sbx_tables.h"
 
 namespace {
 
 thread_local std::string g_create_error;
-
-constexpr uint32_t kMinLog2N = 8, kMaxLog2M = 14;                      // fused (single-SM) kernel: M <= 16384
-constexpr uint32_t kMaxLog2NLarge = 16, kMaxLog2MLarge = 18;             // multi-kernel path of stft_large.cuh
 
 int ilog2_exact(uint32_t v)
 {
@@ -51,109 +48,6 @@ sbx_status cuda_fail(const sbx_plan *p, cudaError_t e, const char *what)
     return fail(p, SBX_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 
-// ---- kernel dispatch ---------------------------------------------------------------------------
-constexpr size_t kMaxSmemOptIn = 227 * 1024;           // opt-in dynamic shared memory per CTA on sm_100
-
-// Opt a kernel in to `bytes` of dynamic shared memory, once per device.  `done` is the kernel's own flag array
-// (one static per template instance); the attribute call is idempotent, so two host threads racing on the first
-// launch only repeat it.
-constexpr int kMaxDevices = 64;
-template <class Kernel> cudaError_t allow_smem(Kernel kernel, size_t bytes, std::atomic<bool> (&done)[kMaxDevices])
-{
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
-    if (done[dev].load(std::memory_order_acquire)) return cudaSuccess;
-    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e == cudaSuccess) done[dev].store(true, std::memory_order_release);
-    return e;
-}
-
-template <class G>
-cudaError_t launch_geom(sbx_plan *p, const KernelArgs &args, uint64_t n_frames, cudaStream_t stream)
-{
-    constexpr int CH = G::CH;
-    static std::atomic<bool> configured[kMaxDevices], configured_p[kMaxDevices];
-    cudaError_t e = allow_smem(fused_frames_kernel<G>, G::SMEM_BYTES, configured);
-    if (e != cudaSuccess) return e;
-    const uint64_t ctas = (n_frames + G::FRAMES_PER_CTA - 1) / G::FRAMES_PER_CTA;
-    if (ctas == 0) return cudaSuccess;
-    if (ctas > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-
-    // Persistent, TMA-staged variant: grid = SMs x resident CTAs, the next unit's PCM span prefetched into shared
-    // memory by cp.async.bulk while the current unit is transformed.  Used where only ONE CTA fits an SM
-    // (M = 16384: 128 KB of transform buffer), i.e. where no second CTA hides the load latency of pass 0:
-    // measured on a B200, cfg3 19.9 -> 21.8 M frames/s.  With two or more resident CTAs the one-CTA-per-unit
-    // grid is faster (cfg1: 51.3 vs 47.7 M frames/s; staggering the start of co-resident persistent CTAs by
-    // 3-12 k cycles changed nothing, so it is not a lock-step effect -- the extra 18 KB of staging per CTA
-    // leaves less L1 for the plan tables, and there is one more barrier per unit).
-    // Needs 16-byte aligned sample spans and enough units to fill the machine.
-    constexpr uint32_t FPC = G::FRAMES_PER_CTA;
-    const uint32_t unit_stride_bytes = FPC * args.hop * CH * 4u;
-    const uint32_t span_bytes = (G::N + (FPC - 1) * args.hop) * CH * 4u;
-    static const bool disabled = std::getenv("SBX_NO_PERSISTENT") != nullptr;
-    const bool aligned = (unit_stride_bytes % 16u) == 0 && (span_bytes % 16u) == 0 &&
-                         (reinterpret_cast<uintptr_t>(args.pcm) % 16u) == 0;
-    const size_t smem_p = (size_t)G::SMEM_BYTES + span_bytes;
-    constexpr size_t kPersistentDynMax = kMaxSmemOptIn - 64;     // the kernel also has a static mbarrier
-    if (!disabled && aligned && smem_p <= kPersistentDynMax) {
-        // the opt-in is the device maximum (the staging span depends on the plan's hop); occupancy and grid are
-        // per plan and channel layout
-        e = allow_smem(fused_frames_persistent_kernel<G>, kPersistentDynMax, configured_p);
-        if (e != cudaSuccess) return e;
-        sbx_plan::PersistentGeom &pg = p->pgeom[G::REAL ? 2 : CH - 1];
-        if (!pg.ready) {
-            int occ = 0, sms = 0;
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused_frames_persistent_kernel<G>, G::THREADS, smem_p);
-            if (e != cudaSuccess) return e;
-            e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->cfg.device);
-            if (e != cudaSuccess) return e;
-            pg.ctas = occ * sms;
-            pg.occ = occ;
-            pg.smem = smem_p;
-            pg.ready = true;
-        }
-        static const bool forced = std::getenv("SBX_FORCE_PERSISTENT") != nullptr;
-        if (pg.ctas > 0 && ctas >= (uint64_t)pg.ctas * 2 && (pg.occ == 1 || forced)) {
-            fused_frames_persistent_kernel<G><<<(unsigned)pg.ctas, G::THREADS, pg.smem, stream>>>(args, (uint32_t)ctas);
-            return cudaGetLastError();
-        }
-    }
-    fused_frames_kernel<G><<<(unsigned)ctas, G::THREADS, G::SMEM_BYTES, stream>>>(args);
-    return cudaGetLastError();
-}
-
-template <int LOG2N, int LOG2PAD>
-cudaError_t launch_ch(sbx_plan *p, int channels, const KernelArgs &args, uint64_t n_frames, cudaStream_t stream)
-{
-    if constexpr (LOG2N + LOG2PAD > (int)kMaxLog2M) {
-        return cudaErrorInvalidConfiguration;
-    } else {
-        return channels == 1 ? launch_geom<Geom<LOG2N, LOG2PAD, 1>>(p, args, n_frames, stream)
-                             : launch_geom<Geom<LOG2N, LOG2PAD, 2>>(p, args, n_frames, stream);
-    }
-}
-
-template <int LOG2N>
-cudaError_t launch_pad(sbx_plan *p, int channels, const KernelArgs &args, uint64_t n_frames, cudaStream_t stream)
-{
-    switch (p->log2pad) {
-        case 0: return launch_ch<LOG2N, 0>(p, channels, args, n_frames, stream);
-        case 1: return launch_ch<LOG2N, 1>(p, channels, args, n_frames, stream);
-        case 2: return launch_ch<LOG2N, 2>(p, channels, args, n_frames, stream);
-        default: return cudaErrorInvalidConfiguration;
-    }
-}
-
-// REAL geometry: one mono frame per CTA, transformed as the packed sequence of N/2 sample pairs (M/2 points).
-// Wins where a frame PAIR no longer fits two CTAs per SM (M >= 16384) and makes M = 32768 a single-kernel path.
-template <int LOG2NC, int LOG2PAD>
-cudaError_t launch_real_one(sbx_plan *p, const KernelArgs &a, uint64_t n_frames, cudaStream_t stream)
-{
-    return launch_geom<Geom<LOG2NC, LOG2PAD, 2, true>>(p, a, n_frames, stream);
-}
-
 bool real_path_wanted(const sbx_plan *p, int channels, const float *d_pcm)
 {
     return channels == 1 && p->use_real && (p->hop & 1u) == 0 && (reinterpret_cast<uintptr_t>(d_pcm) & 7u) == 0;
@@ -168,39 +62,6 @@ bool choose_real(bool real_ok, bool real_auto)
     return real_auto;
 }
 
-sbx_status launch_real(sbx_plan *p, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba, float *d_mags, cudaStream_t stream)
-{
-    KernelArgs a = p->base_args();
-    a.pcm = d_pcm;
-    a.rgba = d_rgba;
-    a.mags_out = d_mags;
-    a.n_frames = n_frames;
-    a.twp = p->d_twp_real;
-    a.hop = p->hop / 2;                                    // in sample pairs
-    cudaError_t e = cudaErrorInvalidConfiguration;
-    switch (p->log2n + p->log2pad) {
-        case 13:
-            if (p->log2pad == 0) e = launch_real_one<12, 0>(p, a, n_frames, stream);
-            else if (p->log2pad == 1) e = launch_real_one<11, 1>(p, a, n_frames, stream);
-            else if (p->log2pad == 2) e = launch_real_one<10, 2>(p, a, n_frames, stream);
-            break;
-        case 14:
-            if (p->log2pad == 0) e = launch_real_one<13, 0>(p, a, n_frames, stream);
-            else if (p->log2pad == 1) e = launch_real_one<12, 1>(p, a, n_frames, stream);
-            else if (p->log2pad == 2) e = launch_real_one<11, 2>(p, a, n_frames, stream);
-            break;
-        case 15:
-            if (p->log2pad == 0) e = launch_real_one<14, 0>(p, a, n_frames, stream);
-            else if (p->log2pad == 1) e = launch_real_one<13, 1>(p, a, n_frames, stream);
-            else if (p->log2pad == 2) e = launch_real_one<12, 2>(p, a, n_frames, stream);
-            break;
-        default: break;
-    }
-    if (e != cudaSuccess) return cuda_fail(p, e, "fused_frames_kernel (real-sequence geometry) launch");
-    if (n_frames) p->launches += 1;
-    return SBX_OK;
-}
-
 sbx_status launch_fused(sbx_plan *p, int channels, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba,
                         float *d_mags, cudaStream_t stream)
 {
@@ -212,139 +73,10 @@ sbx_status launch_fused(sbx_plan *p, int channels, const float *d_pcm, uint64_t 
     a.rgba = d_rgba;
     a.mags_out = d_mags;
     a.n_frames = n_frames;
-    cudaError_t e;
-    switch (p->log2n) {
-        case 8: e = launch_pad<8>(p, channels, a, n_frames, stream); break;
-        case 9: e = launch_pad<9>(p, channels, a, n_frames, stream); break;
-        case 10: e = launch_pad<10>(p, channels, a, n_frames, stream); break;
-        case 11: e = launch_pad<11>(p, channels, a, n_frames, stream); break;
-        case 12: e = launch_pad<12>(p, channels, a, n_frames, stream); break;
-        case 13: e = launch_pad<13>(p, channels, a, n_frames, stream); break;
-        case 14: e = launch_pad<14>(p, channels, a, n_frames, stream); break;      // P = 1 only (M <= 16384)
-        default: e = cudaErrorInvalidConfiguration; break;
-    }
+    const cudaError_t e = p->log2n <= 10 ? launch_fused_small(p, channels, a, n_frames, stream)
+                                         : launch_fused_big(p, channels, a, n_frames, stream);
     if (e != cudaSuccess) return cuda_fail(p, e, "fused_frames_kernel launch");
     if (n_frames) p->launches += 1;
-    return SBX_OK;
-}
-
-// ---- generic path (window not a power of two) -----------------------------------------------------
-sbx_status launch_generic(sbx_plan *p, int channels, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba,
-                          float *d_mags, cudaStream_t stream)
-{
-    if (n_frames == 0) return SBX_OK;
-    GenericArgs g{};
-    g.k = p->base_args();
-    g.k.pcm = d_pcm;
-    g.k.rgba = d_rgba;
-    g.k.mags_out = d_mags;
-    g.k.n_frames = n_frames;
-    g.twm = p->d_twm;
-    g.pos_tab = p->d_pos_tab;
-    g.n = p->n; g.pad = p->pad; g.m = p->m;
-    g.npass = (uint32_t)p->radix.size();
-    for (size_t i = 0; i < p->radix.size(); ++i) { g.radix[i] = p->radix[i]; g.stride[i] = p->stride[i]; }
-    const size_t smem = (size_t)p->m * 12;                      // transform [M] + magnitudes [M/2], float2
-    const uint64_t ctas = channels == 1 ? (n_frames + 1) / 2 : n_frames;
-    if (ctas > 0x7fffffffull) return fail(p, SBX_ERR_INVALID_ARGUMENT, "too many frames in one launch");
-    static std::atomic<bool> configured1[kMaxDevices], configured2[kMaxDevices];
-    cudaError_t e;
-    if (channels == 1) {
-        e = allow_smem(generic_frames_kernel<1>, kMaxSmemOptIn, configured1);
-        if (e == cudaSuccess) { generic_frames_kernel<1><<<(unsigned)ctas, GENERIC_THREADS, smem, stream>>>(g); e = cudaGetLastError(); }
-    } else {
-        e = allow_smem(generic_frames_kernel<2>, kMaxSmemOptIn, configured2);
-        if (e == cudaSuccess) { generic_frames_kernel<2><<<(unsigned)ctas, GENERIC_THREADS, smem, stream>>>(g); e = cudaGetLastError(); }
-    }
-    if (e != cudaSuccess) return cuda_fail(p, e, "generic_frames_kernel launch");
-    p->launches += 1;
-    return SBX_OK;
-}
-
-// ---- large path (M > 16384): four kernels per chunk of units --------------------------------------
-template <int LOG2N, int LOG2PAD, int CH>
-cudaError_t launch_large_one(const LargeArgs &la, bool want_rgba, cudaStream_t stream)
-{
-    using GL = GeomL<LOG2N, LOG2PAD>;
-    const unsigned units = la.units;
-    large_first_kernel<LOG2N, LOG2PAD, CH><<<units * GL::PAD * (LARGE_BLOCK / LARGE_THREADS), LARGE_THREADS, 0, stream>>>(la);
-    large_block_kernel<<<units * (GL::M / LARGE_BLOCK), LARGE_THREADS, 0, stream>>>(la);
-    static std::atomic<bool> split_configured[kMaxDevices];
-    cudaError_t e = allow_smem(large_split_kernel<LOG2N, LOG2PAD, CH>, GL::SPLIT_SMEM, split_configured);
-    if (e != cudaSuccess) return e;
-    large_split_kernel<LOG2N, LOG2PAD, CH><<<units * (GL::Q / 2), LARGE_THREADS, GL::SPLIT_SMEM, stream>>>(la);
-    if (want_rgba)
-        large_colour_kernel<CH == 1><<<dim3(units, la.k.n_chunks), LARGE_THREADS, 0, stream>>>(la, la.magbuf, (size_t)GL::M / 2);
-    return cudaGetLastError();
-}
-
-template <int LOG2N, int LOG2PAD>
-cudaError_t launch_large_ch(int channels, const LargeArgs &la, bool want_rgba, cudaStream_t stream)
-{
-    if constexpr (LOG2N + LOG2PAD <= (int)kMaxLog2M || LOG2N + LOG2PAD > (int)kMaxLog2MLarge) {
-        return cudaErrorInvalidConfiguration;
-    } else {
-        return channels == 1 ? launch_large_one<LOG2N, LOG2PAD, 1>(la, want_rgba, stream)
-                             : launch_large_one<LOG2N, LOG2PAD, 2>(la, want_rgba, stream);
-    }
-}
-
-template <int LOG2N>
-cudaError_t launch_large_pad(int log2pad, int channels, const LargeArgs &la, bool want_rgba, cudaStream_t stream)
-{
-    switch (log2pad) {
-        case 0: return launch_large_ch<LOG2N, 0>(channels, la, want_rgba, stream);
-        case 1: return launch_large_ch<LOG2N, 1>(channels, la, want_rgba, stream);
-        case 2: return launch_large_ch<LOG2N, 2>(channels, la, want_rgba, stream);
-        default: return cudaErrorInvalidConfiguration;
-    }
-}
-
-sbx_status launch_large(sbx_plan *p, int channels, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba,
-                        float *d_mags, cudaStream_t stream)
-{
-    if (n_frames == 0) return SBX_OK;
-    if (p->large_units == 0) {
-        // scratch: (M + M/2) float2 per unit, SBX_LARGE_SCRATCH_MB (default 512) MiB per chunk of units.  Measured
-        // on a B200 (cfg5, N = 65536): 512 MiB 0.68 M frames/s, 96 MiB (L2-resident) 0.57, 48 MiB 0.53 -- bigger
-        // grids beat L2 residency of the hand-off between the four kernels.
-        const size_t per_unit = (size_t)p->m * 12;
-        const char *env = std::getenv("SBX_LARGE_SCRATCH_MB");
-        const uint64_t budget_mb = env && std::atoi(env) > 0 ? (uint64_t)std::atoi(env) : 512u;
-        uint64_t units = (budget_mb << 20) / per_unit;
-        units = units < 1 ? 1 : (units > 8192 ? 8192 : units);
-        cudaError_t e = cudaMalloc(&p->d_zbuf, units * (size_t)p->m * sizeof(float2));
-        if (e == cudaSuccess) e = cudaMalloc(&p->d_magbuf, units * (size_t)(p->m / 2) * sizeof(float2));
-        if (e != cudaSuccess) { cudaFree(p->d_zbuf); p->d_zbuf = nullptr; return cuda_fail(p, e, "cudaMalloc(large-transform scratch)"); }
-        p->large_units = (uint32_t)units;
-    }
-    const uint32_t per = channels == 1 ? 2 : 1;
-    const uint64_t total_units = (n_frames + per - 1) / per;
-    LargeArgs la{};
-    la.k = p->base_args();
-    la.k.pcm = d_pcm;
-    la.k.rgba = d_rgba;
-    la.k.mags_out = d_mags;
-    la.k.n_frames = n_frames;
-    la.twp_block = p->d_twp_block;
-    la.zbuf = p->d_zbuf;
-    la.magbuf = p->d_magbuf;
-    la.log2n = (uint32_t)p->log2n;
-    la.log2pad = (uint32_t)p->log2pad;
-    for (uint64_t u0 = 0; u0 < total_units; u0 += p->large_units) {
-        la.frame_base = u0 * per;
-        la.units = (uint32_t)(total_units - u0 < p->large_units ? total_units - u0 : p->large_units);
-        cudaError_t e;
-        switch (p->log2n) {
-            case 13: e = launch_large_pad<13>(p->log2pad, channels, la, d_rgba != nullptr, stream); break;
-            case 14: e = launch_large_pad<14>(p->log2pad, channels, la, d_rgba != nullptr, stream); break;
-            case 15: e = launch_large_pad<15>(p->log2pad, channels, la, d_rgba != nullptr, stream); break;
-            case 16: e = launch_large_pad<16>(p->log2pad, channels, la, d_rgba != nullptr, stream); break;
-            default: e = cudaErrorInvalidConfiguration; break;
-        }
-        if (e != cudaSuccess) return cuda_fail(p, e, "large-transform kernels launch");
-        p->launches += d_rgba != nullptr ? 4 : 3;
-    }
     return SBX_OK;
 }
 
@@ -483,6 +215,10 @@ sbx::KernelArgs sbx_plan::base_args() const
 
 using sbx::cuda_fail;
 using sbx::fail;
+using sbx::kMaxLog2M;
+using sbx::kMaxLog2MLarge;
+using sbx::kMaxLog2NLarge;
+using sbx::kMinLog2N;
 
 #define SBX_CUDA(plan, call)                                              \
     do {                                                                  \
