@@ -157,6 +157,7 @@ def cpu_reference_rate(frames_budget_s=12.0, threads=None):
     rate, frames, dt = results[pocket]
     other = {("pocketfft" if k else "radix2"): round(v[0], 1) for k, v in results.items()}
     fft = "pocketfft complex64 (scipy.fft)" if pocket else "oracle radix-2 f32 FFT"
+    cpu_reference_rate.last_step_ms = dt * 1e3                      # duration of the timed sample (the arm's "step")
     return rate, threads, (f"{frames} frames of the workload ({dt:.1f} s, {threads} threads over frames, FFT stage: {fft} standing in "
                            f"for FFTW; window/exp/log recomputed per frame as the reference does; both FFT stages: {other} frames/s)")
 
@@ -165,20 +166,21 @@ def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path (oracle port), all host threads."""
     if rank != 0:
         return
-    rates = []
+    rates, step_ms = [], []
     threads, sample = None, ""
     for i in range(args.warmup + args.steps):
         rate, threads, sample = cpu_reference_rate(frames_budget_s=min(8.0, 120.0 / max(1, args.steps + args.warmup)))
         if i >= args.warmup:
             rates.append(rate)
+            step_ms.append(cpu_reference_rate.last_step_ms)
     value = float(np.mean(rates))
     peaks, src = measured_peaks()
     out = {
         "impl": "reference", "metric": "stft_frames_per_sec", "value": value, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": float(np.mean(step_ms)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU path; n_gpus is the arm it is paired with"},
+        "config": {"workload": WORKLOAD, "note": "CPU path; n_gpus is the arm it is paired with; a step is one bounded sample of the workload (cpu_baseline.sample)"},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
