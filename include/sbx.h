@@ -161,6 +161,18 @@ SBX_API sbx_status sbx_magnitudes_batch_device(sbx_plan *plan, const float *d_pc
 
 /* ---- feed formats of the GL widget (GPUSpectrogram) -------------------------------------------- */
 
+/* Several equally long recordings in one call (BASELINE cfg4: 64 planar channels; the reference runs one
+ * AudioStreamTransform per stream, src/fourier/audio_transform.rs:14-42): sequence s starts
+ * s * sequence_stride_samples samples into d_pcm (each sample = `channels` floats) and its frames land at
+ * d_rgba + s * frames * H * 4, frames = sbx_num_frames(n_samples_per_sequence), returned through
+ * *frames_per_sequence_out.  rgba_capacity_frames counts all sequences.  The shared-memory-resident kernels take
+ * all sequences in ONE grid (no per-sequence tail); the M > 16384 and mixed-radix paths launch per sequence.
+ * DEVICE pointers, asynchronous on the plan's stream. */
+SBX_API sbx_status sbx_process_batch_device_planar(sbx_plan *plan, const float *d_pcm, uint32_t n_sequences,
+                                                   uint64_t sequence_stride_samples, uint64_t n_samples_per_sequence,
+                                                   uint8_t *d_rgba, uint64_t rgba_capacity_frames,
+                                                   uint64_t *frames_per_sequence_out);
+
 /* Batched FastFourierTransform::process with the rows packed as IEEE binary16 pairs: the texel format of
  * GPUSpectrogram's F16F16 ring texture (src/widgets/gpu_spectrogram.rs:218-227,255-275), so the rows can be
  * uploaded without a CPU-side Vec<(f32,f32)>.  d_mags_f16 = frames x K x (L,R) uint16 (binary16 bits,

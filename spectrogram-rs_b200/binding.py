@@ -45,6 +45,7 @@ SYMBOLS = {
     "sbx_colorize_magnitudes": (C.c_int32, [_vp, _vp, C.c_uint64, _vp]),
     "sbx_process_batch": (C.c_int32, [_vp, _vp, C.c_uint64, _vp, C.c_uint64, _u64p]),
     "sbx_process_batch_device": (C.c_int32, [_vp, _vp, C.c_uint64, _vp, C.c_uint64, _u64p]),
+    "sbx_process_batch_device_planar": (C.c_int32, [_vp, _vp, C.c_uint32, C.c_uint64, C.c_uint64, _vp, C.c_uint64, _u64p]),
     "sbx_magnitudes_batch_device": (C.c_int32, [_vp, _vp, C.c_uint64, _vp, C.c_uint64, _u64p]),
     "sbx_magnitudes_batch_device_f16": (C.c_int32, [_vp, _vp, C.c_uint64, _vp, C.c_uint64, _u64p]),
     "sbx_palette_table": (C.c_int32, [_vp, C.c_uint32, _vp]),

@@ -6,12 +6,13 @@ namespace sbx {
 // REAL geometry: one mono frame per CTA, transformed as the packed sequence of N/2 sample pairs (M/2 points).
 // Wins where a frame PAIR no longer fits two CTAs per SM (M >= 16384) and makes M = 32768 a single-kernel path.
 template <int LOG2NC, int LOG2PAD>
-cudaError_t launch_real_one(sbx_plan *p, const KernelArgs &a, uint64_t n_frames, cudaStream_t stream)
+cudaError_t launch_real_one(sbx_plan *p, const KernelArgs &a, uint64_t n_frames, cudaStream_t stream, Sequences seqs)
 {
-    return launch_geom<Geom<LOG2NC, LOG2PAD, 2, true>>(p, a, n_frames, stream);
+    return launch_geom<Geom<LOG2NC, LOG2PAD, 2, true>>(p, a, n_frames, stream, seqs);
 }
 
-sbx_status launch_real(sbx_plan *p, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba, float *d_mags, cudaStream_t stream)
+sbx_status launch_real(sbx_plan *p, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba, float *d_mags, cudaStream_t stream,
+                       Sequences seqs)
 {
     KernelArgs a = p->base_args();
     a.pcm = d_pcm;
@@ -23,19 +24,19 @@ sbx_status launch_real(sbx_plan *p, const float *d_pcm, uint64_t n_frames, uint8
     cudaError_t e = cudaErrorInvalidConfiguration;
     switch (p->log2n + p->log2pad) {
         case 13:
-            if (p->log2pad == 0) e = launch_real_one<12, 0>(p, a, n_frames, stream);
-            else if (p->log2pad == 1) e = launch_real_one<11, 1>(p, a, n_frames, stream);
-            else if (p->log2pad == 2) e = launch_real_one<10, 2>(p, a, n_frames, stream);
+            if (p->log2pad == 0) e = launch_real_one<12, 0>(p, a, n_frames, stream, seqs);
+            else if (p->log2pad == 1) e = launch_real_one<11, 1>(p, a, n_frames, stream, seqs);
+            else if (p->log2pad == 2) e = launch_real_one<10, 2>(p, a, n_frames, stream, seqs);
             break;
         case 14:
-            if (p->log2pad == 0) e = launch_real_one<13, 0>(p, a, n_frames, stream);
-            else if (p->log2pad == 1) e = launch_real_one<12, 1>(p, a, n_frames, stream);
-            else if (p->log2pad == 2) e = launch_real_one<11, 2>(p, a, n_frames, stream);
+            if (p->log2pad == 0) e = launch_real_one<13, 0>(p, a, n_frames, stream, seqs);
+            else if (p->log2pad == 1) e = launch_real_one<12, 1>(p, a, n_frames, stream, seqs);
+            else if (p->log2pad == 2) e = launch_real_one<11, 2>(p, a, n_frames, stream, seqs);
             break;
         case 15:
-            if (p->log2pad == 0) e = launch_real_one<14, 0>(p, a, n_frames, stream);
-            else if (p->log2pad == 1) e = launch_real_one<13, 1>(p, a, n_frames, stream);
-            else if (p->log2pad == 2) e = launch_real_one<12, 2>(p, a, n_frames, stream);
+            if (p->log2pad == 0) e = launch_real_one<14, 0>(p, a, n_frames, stream, seqs);
+            else if (p->log2pad == 1) e = launch_real_one<13, 1>(p, a, n_frames, stream, seqs);
+            else if (p->log2pad == 2) e = launch_real_one<12, 2>(p, a, n_frames, stream, seqs);
             break;
         default: break;
     }

@@ -85,16 +85,20 @@ struct sbx_plan {
 };
 
 namespace sbx {
-// launches the fused kernel for `channels`-layout PCM on `stream`
+// equally long PCM sequences (planar channels) handled by one call: sequence s starts s * stride_floats into the PCM
+// buffer and writes frames [s * n_frames, (s + 1) * n_frames) of the output
+struct Sequences { uint32_t count = 1; unsigned long long stride_floats = 0; };
+// launches the plan's kernel family for `channels`-layout PCM on `stream`
 sbx_status launch_fused(sbx_plan *p, int channels, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba,
-                        float *d_mags, cudaStream_t stream);
+                        float *d_mags, cudaStream_t stream, Sequences seqs = {});
 sbx_status launch_generic(sbx_plan *p, int channels, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba,
                           float *d_mags, cudaStream_t stream);
 sbx_status launch_large(sbx_plan *p, int channels, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba,
                         float *d_mags, cudaStream_t stream);
-sbx_status launch_real(sbx_plan *p, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba, float *d_mags, cudaStream_t stream);
-cudaError_t launch_fused_small(sbx_plan *p, int channels, const KernelArgs &a, uint64_t n_frames, cudaStream_t stream);   // N <= 1024
-cudaError_t launch_fused_big(sbx_plan *p, int channels, const KernelArgs &a, uint64_t n_frames, cudaStream_t stream);     // N >= 2048
+sbx_status launch_real(sbx_plan *p, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba, float *d_mags, cudaStream_t stream,
+                       Sequences seqs);
+cudaError_t launch_fused_small(sbx_plan *p, int channels, const KernelArgs &a, uint64_t n_frames, cudaStream_t stream, Sequences seqs);   // N <= 1024
+cudaError_t launch_fused_big(sbx_plan *p, int channels, const KernelArgs &a, uint64_t n_frames, cudaStream_t stream, Sequences seqs);     // N >= 2048
 sbx_status launch_colourise(sbx_plan *p, const float *d_mags, uint64_t n_frames, uint8_t *d_rgba, cudaStream_t stream);
 sbx_status fail(const sbx_plan *p, sbx_status st, const std::string &msg);
 sbx_status cuda_fail(const sbx_plan *p, cudaError_t e, const char *what);

@@ -28,16 +28,24 @@ template <class Kernel> cudaError_t allow_smem(Kernel kernel, size_t bytes, std:
     return e;
 }
 
+// seqs.count > 1: that many equally long sequences of n_frames frames each in one grid (KernelArgs::units_per_seq)
 template <class G>
-cudaError_t launch_geom(sbx_plan *p, const KernelArgs &args, uint64_t n_frames, cudaStream_t stream)
+cudaError_t launch_geom(sbx_plan *p, KernelArgs args, uint64_t n_frames, cudaStream_t stream, Sequences seqs = {})
 {
     constexpr int CH = G::CH;
     static std::atomic<bool> configured[kMaxDevices], configured_p[kMaxDevices];
     cudaError_t e = allow_smem(fused_frames_kernel<G>, G::SMEM_BYTES, configured);
     if (e != cudaSuccess) return e;
-    const uint64_t ctas = (n_frames + G::FRAMES_PER_CTA - 1) / G::FRAMES_PER_CTA;
+    const uint64_t units = (n_frames + G::FRAMES_PER_CTA - 1) / G::FRAMES_PER_CTA;
+    const uint64_t ctas = units * seqs.count;
     if (ctas == 0) return cudaSuccess;
     if (ctas > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    if (seqs.count > 1) {
+        args.units_per_seq = (uint32_t)units;
+        args.seq_stride = seqs.stride_floats;
+        fused_frames_kernel<G><<<(unsigned)ctas, G::THREADS, G::SMEM_BYTES, stream>>>(args);
+        return cudaGetLastError();
+    }
 
     // Persistent, TMA-staged variant: grid = SMs x resident CTAs, the next unit's PCM span prefetched into shared
     // memory by cp.async.bulk while the current unit is transformed.  Used where only ONE CTA fits an SM

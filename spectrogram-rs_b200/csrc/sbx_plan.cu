@@ -48,9 +48,10 @@ sbx_status cuda_fail(const sbx_plan *p, cudaError_t e, const char *what)
     return fail(p, SBX_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 
-bool real_path_wanted(const sbx_plan *p, int channels, const float *d_pcm)
+bool real_path_wanted(const sbx_plan *p, int channels, const float *d_pcm, Sequences seqs)
 {
-    return channels == 1 && p->use_real && (p->hop & 1u) == 0 && (reinterpret_cast<uintptr_t>(d_pcm) & 7u) == 0;
+    return channels == 1 && p->use_real && (p->hop & 1u) == 0 && (reinterpret_cast<uintptr_t>(d_pcm) & 7u) == 0 &&
+           (seqs.stride_floats & 1u) == 0;
 }
 
 // SBX_REAL=0 / 1 overrides the plan-time default (tables::HostTables::real_auto): 1 = wherever the tables exist.
@@ -63,18 +64,28 @@ bool choose_real(bool real_ok, bool real_auto)
 }
 
 sbx_status launch_fused(sbx_plan *p, int channels, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba,
-                        float *d_mags, cudaStream_t stream)
+                        float *d_mags, cudaStream_t stream, Sequences seqs)
 {
-    if (real_path_wanted(p, channels, d_pcm)) return launch_real(p, d_pcm, n_frames, d_rgba, d_mags, stream);
-    if (p->generic) return launch_generic(p, channels, d_pcm, n_frames, d_rgba, d_mags, stream);
-    if (p->large) return launch_large(p, channels, d_pcm, n_frames, d_rgba, d_mags, stream);
+    if (real_path_wanted(p, channels, d_pcm, seqs)) return launch_real(p, d_pcm, n_frames, d_rgba, d_mags, stream, seqs);
+    if (p->generic || p->large) {
+        // the mixed-radix and multi-kernel paths take one sequence per launch
+        for (uint32_t s = 0; s < seqs.count; ++s) {
+            const float *pcm = d_pcm + (size_t)s * seqs.stride_floats;
+            uint8_t *rgba = d_rgba ? d_rgba + (size_t)s * n_frames * p->rows * 4 : nullptr;
+            float *mags = d_mags ? d_mags + (size_t)s * n_frames * p->k_out * 2 : nullptr;
+            const sbx_status st = p->generic ? launch_generic(p, channels, pcm, n_frames, rgba, mags, stream)
+                                             : launch_large(p, channels, pcm, n_frames, rgba, mags, stream);
+            if (st != SBX_OK) return st;
+        }
+        return SBX_OK;
+    }
     KernelArgs a = p->base_args();
     a.pcm = d_pcm;
     a.rgba = d_rgba;
     a.mags_out = d_mags;
     a.n_frames = n_frames;
-    const cudaError_t e = p->log2n <= 10 ? launch_fused_small(p, channels, a, n_frames, stream)
-                                         : launch_fused_big(p, channels, a, n_frames, stream);
+    const cudaError_t e = p->log2n <= 10 ? launch_fused_small(p, channels, a, n_frames, stream, seqs)
+                                         : launch_fused_big(p, channels, a, n_frames, stream, seqs);
     if (e != cudaSuccess) return cuda_fail(p, e, "fused_frames_kernel launch");
     if (n_frames) p->launches += 1;
     return SBX_OK;
@@ -546,6 +557,29 @@ SBX_API sbx_status sbx_process_batch_device(sbx_plan *p, const float *d_pcm, uin
 {
     if (p && !d_rgba && sbx_num_frames(p, n_samples)) return fail(p, SBX_ERR_INVALID_ARGUMENT, "d_rgba is NULL");
     return batch_device(p, d_pcm, n_samples, d_rgba, nullptr, rgba_capacity_frames, frames_out);
+}
+
+SBX_API sbx_status sbx_process_batch_device_planar(sbx_plan *p, const float *d_pcm, uint32_t n_sequences, uint64_t sequence_stride_samples,
+                                                   uint64_t n_samples_per_sequence, uint8_t *d_rgba, uint64_t rgba_capacity_frames,
+                                                   uint64_t *frames_per_sequence_out)
+{
+    if (frames_per_sequence_out) *frames_per_sequence_out = 0;
+    if (!p) return SBX_ERR_INVALID_ARGUMENT;
+    const uint64_t frames = sbx_num_frames(p, n_samples_per_sequence);
+    if (frames == 0 || n_sequences == 0) return SBX_OK;
+    if (!d_pcm || !d_rgba) return fail(p, SBX_ERR_INVALID_ARGUMENT, "NULL device buffer");
+    if (n_sequences > 1 && sequence_stride_samples < n_samples_per_sequence)
+        return fail(p, SBX_ERR_INVALID_ARGUMENT, "sequence_stride_samples is smaller than n_samples_per_sequence");
+    if (frames > rgba_capacity_frames / n_sequences)
+        return fail(p, SBX_ERR_BUFFER_TOO_SMALL, "output capacity is smaller than n_sequences * frames per sequence");
+    if ((reinterpret_cast<uintptr_t>(d_pcm) & 15u) != 0) return fail(p, SBX_ERR_INVALID_ARGUMENT, "d_pcm must be 16-byte aligned");
+    SBX_CUDA(p, cudaSetDevice(p->cfg.device));
+    sbx::Sequences seqs;
+    seqs.count = n_sequences;
+    seqs.stride_floats = sequence_stride_samples * p->channels;
+    const sbx_status st = sbx::launch_fused(p, (int)p->channels, d_pcm, frames, d_rgba, nullptr, p->stream, seqs);
+    if (st == SBX_OK && frames_per_sequence_out) *frames_per_sequence_out = frames;
+    return st;
 }
 
 SBX_API sbx_status sbx_magnitudes_batch_device(sbx_plan *p, const float *d_pcm, uint64_t n_samples, float *d_mags_lr,

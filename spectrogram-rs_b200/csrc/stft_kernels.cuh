@@ -62,7 +62,11 @@ struct KernelArgs {
     const float *thr;            // [2][256] pairs (ts[i], ts[i+1]) of step thresholds with sentinels: colour index, alpha
     const uint32_t *lut;         // [256] packed r | g<<8 | b<<16 | 255<<24
     const uint4 *ctab;           // [256] {ts[i], ts[i+1], lut[i], 0}: the colour step and its colour in one 16-byte load
-    unsigned long long n_frames;
+    unsigned long long n_frames; // frames per sequence
+    // several equally long sequences (planar channels) in one launch: units_per_seq CTAs each, seq_stride FLOATS apart
+    // in pcm; sequence s writes frames [s * n_frames, (s+1) * n_frames).  units_per_seq = 0: one sequence.
+    unsigned long long seq_stride;
+    uint32_t units_per_seq;
     uint32_t hop, rows, k_out, n_chunks;
     float scale;                 // 2 / N     (fft.rs:92)
     float guess_a[2], guess_b[2];// step guess = log2(p + eps) * a + b   (colour, alpha)
@@ -1090,12 +1094,17 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) fused_frames_kernel(c
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *z = reinterpret_cast<float2 *>(smem_raw);
 
-    const unsigned long long frame0 = (unsigned long long)blockIdx.x * G::FRAMES_PER_CTA;
+    unsigned long long unit = blockIdx.x, seq = 0;
+    if (a.units_per_seq != 0) {                                   // planar sequences: CTA -> (sequence, unit within it)
+        seq = unit / a.units_per_seq;
+        unit -= seq * a.units_per_seq;
+    }
+    const unsigned long long frame0 = unit * G::FRAMES_PER_CTA;   // within the sequence
     const bool second_valid = G::CH == 1 && frame0 + 1 < a.n_frames;
 
-    pass_first<G, false>(z, a, a.pcm + frame0 * (unsigned long long)a.hop * G::CH, second_valid);
+    pass_first<G, false>(z, a, a.pcm + seq * a.seq_stride + frame0 * (unsigned long long)a.hop * G::CH, second_valid);
     __syncthreads();
-    frame_tail<G>(z, a, frame0, second_valid);
+    frame_tail<G>(z, a, seq * a.n_frames + frame0, second_valid);
 }
 
 // ---- persistent variant: grid = SMs x resident CTAs, PCM staged through shared memory by bulk async copies ----

@@ -165,6 +165,14 @@ class Plan:
         self._check(self._lib.sbx_palette_table(self._h, resolution, out.ctypes.data))
         return out
 
+    def process_batch_device_planar(self, d_pcm, n_sequences, sequence_stride_samples, n_samples_per_sequence, d_rgba,
+                                    capacity_frames):
+        """n_sequences equally long recordings (planar channels) in one call; returns frames per sequence."""
+        got = C.c_uint64(0)
+        self._check(self._lib.sbx_process_batch_device_planar(self._h, _ptr(d_pcm), n_sequences, sequence_stride_samples,
+                                                              n_samples_per_sequence, _ptr(d_rgba), capacity_frames, C.byref(got)))
+        return int(got.value)
+
     def blit_columns_device(self, d_columns, n_frames, d_image, width, rowstride_bytes, first_column=0):
         """The column store of SimpleSpectrogram (simple_spectrogram.rs:141-164) on the device: column f of
         d_columns (frames x rows x 4) -> image column (first_column + f) % width of a row-major RGBA8 image.

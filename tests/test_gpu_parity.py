@@ -375,6 +375,37 @@ def test_outputs_stay_inside_their_buffers(sbx, magma, n, pad, ch, hop, rows):
         assert (h[guard:guard + frames] != 0x7E7E).any(axis=(1, 2)).all()
 
 
+@pytest.mark.parametrize("n,pad,ch,hop,rows", [
+    (4096, 2, 1, 512, 1024),          # cfg4: mono frame pairs; odd frame count -> a half-filled pair ends every channel
+    (2048, 2, 2, 2048, 256), (8192, 2, 1, 256, 512), (8192, 2, 1, 255, 128), (8192, 4, 1, 1024, 64),
+    (2400, 2, 2, 58, 128), (16384, 4, 2, 2048, 64)])
+def test_planar_sequences_equal_per_sequence_batches(sbx, magma, n, pad, ch, hop, rows):
+    """sbx_process_batch_device_planar: several equally long recordings in one call == one call per recording
+    (every kernel family; a padded stride between the sequences)."""
+    import torch
+    n_seq, frames, gap = 5, 7, 6
+    ns = n + hop * (frames - 1) + 1
+    stride = (ns + gap + 3) // 4 * 4                   # the per-sequence reference calls need 16-byte aligned starts
+    rng = np.random.Generator(np.random.PCG64(11))
+    shape = (n_seq, stride) if ch == 1 else (n_seq, stride, 2)
+    pcm = (0.2 * rng.standard_normal(shape)).astype(np.float32)
+    with sbx.Plan(window_n=n, pad_factor=pad, hop=hop, rows_h=rows, channels=ch, lut=magma) as plan:
+        d = torch.from_numpy(pcm).cuda()
+        out = torch.full((n_seq + 1, frames, rows, 4), 0x5A, dtype=torch.uint8, device="cuda")
+        assert plan.process_batch_device_planar(d, n_seq, stride, ns, out, n_seq * frames) == frames
+        ref = torch.zeros((n_seq, frames, rows, 4), dtype=torch.uint8, device="cuda")
+        for s in range(n_seq):
+            assert plan.process_batch_device(d[s], ns, ref[s], frames) == frames
+        plan.synchronize()
+        o = out.cpu().numpy()
+        assert np.array_equal(o[:n_seq], ref.cpu().numpy())
+        assert (o[n_seq] == 0x5A).all()
+        with pytest.raises(sbx.SbxError):
+            plan.process_batch_device_planar(d, n_seq, ns - 1, ns, out, n_seq * frames)       # overlapping sequences
+        with pytest.raises(sbx.SbxError):
+            plan.process_batch_device_planar(d, n_seq, stride, ns, out, n_seq * frames - 1)   # capacity
+
+
 def test_column_store_blit(sbx, magma):
     """a-9: the scrolling column store of SimpleSpectrogram (simple_spectrogram.rs:141-164) on the device: columns
     land in a row-major image at (cursor + f) % width; wrap-around, padded row stride, more frames than columns."""
