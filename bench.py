@@ -121,6 +121,37 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pins this rank to the CPUs NVML reports as local to its GPU (before CUDA starts its threads), so that the
+    pinned host buffers of the end-to-end leg are first-touched on the GPU's own socket and its PCIe traffic does
+    not cross the inter-socket link: what `numactl --cpunodebind` does for a per-GPU service process.
+    SBX_BENCH_NUMA=0 disables it.  Returns a short description for the JSON line."""
+    if os.environ.get("SBX_BENCH_NUMA", "1") == "0":
+        return "off"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        index = local_rank
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        if visible:
+            ids = [v.strip() for v in visible.split(",") if v.strip()]
+            if local_rank < len(ids) and ids[local_rank].isdigit():
+                index = int(ids[local_rank])
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (max(os.cpu_count() or 1, max(os.sched_getaffinity(0)) + 1) + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        local = {64 * w + b for w in range(words) for b in range(64) if (int(mask[w]) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        bind_to_gpu_numa_node.original = allowed
+        use = local & allowed
+        if not use or use == allowed:
+            return f"no narrower GPU-local cpu set ({len(allowed)} cpus allowed)"
+        os.sched_setaffinity(0, use)
+        return f"bound to {len(use)} of {len(allowed)} cpus (NVML cpu affinity of GPU {index})"
+    except Exception as exc:                                          # no NVML, cpuset restrictions, ...
+        return f"unavailable ({type(exc).__name__})"
+
+
 def cpu_reference_rate(frames_budget_s=12.0, threads=None):
     """frames/s of the CPU oracle on this box's host cores, on a bounded sample of the workload.  Two FFT stages are
     timed -- the oracle's own radix-2 f32 FFT and pocketfft (scipy.fft, complex64), neither of which is FFTW
@@ -210,6 +241,8 @@ def main():
         run_reference(args, rank, world)
         return
 
+    numa = bind_to_gpu_numa_node(local_rank)
+    log(f"[rank {rank}] numa: {numa}")
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -324,7 +357,7 @@ def main():
                      "fp32_tflops_5MlogM": value / world * FLOPS_FRAME / 1e12,
                      "note": "path is FP32/shared-memory bound at this hop (44-87 flop/B vs a 12 flop/B ridge, SURVEY.md D6)"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": ns_e * 4, "d2h_bytes_per_step": Fe * ROWS * 4,
-                "frames_per_gpu_per_step": Fe, "steps": e2e_steps, "api": "sbx_process_batch (host pointers, pinned)",
+                "frames_per_gpu_per_step": Fe, "steps": e2e_steps, "api": "sbx_process_batch (host pointers, pinned)", "numa": numa,
                 "d2h_gbs_per_gpu": e2e_value / world * ROWS * 4 / 1e9, "h2d_gbs_per_gpu": e2e_value / world * HOP * 4 / 1e9,
                 "note": "bound by the PCIe D2H of the RGBA output (4 KB per frame): chunked, three streams, H2D/kernel/D2H overlapped"},
         "gpu_launches": launches * world,
@@ -341,6 +374,8 @@ def main():
             lat = out["extra"]["cfg2_live_latency_us"]
             out["live_latency_us"] = {"p50": lat["p50"], "p99": lat["p99"], "workload": "cfg2: 48 kHz stereo, 2048-pt frames, one at a time from the pinned ring, 1 GPU"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        if getattr(bind_to_gpu_numa_node, "original", None):          # the CPU baseline gets every host core back
+            os.sched_setaffinity(0, bind_to_gpu_numa_node.original)
         rate, cores, sample = cpu_reference_rate()
         out["cpu_baseline"] = {"value": rate, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
     if rank == 0:
