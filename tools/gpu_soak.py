@@ -19,6 +19,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--cases", type=int, default=300)
 ap.add_argument("--seed", type=int, default=1)
 ap.add_argument("--seconds", type=float, default=240.0)
+ap.add_argument("--real-bias", action="store_true", help="mostly mono, even hops, transform lengths 8192 .. 32768 (the real-sequence geometry)")
 a = ap.parse_args()
 rng = np.random.Generator(np.random.PCG64(a.seed))
 lut = signals.lut("magma")
@@ -36,6 +37,8 @@ for case in range(a.cases):
         n = int(rng.choice(pow2))
         pads = [p for p in (1, 2, 4) if n * p <= 262144 and (n * p <= 16384 or n >= 8192)]
         pad = int(rng.choice(pads))
+    if a.real_bias and rng.random() < 0.8:
+        n, pad = [(2048, 4), (4096, 2), (8192, 1), (4096, 4), (8192, 2), (16384, 1), (8192, 4), (16384, 2), (32768, 1)][int(rng.integers(0, 9))]
     m = n * pad
     sr = float(rng.choice([8000.0, 22050.0, 44100.0, 48000.0, 96000.0, 192000.0]))
     hop = max(1, int(rng.choice([1, 2, 3, n // 8, n // 4, n // 2, n, n + 17, int(rng.integers(1, 2 * n))])))
@@ -45,6 +48,8 @@ for case in range(a.cases):
     f_max = float(rng.choice([f_min * 1.5, 4000.0, sr / 2, 22030.0, sr]))
     f_max = f_max if f_max > f_min else f_min * 2
     interp, scheme, ch = int(rng.integers(0, 2)), int(rng.integers(0, 2)), int(rng.integers(1, 3))
+    if a.real_bias and rng.random() < 0.8:
+        ch, hop = 1, max(2, hop & ~1)
     frames = int(rng.integers(1, 6))
     real = str(rng.choice(["", "0", "1"]))
     os.environ.pop("SBX_REAL", None)
