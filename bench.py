@@ -359,7 +359,8 @@ def main():
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": ns_e * 4, "d2h_bytes_per_step": Fe * ROWS * 4,
                 "frames_per_gpu_per_step": Fe, "steps": e2e_steps, "api": "sbx_process_batch (host pointers, pinned)", "numa": numa,
                 "d2h_gbs_per_gpu": e2e_value / world * ROWS * 4 / 1e9, "h2d_gbs_per_gpu": e2e_value / world * HOP * 4 / 1e9,
-                "note": "bound by the PCIe D2H of the RGBA output (4 KB per frame): chunked, three streams, H2D/kernel/D2H overlapped"},
+                "note": "bound by the PCIe D2H of the RGBA output (4 KB per frame): chunked, three streams, H2D/kernel/D2H overlapped"
+                        + ("; with several GPUs the ranks share the host's PCIe / memory path (DESIGN.md section 6)" if world > 1 else "")},
         "gpu_launches": launches * world,
         "clocks": clocks,
     }
