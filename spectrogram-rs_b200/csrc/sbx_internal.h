@@ -76,6 +76,9 @@ struct sbx_plan {
     // launch geometry of the persistent kernel for this plan's hop, per channel layout (index CH - 1; 2 = REAL)
     struct PersistentGeom { bool ready = false; int ctas = 0, occ = 0; size_t smem = 0; } pgeom[3];
 
+    // set by sbx_live while it captures its single-frame graphs (KernelArgs::done_flag / done_count), else NULL
+    unsigned int *live_done_flag = nullptr, *live_done_count = nullptr;
+
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;      // current stream (own or caller's)
     uint64_t launches = 0;
@@ -99,6 +102,8 @@ sbx_status launch_real(sbx_plan *p, const float *d_pcm, uint64_t n_frames, uint8
                        Sequences seqs);
 cudaError_t launch_fused_small(sbx_plan *p, int channels, const KernelArgs &a, uint64_t n_frames, cudaStream_t stream, Sequences seqs);   // N <= 1024
 cudaError_t launch_fused_big(sbx_plan *p, int channels, const KernelArgs &a, uint64_t n_frames, cudaStream_t stream, Sequences seqs);     // N >= 2048
+bool wide_available(const sbx_plan *p);                                                                                 // sbx_dispatch_wide.cu
+cudaError_t launch_fused_wide(sbx_plan *p, const KernelArgs &a, cudaStream_t stream);                                   // one stereo frame
 sbx_status launch_colourise(sbx_plan *p, const float *d_mags, uint64_t n_frames, uint8_t *d_rgba, cudaStream_t stream);
 sbx_status fail(const sbx_plan *p, sbx_status st, const std::string &msg);
 sbx_status cuda_fail(const sbx_plan *p, cudaError_t e, const char *what);

@@ -54,7 +54,9 @@ cudaError_t launch_geom(sbx_plan *p, KernelArgs args, uint64_t n_frames, cudaStr
     // grid is faster (cfg1: 51.3 vs 47.7 M frames/s; staggering the start of co-resident persistent CTAs by
     // 3-12 k cycles changed nothing, so it is not a lock-step effect -- the extra 18 KB of staging per CTA
     // leaves less L1 for the plan tables, and there is one more barrier per unit).
-    // Needs 16-byte aligned sample spans and enough units to fill the machine.
+    // Needs 16-byte aligned sample spans and enough units to fill the machine.  (Never for the WIDE single-frame
+    // geometries.)
+    if constexpr (!G::WIDE) {
     constexpr uint32_t FPC = G::FRAMES_PER_CTA;
     const uint32_t unit_stride_bytes = FPC * args.hop * CH * 4u;
     const uint32_t span_bytes = (G::N + (FPC - 1) * args.hop) * CH * 4u;
@@ -86,6 +88,7 @@ cudaError_t launch_geom(sbx_plan *p, KernelArgs args, uint64_t n_frames, cudaStr
             return cudaGetLastError();
         }
     }
+    }  // !G::WIDE
     fused_frames_kernel<G><<<(unsigned)ctas, G::THREADS, G::SMEM_BYTES, stream>>>(args);
     return cudaGetLastError();
 }

@@ -29,6 +29,12 @@ struct sbx_live {
     cudaStream_t stream = nullptr;
     cudaGraphExec_t graph_col = nullptr, graph_mags = nullptr;
     bool zero_copy = true;                 // kernel reads/writes the pinned host buffers directly (one graph node)
+    // completion by polling (zero-copy graphs only): the kernel stores a launch counter to *h_flag when the column is
+    // visible; the consumer spins on it instead of paying cudaStreamSynchronize's completion path
+    bool poll = false;
+    unsigned int *h_flag = nullptr;        // pinned
+    unsigned int *d_count = nullptr;       // device
+    unsigned int seq = 0;                  // flagged launches issued so far
 };
 
 using sbx::cuda_fail;
@@ -50,7 +56,9 @@ static sbx_status build_graph(sbx_live *lv, bool column, cudaGraphExec_t *out)
     if (lv->zero_copy) {
         // pinned host memory is device-addressable (UVA): the 16 KB window is read and the 4 KB column written
         // over PCIe by the kernel itself -- one graph node, no copy-engine hand-offs
+        if (lv->poll) { p->live_done_flag = lv->h_flag; p->live_done_count = lv->d_count; }
         st = sbx::launch_fused(p, 2, lv->h_in, 1, column ? lv->h_col : nullptr, column ? nullptr : lv->h_mags, lv->stream);
+        p->live_done_flag = p->live_done_count = nullptr;
     } else {
         e = cudaMemcpyAsync(lv->d_in, lv->h_in, (size_t)p->n * 2 * sizeof(float), cudaMemcpyHostToDevice, lv->stream);
         if (e == cudaSuccess)
@@ -84,6 +92,8 @@ SBX_API void sbx_live_destroy(sbx_live *lv)
     if (lv->h_in) cudaFreeHost(lv->h_in);
     if (lv->h_mags) cudaFreeHost(lv->h_mags);
     if (lv->h_col) cudaFreeHost(lv->h_col);
+    if (lv->h_flag) cudaFreeHost(lv->h_flag);
+    cudaFree(lv->d_count);
     cudaFree(lv->d_in); cudaFree(lv->d_mags); cudaFree(lv->d_col);
     if (lv->stream) cudaStreamDestroy(lv->stream);
     delete lv;
@@ -101,9 +111,12 @@ SBX_API sbx_status sbx_live_create(sbx_plan *p, uint32_t ring_capacity_samples, 
     lv->capacity = ring_capacity_samples;
     // SBX_LIVE_COPY=1 selects the three-node graph (H2D copy -> kernel -> D2H copy) instead of zero-copy access.
     // The multi-kernel large path and the mixed-radix path (which re-reads every sample P times) always stage
-    // through device memory.  Measured p50 on a B200, cfg2 (N 2048 stereo): 26.5 us zero-copy, 31.8 us with copies.
+    // through device memory.  Measured p50 on a B200, cfg2 (N 2048 stereo): 21.0 us zero-copy (WIDE geometry, polled completion), 31.8 us with copies.
     const char *env = std::getenv("SBX_LIVE_COPY");
     lv->zero_copy = !(env && env[0] == '1') && !p->large && !p->generic;
+    // SBX_LIVE_POLL=0: wait with cudaStreamSynchronize instead of polling the completion flag
+    const char *env_poll = std::getenv("SBX_LIVE_POLL");
+    lv->poll = lv->zero_copy && !(env_poll && env_poll[0] == '0');
     cudaError_t e = cudaMallocHost(&lv->ring, (size_t)lv->capacity * 2 * sizeof(float));
     if (e == cudaSuccess) e = cudaMallocHost(&lv->h_in, (size_t)p->n * 2 * sizeof(float));
     if (e == cudaSuccess) e = cudaMallocHost(&lv->h_mags, (size_t)p->k_out * 2 * sizeof(float));
@@ -112,6 +125,11 @@ SBX_API sbx_status sbx_live_create(sbx_plan *p, uint32_t ring_capacity_samples, 
     if (e == cudaSuccess) e = cudaMalloc(&lv->d_mags, (size_t)p->k_out * 2 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&lv->d_col, (size_t)p->rows * 4);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&lv->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess && lv->poll) {
+        e = cudaMallocHost(&lv->h_flag, sizeof(unsigned int));
+        if (e == cudaSuccess) { *lv->h_flag = 0; e = cudaMalloc(&lv->d_count, sizeof(unsigned int)); }
+        if (e == cudaSuccess) e = cudaMemset(lv->d_count, 0, sizeof(unsigned int));
+    }
     if (e != cudaSuccess) { sbx_live_destroy(lv); return cuda_fail(p, e, "live buffers"); }
     // one eager launch configures the kernel attributes outside of stream capture
     std::memset(lv->h_in, 0, (size_t)p->n * 2 * sizeof(float));
@@ -170,7 +188,28 @@ static sbx_status live_pop(sbx_live *lv, uint8_t *rgba, float *out_lr)
     SBX_CUDA(p, cudaSetDevice(p->cfg.device));
     SBX_CUDA(p, cudaGraphLaunch(rgba ? lv->graph_col : lv->graph_mags, lv->stream));
     p->launches += 1;
-    SBX_CUDA(p, cudaStreamSynchronize(lv->stream));
+    bool done = false;
+    if (lv->poll) {
+        // the kernel stores the launch counter once the column is visible in pinned memory; a lost or faulted launch
+        // falls through to the stream synchronize below, which reports it
+        const unsigned int expect = ++lv->seq;
+        volatile unsigned int *flag = lv->h_flag;
+        timespec t0;
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        for (uint32_t spins = 0; !done; ++spins) {
+            if (*flag == expect) { done = true; break; }
+            if ((spins & 0x3ffu) == 0x3ffu) {
+                timespec t1;
+                clock_gettime(CLOCK_MONOTONIC, &t1);
+                if ((t1.tv_sec - t0.tv_sec) * 1000000000ll + (t1.tv_nsec - t0.tv_nsec) > 2000000ll) break;   // 2 ms
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+    }
+    if (!done) {
+        SBX_CUDA(p, cudaStreamSynchronize(lv->stream));
+        if (lv->poll) lv->seq = *lv->h_flag;          // resynchronise the counter after a timeout
+    }
     if (rgba) std::memcpy(rgba, lv->h_col, (size_t)p->rows * 4);
     else std::memcpy(out_lr, lv->h_mags, (size_t)p->k_out * 2 * sizeof(float));
     lv->head.store(head + skip, std::memory_order_release);

@@ -84,8 +84,13 @@ sbx_status launch_fused(sbx_plan *p, int channels, const float *d_pcm, uint64_t 
     a.rgba = d_rgba;
     a.mags_out = d_mags;
     a.n_frames = n_frames;
-    const cudaError_t e = p->log2n <= 10 ? launch_fused_small(p, channels, a, n_frames, stream, seqs)
-                                         : launch_fused_big(p, channels, a, n_frames, stream, seqs);
+    if (n_frames == 1 && seqs.count == 1) { a.done_flag = p->live_done_flag; a.done_count = p->live_done_count; }
+    // a lone stereo frame (single-frame entry points, live graphs) is latency-bound: WIDE geometry; SBX_WIDE=0 disables
+    static const bool no_wide = [] { const char *e = std::getenv("SBX_WIDE"); return e && e[0] == '0'; }();
+    const bool wide = n_frames == 1 && seqs.count == 1 && channels == 2 && !no_wide && wide_available(p);
+    const cudaError_t e = wide ? launch_fused_wide(p, a, stream)
+                               : (p->log2n <= 10 ? launch_fused_small(p, channels, a, n_frames, stream, seqs)
+                                                 : launch_fused_big(p, channels, a, n_frames, stream, seqs));
     if (e != cudaSuccess) return cuda_fail(p, e, "fused_frames_kernel launch");
     if (n_frames) p->launches += 1;
     return SBX_OK;

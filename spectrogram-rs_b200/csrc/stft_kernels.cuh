@@ -67,6 +67,10 @@ struct KernelArgs {
     // in pcm; sequence s writes frames [s * n_frames, (s+1) * n_frames).  units_per_seq = 0: one sequence.
     unsigned long long seq_stride;
     uint32_t units_per_seq;
+    // live single-frame launches: the CTA publishes its completion to a polling host thread -- *done_count (device)
+    // is incremented and the new value stored to *done_flag (pinned host memory) after a system-scope fence
+    unsigned int *done_flag;
+    unsigned int *done_count;
     uint32_t hop, rows, k_out, n_chunks;
     float scale;                 // 2 / N     (fft.rs:92)
     float guess_a[2], guess_b[2];// step guess = log2(p + eps) * a + b   (colour, alpha)
@@ -298,18 +302,22 @@ __device__ __forceinline__ uint32_t ldg_tab(const uint32_t *p)
 // ----------------------------------------------------------------------------------------------
 // REAL_: the complex sequence is the even/odd packing z[n] = x[2n] + i x[2n+1] of ONE real (mono) frame of 2 N
 // samples, zero-padded to 2 M; addressed like stereo PCM (CH_ = 2) with hop/2 pairs between frames.
-template <int LOG2N_, int LOG2PAD_, int CH_, bool REAL_ = false> struct Geom {
+// WIDE_: single-frame (latency) variant -- up to four times the threads (M/4, at most 1024): the transform passes
+// keep 16 points per thread (the extra warps idle there), the split, resample and colour phases spread over all.
+template <int LOG2N_, int LOG2PAD_, int CH_, bool REAL_ = false, bool WIDE_ = false> struct Geom {
     static constexpr int LOG2N = LOG2N_, LOG2PAD = LOG2PAD_, CH = CH_;
-    static constexpr bool REAL = REAL_;
+    static constexpr bool REAL = REAL_, WIDE = WIDE_;
     static_assert(!REAL_ || CH_ == 2, "the real-sequence packing reads sample pairs");
     static constexpr int N = 1 << LOG2N, PAD = 1 << LOG2PAD, LOG2M = LOG2N + LOG2PAD, M = 1 << LOG2M;
     static constexpr int REM = LOG2N & 3;                  // first pass radix 2^REM when REM != 0
     static constexpr int NPASS = LOG2N / 4 + (REM ? 1 : 0);
-    static constexpr int THREADS = (M >> SBX_EPT_LOG2) < 64 ? 64 : ((M >> SBX_EPT_LOG2) > SBX_MAX_THREADS ? SBX_MAX_THREADS : (M >> SBX_EPT_LOG2));
+    static constexpr int BASE_THREADS = (M >> SBX_EPT_LOG2) < 64 ? 64 : ((M >> SBX_EPT_LOG2) > SBX_MAX_THREADS ? SBX_MAX_THREADS : (M >> SBX_EPT_LOG2));
+    static constexpr int WIDE_THREADS = (M / 4) > 1024 ? 1024 : (M / 4);
+    static constexpr int THREADS = (WIDE_ && WIDE_THREADS > BASE_THREADS) ? WIDE_THREADS : BASE_THREADS;
     // register budget: 64 per thread (THREADS * MIN_CTAS = 1024).  Without the second launch bound ptxas aims
     // for three resident 512-thread CTAs at cfg1, caps the kernel at 40 registers and spills (measured: 49 vs
     // 52.5 M frames/s); the kernel needs 79 unconstrained and fits 64 without spilling.
-    static constexpr int MIN_CTAS = THREADS >= 1024 ? 1 : (THREADS == 256 ? SBX_MIN_CTAS_256 : 1024 / THREADS);
+    static constexpr int MIN_CTAS = (WIDE_ || THREADS >= 1024) ? 1 : (THREADS == 256 ? SBX_MIN_CTAS_256 : 1024 / THREADS);
     static constexpr int FRAMES_PER_CTA = CH == 1 ? 2 : 1;
     static constexpr int SMEM_BYTES = M * 8;
     static __host__ __device__ constexpr int log2r(int p) { return (REM != 0 && p == 0) ? REM : 4; }
@@ -1105,6 +1113,17 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) fused_frames_kernel(c
     pass_first<G, false>(z, a, a.pcm + seq * a.seq_stride + frame0 * (unsigned long long)a.hop * G::CH, second_valid);
     __syncthreads();
     frame_tail<G>(z, a, seq * a.n_frames + frame0, second_valid);
+    if (a.done_flag != nullptr) {
+        // the barrier orders every thread's output stores before thread 0's fence; the fence is cumulative, so a host
+        // thread that observes the flag also observes the column
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int v = *a.done_count + 1u;
+            *a.done_count = v;
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned int *>(a.done_flag) = v;
+        }
+    }
 }
 
 // ---- persistent variant: grid = SMs x resident CTAs, PCM staged through shared memory by bulk async copies ----

@@ -62,12 +62,13 @@ def make_config(lut_rgb, sample_rate=48000.0, window_n=4096, pad_factor=2, hop=5
     return cfg
 
 
-def batch(cfg, pcm, want_mags=True, want_rgba=True, staged=False, real=None):
+def batch(cfg, pcm, want_mags=True, want_rgba=True, staged=False, real=None, wide=False):
     """staged=True emulates the persistent kernel's pass 0 (PCM span in a stage buffer).
     real: mono batches on the real-sequence geometry (one frame per CTA) -- None: the product's default choice,
     False / True: what SBX_REAL=0 / 1 selects in the product."""
     lib().emu_set_staged(1 if staged else 0)
     lib().emu_set_real(2 if real is None else (1 if real else 0))
+    lib().emu_set_wide(1 if wide else 0)                   # stereo: the WIDE single-frame geometries (more threads per CTA)
     pcm = np.ascontiguousarray(pcm, dtype=np.float32)
     n_samples = pcm.shape[0]
     n, hop = cfg.window_n, cfg.hop

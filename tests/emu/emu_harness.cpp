@@ -10,6 +10,7 @@
 namespace {
 
 bool g_emu_staged = false;
+bool g_emu_wide = false;                // stereo frames on the WIDE (single-frame latency) geometries
 int g_emu_real = 2;                     // mono batches on the REAL geometry: 0 never, 1 wherever its tables exist, 2 the product's default
 
 template <class G, int P, int END = G::NPASS> struct EmuPasses {
@@ -93,8 +94,12 @@ template <int LOG2N, int LOG2PAD>
 int emu_dispatch_ch(int ch, const sbx::KernelArgs &a, unsigned long long f0, float *mags, uint8_t *rgba)
 {
     if constexpr (LOG2N + LOG2PAD > 14) return -2;
-    else return ch == 1 ? emu_cta<sbx::Geom<LOG2N, LOG2PAD, 1>>(a, f0, mags, rgba)
-                        : emu_cta<sbx::Geom<LOG2N, LOG2PAD, 2>>(a, f0, mags, rgba);
+    else {
+        if constexpr (LOG2N + LOG2PAD >= 9 && LOG2N + LOG2PAD <= 12)
+            if (ch == 2 && g_emu_wide) return emu_cta<sbx::Geom<LOG2N, LOG2PAD, 2, false, true>>(a, f0, mags, rgba);
+        return ch == 1 ? emu_cta<sbx::Geom<LOG2N, LOG2PAD, 1>>(a, f0, mags, rgba)
+                       : emu_cta<sbx::Geom<LOG2N, LOG2PAD, 2>>(a, f0, mags, rgba);
+    }
 }
 template <int LOG2N>
 int emu_dispatch_pad(int lp, int ch, const sbx::KernelArgs &a, unsigned long long f0, float *mags, uint8_t *rgba)
@@ -333,6 +338,9 @@ void emu_set_staged(int staged) { g_emu_staged = staged != 0; }
 
 __attribute__((visibility("default")))
 void emu_set_real(int mode) { g_emu_real = mode; }
+
+__attribute__((visibility("default")))
+void emu_set_wide(int wide) { g_emu_wide = wide != 0; }
 
 // host tables of the product, exposed so CPU tests can compare them with the oracle bit for bit
 __attribute__((visibility("default")))

@@ -112,6 +112,23 @@ def test_real_sequence_geometry_needs_an_even_hop(magma):
     assert np.array_equal(m_auto, m_pair) and np.array_equal(c_auto, c_pair)
 
 
+@pytest.mark.parametrize("n,pad,hop,rows,interp,scheme", [
+    (256, 2, 64, 64, 0, 0), (512, 1, 128, 33, 0, 0), (1024, 4, 256, 256, 1, 0), (2048, 2, 2048, 1024, 0, 0),
+    (2048, 1, 512, 512, 0, 1), (4096, 1, 1024, 256, 0, 0), (256, 4, 64, 100, 1, 1), (1024, 2, 300, 2048, 0, 0)])
+def test_wide_single_frame_geometry(magma, n, pad, hop, rows, interp, scheme):
+    """Single stereo frames (sbx_process_column, the live graphs) run the same phases with up to four times the
+    threads per CTA (Geom<.., WIDE>): another thread -> bin / row / sample mapping, the same arithmetic, so the
+    result must equal the batch geometry bit for bit (and the oracle within tolerance)."""
+    pcm = signals.stereo_loopback(n + 2 * hop)
+    cfg = emu.make_config(magma, window_n=n, pad_factor=pad, hop=hop, rows_h=rows, channels=2, interp=interp, scheme=scheme)
+    m_wide, c_wide = emu.batch(cfg, pcm, wide=True)
+    m_base, c_base = emu.batch(cfg, pcm, wide=False)
+    assert np.array_equal(m_wide, m_base) and np.array_equal(c_wide, c_base)
+    p = oracle.params(window_n=n, pad_factor=pad, hop=hop, rows_h=rows, interp=interp, stereo_scheme=scheme)
+    _, o_mags = oracle.batch(p, pcm, 2, magma, want_mags=True)
+    assert (np.abs(m_wide - o_mags) / np.abs(o_mags).max(axis=(1, 2), keepdims=True)).max() <= MAG_TOL
+
+
 @pytest.mark.parametrize("name,kw,ch,lut", [
     ("cfg1_sweep_mono", dict(sample_rate=48000.0, window_n=4096, pad_factor=2, hop=512, rows_h=1024), 1, "magma"),
     ("cfg2_stereo_live", dict(sample_rate=48000.0, window_n=2048, pad_factor=2, hop=2048, rows_h=1024), 2, "magma"),
