@@ -442,7 +442,7 @@ def extras(sbx, signals, torch):
     lat = np.concatenate([live.measure(lr[(i % 64) * 2048:(i % 64 + 1) * 2048], 100) for i in range(100)])
     res["cfg2_live_latency_us"] = {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
                                    "mean": float(lat.mean()), "samples": int(lat.size),
-                                   "what": "host CLOCK_MONOTONIC around: push 2048 stereo samples into the pinned ring + pop one RGBA column (one CUDA graph: H2D 16 KB -> fused kernel -> D2H 4 KB, then stream sync); native loop sbx_live_measure"}
+                                   "what": "host CLOCK_MONOTONIC around: push 2048 stereo samples into the pinned ring + pop one RGBA column (one CUDA graph with a single kernel node that reads the 16 KB pinned window and writes the 4 KB pinned column itself; completion polled on a pinned flag); native loop sbx_live_measure"}
     # the same frame, kernel only (device-resident input and output, CUDA events on the launching stream)
     d_lr = torch.from_numpy(lr[:2048]).cuda()
     d_col = torch.empty((1, 1024, 4), dtype=torch.uint8, device="cuda")
