@@ -111,7 +111,9 @@ SBX_API sbx_status sbx_live_create(sbx_plan *p, uint32_t ring_capacity_samples, 
     lv->capacity = ring_capacity_samples;
     // SBX_LIVE_COPY=1 selects the three-node graph (H2D copy -> kernel -> D2H copy) instead of zero-copy access.
     // The multi-kernel large path and the mixed-radix path (which re-reads every sample P times) always stage
-    // through device memory.  Measured p50 on a B200, cfg2 (N 2048 stereo): 21.0 us zero-copy (WIDE geometry, polled completion), 31.8 us with copies.
+    // through device memory (measured: zero-copy makes the mixed-radix N = 2400 frame slower, 46.9 vs 42.7 us).
+    // Measured p50 on a B200, cfg2 (N 2048 stereo): 16.2 us zero-copy (WIDE geometry, polled completion; a plain
+    // kernel launch instead of the one-node graph: 17.6 us), 31.8 us with copy nodes.
     const char *env = std::getenv("SBX_LIVE_COPY");
     lv->zero_copy = !(env && env[0] == '1') && !p->large && !p->generic;
     // SBX_LIVE_POLL=0: wait with cudaStreamSynchronize instead of polling the completion flag
@@ -158,11 +160,18 @@ SBX_API uint32_t sbx_live_push(sbx_live *lv, const float *samples, uint32_t n_sa
     const uint64_t head = lv->head.load(std::memory_order_acquire);
     const uint32_t free_slots = lv->capacity - (uint32_t)(tail - head);
     const uint32_t n = n_samples < free_slots ? n_samples : free_slots;
-    for (uint32_t i = 0; i < n; ++i) {
-        float *dst = lv->ring + 2 * ((tail + i) % lv->capacity);
-        if (channels == 1) { dst[0] = samples[i]; dst[1] = samples[i]; }      // audio_input_list_model.rs:67
-        else { dst[0] = samples[2 * i]; dst[1] = samples[2 * i + 1]; }        // :70
-    }
+    // at most two contiguous runs (the ring wraps once); no per-sample modulo
+    const uint32_t start = (uint32_t)(tail % lv->capacity);
+    const uint32_t first = lv->capacity - start < n ? lv->capacity - start : n;
+    auto put = [&](float *dst, const float *src, uint32_t count) {
+        if (channels == 2) {
+            std::memcpy(dst, src, (size_t)count * 2 * sizeof(float));           // audio_input_list_model.rs:70
+        } else {
+            for (uint32_t i = 0; i < count; ++i) { dst[2 * i] = src[i]; dst[2 * i + 1] = src[i]; }   // (s, s), :67
+        }
+    };
+    put(lv->ring + 2 * (size_t)start, samples, first);
+    if (first < n) put(lv->ring, samples + (size_t)first * channels, n - first);
     lv->tail.store(tail + n, std::memory_order_release);
     return n;
 }
