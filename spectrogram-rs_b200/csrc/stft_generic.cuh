@@ -13,7 +13,10 @@
 
 namespace sbx {
 
-constexpr int GENERIC_THREADS = 256;
+#ifndef SBX_GENERIC_THREADS
+#define SBX_GENERIC_THREADS 256
+#endif
+constexpr int GENERIC_THREADS = SBX_GENERIC_THREADS;
 constexpr int GENERIC_MAX_PASSES = 12;
 
 struct GenericArgs {
