@@ -6,6 +6,7 @@
 //   HeapRb::new(cap).split()                                src/devices/audio_input_list_model.rs:30
 // Header-only; link with -lsbx_b200.  All arithmetic happens in the library, on the GPU.
 #pragma once
+#include <algorithm>
 #include <atomic>
 #include <cstdint>
 #include <cstring>
@@ -38,7 +39,11 @@ class HeapRb {
     {
         const uint64_t tail = tail_.load(std::memory_order_relaxed), head = head_.load(std::memory_order_acquire);
         size_t room = cap_ - static_cast<size_t>(tail - head), n = 0;
-        for (; first != last && n < room; ++first, ++n) buf_[(tail + n) % cap_] = *first;
+        size_t at = static_cast<size_t>(tail % cap_);                       // running index: no per-sample modulo
+        for (; first != last && n < room; ++first, ++n) {
+            buf_[at] = *first;
+            if (++at == cap_) at = 0;
+        }
         tail_.store(tail + n, std::memory_order_release);
         return n;
     }
@@ -59,7 +64,9 @@ class HeapRb {
     {
         const uint64_t head = head_.load(std::memory_order_relaxed);
         const size_t n = std::min(max, len());
-        for (size_t i = 0; i < n; ++i) out[i] = buf_[(head + i) % cap_];
+        const size_t start = static_cast<size_t>(head % cap_), first = std::min(n, cap_ - start);
+        std::copy(buf_.begin() + start, buf_.begin() + start + first, out);
+        std::copy(buf_.begin(), buf_.begin() + (n - first), out + first);
         return n;
     }
     size_t skip(size_t n)                                     // Consumer::skip
