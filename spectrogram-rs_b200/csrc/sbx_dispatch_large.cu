@@ -9,17 +9,15 @@ sbx_status launch_generic(sbx_plan *p, int channels, const float *d_pcm, uint64_
                           float *d_mags, cudaStream_t stream)
 {
     if (n_frames == 0) return SBX_OK;
-    GenericArgs g{};
+    GenericArgs g = p->generic_passes;                          // radices, strides, table offsets
     g.k = p->base_args();
     g.k.pcm = d_pcm;
     g.k.rgba = d_rgba;
     g.k.mags_out = d_mags;
     g.k.n_frames = n_frames;
     g.twm = p->d_twm;
+    g.twg = p->d_twg;
     g.pos_tab = p->d_pos_tab;
-    g.n = p->n; g.pad = p->pad; g.m = p->m;
-    g.npass = (uint32_t)p->radix.size();
-    for (size_t i = 0; i < p->radix.size(); ++i) { g.radix[i] = p->radix[i]; g.stride[i] = p->stride[i]; }
     const size_t smem = (size_t)p->m * 12;                      // transform [M] + magnitudes [M/2], float2
     const uint64_t ctas = channels == 1 ? (n_frames + 1) / 2 : n_frames;
     if (ctas > 0x7fffffffull) return fail(p, SBX_ERR_INVALID_ARGUMENT, "too many frames in one launch");

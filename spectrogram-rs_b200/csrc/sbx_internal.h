@@ -37,6 +37,8 @@ struct sbx_plan {
     float2 *d_twm = nullptr;
     uint32_t *d_pos_tab = nullptr;
     std::vector<uint32_t> radix, stride;
+    sbx::GenericArgs generic_passes{};  // pass description (radices, strides, table offsets), filled at plan creation
+    float2 *d_twg = nullptr;            // per-pass twiddle planes
 
     // REAL geometry (mono batches of long windows, one frame per CTA): tables of the half-length packed transform
     bool real_ok = false;               // tables exist

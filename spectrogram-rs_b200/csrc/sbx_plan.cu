@@ -309,7 +309,7 @@ SBX_API void sbx_plan_destroy(sbx_plan *p)
         cudaFree(s.d_rgba);
     }
     cudaFree(p->d_window); cudaFree(p->d_wtw); cudaFree(p->d_twp); cudaFree(p->d_rowmap); cudaFree(p->d_rowinfo); cudaFree(p->d_chunks);
-    cudaFree(p->d_samp); cudaFree(p->d_f16_scratch); cudaFree(p->d_twm); cudaFree(p->d_pos_tab); cudaFree(p->d_twp_block); cudaFree(p->d_zbuf); cudaFree(p->d_magbuf);
+    cudaFree(p->d_samp); cudaFree(p->d_f16_scratch); cudaFree(p->d_twm); cudaFree(p->d_twg); cudaFree(p->d_pos_tab); cudaFree(p->d_twp_block); cudaFree(p->d_zbuf); cudaFree(p->d_magbuf);
     cudaFree(p->d_thr); cudaFree(p->d_lut); cudaFree(p->d_ctab); cudaFree(p->d_twp_real); cudaFree(p->d_wtw4); cudaFree(p->d_rtw); cudaFree(p->d_frame); cudaFree(p->d_mags1); cudaFree(p->d_col);
     if (p->h_frame) cudaFreeHost(p->h_frame);
     if (p->h_col) cudaFreeHost(p->h_col);
@@ -394,6 +394,7 @@ SBX_API sbx_status sbx_plan_create(const sbx_config *cfg, sbx_plan **out_plan)
     p->generic = t.generic;
     p->radix = t.radix;
     p->stride = t.stride;
+    if (t.generic) sbx::tables::fill_generic_passes(t, p->generic_passes);
     p->h_window = t.window;
     p->h_rowmap = t.rowmap;
     p->h_thr_raw = t.thr_raw;
@@ -422,6 +423,7 @@ SBX_API sbx_status sbx_plan_create(const sbx_config *cfg, sbx_plan **out_plan)
     SBX_TRY(upload(&p->d_wtw4, t.wtw4.data(), t.wtw4.size() * sizeof(float)));
     SBX_TRY(upload(&p->d_rtw, t.rtw.data(), t.rtw.size() * sizeof(float)));
     SBX_TRY(upload(&p->d_twm, t.twm.data(), t.twm.size() * sizeof(float)));
+    SBX_TRY(upload(&p->d_twg, t.twg.data(), t.twg.size() * sizeof(float)));
     SBX_TRY(upload(&p->d_pos_tab, t.pos_tab.data(), t.pos_tab.size() * sizeof(uint32_t)));
     SBX_TRY(upload(&p->d_twp_block, t.twp_block.data(), t.twp_block.size() * sizeof(float)));
     SBX_TRY(upload(&p->d_rowmap, p->h_rowmap.data(), p->rows * sizeof(sbx::RowMap)));

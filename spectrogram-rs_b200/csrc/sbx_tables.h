@@ -101,6 +101,8 @@ struct HostTables {
     std::vector<float> twm;             // generic: [M] x (re, im) full twiddle table W_M^t
     std::vector<uint32_t> pos_tab;      // generic: [M] position of bin kk
     std::vector<uint32_t> radix, stride;// generic: per-pass radix and butterfly stride
+    std::vector<float> twg;             // generic: per-pass twiddle planes, see GenericArgs::twg
+    std::vector<uint32_t> tw_off;       // generic: first entry of each pass in twg
     std::vector<RowMap> rowmap;         // [H]
     std::vector<uint32_t> rowinfo;      // [H] n | first scratch slot << 16 (what the kernels read)
     std::vector<RowChunk> chunks;       // rows grouped so that a chunk's samples fit the kernel's scratch area
@@ -153,7 +155,7 @@ inline void build(const sbx_config &cfg, HostTables &t)
         }
 
     // ---- transform tables ----------------------------------------------------------------------
-    t.twm.clear(); t.pos_tab.clear(); t.radix.clear(); t.stride.clear();
+    t.twm.clear(); t.pos_tab.clear(); t.radix.clear(); t.stride.clear(); t.twg.clear(); t.tw_off.clear();
     if (t.generic) {
         // radix list from {16, 8, 4, 2, 3, 5, 7}; a left-over factor means a prime > 7: unsupported
         uint32_t rest = t.n;
@@ -168,6 +170,19 @@ inline void build(const sbx_config &cfg, HostTables &t)
             const double ang = -2.0 * M_PI * (double)k / (double)t.m;
             t.twm[2 * (size_t)k] = (float)std::cos(ang);
             t.twm[2 * (size_t)k + 1] = (float)std::sin(ang);
+        }
+        // per-pass twiddle planes (all passes but the last): plane q-1, entry lo = W_(S R)^(lo q), contiguous in lo
+        t.twg.clear(); t.tw_off.clear();
+        for (size_t p = 0; p < t.radix.size(); ++p) {
+            t.tw_off.push_back((uint32_t)(t.twg.size() / 2));
+            if (p + 1 == t.radix.size()) break;
+            const uint32_t R = t.radix[p], S = t.stride[p];
+            for (uint32_t q = 1; q < R; ++q)
+                for (uint32_t lo = 0; lo < S; ++lo) {
+                    const double ang = -2.0 * M_PI * (double)(((uint64_t)lo * q) % ((uint64_t)S * R)) / (double)((uint64_t)S * R);
+                    t.twg.push_back((float)std::cos(ang));
+                    t.twg.push_back((float)std::sin(ang));
+                }
         }
         // bin kk = P k + q0, k = sum d_p (R_0 .. R_(p-1))  ->  position q0 N + sum d_p S_p
         t.pos_tab.resize(t.m);
@@ -347,6 +362,20 @@ inline void build(const sbx_config &cfg, HostTables &t)
         std::memcpy(&t.ctab[4 * i], &t.thr[2 * i], 8);                 // (ts[i], ts[i+1]) of the colour set
         t.ctab[4 * i + 2] = t.lut[i];
         t.ctab[4 * i + 3] = 0;
+    }
+}
+
+// run-time pass description of the mixed-radix path (device pointers are set by the caller)
+inline void fill_generic_passes(const HostTables &t, GenericArgs &g)
+{
+    g.n = t.n; g.pad = t.pad; g.m = t.m;
+    g.npass = (uint32_t)t.radix.size();
+    for (size_t i = 0; i < t.radix.size(); ++i) {
+        g.radix[i] = t.radix[i];
+        g.stride[i] = t.stride[i];
+        g.per_sub[i] = t.n / t.radix[i];
+        g.tw_off[i] = t.tw_off[i];
+        g.inv_stride[i] = (uint32_t)((1ull << 32) / t.stride[i]) + 1u;      // unused (and wraps) for S = 1
     }
 }
 

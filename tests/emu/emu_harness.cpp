@@ -295,8 +295,8 @@ long long emu_batch(const sbx_config *cfg, const float *pcm, unsigned long long 
         g.k = a;
         g.twm = reinterpret_cast<const float2 *>(t.twm.data());
         g.pos_tab = t.pos_tab.data();
-        g.n = t.n; g.pad = t.pad; g.m = t.m; g.npass = (uint32_t)t.radix.size();
-        for (size_t i = 0; i < t.radix.size(); ++i) { g.radix[i] = t.radix[i]; g.stride[i] = t.stride[i]; }
+        sbx::tables::fill_generic_passes(t, g);
+        g.twg = reinterpret_cast<const float2 *>(t.twg.data());
         const int st = ch == 1 ? emu_generic<1>(g, frames, mags_lr, rgba) : emu_generic<2>(g, frames, mags_lr, rgba);
         return st != 0 ? st : (long long)frames;
     }
