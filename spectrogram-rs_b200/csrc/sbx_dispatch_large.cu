@@ -15,6 +15,7 @@ sbx_status launch_generic(sbx_plan *p, int channels, const float *d_pcm, uint64_
     g.k.rgba = d_rgba;
     g.k.mags_out = d_mags;
     g.k.n_frames = n_frames;
+    if (n_frames == 1) { g.k.done_flag = p->live_done_flag; g.k.done_count = p->live_done_count; }
     g.twm = p->d_twm;
     g.twg = p->d_twg;
     g.pos_tab = p->d_pos_tab;

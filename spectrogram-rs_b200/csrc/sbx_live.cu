@@ -110,12 +110,12 @@ SBX_API sbx_status sbx_live_create(sbx_plan *p, uint32_t ring_capacity_samples, 
     lv->plan = p;
     lv->capacity = ring_capacity_samples;
     // SBX_LIVE_COPY=1 selects the three-node graph (H2D copy -> kernel -> D2H copy) instead of zero-copy access.
-    // The multi-kernel large path and the mixed-radix path (which re-reads every sample P times) always stage
-    // through device memory (measured: zero-copy makes the mixed-radix N = 2400 frame slower, 46.9 vs 42.7 us).
+    // The multi-kernel large path always stages through device memory.  The mixed-radix path reads every sample
+    // once (generic_load), so zero-copy pays there too: N = 2400 p50 26.9 us against 30.8 us with copy nodes.
     // Measured p50 on a B200, cfg2 (N 2048 stereo): 16.2 us zero-copy (WIDE geometry, polled completion; a plain
     // kernel launch instead of the one-node graph: 17.6 us), 31.8 us with copy nodes.
     const char *env = std::getenv("SBX_LIVE_COPY");
-    lv->zero_copy = !(env && env[0] == '1') && !p->large && !p->generic;
+    lv->zero_copy = !(env && env[0] == '1') && !p->large;
     // SBX_LIVE_POLL=0: wait with cudaStreamSynchronize instead of polling the completion flag
     const char *env_poll = std::getenv("SBX_LIVE_POLL");
     lv->poll = lv->zero_copy && !(env_poll && env_poll[0] == '0');

@@ -7,7 +7,7 @@
 // This is the low-rate live path (819 frames/s in the reference), so it trades the fused kernel's
 // swizzles and compile-time index math for generality: bin -> position comes from a host table, twiddles
 // from per-pass planes (contiguous in the butterfly index), divisions by host-computed reciprocals.
-// Measured on a B200, N = 2400 stereo: 17.9 M frames/s in batch, 31 us per live frame (12.0 M / 41 us with
+// Measured on a B200, N = 2400 stereo: 18.3 M frames/s in batch, 27 us per live frame (12.0 M / 41 us with
 // strided loads from the full W_M table and run-time divisions).  One CTA per frame (stereo) or frame pair (mono); the transform (M float2)
 // and the magnitudes (M/2 float2) live in shared memory: M <= 16384.
 #pragma once
@@ -86,9 +86,8 @@ __device__ __forceinline__ void generic_load(float2 *z, const GenericArgs &g, un
     const KernelArgs &a = g.k;
     const float *pa = a.pcm + frame0 * (unsigned long long)a.hop * CH;
     const float *pb = pa + a.hop;
-    for (uint32_t i = threadIdx.x; i < g.m; i += GENERIC_THREADS) {
-        uint32_t n;
-        const uint32_t q0 = run_of(i, g.n, n);
+    // every sample is read ONCE and feeds all P sub-transforms (the live path reads it from pinned host memory)
+    for (uint32_t n = threadIdx.x; n < g.n; n += GENERIC_THREADS) {
         float2 s;
         if constexpr (CH == 2) {
             s = __ldg(reinterpret_cast<const float2 *>(pa) + n);
@@ -98,8 +97,9 @@ __device__ __forceinline__ void generic_load(float2 *z, const GenericArgs &g, un
         }
         const float wn = __ldg(a.window + n);
         s.x *= wn;  s.y *= wn;                                            // fft.rs:57-63
-        if (q0 != 0) s = cmul(s, __ldg(g.twm + n * q0));                  // n q0 < N P = M
-        z[i] = s;
+        z[n] = s;
+        for (uint32_t q0 = 1; q0 < g.pad; ++q0)
+            z[(size_t)q0 * g.n + n] = cmul(s, __ldg(g.twm + n * q0));     // n q0 < N P = M
     }
 }
 
@@ -186,6 +186,15 @@ __global__ void __launch_bounds__(GENERIC_THREADS) generic_frames_kernel(const G
             resample_samples<GENERIC_THREADS>(mags, z, a, ck);
             __syncthreads();
             colour_rows<CH == 1, GENERIC_THREADS>(z, a.thr, a.lut, a, ck, frame0, second_valid);
+        }
+    }
+    if (a.done_flag != nullptr) {                                         // live single frame, see fused_frames_kernel
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int v = *a.done_count + 1u;
+            *a.done_count = v;
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned int *>(a.done_flag) = v;
         }
     }
 }
