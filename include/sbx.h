@@ -225,8 +225,10 @@ SBX_API sbx_status sbx_get_window(const sbx_plan *plan, float *w);
 /* ---- live path: the SPSC ring + hop cursor of L1/L2 --------------------------------------- */
 /* Pinned-host ring of (l,r) samples (capacity as HeapRb::new(4096),
  * src/devices/audio_input_list_model.rs:30) with AudioStreamTransform's cursor semantics
- * (src/fourier/audio_transform.rs:34-42) and one captured CUDA graph
- * (H2D -> fused kernel -> D2H) per frame. */
+ * (src/fourier/audio_transform.rs:34-42) and one captured CUDA graph per frame: a single kernel node that reads
+ * the pinned window and writes the pinned column itself and signals completion through a pinned flag the consumer
+ * polls (M <= 16384 and the mixed-radix path), or H2D copy -> kernels -> D2H copy + stream synchronize (M > 16384,
+ * SBX_LIVE_COPY=1).  One producer thread (push) and one consumer thread (pop) may run concurrently. */
 /* The live stream borrows the plan: destroy it (sbx_live_destroy) before sbx_plan_destroy(plan). */
 SBX_API sbx_status sbx_live_create(sbx_plan *plan, uint32_t ring_capacity_samples, sbx_live **out_live);
 SBX_API void       sbx_live_destroy(sbx_live *live);
