@@ -8,7 +8,9 @@
 // swizzles and compile-time index math for generality: bin -> position comes from a host table, twiddles
 // from per-pass planes (contiguous in the butterfly index), divisions by host-computed reciprocals.
 // Measured on a B200, N = 2400 stereo: 18.3 M frames/s in batch, 27 us per live frame (12.0 M / 41 us with
-// strided loads from the full W_M table and run-time divisions).  One CTA per frame (stereo) or frame pair (mono); the transform (M float2)
+// strided loads from the full W_M table and run-time divisions).  Composite radices evaluated in registers
+// (20, 21, 15, ...: 2400 = 20*20*6, three passes instead of five) were measured and rejected: 128 registers halve
+// the occupancy and the batch rate drops to 12.8 M frames/s, with no gain for the single live frame.  One CTA per frame (stereo) or frame pair (mono); the transform (M float2)
 // and the magnitudes (M/2 float2) live in shared memory: M <= 16384.
 #pragma once
 #include "stft_kernels.cuh"
