@@ -11,6 +11,9 @@
 // sequences afterwards.  Long mono windows (real length >= 16384, Geom<.., REAL = true>) instead give
 // every frame its own CTA: z[n] = x[2n] + i x[2n+1] halves the transform (the even/odd split of a real
 // sequence), so the buffer is 64 KB instead of 128 KB per unit and two CTAs fit an SM.
+// Other launch shapes of the same phases: a persistent grid with cp.async.bulk-staged PCM where one CTA owns an
+// SM (fused_frames_persistent_kernel), several equally long recordings in one grid (KernelArgs::units_per_seq),
+// and a lone stereo frame on four times the threads with a polled completion flag (Geom<.., WIDE>, done_flag).
 //
 // FFT structure (see tools/fft_model.py for the numpy model of the index math):
 //   * the zero padding is never materialised: the radix-P DIF step over a sequence whose last
