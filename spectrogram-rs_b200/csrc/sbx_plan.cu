@@ -690,7 +690,8 @@ SBX_API sbx_status sbx_process_batch(sbx_plan *p, const float *pcm, uint64_t n_s
 
     if (p->chunk_frames == 0) {
         // at most ~32 MiB of RGBA (SBX_BATCH_CHUNK_MB) and ~64 MiB of PCM per chunk, even frame count (mono pairs),
-        // at least 2 frames
+        // at least 2 frames.  Measured end to end on a B200 (cfg1, 131072 frames per call): 8 / 32 / 128 MiB chunks
+        // -> 12.2 / 12.1 / 11.0 M frames/s; the D2H link (~50 GB/s) is the limit, not the chunking.
         const char *env = std::getenv("SBX_BATCH_CHUNK_MB");
         const uint64_t chunk_mb = env && std::atoi(env) > 0 ? (uint64_t)std::atoi(env) : 32u;
         uint64_t cf = (chunk_mb << 20) / ((uint64_t)p->rows * 4);
