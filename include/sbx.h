@@ -51,7 +51,9 @@ enum { SBX_INTERP_CUBIC = 0,      /* cubic_interpolate, the interpolator the ref
 enum { SBX_SCHEME_MONO = 0,       /* ColorScheme::new_mono: colour = gradient(dB), alpha = 255
                                      (src/colorscheme.rs:67-70) */
        SBX_SCHEME_STEREO = 1 };   /* ColorScheme::new_stereo: colour = gradient(l/(|l|+|r|)),
-                                     alpha = normalised dB (src/colorscheme.rs:63-66) */
+                                     alpha = normalised dB (src/colorscheme.rs:63-66).  The gradient is read as
+                                     lut_rgb[clamp(floor(pan * 256))]: a 256-step quantisation of the reference's
+                                     continuous stereo gradients (see lut_rgb below) */
 
 /*
  * Everything the reference hard-codes as literals (SURVEY.md section 5 "Config"), as one struct.
@@ -77,7 +79,14 @@ typedef struct sbx_config {
     int32_t  device;        /* CUDA device ordinal */
     uint32_t reserved;
     uint8_t  lut_rgb[768];  /* 256 x (r,g,b): gradient.eval_continuous((i+0.5)/256), i = 0..255
-                               (src/colorscheme.rs:69).  See sbx_builtin_lut(). */
+                               (src/colorscheme.rs:69).  See sbx_builtin_lut().
+                               EXACT only for colorous' 256-entry ramps (MAGMA, VIRIDIS, INFERNO, PLASMA), where
+                               eval_continuous(t) itself is table[clamp(floor(t*256))].  Every other gradient the
+                               reference lists (the stereo schemes RED_YELLOW_BLUE -- the app default --, RED_BLUE,
+                               SPECTRAL, ...; CIVIDIS, TURBO, REDS, ...) is a continuous spline/polynomial in
+                               colorous: the library evaluates it at 256 steps, so an r/g/b value can differ from
+                               eval_continuous(t) by the gradient's change over half a step (a few LSB where the
+                               gradient is steep).  Alpha (stereo schemes) and the step index are exact either way. */
 } sbx_config;
 
 /* Reference defaults: 48 kHz, N 4096, P 2, hop 512, H 1024, 32..22030 Hz, -70..-10 dB, eps 1e-7,
@@ -150,7 +159,14 @@ SBX_API sbx_status sbx_process_batch(sbx_plan *plan, const float *pcm, uint64_t 
                                      uint8_t *rgba, uint64_t rgba_capacity_frames, uint64_t *frames_out);
 
 /* Same, DEVICE pointers, asynchronous on the plan's stream (sbx_synchronize() to wait).
- * d_pcm must be 16-byte aligned. */
+ * d_pcm must be 16-byte aligned.
+ * Mono plans (channels = 1) transform frames two at a time -- frame 2c of the call as the real part and frame 2c+1
+ * as the imaginary part of one complex sequence, separated afterwards by the reference's own conjugate-symmetry split
+ * (src/fourier/fft.rs:81-89).  A frame's magnitudes therefore depend, in the last bit (about 1e-7 of the pair's
+ * peak), on which slot it takes and on its partner: two calls return byte-identical columns for a frame only if it is
+ * paired identically, i.e. if d_pcm of the second call starts an EVEN number of frames (a multiple of 2*hop samples)
+ * after the first.  sharding.time_blocks / sbx_process_batch chunk on even frame counts for this reason.  (The
+ * real-sequence geometry, sbx_kernel_path() == "fused-real", has no such dependence.) */
 SBX_API sbx_status sbx_process_batch_device(sbx_plan *plan, const float *d_pcm, uint64_t n_samples,
                                             uint8_t *d_rgba, uint64_t rgba_capacity_frames, uint64_t *frames_out);
 

@@ -178,6 +178,9 @@ class SpectrogramColumns:
 
     def _make_plan(self, sample_rate, n):
         hop = max(1, samples_from_seconds(np.float32(self.stride), np.float32(sample_rate)))
+        old = getattr(self, "plan", None)
+        if old is not None:
+            old.close()                     # re-plan (simple_spectrogram.rs:214-219): release the previous plan now
         self.plan = Plan(sample_rate=sample_rate, window_n=n, pad_factor=self._pad, hop=hop, rows_h=self.height,
                          channels=2, lut=self.palette.lut, device=self._device,
                          scheme=binding.SCHEME_STEREO if self.palette.is_stereo else binding.SCHEME_MONO)

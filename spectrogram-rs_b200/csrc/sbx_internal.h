@@ -53,6 +53,9 @@ struct sbx_plan {
     float2 *d_zbuf = nullptr;           // [large_units][M]
     float2 *d_magbuf = nullptr;         // [large_units][M/2]
     uint32_t large_units = 0;           // scratch capacity in units (frame pairs / frames)
+    // d_zbuf / d_magbuf are plan-wide: launches of the large path on DIFFERENT streams (the chunk pipeline of
+    // sbx_process_batch) must not overlap.  Every such launch waits for this event and re-records it.
+    cudaEvent_t large_scratch_free = nullptr;
     float *d_thr = nullptr;
     uint32_t *d_lut = nullptr;
     uint4 *d_ctab = nullptr;

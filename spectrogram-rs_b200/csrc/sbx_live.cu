@@ -16,6 +16,7 @@
 
 struct sbx_live {
     sbx_plan *plan = nullptr;
+    int device = 0;                        // copied from the plan: sbx_live_destroy must not touch the plan (it may be gone)
     uint32_t capacity = 0;                 // samples
     float *ring = nullptr;                 // pinned, capacity x (l,r)
     std::atomic<uint64_t> head{0};         // total samples consumed
@@ -84,7 +85,7 @@ extern "C" {
 SBX_API void sbx_live_destroy(sbx_live *lv)
 {
     if (!lv) return;
-    if (lv->plan) cudaSetDevice(lv->plan->cfg.device);
+    cudaSetDevice(lv->device);              // never lv->plan: a caller may have destroyed the plan first
     if (lv->stream) cudaStreamSynchronize(lv->stream);
     if (lv->graph_col) cudaGraphExecDestroy(lv->graph_col);
     if (lv->graph_mags) cudaGraphExecDestroy(lv->graph_mags);
@@ -108,6 +109,7 @@ SBX_API sbx_status sbx_live_create(sbx_plan *p, uint32_t ring_capacity_samples, 
     sbx_live *lv = new (std::nothrow) sbx_live();
     if (!lv) return fail(p, SBX_ERR_OUT_OF_MEMORY, "out of host memory");
     lv->plan = p;
+    lv->device = p->cfg.device;
     lv->capacity = ring_capacity_samples;
     // SBX_LIVE_COPY=1 selects the three-node graph (H2D copy -> kernel -> D2H copy) instead of zero-copy access.
     // The multi-kernel large path always stages through device memory.  The mixed-radix path reads every sample

@@ -313,6 +313,7 @@ SBX_API void sbx_plan_destroy(sbx_plan *p)
     cudaFree(p->d_thr); cudaFree(p->d_lut); cudaFree(p->d_ctab); cudaFree(p->d_twp_real); cudaFree(p->d_wtw4); cudaFree(p->d_rtw); cudaFree(p->d_frame); cudaFree(p->d_mags1); cudaFree(p->d_col);
     if (p->h_frame) cudaFreeHost(p->h_frame);
     if (p->h_col) cudaFreeHost(p->h_col);
+    if (p->large_scratch_free) cudaEventDestroy(p->large_scratch_free);
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
     delete p;
 }
@@ -334,6 +335,8 @@ SBX_API sbx_status sbx_plan_create(const sbx_config *cfg, sbx_plan **out_plan)
             return fail(nullptr, SBX_ERR_UNSUPPORTED, "non-power-of-two windows need window_n * pad_factor <= 19370 (one SM's shared memory)");
         if (((cfg->window_n * cfg->pad_factor) & 1u) != 0)
             return fail(nullptr, SBX_ERR_UNSUPPORTED, "window_n * pad_factor must be even");
+        if (cfg->window_n * cfg->pad_factor < 8)
+            return fail(nullptr, SBX_ERR_UNSUPPORTED, "window_n * pad_factor must be >= 8");
         uint32_t rest = cfg->window_n;
         for (uint32_t f : {2u, 3u, 5u, 7u})
             while (rest % f == 0) rest /= f;
@@ -387,9 +390,10 @@ SBX_API sbx_status sbx_plan_create(const sbx_config *cfg, sbx_plan **out_plan)
     p->scale = t.scale;
     if (!t.ok) {
         delete p;
+        // (prime factors > 7 and transforms shorter than 8 were rejected above with their own messages)
         return fail(nullptr, SBX_ERR_UNSUPPORTED, t.generic && t.radix.empty()
-                        ? "window_n has a prime factor larger than 7 (supported radices: 2, 3, 4, 5, 7, 8, 16)"
-                        : "window_n cannot be factored into supported radices, or a row of the bin map averages more samples than the shared-memory scratch holds");
+                        ? "window_n needs more radix passes than the mixed-radix kernel runs (GENERIC_MAX_PASSES)"
+                        : "a row of the bin map averages more samples than the shared-memory scratch holds, or the bin count exceeds the sample table's index width");
     }
     p->generic = t.generic;
     p->radix = t.radix;
@@ -728,8 +732,24 @@ SBX_API sbx_status sbx_process_batch(sbx_plan *p, const float *pcm, uint64_t n_s
         cudaError_t e = cudaMemcpyAsync(s.d_pcm, pcm + (size_t)f0 * p->hop * p->channels,
                                         samples * p->channels * sizeof(float), cudaMemcpyHostToDevice, s.stream);
         if (e != cudaSuccess) { st = cuda_fail(p, e, "batch H2D copy"); break; }
+        // The multi-kernel path works in ONE plan-wide scratch (d_zbuf, d_magbuf): chunk k+1's kernels on the next
+        // slot stream must not start before chunk k's have finished with it.  Only the kernels are chained -- the
+        // H2D copy above and the D2H copy below still overlap with the neighbouring chunks' kernels.
+        if (p->large) {
+            if (!p->large_scratch_free) {
+                e = cudaEventCreateWithFlags(&p->large_scratch_free, cudaEventDisableTiming);
+                if (e != cudaSuccess) { st = cuda_fail(p, e, "cudaEventCreate(large scratch)"); break; }
+            } else {
+                e = cudaStreamWaitEvent(s.stream, p->large_scratch_free, 0);
+                if (e != cudaSuccess) { st = cuda_fail(p, e, "cudaStreamWaitEvent(large scratch)"); break; }
+            }
+        }
         st = sbx::launch_fused(p, (int)p->channels, s.d_pcm, nf, s.d_rgba, nullptr, s.stream);
         if (st != SBX_OK) break;
+        if (p->large) {
+            e = cudaEventRecord(p->large_scratch_free, s.stream);
+            if (e != cudaSuccess) { st = cuda_fail(p, e, "cudaEventRecord(large scratch)"); break; }
+        }
         e = cudaMemcpyAsync(rgba + (size_t)f0 * p->rows * 4, s.d_rgba, (size_t)nf * p->rows * 4,
                             cudaMemcpyDeviceToHost, s.stream);
         if (e != cudaSuccess) st = cuda_fail(p, e, "batch D2H copy");

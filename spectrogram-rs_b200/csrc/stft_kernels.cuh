@@ -879,6 +879,13 @@ __device__ __forceinline__ void resample_samples(const T *mags, T *scratch, cons
     else resample_samples_impl<THREADS, false>(mags, scratch, a, ck);
 }
 
+// Stereo-scheme gradient index of a mono pixel (l == r >= 0): floor(l / (|l| + |l|) * 256) with the reference's f32
+// sum -- 128 while l + l is finite, 0 once it overflows (l > FLT_MAX / 2: l / inf = 0) and for l = 0 or NaN (NaN -> 0)
+__device__ __forceinline__ uint32_t pan_index_equal(float l)
+{
+    return (l > 0.0f && __fadd_rn(l, l) <= 3.402823466e+38f) ? 128u : 0u;
+}
+
 // Phase B: one thread per row: sequential mean of its samples (the reference's summation order,
 // ifs.rs:71-73), dB step, LUT, packed RGBA store.  Two rows per thread are kept in flight (their
 // loads and the dependent chains of the two colour look-ups overlap).
@@ -902,8 +909,9 @@ __device__ __forceinline__ void colour_one_row(float ax, float ay, uint32_t n, u
             outA[row] = cA;
             if (second_valid) outB[row] = cB;
         } else {
-            // l == r: pan = l / (|l| + |r|) = 0.5 for finite l > 0, else NaN or negative -> index 0
-            const uint32_t panA = (ax > 0.0f && ax < 3.0e38f) ? 128u : 0u, panB = (ay > 0.0f && ay < 3.0e38f) ? 128u : 0u;
+            // l == r: pan = l / (|l| + |r|) = 0.5 while the f32 sum l + l is finite (l <= FLT_MAX / 2); beyond that the
+            // reference divides by inf -> pan 0, and l = 0 or NaN gives NaN -> index 0 as well
+            const uint32_t panA = pan_index_equal(ax), panB = pan_index_equal(ay);
             outA[row] = (ldg_tab(lut + panA) & 0x00ffffffu) | ((uint32_t)step_index(thr_a, pA, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
             if (second_valid)
                 outB[row] = (ldg_tab(lut + panB) & 0x00ffffffu) | ((uint32_t)step_index(thr_a, pB, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
@@ -930,7 +938,7 @@ __device__ __forceinline__ void colour_one_row_single(float ax, uint32_t n, uint
     if (a.scheme == 0) {
         out[row] = step_colour(a, p);
     } else {
-        const uint32_t pan = (ax > 0.0f && ax < 3.0e38f) ? 128u : 0u;        // l / (|l| + |l|), see colour_one_row
+        const uint32_t pan = pan_index_equal(ax);                            // l / (|l| + |l|), see colour_one_row
         out[row] = (ldg_tab(a.lut + pan) & 0x00ffffffu) |
                    ((uint32_t)step_index(a.thr + THR_STRIDE, p, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
     }

@@ -1,6 +1,7 @@
 """Thin RAII wrapper over the C ABI (include/sbx.h).  Every transform goes through libsbx_b200.so;
 nothing here computes spectra on the CPU."""
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -50,6 +51,7 @@ class Plan:
                  scheme=binding.SCHEME_MONO, lut="magma", device=0):
         self._lib = binding.load()
         self._h = None
+        self._live = weakref.WeakSet()      # live streams hold graphs and buffers of this plan: closed before it
         cfg = SbxConfig()
         self._lib.sbx_config_default(C.byref(cfg))
         cfg.sample_rate, cfg.window_n, cfg.pad_factor, cfg.hop = sample_rate, window_n, pad_factor, hop
@@ -77,6 +79,8 @@ class Plan:
     # -- lifetime -----------------------------------------------------------------------------
     def close(self):
         if self._h is not None:
+            for lv in list(self._live):     # a stream must never outlive its plan (sbx.h: lifetime of sbx_live)
+                lv.close()
             self._lib.sbx_plan_destroy(self._h)
             self._h = None
 
@@ -231,6 +235,7 @@ class LiveStream:
         h = C.c_void_p()
         plan._check(self._lib.sbx_live_create(plan.handle, ring_capacity, C.byref(h)))
         self._h = h
+        plan._live.add(self)
 
     def close(self):
         if self._h is not None:

@@ -583,3 +583,68 @@ def test_seeded_random_configurations(sbx, magma):
             rec = np.stack([oracle.column_from_magnitudes(p, g_mags[f], magma) for f in range(frames)])
             assert np.array_equal(plan.colorize_magnitudes(g_mags), rec), (case, kw)
             assert np.array_equal(g_rgba, rec), (case, kw)
+
+
+@pytest.mark.parametrize("n,pad,ch,hop", [(16384, 4, 2, 1021), (16384, 4, 1, 1024), (32768, 2, 2, 4096)])
+def test_large_path_host_batch_over_several_chunks(sbx, magma, monkeypatch, n, pad, ch, hop):
+    """sbx_process_batch pipelines chunks over three slot streams, and the multi-kernel path (M > 16384) works in ONE
+    plan-wide scratch: the chunks' kernels must be serialised (round-1 ADVICE, high).  1 MiB chunks -> many chunks in
+    flight; the bytes must equal the single-stream device batch, and repeat identically."""
+    import torch
+    monkeypatch.setenv("SBX_BATCH_CHUNK_MB", "1")
+    rows = 1024
+    frames = 3 * (1 << 20) // (rows * 4) + 37                       # > 3 chunks of 256 frames
+    n_samples = n + hop * (frames - 1)
+    rng = np.random.Generator(np.random.PCG64(5))
+    shape = (n_samples,) if ch == 1 else (n_samples, 2)
+    # a different spectrum in every stretch, so that a column computed from another chunk's scratch cannot match
+    t = np.arange(n_samples, dtype=np.float64)
+    tone = np.sin(2 * np.pi * (200.0 + 6000.0 * t / n_samples) * t / 48000.0)
+    pcm = (0.3 * tone.reshape((-1,) + (1,) * (len(shape) - 1)) + 0.05 * rng.standard_normal(shape)).astype(np.float32)
+    with sbx.Plan(window_n=n, pad_factor=pad, hop=hop, rows_h=rows, channels=ch, lut=magma) as plan:
+        assert plan.kernel_path == "large"
+        d_pcm = torch.from_numpy(pcm).cuda()
+        d_rgba = torch.zeros((frames, rows, 4), dtype=torch.uint8, device="cuda")
+        assert plan.process_batch_device(d_pcm, n_samples, d_rgba, frames) == frames
+        plan.synchronize()
+        want = d_rgba.cpu().numpy()
+        for _ in range(3):
+            got = plan.process_batch(pcm)
+            assert got.shape == want.shape
+            bad = (got != want).any(axis=(1, 2))
+            assert not bad.any(), f"{int(bad.sum())} of {frames} columns differ, first at frame {int(np.argmax(bad))}"
+
+
+def test_stereo_scheme_pan_of_huge_equal_magnitudes(sbx, viridis):
+    """pan = l / (|l| + |r|) in f32: for l == r the sum overflows to inf above FLT_MAX / 2 and the reference gets
+    pan 0 (index 0), not 0.5 (round-1 ADVICE: the shortcut compared against 3e38)."""
+    n, rows = 1024, 64
+    p = oracle.params(window_n=n, pad_factor=2, rows_h=rows, stereo_scheme=1)
+    k = n - 1
+    vals = np.array([1.0, 1.5e38, 1.7014117e38, 1.7014118e38, np.float32(1.7014118e38) * np.float32(1.0000002),
+                     1.8e38, 2.9e38, 3.2e38, 3.4e38, 0.0], np.float32)
+    mags = np.repeat(vals[:, None, None], k, axis=1).repeat(2, axis=2).astype(np.float32)       # l == r in every bin
+    want = np.stack([oracle.column_from_magnitudes(p, mags[f], viridis) for f in range(len(vals))])
+    with sbx.Plan(window_n=n, pad_factor=2, rows_h=rows, channels=2, lut=viridis, scheme=1) as plan:
+        assert np.array_equal(plan.colorize_magnitudes(mags), want)
+    # the mono-pair shortcut (pan_index_equal) sees the same values through a mono batch: colours 128 or 0
+    assert (want[0, :, :3] == viridis[128]).all() and (want[5, :, :3] == viridis[0]).all()
+
+
+def test_live_stream_survives_plan_close(sbx, magma):
+    """Plan.close() first closes its live streams (sbx_live_destroy never dereferences the plan): no use-after-free
+    when a caller closes the plan before the stream object is collected."""
+    plan = sbx.Plan(window_n=1024, hop=1024, rows_h=128, lut=magma)
+    live = plan.live()
+    live.push(signals.stereo_loopback(1024))
+    assert live.pop_column() is not None
+    plan.close()
+    assert live._h is None
+    live.close()                                                    # idempotent
+    del live
+
+
+def test_tiny_power_of_two_window_message(sbx, magma):
+    with pytest.raises(sbx.SbxError) as e:
+        sbx.Plan(window_n=4, pad_factor=1, lut=magma)
+    assert e.value.status == -2 and ">= 8" in str(e.value)
