@@ -223,7 +223,8 @@ SBX_API uint64_t   sbx_launch_count(const sbx_plan *plan);
 /* Which kernel family the plan's batch entry points run for its channel layout (evidence for bench.py and the
  * tests; static string): "fused-pair" (two mono frames per CTA), "fused-real" (one mono frame per CTA as the
  * even/odd packed half-length sequence; needs an even hop, else "fused-pair" / "large" runs), "fused-stereo",
- * "large" (four kernels, M > 16384) or "generic" (window not a power of two). */
+ * "fused-pair-q2" / "fused-stereo-q2" (pad factor 2: both sub-transforms of a unit in the two lanes of packed FP32
+ * instructions, stft_q2.cuh), "large" (four kernels, M > 16384) or "generic" (window not a power of two). */
 SBX_API const char *sbx_kernel_path(const sbx_plan *plan);
 
 /* ---- introspection for the bit-exactness tests ------------------------------------------- */

@@ -22,10 +22,11 @@ UNITS = [
     ("fused0", "sbx_dispatch_fused.cu", ["-DSBX_FUSED_PART=0"]),
     ("fused1", "sbx_dispatch_fused.cu", ["-DSBX_FUSED_PART=1"]),
     ("real", "sbx_dispatch_real.cu", []),
+    ("q2", "sbx_dispatch_q2.cu", []),
     ("wide", "sbx_dispatch_wide.cu", []),
     ("large", "sbx_dispatch_large.cu", []),
 ]
-DEPS = sorted({u[1] for u in UNITS}) + ["stft_kernels.cuh", "stft_large.cuh", "stft_generic.cuh", "sbx_internal.h", "sbx_launch.h",
+DEPS = sorted({u[1] for u in UNITS}) + ["stft_kernels.cuh", "stft_q2.cuh", "sbx_pk.cuh", "stft_large.cuh", "stft_generic.cuh", "sbx_internal.h", "sbx_launch.h",
                                          "sbx_tables.h", "luts.inc", os.path.join("..", "..", "include", "sbx.h")]
 
 NVCC_FLAGS = [

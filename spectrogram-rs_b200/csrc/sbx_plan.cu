@@ -63,6 +63,18 @@ bool choose_real(bool real_ok, bool real_auto)
     return real_auto;
 }
 
+// Plan-time choice between fused_frames_kernel and fused_q2_kernel (stft_q2.cuh) where both exist, per channel layout.
+// SBX_Q2=0 / 1 overrides the measured default (read when the plan is created).
+static bool choose_q2(const sbx_plan *p, int channels)
+{
+    if (!q2_available(p)) return false;
+    const char *env = std::getenv("SBX_Q2");
+    if (env && env[0] == '0') return false;
+    if (env && env[0] == '1') return true;
+    (void)channels;
+    return false;
+}
+
 sbx_status launch_fused(sbx_plan *p, int channels, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba,
                         float *d_mags, cudaStream_t stream, Sequences seqs)
 {
@@ -88,7 +100,10 @@ sbx_status launch_fused(sbx_plan *p, int channels, const float *d_pcm, uint64_t 
     // a lone stereo frame (single-frame entry points, live graphs) is latency-bound: WIDE geometry; SBX_WIDE=0 disables
     static const bool no_wide = [] { const char *e = std::getenv("SBX_WIDE"); return e && e[0] == '0'; }();
     const bool wide = n_frames == 1 && seqs.count == 1 && channels == 2 && !no_wide && wide_available(p);
+    // pad factor 2, N = 2048 .. 8192: both sub-transforms in packed FP32 lanes (stft_q2.cuh)
+    const bool q2 = !wide && p->use_q2[channels - 1];
     const cudaError_t e = wide ? launch_fused_wide(p, a, stream)
+                        : q2 ? launch_fused_q2(p, channels, a, n_frames, stream, seqs)
                                : (p->log2n <= 10 ? launch_fused_small(p, channels, a, n_frames, stream, seqs)
                                                  : launch_fused_big(p, channels, a, n_frames, stream, seqs));
     if (e != cudaSuccess) return cuda_fail(p, e, "fused_frames_kernel launch");
@@ -405,6 +420,7 @@ SBX_API sbx_status sbx_plan_create(const sbx_config *cfg, sbx_plan **out_plan)
     p->large = t.large;
     p->real_ok = t.real_ok;
     p->use_real = sbx::choose_real(t.real_ok, t.real_auto);
+    for (int c = 1; c <= 2; ++c) p->use_q2[c - 1] = sbx::choose_q2(p, c);
     p->n_chunks = (uint32_t)t.chunks.size();
     p->taps_clamped = t.taps_clamped ? 1 : 0;
     for (int i = 0; i < 2; ++i) { p->guess_a[i] = t.guess_a[i]; p->guess_b[i] = t.guess_b[i]; }
@@ -464,6 +480,7 @@ SBX_API const char *sbx_kernel_path(const sbx_plan *p)
     if (p->generic) return "generic";
     if (p->channels == 1 && p->use_real && (p->hop & 1u) == 0) return "fused-real";
     if (p->large) return "large";
+    if (p->use_q2[p->channels - 1]) return p->channels == 1 ? "fused-pair-q2" : "fused-stereo-q2";
     return p->channels == 1 ? "fused-pair" : "fused-stereo";
 }
 

@@ -1,0 +1,291 @@
+// stft_q2.cuh -- the fused frame kernel for pad factor 2, two sub-transforms per thread in packed FP32 lanes.
+//
+// At P = 2 the zero-padded M-point transform is two N-point sub-transforms (stft_kernels.cuh): q0 = 0 over z[n] w[n]
+// (even bins) and q0 = 1 over z[n] w[n] W_M^n (odd bins).  Both run the SAME butterflies with the SAME twiddles, so
+// one thread takes butterfly j of both and keeps them in the two lanes of Blackwell's packed FP32 instructions
+// (sbx_pk.cuh: FADD2 / FMUL2 / FFMA2) -- every add, multiply, rotation and twiddle of the transform is one
+// instruction for the pair, every shared-memory access is 128 bits, PCM / window / twiddle values are loaded once
+// instead of twice, and the CTA has N/16 threads with 128 registers instead of N/8 with 64.
+//
+// Shared-memory element i (16 bytes) = (A[i].re, B[i].re, A[i].im, B[i].im), A = sub-transform 0, B = sub-transform
+// 1, i = position in the in-place DIF (digit-reversed on output), XOR-swizzled in its low 3 bits so that the
+// strided passes (a quarter warp = 8 consecutive elements = one 128-byte line) and the stride-1 pass (a quarter warp
+// = 8 different rows) are both conflict-free.
+//
+// The last pass is fused with the L/R split as in last_pass_keep_own: thread j takes the row holding bins
+// k = j + (N/16) d, d = 0..15, of both sub-transforms -- kk = 2k (A) and 2k + 1 (B).  d < 8 are its own bins; d >= 8 are
+// the partners M - kk of other threads' bins: A[N - k] for thread N/16 - j, B[N - 1 - k] for thread N/16 - 1 - j.  They
+// are exchanged through four planar float arrays in the upper half of the buffer (32-bit accesses, conflict-free
+// on both sides), after which the split itself is lane-uniform again: (L_A, L_B) and (R_A, R_B) come out of the same
+// packed instructions, and the magnitudes of bins kk, kk + 1 leave as one 16-byte store in natural bin order -- the
+// layout resample_samples / colour_rows of stft_kernels.cuh expect.
+#pragma once
+#include "sbx_pk.cuh"
+#include "stft_kernels.cuh"
+
+namespace sbx {
+
+template <int LOG2N_, int CH_> struct Q2Geom {
+    using GB = Geom<LOG2N_, 0, CH_>;                       // radix plan / digit reversal of the N-point sub-transform
+    static constexpr int LOG2N = LOG2N_, CH = CH_, LOG2PAD = 1, PAD = 2;
+    static constexpr int N = 1 << LOG2N, M = 2 * N, LOG2M = LOG2N + 1;
+    static constexpr int NPASS = GB::NPASS;
+    static constexpr int THREADS = N / 16;                 // one radix-16 butterfly PAIR per thread and pass
+    // register budget 128 per thread: THREADS * MIN_CTAS = 512 (the whole register file at 128 each)
+    static constexpr int MIN_CTAS = THREADS >= 512 ? 1 : 512 / THREADS;
+    static constexpr int FRAMES_PER_CTA = CH == 1 ? 2 : 1;
+    static constexpr int SMEM_BYTES = M * 8;
+    static_assert(LOG2N >= 9 && NPASS >= 2, "q2 geometry: N >= 512");
+    static __host__ __device__ constexpr int log2r(int p) { return GB::log2r(p); }
+    static __host__ __device__ constexpr int log2stride(int p) { return GB::log2stride(p); }
+    static __host__ __device__ constexpr int tw_offset(int p) { return GB::tw_offset(p); }
+    static __host__ __device__ constexpr int pos_of_k(int k) { return GB::pos_of_bin(k); }      // digit reversal
+
+    // Swizzle key: key bit b = position bit 4 + b, XORed with one of the position bits the three lowest bits of k map to
+    // (where those are not bits 4..6 already): the lanes of the stride-1 pass differ exactly in those bits.
+    static __host__ __device__ constexpr int kbit_pos(int j)
+    {
+        const int p = pos_of_k(1 << j);
+        int b = 0;
+        while ((1 << b) < p) ++b;
+        return b;
+    }
+    static __host__ __device__ constexpr int key_ext_src(int b)
+    {
+        bool used[3] = {false, false, false};
+        int ext[3] = {-1, -1, -1};
+        for (int j = 0; j < 3; ++j) {
+            const int pb = kbit_pos(j);
+            if (pb >= 4 && pb <= 6) used[pb - 4] = true;
+        }
+        int next = 0;
+        for (int j = 0; j < 3; ++j) {
+            const int pb = kbit_pos(j);
+            if (pb > 6) {
+                while (next < 3 && used[next]) ++next;
+                if (next < 3) { ext[next] = pb; used[next] = true; }
+            }
+        }
+        return ext[b];
+    }
+    static __host__ __device__ constexpr int qkey(int i)
+    {
+        int k = (i >> 4) & 7;
+        constexpr int e0 = key_ext_src(0), e1 = key_ext_src(1), e2 = key_ext_src(2);
+        if (e0 >= 0) k ^= (i >> (e0 >= 0 ? e0 : 0)) & 1;
+        if (e1 >= 0) k ^= ((i >> (e1 >= 0 ? e1 : 0)) & 1) << 1;
+        if (e2 >= 0) k ^= ((i >> (e2 >= 0 ? e2 : 0)) & 1) << 2;
+        return k;
+    }
+    // element index -> physical 16-byte slot; XOR-linear: qsw(a | b) = qsw(a) ^ qsw(b) for bit-disjoint a, b
+    static __host__ __device__ constexpr int qsw(int i) { return i ^ qkey(i); }
+};
+
+// physical slot of element (base + off): `off` a compile-time multiple of 16 whose bits are clear in base, bx = qsw(base)
+#define SBX_QAT(G, bx, off) (((bx) ^ G::qkey(off)) + (off))
+
+// ---- pass 0: PCM -> window (A) / window * W_M^n (B) -> radix butterfly -> twiddle -> shared memory ----------------
+// SHIFT > 0 (mono pairs): hop == SHIFT * S, frame B's input r is frame A's input r + SHIFT (R + SHIFT loads, not 2 R)
+template <class G, int SHIFT>
+__device__ __forceinline__ void q2_first_inputs(cpk (&v)[1 << G::log2r(0)], const KernelArgs &a, const float *pa_lo,
+                                                const float *pb_lo, bool second_valid, int lo)
+{
+    constexpr int R = 1 << G::log2r(0), S = 1 << G::log2stride(0);
+    const float *win_lo = a.window + lo;
+    const float2 *wtw_lo = a.wtw + lo;                           // window[n] * W_M^n: the q0 = 1 factor
+    float xs[SHIFT > 0 ? R + SHIFT : 1];
+    if constexpr (SHIFT > 0) {
+#pragma unroll
+        for (int r = 0; r < R + SHIFT; ++r)
+            xs[r] = (r < R || second_valid) ? ldg_pcm(pa_lo + r * S) : 0.0f;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        float2 s;
+        if constexpr (SHIFT > 0) {
+            s.x = xs[r];
+            s.y = second_valid ? xs[r + SHIFT] : 0.0f;
+        } else if constexpr (G::CH == 2) {
+            s = ldg_pcm2(reinterpret_cast<const float2 *>(pa_lo) + r * S);
+        } else {
+            s.x = ldg_pcm(pa_lo + r * S);
+            s.y = second_valid ? ldg_pcm(pb_lo + r * S) : 0.0f;
+        }
+        const float wn = ldg_tab(win_lo + r * S);                // fft.rs:57-63 (complex * f32)
+        const float2 wc = ldg_tab(wtw_lo + r * S);
+        v[r].re = pk_make(s.x * wn, s.x * wc.x - s.y * wc.y);
+        v[r].im = pk_make(s.y * wn, s.x * wc.y + s.y * wc.x);
+    }
+}
+
+template <class G>
+__device__ __forceinline__ void q2_pass_first(float4 *e, const KernelArgs &a, const float *pa, bool second_valid)
+{
+    constexpr int LR = G::log2r(0), R = 1 << LR, LS = G::log2stride(0), S = 1 << LS;
+    for (int lo = threadIdx.x; lo < S; lo += G::THREADS) {
+        const float *pa_lo = pa + (size_t)lo * G::CH;
+        const float *pb_lo = pa_lo + a.hop;
+        cpk v[R];
+        if constexpr (G::CH == 1 && R >= 8) {
+            const uint32_t hop = a.hop;                          // the common overlaps: hop = S or 2 S (cfg1, cfg4)
+            if (hop == 2u * S) q2_first_inputs<G, 2>(v, a, pa_lo, pb_lo, second_valid, lo);
+            else if (hop == 1u * S) q2_first_inputs<G, 1>(v, a, pa_lo, pb_lo, second_valid, lo);
+            else q2_first_inputs<G, 0>(v, a, pa_lo, pb_lo, second_valid, lo);
+        } else {
+            q2_first_inputs<G, 0>(v, a, pa_lo, pb_lo, second_valid, lo);
+        }
+        PkButterfly<R>::run(v);
+        const cpk w1 = cpk_dup(ldg_tab(a.twp + lo));             // W_N^lo
+        const cpk w4 = R >= 8 ? cpk_dup(ldg_tab(a.twp + 2 * S + lo)) : w1;
+        pk_apply_twiddles<R>(v, w1, w4);
+        const int bx = G::qsw(lo);
+#pragma unroll
+        for (int q = 0; q < R; ++q) cpk_sts(e + SBX_QAT(G, bx, q * S), v[q]);
+    }
+}
+
+// ---- passes 1 .. NPASS-2: in-place radix-16 at stride S = 2^LS, one butterfly pair per thread ---------------------
+template <class G, int P>
+__device__ __forceinline__ void q2_pass_inplace(float4 *e, const KernelArgs &a)
+{
+    constexpr int LS = G::log2stride(P), S = 1 << LS;
+    static_assert(S >= 16, "the stride-1 pass is q2_last_load");
+    const int u = threadIdx.x;
+    const int lo = u & (S - 1), hi = u >> LS;
+    const int bx = G::qsw((hi << (LS + 4)) + lo);
+    cpk v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = cpk_lds(e + SBX_QAT(G, bx, r * S));
+    PkButterfly<16>::run(v);
+    const float2 *tw = a.twp + G::tw_offset(P) + lo;             // W_(16 S)^(lo q)
+    pk_apply_twiddles<16>(v, cpk_dup(ldg_tab(tw)), cpk_dup(ldg_tab(tw + 2 * S)));
+#pragma unroll
+    for (int q = 0; q < 16; ++q) cpk_sts(e + SBX_QAT(G, bx, q * S), v[q]);
+}
+
+template <class G, int P, int END> struct Q2RunPasses {
+    static __device__ __forceinline__ void run(float4 *e, const KernelArgs &a)
+    {
+        if constexpr (P < END) {
+            q2_pass_inplace<G, P>(e, a);
+            __syncthreads();
+            Q2RunPasses<G, P + 1, END>::run(e, a);
+        }
+    }
+};
+
+// ---- last pass (stride 1) fused with the L/R split -------------------------------------------------------------------
+// phase 1: thread j loads the row of bins k = j + THREADS d and runs the butterfly: v[d] = (A[k], B[k])
+template <class G>
+__device__ __forceinline__ void q2_last_load(const float4 *e, cpk (&v)[16])
+{
+    const int row = G::pos_of_k(threadIdx.x) >> 4;
+    const float4 *rowp = e + (row << 4);
+    const int key = G::qkey(row << 4);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = cpk_lds(rowp + (r ^ key));
+    PkButterfly<16>::run(v);
+}
+
+// phase 2 (every row is in registers): bins d >= 8 go to the threads whose partners they are.  pb = four planes of
+// 8 x THREADS floats: A.re, A.im, B.re, B.im of reader jr's partner for its own bin d at [d * THREADS + jr].
+template <class G>
+__device__ __forceinline__ void q2_partner_write(float *pb, const cpk (&v)[16])
+{
+    constexpr int NT = G::THREADS;
+    const int j = threadIdx.x;
+    // A[k], k = j + NT e, is the partner of A[N - k] = bin (NT - j) + NT (15 - e); for j = 0: bin 0 + NT (16 - e), and
+    // e = 8 is the Nyquist bin kk = M/2 (dropped, fft.rs:33)
+    const int ja = ((NT - j) & (NT - 1)) + (j == 0 ? NT : 0);    // j = 0: one digit up
+    // B[k] is the partner of B[N - 1 - k] = bin (NT - 1 - j) + NT (15 - e)
+    const int jb = NT - 1 - j;
+#pragma unroll
+    for (int e = 8; e < 16; ++e) {
+        const int d = 15 - e;
+        if (e != 8 || j != 0) {
+            pb[d * NT + ja] = pk_lo(v[e].re);
+            pb[8 * NT + d * NT + ja] = pk_lo(v[e].im);
+        }
+        pb[16 * NT + d * NT + jb] = pk_hi(v[e].re);
+        pb[24 * NT + d * NT + jb] = pk_hi(v[e].im);
+    }
+}
+
+// phase 3: own bins d < 8 with their partners -> (L, R) * 2/N for bins kk = 2k (A) and 2k + 1 (B), written over the
+// lower half of the buffer in natural bin order: mags[kk] = (L, R), two bins per 16-byte store
+//   L = |a + conj b| / 2 * (2/N),  R = |a - conj b| / 2 * (2/N),  a = Z[kk], b = Z[M - kk]       (fft.rs:81-95)
+template <class G>
+__device__ __forceinline__ void q2_split_emit(float2 *mags, const float *pb, const KernelArgs &a, const cpk (&v)[16])
+{
+    constexpr int NT = G::THREADS;
+    const int j = threadIdx.x;
+    const float hs = 0.5f * a.scale;                             // exact: a power-of-two scaling of 2/N
+    float4 *out = reinterpret_cast<float4 *>(mags);
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+        const pk yre = pk_make(pb[d * NT + j], pb[16 * NT + d * NT + j]);
+        const pk yim = pk_make(pb[8 * NT + d * NT + j], pb[24 * NT + d * NT + j]);
+        const pk lx = pk_add(v[d].re, yre), ly = pk_sub(v[d].im, yim);     // a + conj b
+        const pk rx = pk_sub(v[d].re, yre), ry = pk_add(v[d].im, yim);     // a - conj b
+        const pk l2 = pk_fma(lx, lx, pk_mul(ly, ly)), r2 = pk_fma(rx, rx, pk_mul(ry, ry));
+        // kk = 0 (j = 0, d = 0, lane A) is DC: its partner slot was never written and its magnitude is never read
+        out[j + NT * d] = make_float4(fast_sqrt(pk_lo(l2)) * hs, fast_sqrt(pk_lo(r2)) * hs,
+                                      fast_sqrt(pk_hi(l2)) * hs, fast_sqrt(pk_hi(r2)) * hs);
+    }
+}
+
+#ifndef SBX_EMU
+template <class G>
+__global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) fused_q2_kernel(const KernelArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 *e = reinterpret_cast<float4 *>(smem_raw);
+    float2 *z = reinterpret_cast<float2 *>(smem_raw);
+    float *pb = reinterpret_cast<float *>(smem_raw + (size_t)G::M * 4);       // upper half: partner planes, then scratch
+
+    unsigned long long unit = blockIdx.x, seq = 0;
+    if (a.units_per_seq != 0) {                                   // planar sequences: CTA -> (sequence, unit within it)
+        seq = unit / a.units_per_seq;
+        unit -= seq * a.units_per_seq;
+    }
+    const unsigned long long frame0 = unit * G::FRAMES_PER_CTA;
+    const bool second_valid = G::CH == 1 && frame0 + 1 < a.n_frames;
+
+    q2_pass_first<G>(e, a, a.pcm + seq * a.seq_stride + frame0 * (unsigned long long)a.hop * G::CH, second_valid);
+    __syncthreads();
+    Q2RunPasses<G, 1, G::NPASS - 1>::run(e, a);
+    cpk v[16];
+    q2_last_load<G>(e, v);
+    __syncthreads();
+    q2_partner_write<G>(pb, v);
+    __syncthreads();
+    q2_split_emit<G>(z, pb, a, v);
+    __syncthreads();
+
+    const unsigned long long out_frame0 = seq * a.n_frames + frame0;
+    if (a.mags_out != nullptr) {
+        float2 *out = reinterpret_cast<float2 *>(a.mags_out) + out_frame0 * a.k_out;
+        for (uint32_t j = threadIdx.x; j < a.k_out; j += G::THREADS) {
+            const float2 m = z[j + 1];
+            if constexpr (G::CH == 1) {
+                out[j] = make_float2(m.x, m.x);
+                if (second_valid) out[a.k_out + j] = make_float2(m.y, m.y);
+            } else {
+                out[j] = m;
+            }
+        }
+    }
+    if (a.rgba != nullptr) resample_colour<G::LOG2M, G::CH == 1, G::THREADS>(z, a, out_frame0, second_valid);
+    if (a.done_flag != nullptr) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int v2 = *a.done_count + 1u;
+            *a.done_count = v2;
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned int *>(a.done_flag) = v2;
+        }
+    }
+}
+#endif  // SBX_EMU
+
+}  // namespace sbx

@@ -198,7 +198,7 @@ class Plan:
 
     @property
     def kernel_path(self):
-        """'fused-pair' | 'fused-real' | 'fused-stereo' | 'large' | 'generic' (sbx_kernel_path)."""
+        """'fused-pair[-q2]' | 'fused-real' | 'fused-stereo[-q2]' | 'large' | 'generic' (sbx_kernel_path)."""
         return self._lib.sbx_kernel_path(self._h).decode()
 
     # -- introspection -----------------------------------------------------------------------

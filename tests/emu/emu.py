@@ -25,7 +25,7 @@ binding = _binding()
 
 def build(force=False):
     deps = [os.path.join(HERE, f) for f in ("emu_harness.cpp", "emu_shim.h")] + \
-           [os.path.join(CSRC, f) for f in ("stft_kernels.cuh", "stft_large.cuh", "stft_generic.cuh", "sbx_tables.h")]
+           [os.path.join(CSRC, f) for f in ("stft_kernels.cuh", "stft_q2.cuh", "sbx_pk.cuh", "stft_large.cuh", "stft_generic.cuh", "sbx_tables.h")]
     if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps):
         subprocess.run(["g++", "-O1", "-std=c++17", "-I", HERE, "-ffp-contract=off", "-fPIC", "-shared",
                         "-fvisibility=hidden", "-o", LIB_PATH, os.path.join(HERE, "emu_harness.cpp")],
@@ -62,12 +62,13 @@ def make_config(lut_rgb, sample_rate=48000.0, window_n=4096, pad_factor=2, hop=5
     return cfg
 
 
-def batch(cfg, pcm, want_mags=True, want_rgba=True, staged=False, real=None, wide=False):
+def batch(cfg, pcm, want_mags=True, want_rgba=True, staged=False, real=None, wide=False, q2=False):
     """staged=True emulates the persistent kernel's pass 0 (PCM span in a stage buffer).
     real: mono batches on the real-sequence geometry (one frame per CTA) -- None: the product's default choice,
     False / True: what SBX_REAL=0 / 1 selects in the product."""
     lib().emu_set_staged(1 if staged else 0)
     lib().emu_set_real(2 if real is None else (1 if real else 0))
+    lib().emu_set_q2(1 if q2 else 0)                       # pad factor 2: the packed-lane kernel of stft_q2.cuh
     lib().emu_set_wide(1 if wide else 0)                   # stereo: the WIDE single-frame geometries (more threads per CTA)
     pcm = np.ascontiguousarray(pcm, dtype=np.float32)
     n_samples = pcm.shape[0]

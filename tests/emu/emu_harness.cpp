@@ -3,6 +3,7 @@
 // turn, with the product's own host tables (sbx_tables.h).
 #define SBX_EMU 1
 #include "../../spectrogram-rs_b200/csrc/stft_large.cuh"
+#include "../../spectrogram-rs_b200/csrc/stft_q2.cuh"
 #include "../../spectrogram-rs_b200/csrc/sbx_tables.h"
 
 #include <vector>
@@ -11,6 +12,7 @@ namespace {
 
 bool g_emu_staged = false;
 bool g_emu_wide = false;                // stereo frames on the WIDE (single-frame latency) geometries
+bool g_emu_q2 = false;                  // pad factor 2 on the packed-lane kernel of stft_q2.cuh
 int g_emu_real = 2;                     // mono batches on the REAL geometry: 0 never, 1 wherever its tables exist, 2 the product's default
 
 template <class G, int P, int END = G::NPASS> struct EmuPasses {
@@ -90,9 +92,61 @@ int emu_cta(const sbx::KernelArgs &a, unsigned long long frame0, float *mags_out
     return 0;
 }
 
+// one CTA of fused_q2_kernel (stft_q2.cuh): the same barrier-delimited phases, each thread's row kept between them
+template <class G, int P, int END> struct EmuQ2Passes {
+    static void run(float4 *e, const sbx::KernelArgs &a)
+    {
+        if constexpr (P < END) {
+            for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::q2_pass_inplace<G, P>(e, a); }
+            EmuQ2Passes<G, P + 1, END>::run(e, a);
+        }
+    }
+};
+template <class G>
+int emu_cta_q2(const sbx::KernelArgs &a, unsigned long long frame0, float *mags_out, uint8_t *rgba)
+{
+    std::vector<float4> e(G::N);
+    float2 *z = reinterpret_cast<float2 *>(e.data());
+    float *pb = reinterpret_cast<float *>(e.data()) + G::M;                       // upper half (bytes M * 4 ..)
+    const bool second_valid = G::CH == 1 && frame0 + 1 < a.n_frames;
+    const float *src = a.pcm + frame0 * (unsigned long long)a.hop * G::CH;
+    for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::q2_pass_first<G>(e.data(), a, src, second_valid); }
+    EmuQ2Passes<G, 1, G::NPASS - 1>::run(e.data(), a);
+    struct Row { sbx::cpk v[16]; };
+    std::vector<Row> rows(G::THREADS);
+    for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::q2_last_load<G>(e.data(), rows[t].v); }
+    for (float4 &x : e) x = make_float4(NAN, NAN, NAN, NAN);                      // the buffer is dead once every row is in registers
+    for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::q2_partner_write<G>(pb, rows[t].v); }
+    for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::q2_split_emit<G>(z, pb, a, rows[t].v); }
+    if (mags_out) {
+        for (uint32_t j = 0; j < a.k_out; ++j) {
+            const float2 m = z[j + 1];
+            float *o = mags_out + (size_t)frame0 * a.k_out * 2;
+            if (G::CH == 1) {
+                o[2 * j] = m.x; o[2 * j + 1] = m.x;
+                if (second_valid) { o[2 * (a.k_out + j)] = m.y; o[2 * (a.k_out + j) + 1] = m.y; }
+            } else { o[2 * j] = m.x; o[2 * j + 1] = m.y; }
+        }
+    }
+    if (rgba) {
+        sbx::KernelArgs b = a;
+        b.rgba = rgba;
+        float2 *scratch = z + G::M / 2;
+        for (uint32_t c = 0; c < a.n_chunks; ++c) {
+            const sbx::RowChunk ck = a.chunks[c];
+            for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::resample_samples<G::THREADS>(z, scratch, b, ck); }
+            for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::colour_rows<G::CH == 1, G::THREADS>(scratch, a.thr, a.lut, b, ck, frame0, second_valid); }
+        }
+    }
+    return 0;
+}
+
 template <int LOG2N, int LOG2PAD>
 int emu_dispatch_ch(int ch, const sbx::KernelArgs &a, unsigned long long f0, float *mags, uint8_t *rgba)
 {
+    if constexpr (LOG2PAD == 1 && LOG2N >= 9 && LOG2N <= 13)
+        if (g_emu_q2) return ch == 1 ? emu_cta_q2<sbx::Q2Geom<LOG2N, 1>>(a, f0, mags, rgba)
+                                     : emu_cta_q2<sbx::Q2Geom<LOG2N, 2>>(a, f0, mags, rgba);
     if constexpr (LOG2N + LOG2PAD > 14) return -2;
     else {
         if constexpr (LOG2N + LOG2PAD >= 9 && LOG2N + LOG2PAD <= 12)
@@ -341,6 +395,9 @@ void emu_set_real(int mode) { g_emu_real = mode; }
 
 __attribute__((visibility("default")))
 void emu_set_wide(int wide) { g_emu_wide = wide != 0; }
+
+__attribute__((visibility("default")))
+void emu_set_q2(int q2) { g_emu_q2 = q2 != 0; }
 
 // host tables of the product, exposed so CPU tests can compare them with the oracle bit for bit
 __attribute__((visibility("default")))

@@ -648,3 +648,61 @@ def test_tiny_power_of_two_window_message(sbx, magma):
     with pytest.raises(sbx.SbxError) as e:
         sbx.Plan(window_n=4, pad_factor=1, lut=magma)
     assert e.value.status == -2 and ">= 8" in str(e.value)
+
+
+Q2_CASES = [
+    # (N, channels, hop, H, interp, scheme): pad factor 2, N = 2048 .. 8192 -- the packed-lane kernel of stft_q2.cuh
+    (4096, 1, 512, 1024, 0, 0),        # cfg1 / cfg4 geometry (hop = 2 S: shared PCM loads)
+    (4096, 1, 256, 512, 1, 0),         # hop = S
+    (4096, 1, 333, 300, 0, 1),         # ragged hop, stereo scheme on mono pairs
+    (2048, 2, 2048, 1024, 0, 0),       # cfg2 geometry
+    (2048, 1, 100, 128, 0, 0),
+    (4096, 2, 512, 1024, 1, 1),
+    (8192, 2, 1024, 1024, 0, 0),       # M = 16384: one 512-thread CTA per SM
+    (8192, 1, 255, 512, 0, 0),         # odd hop: the mono pair kernel, not the real-sequence geometry
+]
+
+
+@pytest.mark.parametrize("n,ch,hop,rows,interp,scheme", Q2_CASES)
+def test_q2_packed_lane_kernel(sbx, magma, monkeypatch, n, ch, hop, rows, interp, scheme):
+    """fused_q2_kernel against the oracle, and against fused_frames_kernel on the same input (same tolerance: the two
+    differ only in rounding); planar multi-sequence launches and the magnitude output included."""
+    import torch
+    frames = 9
+    n_samples = n + hop * (frames - 1) + 3
+    pcm = _pcm(ch, n_samples, seed=11)
+    p = oracle.params(window_n=n, pad_factor=2, hop=hop, rows_h=rows, interp=interp, stereo_scheme=scheme)
+    o_rgba, o_mags = oracle.batch(p, pcm, ch, magma, want_mags=True)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("SBX_Q2", mode)
+        monkeypatch.setenv("SBX_REAL", "0")
+        with sbx.Plan(window_n=n, pad_factor=2, hop=hop, rows_h=rows, channels=ch, interp=interp, scheme=scheme, lut=magma) as plan:
+            assert plan.kernel_path.endswith("-q2") == (mode == "1")
+            d_pcm = torch.from_numpy(pcm).cuda()
+            d_mags = torch.zeros((frames, plan.k, 2), dtype=torch.float32, device="cuda")
+            d_rgba = torch.zeros((frames, rows, 4), dtype=torch.uint8, device="cuda")
+            assert plan.magnitudes_batch_device(d_pcm, n_samples, d_mags, frames) == frames
+            assert plan.process_batch_device(d_pcm, n_samples, d_rgba, frames) == frames
+            plan.synchronize()
+            g_mags, g_rgba = d_mags.cpu().numpy(), d_rgba.cpu().numpy()
+            peak = np.abs(o_mags).max(axis=(1, 2), keepdims=True)
+            assert (np.abs(g_mags - o_mags) / peak).max() <= MAG_TOL
+            assert np.array_equal(plan.colorize_magnitudes(g_mags), g_rgba)           # fused == its own magnitudes coloured
+            assert np.array_equal(plan.process_batch(pcm), g_rgba)
+            assert (g_rgba != o_rgba).any(axis=2).mean() <= 2e-3
+            if mode == "1" and hop % 4 == 0:
+                # three planar sequences in one grid == three separate batches
+                seq = n_samples + (-n_samples) % 4
+                planar = np.zeros((3, seq) + pcm.shape[1:], np.float32)
+                for s in range(3):
+                    planar[s, :n_samples] = np.roll(pcm, 17 * s, axis=0)
+                d_pl = torch.from_numpy(planar).cuda()
+                d_out = torch.zeros((3, frames, rows, 4), dtype=torch.uint8, device="cuda")
+                assert plan.process_batch_device_planar(d_pl, 3, seq, n_samples, d_out, 3 * frames) == frames
+                plan.synchronize()
+                for s in range(3):
+                    assert np.array_equal(d_out[s].cpu().numpy(), plan.process_batch(planar[s, :n_samples]))
+            out[mode] = g_mags
+    peak = np.abs(out["0"]).max(axis=(1, 2), keepdims=True)
+    assert (np.abs(out["1"] - out["0"]) / peak).max() <= MAG_TOL
