@@ -71,8 +71,10 @@ static bool choose_q2(const sbx_plan *p, int channels)
     const char *env = std::getenv("SBX_Q2");
     if (env && env[0] == '0') return false;
     if (env && env[0] == '1') return true;
+    // measured on a B200, M frames/s (fused_frames_kernel -> fused_q2_kernel): N = 4096 mono 58.6 -> 63.8, stereo 29.7 -> 32.7;
+    // N = 2048 stereo 56.5 -> 57.6; N = 8192 stereo (one 512-thread CTA per SM either way) 12.6 -> 12.5
     (void)channels;
-    return false;
+    return p->log2n <= 12;
 }
 
 sbx_status launch_fused(sbx_plan *p, int channels, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba,
@@ -238,6 +240,7 @@ sbx::KernelArgs sbx_plan::base_args() const
     a.k_out = k_out;
     a.scale = scale;
     a.db_eps = cfg.db_eps;
+    a.neg_zero = -0.0f;
     for (int i = 0; i < 2; ++i) { a.guess_a[i] = guess_a[i]; a.guess_b[i] = guess_b[i]; }
     a.interp = (int)cfg.interp;
     a.scheme = (int)cfg.scheme;

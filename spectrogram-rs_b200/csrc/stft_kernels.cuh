@@ -32,6 +32,8 @@
 #endif
 #include <stdint.h>
 
+#include "sbx_pk.cuh"
+
 namespace sbx {
 
 struct RowMap {            // one output row py (0 = lowest frequency) of the log-frequency bin map
@@ -78,11 +80,15 @@ struct KernelArgs {
     float scale;                 // 2 / N     (fft.rs:92)
     float guess_a[2], guess_b[2];// step guess = log2(p + eps) * a + b   (colour, alpha)
     float db_eps;
+    float neg_zero;              // -0.0f, opaque to the compiler: stft_q2.cuh writes exactly rounded products as fma(x, y, -0.0)
     int interp;                  // 0 cubic, 1 cosine
     int scheme;                  // 0 mono gradient, 1 stereo pan gradient
     int taps_clamped;            // 1 if any cubic tap index needs clamping to [0, K-1] (spectrum edges)
 };
 
+#ifndef SBX_PK_RESAMPLE
+#define SBX_PK_RESAMPLE 0        // 1: the classic kernels resample / sum rows with packed (L, R) instructions too (pk_resample_colour)
+#endif
 #ifndef SBX_EPT_LOG2
 #define SBX_EPT_LOG2 4           // log2 of the transform points each thread owns per pass (4: M/16 threads, 5: M/32)
 #endif
@@ -988,6 +994,136 @@ __device__ __forceinline__ void colour_rows(const float2 *scratch, const float *
     }
 }
 
+// ---- log-frequency resample + row means on packed (L, R) pairs ------------------------------------------------------
+// The same operations in the same order with the same roundings as interp_sample / colour_rows of stft_kernels.cuh --
+// bit-identical results -- with both channels (or both frames of a mono pair) in the two lanes of one instruction.
+// ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (it honours .rn only for scalar f32), which would change the
+// reference's rounding, so every product that feeds a sum is written fma(x, y, -0.0): one rounding, and nothing left
+// to contract.  -0.0 comes from the kernel arguments (KernelArgs::neg_zero) so that it is not folded back into a multiply.
+__device__ __forceinline__ pk pk_ld2(const float2 *p)
+{
+#ifdef SBX_EMU
+    return pk_make(p->x, p->y);
+#else
+    return *reinterpret_cast<const pk *>(p);
+#endif
+}
+__device__ __forceinline__ void pk_st2(float2 *p, pk v)
+{
+#ifdef SBX_EMU
+    *p = make_float2(v.lo, v.hi);
+#else
+    *reinterpret_cast<pk *>(p) = v;
+#endif
+}
+__device__ __forceinline__ pk pk_mul_exact(pk a, pk b, pk negzero) { return pk_fma(a, b, negzero); }
+
+template <bool CLAMP>
+__device__ __forceinline__ pk pk_interp_sample(const float2 *mags, const KernelArgs &a, int x1, float w, int k_last, pk negzero)
+{
+    if (a.interp == 0) {                                                     // cubic_interpolate, ifs.rs:88-105
+        const pk m1 = pk_dup(w);
+        const pk m2 = pk_mul(m1, m1), m3 = pk_mul(m1, m2);
+        pk y0, y1, y2, y3;
+        if constexpr (CLAMP) {
+            y0 = pk_ld2(mags + (x1 > 0 ? x1 - 1 : 0) + 1);
+            y1 = pk_ld2(mags + x1 + 1);
+            y2 = pk_ld2(mags + min(x1 + 1, k_last) + 1);
+            y3 = pk_ld2(mags + min(x1 + 2, k_last) + 1);
+        } else {
+            const float2 *m = mags + x1;
+            y0 = pk_ld2(m); y1 = pk_ld2(m + 1); y2 = pk_ld2(m + 2); y3 = pk_ld2(m + 3);
+        }
+        const pk a0 = pk_add(pk_sub(pk_sub(y3, y2), y0), y1);
+        const pk a1 = pk_sub(pk_sub(y0, y1), a0);
+        const pk a2 = pk_sub(y2, y0);
+        return pk_add(pk_add(pk_mul_exact(a0, m3, negzero), pk_mul_exact(a1, m2, negzero)), pk_add(pk_mul_exact(a2, m1, negzero), y1));
+    } else {                                                                 // cosine_interpolate, ifs.rs:78-86
+        const float omt = __fsub_rn(1.0f, w);
+        const pk yl = pk_ld2(mags + x1 + 1), yh = pk_ld2(mags + min(x1 + 1, k_last) + 1);
+        return pk_add(pk_mul_exact(yl, pk_dup(omt), negzero), pk_mul_exact(yh, pk_dup(w), negzero));
+    }
+}
+
+// phase A: one lane per (row, sample), UNROLL table loads in flight per thread
+template <int THREADS, int UNROLL, bool CLAMP>
+__device__ __forceinline__ void pk_resample_samples_impl(const float2 *mags, float2 *scratch, const KernelArgs &a, const RowChunk ck)
+{
+    const int k_last = (int)a.k_out - 1;
+    const pk negzero = pk_dup(a.neg_zero);
+    const uint32_t count = ck.samp_end - ck.samp_begin;
+    const uint2 *tab = a.samp + ck.samp_begin;
+    for (uint32_t g0 = threadIdx.x; g0 < count; g0 += UNROLL * THREADS) {
+        uint2 sp[UNROLL];
+#pragma unroll
+        for (int i = 0; i < UNROLL; ++i) {
+            const uint32_t g = g0 + i * THREADS;
+            sp[i] = g < count ? ldg_tab(tab + g) : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int i = 0; i < UNROLL; ++i) {
+            const uint32_t g = g0 + i * THREADS;
+            if (g < count)
+                pk_st2(scratch + (sp[i].x >> 17),
+                         pk_interp_sample<CLAMP>(mags, a, (int)(sp[i].x & 0x1ffffu), __uint_as_float(sp[i].y), k_last, negzero));
+        }
+    }
+}
+template <int THREADS, int UNROLL>
+__device__ __forceinline__ void pk_resample_samples(const float2 *mags, float2 *scratch, const KernelArgs &a, const RowChunk ck)
+{
+    if (a.taps_clamped) pk_resample_samples_impl<THREADS, UNROLL, true>(mags, scratch, a, ck);
+    else pk_resample_samples_impl<THREADS, UNROLL, false>(mags, scratch, a, ck);
+}
+
+// phase B: one thread per row, ROWS rows in flight per thread: sequential sums (one FADD2 per sample), mean, colour
+template <bool PAIR, int THREADS, int ROWS>
+__device__ __forceinline__ void pk_colour_rows(const float2 *scratch, const KernelArgs &a, const RowChunk ck,
+                                               unsigned long long frame0, bool second_valid)
+{
+    uint32_t *outA = reinterpret_cast<uint32_t *>(a.rgba) + frame0 * a.rows;
+    uint32_t *outB = outA + a.rows;
+    for (uint32_t py0 = ck.row_begin + threadIdx.x; py0 < ck.row_end; py0 += ROWS * THREADS) {
+        uint32_t n[ROWS], nmax = 0;
+        const float2 *m[ROWS];
+        pk acc[ROWS];
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) {
+            const uint32_t py = py0 + i * THREADS;
+            const uint32_t r = py < ck.row_end ? ldg_tab(a.rowinfo + py) : 0u;       // n = 0: row absent
+            n[i] = r & 0xffffu;
+            m[i] = scratch + (r >> 16);
+            acc[i] = pk_make(0.0f, 0.0f);
+            nmax = n[i] > nmax ? n[i] : nmax;
+        }
+        for (uint32_t s = 0; s < nmax; ++s) {
+#pragma unroll
+            for (int i = 0; i < ROWS; ++i)
+                if (s < n[i]) acc[i] = pk_add(acc[i], pk_ld2(m[i] + s));
+        }
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i)
+            if (n[i] != 0)
+                colour_one_row<PAIR>(pk_lo(acc[i]), pk_hi(acc[i]), n[i], py0 + i * THREADS, a.thr, a.lut, a, outA, outB, second_valid);
+    }
+}
+
+#ifndef SBX_EMU
+template <int LOG2M, bool PAIR, int THREADS, int UNROLL, int ROWS>
+__device__ __forceinline__ void pk_resample_colour(float2 *z, const KernelArgs &a, unsigned long long frame0, bool second_valid)
+{
+    float2 *scratch = z + (1 << (LOG2M - 1));                 // the upper half of the buffer is free again
+    for (uint32_t c = 0; c < a.n_chunks; ++c) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.chunks) + c);
+        const RowChunk ck = {raw.x, raw.y, raw.z, raw.w};
+        if (c != 0) __syncthreads();
+        pk_resample_samples<THREADS, UNROLL>(z, scratch, a, ck);
+        __syncthreads();
+        pk_colour_rows<PAIR, THREADS, ROWS>(scratch, a, ck, frame0, second_valid);
+    }
+}
+#endif
+
 // A row that averages more samples than the scratch area holds (only possible on the large path: few rows over a
 // very long transform).  The row is resampled in parts of `cap` samples; between parts one thread continues
 // the row's sequential sum, so the summation order is still the reference's.  Phase functions for the emulation:
@@ -1102,8 +1238,13 @@ __device__ __forceinline__ void frame_tail(float2 *z, const KernelArgs &a, unsig
                 }
             }
         }
-        if (a.rgba != nullptr)
+        if (a.rgba != nullptr) {
+#if SBX_PK_RESAMPLE
+            pk_resample_colour<G::LOG2M, G::CH == 1, G::THREADS, 4, 2>(z, a, frame0, second_valid);
+#else
             resample_colour<G::LOG2M, G::CH == 1, G::THREADS>(z, a, frame0, second_valid);
+#endif
+        }
     }
 }
 

@@ -23,6 +23,10 @@
 #include "sbx_pk.cuh"
 #include "stft_kernels.cuh"
 
+#ifndef SBX_Q2_THREAD_BUDGET
+#define SBX_Q2_THREAD_BUDGET 768        // 3 CTAs of 256 threads at 80 registers: measured 63.7 vs 58.1 M frames/s (cfg1) against 2 CTAs at 116
+#endif
+
 namespace sbx {
 
 template <int LOG2N_, int CH_> struct Q2Geom {
@@ -31,8 +35,8 @@ template <int LOG2N_, int CH_> struct Q2Geom {
     static constexpr int N = 1 << LOG2N, M = 2 * N, LOG2M = LOG2N + 1;
     static constexpr int NPASS = GB::NPASS;
     static constexpr int THREADS = N / 16;                 // one radix-16 butterfly PAIR per thread and pass
-    // register budget 128 per thread: THREADS * MIN_CTAS = 512 (the whole register file at 128 each)
-    static constexpr int MIN_CTAS = THREADS >= 512 ? 1 : 512 / THREADS;
+    // resident threads per SM the register budget is set for: THREADS * MIN_CTAS = SBX_Q2_THREAD_BUDGET (768 -> 80 registers)
+    static constexpr int MIN_CTAS = THREADS >= SBX_Q2_THREAD_BUDGET ? 1 : SBX_Q2_THREAD_BUDGET / THREADS;
     static constexpr int FRAMES_PER_CTA = CH == 1 ? 2 : 1;
     static constexpr int SMEM_BYTES = M * 8;
     static_assert(LOG2N >= 9 && NPASS >= 2, "q2 geometry: N >= 512");
@@ -234,6 +238,13 @@ __device__ __forceinline__ void q2_split_emit(float2 *mags, const float *pb, con
     }
 }
 
+#ifndef SBX_Q2_RESAMPLE_UNROLL
+#define SBX_Q2_RESAMPLE_UNROLL 8       // sample-table loads in flight per thread (128 registers to spend)
+#endif
+#ifndef SBX_Q2_COLOUR_ROWS
+#define SBX_Q2_COLOUR_ROWS 4           // rows in flight per thread in the colour phase
+#endif
+
 #ifndef SBX_EMU
 template <class G>
 __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) fused_q2_kernel(const KernelArgs a)
@@ -275,7 +286,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) fused_q2_kernel(const
             }
         }
     }
-    if (a.rgba != nullptr) resample_colour<G::LOG2M, G::CH == 1, G::THREADS>(z, a, out_frame0, second_valid);
+    if (a.rgba != nullptr) pk_resample_colour<G::LOG2M, G::CH == 1, G::THREADS, SBX_Q2_RESAMPLE_UNROLL, SBX_Q2_COLOUR_ROWS>(z, a, out_frame0, second_valid);
     if (a.done_flag != nullptr) {
         __syncthreads();
         if (threadIdx.x == 0) {

@@ -134,8 +134,8 @@ int emu_cta_q2(const sbx::KernelArgs &a, unsigned long long frame0, float *mags_
         float2 *scratch = z + G::M / 2;
         for (uint32_t c = 0; c < a.n_chunks; ++c) {
             const sbx::RowChunk ck = a.chunks[c];
-            for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::resample_samples<G::THREADS>(z, scratch, b, ck); }
-            for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::colour_rows<G::CH == 1, G::THREADS>(scratch, a.thr, a.lut, b, ck, frame0, second_valid); }
+            for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::pk_resample_samples<G::THREADS, SBX_Q2_RESAMPLE_UNROLL>(z, scratch, b, ck); }
+            for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::pk_colour_rows<G::CH == 1, G::THREADS, SBX_Q2_COLOUR_ROWS>(scratch, b, ck, frame0, second_valid); }
         }
     }
     return 0;
@@ -319,7 +319,7 @@ long long emu_batch(const sbx_config *cfg, const float *pcm, unsigned long long 
     a.ctab = reinterpret_cast<const uint4 *>(t.ctab);
     a.n_frames = frames;
     a.hop = cfg->hop; a.rows = t.rows; a.k_out = t.k_out;
-    a.scale = t.scale; a.db_eps = cfg->db_eps;
+    a.scale = t.scale; a.db_eps = cfg->db_eps; a.neg_zero = -0.0f;
     for (int i = 0; i < 2; ++i) { a.guess_a[i] = t.guess_a[i]; a.guess_b[i] = t.guess_b[i]; }
     a.interp = (int)cfg->interp; a.scheme = (int)cfg->scheme;
     const int ln = ilog2(t.n), lp = ilog2(t.pad), ch = (int)cfg->channels;

@@ -14,6 +14,8 @@ CFG = {1: dict(sample_rate=48000.0, window_n=4096, pad_factor=2, hop=512, rows_h
        2: dict(sample_rate=48000.0, window_n=2048, pad_factor=2, hop=2048, rows_h=1024, channels=2, lut="magma"),
        3: dict(sample_rate=96000.0, window_n=8192, pad_factor=2, hop=256, rows_h=1024, channels=1, lut="viridis"),
        5: dict(sample_rate=48000.0, window_n=4096, pad_factor=4, hop=512, rows_h=2048, channels=1, lut="magma"),
+       7: dict(sample_rate=96000.0, window_n=8192, pad_factor=2, hop=1024, rows_h=1024, channels=2, lut="viridis"),   # stereo M = 16384
+       8: dict(sample_rate=48000.0, window_n=4096, pad_factor=2, hop=512, rows_h=1024, channels=2, lut="magma"),     # cfg1 geometry, stereo
        6: dict(sample_rate=48000.0, window_n=2400, pad_factor=2, hop=58, rows_h=1024, channels=2, lut="magma")}   # the app's own geometry
 
 ap = argparse.ArgumentParser()
