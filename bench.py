@@ -353,9 +353,11 @@ def main():
                    "bytes_per_frame": B_FRAME},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "fused_frames_kernel<Geom<12,1,1>>", "kernel_ms": kernel_ms,
+                     "kernel": "fused_q2_kernel<Q2Geom<12,1>>" if plan.kernel_path.endswith("-q2") else "fused_frames_kernel<Geom<12,1,1>>",
+                     "kernel_path": plan.kernel_path, "kernel_ms": kernel_ms,
                      "fp32_tflops_5MlogM": value / world * FLOPS_FRAME / 1e12,
-                     "note": "path is FP32/shared-memory bound at this hop (44-87 flop/B vs a 12 flop/B ridge, SURVEY.md D6)"},
+                     "note": "path is L1/shared-memory-pipe and FP32 bound at this hop (44-87 flop/B vs a 12 flop/B ridge, SURVEY.md D6): "
+                             "ncu l1tex 82 %, FMA pipe 50 %, DRAM 1.5 % (profiles/)"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": ns_e * 4, "d2h_bytes_per_step": Fe * ROWS * 4,
                 "frames_per_gpu_per_step": Fe, "steps": e2e_steps, "api": "sbx_process_batch (host pointers, pinned)", "numa": numa,
                 "d2h_gbs_per_gpu": e2e_value / world * ROWS * 4 / 1e9, "h2d_gbs_per_gpu": e2e_value / world * HOP * 4 / 1e9,

@@ -21,6 +21,7 @@ struct sbx_plan {
     std::vector<float> h_thr_raw;       // [2][256] bare thresholds
     float guess_a[2] = {0, 0}, guess_b[2] = {0, 0};
     uint32_t n_chunks = 0;
+    sbx::RowChunk chunk0{};             // chunks[0], passed by value in the kernel arguments
 
     // device tables
     float *d_window = nullptr;

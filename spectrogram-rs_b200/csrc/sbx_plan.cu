@@ -230,6 +230,7 @@ sbx::KernelArgs sbx_plan::base_args() const
     a.rowinfo = d_rowinfo;
     a.chunks = d_chunks;
     a.n_chunks = n_chunks;
+    a.chunk0 = chunk0;
     a.samp = d_samp;
     a.taps_clamped = taps_clamped;
     a.thr = d_thr;
@@ -425,6 +426,7 @@ SBX_API sbx_status sbx_plan_create(const sbx_config *cfg, sbx_plan **out_plan)
     p->use_real = sbx::choose_real(t.real_ok, t.real_auto);
     for (int c = 1; c <= 2; ++c) p->use_q2[c - 1] = sbx::choose_q2(p, c);
     p->n_chunks = (uint32_t)t.chunks.size();
+    if (!t.chunks.empty()) p->chunk0 = t.chunks[0];
     p->taps_clamped = t.taps_clamped ? 1 : 0;
     for (int i = 0; i < 2; ++i) { p->guess_a[i] = t.guess_a[i]; p->guess_b[i] = t.guess_b[i]; }
 

@@ -77,6 +77,8 @@ struct KernelArgs {
     unsigned int *done_flag;
     unsigned int *done_count;
     uint32_t hop, rows, k_out, n_chunks;
+    RowChunk chunk0;             // chunks[0] by value: most plans have a single chunk, and its descriptor would otherwise be
+                                 // an L2 round trip that every thread waits for between the split and the resample
     float scale;                 // 2 / N     (fft.rs:92)
     float guess_a[2], guess_b[2];// step guess = log2(p + eps) * a + b   (colour, alpha)
     float db_eps;
@@ -303,6 +305,45 @@ __device__ __forceinline__ uint32_t ldg_tab(const uint32_t *p)
     return __ldg(p);
 #else
     uint32_t v; asm volatile("ld.global.nc.L1::evict_last.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
+#endif
+}
+
+// Big once-per-CTA tables (window, window * W, sample table: 30-50 KB each per CTA) in the q2 kernel, whose three
+// resident CTAs leave only ~36 KB of L1: they stream through L2 anyway (L1 hit rate 30 %), so they can be kept from
+// evicting the small hot tables (colour steps, row table, twiddles).  0: L1::evict_last like every table, 1: L1::evict_first,
+// (measured, M frames/s at cfg1 / cfg2 geometry / cfg1 stereo: policy 0 64.3 / 55.7 / 32.8, 1: 63.5 / 55.9 / 32.7, 2: 64.6 / 57.5 / 32.9)
+// 2: L1::no_allocate
+#ifndef SBX_Q2_STREAM_POLICY
+#define SBX_Q2_STREAM_POLICY 2
+#endif
+__device__ __forceinline__ float ldg_stream(const float *p)
+{
+#if defined(SBX_EMU) || SBX_Q2_STREAM_POLICY == 0
+    return ldg_tab(p);
+#elif SBX_Q2_STREAM_POLICY == 1
+    float v; asm volatile("ld.global.nc.L1::evict_first.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v;
+#else
+    float v; asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v;
+#endif
+}
+__device__ __forceinline__ float2 ldg_stream(const float2 *p)
+{
+#if defined(SBX_EMU) || SBX_Q2_STREAM_POLICY == 0
+    return ldg_tab(p);
+#elif SBX_Q2_STREAM_POLICY == 1
+    float2 v; asm volatile("ld.global.nc.L1::evict_first.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p)); return v;
+#else
+    float2 v; asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p)); return v;
+#endif
+}
+__device__ __forceinline__ uint2 ldg_stream(const uint2 *p)
+{
+#if defined(SBX_EMU) || SBX_Q2_STREAM_POLICY == 0
+    return ldg_tab(p);
+#elif SBX_Q2_STREAM_POLICY == 1
+    uint2 v; asm volatile("ld.global.nc.L1::evict_first.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p)); return v;
+#else
+    uint2 v; asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p)); return v;
 #endif
 }
 
@@ -1058,7 +1099,7 @@ __device__ __forceinline__ void pk_resample_samples_impl(const float2 *mags, flo
 #pragma unroll
         for (int i = 0; i < UNROLL; ++i) {
             const uint32_t g = g0 + i * THREADS;
-            sp[i] = g < count ? ldg_tab(tab + g) : make_uint2(0u, 0u);
+            sp[i] = g < count ? ldg_stream(tab + g) : make_uint2(0u, 0u);
         }
 #pragma unroll
         for (int i = 0; i < UNROLL; ++i) {
@@ -1114,9 +1155,12 @@ __device__ __forceinline__ void pk_resample_colour(float2 *z, const KernelArgs &
 {
     float2 *scratch = z + (1 << (LOG2M - 1));                 // the upper half of the buffer is free again
     for (uint32_t c = 0; c < a.n_chunks; ++c) {
-        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.chunks) + c);
-        const RowChunk ck = {raw.x, raw.y, raw.z, raw.w};
-        if (c != 0) __syncthreads();
+        RowChunk ck = a.chunk0;
+        if (c != 0) {
+            const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.chunks) + c);
+            ck = RowChunk{raw.x, raw.y, raw.z, raw.w};
+            __syncthreads();
+        }
         pk_resample_samples<THREADS, UNROLL>(z, scratch, a, ck);
         __syncthreads();
         pk_colour_rows<PAIR, THREADS, ROWS>(scratch, a, ck, frame0, second_valid);

@@ -115,8 +115,8 @@ __device__ __forceinline__ void q2_first_inputs(cpk (&v)[1 << G::log2r(0)], cons
             s.x = ldg_pcm(pa_lo + r * S);
             s.y = second_valid ? ldg_pcm(pb_lo + r * S) : 0.0f;
         }
-        const float wn = ldg_tab(win_lo + r * S);                // fft.rs:57-63 (complex * f32)
-        const float2 wc = ldg_tab(wtw_lo + r * S);
+        const float wn = ldg_stream(win_lo + r * S);             // fft.rs:57-63 (complex * f32)
+        const float2 wc = ldg_stream(wtw_lo + r * S);
         v[r].re = pk_make(s.x * wn, s.x * wc.x - s.y * wc.y);
         v[r].im = pk_make(s.y * wn, s.x * wc.y + s.y * wc.x);
     }
@@ -149,8 +149,21 @@ __device__ __forceinline__ void q2_pass_first(float4 *e, const KernelArgs &a, co
 }
 
 // ---- passes 1 .. NPASS-2: in-place radix-16 at stride S = 2^LS, one butterfly pair per thread ---------------------
+// The pass's two twiddle values do not depend on the data: q2_pass_twiddles is called BEFORE the barrier that precedes
+// the pass, so that their latency (an L2 round trip: three resident CTAs leave little L1) overlaps the barrier wait.
+struct Q2Twiddles { float2 w1, w4; };
 template <class G, int P>
-__device__ __forceinline__ void q2_pass_inplace(float4 *e, const KernelArgs &a)
+__device__ __forceinline__ Q2Twiddles q2_pass_twiddles(const KernelArgs &a)
+{
+    constexpr int LS = G::log2stride(P), S = 1 << LS;
+    const float2 *tw = a.twp + G::tw_offset(P) + (threadIdx.x & (S - 1));      // W_(16 S)^(lo q)
+    Q2Twiddles t;
+    t.w1 = ldg_tab(tw);
+    t.w4 = ldg_tab(tw + 2 * S);
+    return t;
+}
+template <class G, int P>
+__device__ __forceinline__ void q2_pass_inplace(float4 *e, const Q2Twiddles &t)
 {
     constexpr int LS = G::log2stride(P), S = 1 << LS;
     static_assert(S >= 16, "the stride-1 pass is q2_last_load");
@@ -161,19 +174,22 @@ __device__ __forceinline__ void q2_pass_inplace(float4 *e, const KernelArgs &a)
 #pragma unroll
     for (int r = 0; r < 16; ++r) v[r] = cpk_lds(e + SBX_QAT(G, bx, r * S));
     PkButterfly<16>::run(v);
-    const float2 *tw = a.twp + G::tw_offset(P) + lo;             // W_(16 S)^(lo q)
-    pk_apply_twiddles<16>(v, cpk_dup(ldg_tab(tw)), cpk_dup(ldg_tab(tw + 2 * S)));
+    pk_apply_twiddles<16>(v, cpk_dup(t.w1), cpk_dup(t.w4));
 #pragma unroll
     for (int q = 0; q < 16; ++q) cpk_sts(e + SBX_QAT(G, bx, q * S), v[q]);
 }
 
+// pass 0's barrier, then passes P .. END-1, each followed by its barrier
 template <class G, int P, int END> struct Q2RunPasses {
     static __device__ __forceinline__ void run(float4 *e, const KernelArgs &a)
     {
         if constexpr (P < END) {
-            q2_pass_inplace<G, P>(e, a);
+            const Q2Twiddles t = q2_pass_twiddles<G, P>(a);
             __syncthreads();
+            q2_pass_inplace<G, P>(e, t);
             Q2RunPasses<G, P + 1, END>::run(e, a);
+        } else {
+            __syncthreads();
         }
     }
 };
@@ -263,8 +279,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) fused_q2_kernel(const
     const bool second_valid = G::CH == 1 && frame0 + 1 < a.n_frames;
 
     q2_pass_first<G>(e, a, a.pcm + seq * a.seq_stride + frame0 * (unsigned long long)a.hop * G::CH, second_valid);
-    __syncthreads();
-    Q2RunPasses<G, 1, G::NPASS - 1>::run(e, a);
+    Q2RunPasses<G, 1, G::NPASS - 1>::run(e, a);              // (each pass is preceded by its barrier; one more at the end)
     cpk v[16];
     q2_last_load<G>(e, v);
     __syncthreads();

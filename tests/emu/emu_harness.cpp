@@ -97,7 +97,7 @@ template <class G, int P, int END> struct EmuQ2Passes {
     static void run(float4 *e, const sbx::KernelArgs &a)
     {
         if constexpr (P < END) {
-            for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::q2_pass_inplace<G, P>(e, a); }
+            for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::q2_pass_inplace<G, P>(e, sbx::q2_pass_twiddles<G, P>(a)); }
             EmuQ2Passes<G, P + 1, END>::run(e, a);
         }
     }
@@ -312,6 +312,7 @@ long long emu_batch(const sbx_config *cfg, const float *pcm, unsigned long long 
     a.rowinfo = t.rowinfo.data();
     a.chunks = t.chunks.data();
     a.n_chunks = (uint32_t)t.chunks.size();
+    if (!t.chunks.empty()) a.chunk0 = t.chunks[0];
     a.samp = reinterpret_cast<const uint2 *>(t.samp.data());
     a.taps_clamped = t.taps_clamped ? 1 : 0;
     a.thr = t.thr.data();
