@@ -41,4 +41,20 @@ cudaError_t launch_fused_q2(sbx_plan *p, int channels, const KernelArgs &a, uint
     }
 }
 
+// real-sequence geometry (one mono frame per CTA as N/2 sample pairs) at pad factor 2: args as launch_real prepares them
+bool q2_real_available(const sbx_plan *p)
+{
+    return p->real_ok && p->log2pad == 1 && p->log2n >= 12 && p->log2n <= 14;
+}
+
+cudaError_t launch_real_q2(sbx_plan *p, const KernelArgs &a, uint64_t n_frames, cudaStream_t stream, Sequences seqs)
+{
+    switch (p->log2n) {
+        case 12: return launch_q2_geom<Q2Geom<11, 2, true>>(a, n_frames, stream, seqs);
+        case 13: return launch_q2_geom<Q2Geom<12, 2, true>>(a, n_frames, stream, seqs);
+        case 14: return launch_q2_geom<Q2Geom<13, 2, true>>(a, n_frames, stream, seqs);
+        default: return cudaErrorInvalidConfiguration;
+    }
+}
+
 }  // namespace sbx

@@ -22,6 +22,12 @@ sbx_status launch_real(sbx_plan *p, const float *d_pcm, uint64_t n_frames, uint8
     a.twp = p->d_twp_real;
     a.hop = p->hop / 2;                                    // in sample pairs
     cudaError_t e = cudaErrorInvalidConfiguration;
+    if (p->use_q2_real) {
+        e = launch_real_q2(p, a, n_frames, stream, seqs);
+        if (e != cudaSuccess) return cuda_fail(p, e, "fused_q2_kernel (real-sequence geometry) launch");
+        if (n_frames) p->launches += 1;
+        return SBX_OK;
+    }
     switch (p->log2n + p->log2pad) {
         case 13:
             if (p->log2pad == 0) e = launch_real_one<12, 0>(p, a, n_frames, stream, seqs);

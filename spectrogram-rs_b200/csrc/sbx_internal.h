@@ -44,6 +44,7 @@ struct sbx_plan {
     // REAL geometry (mono batches of long windows, one frame per CTA): tables of the half-length packed transform
     bool real_ok = false;               // tables exist
     bool use_real = false;              // mono batches take it (plan-time choice, see choose_real)
+    bool use_q2_real = false;           // ... and for the real-sequence geometry
     bool use_q2[2] = {false, false};    // P = 2: the packed-lane kernel of stft_q2.cuh for mono / stereo PCM (choose_q2)
     float2 *d_twp_real = nullptr;
     float4 *d_wtw4 = nullptr;
@@ -111,6 +112,8 @@ cudaError_t launch_fused_small(sbx_plan *p, int channels, const KernelArgs &a, u
 cudaError_t launch_fused_big(sbx_plan *p, int channels, const KernelArgs &a, uint64_t n_frames, cudaStream_t stream, Sequences seqs);     // N >= 2048
 bool q2_available(const sbx_plan *p);                                                                                   // sbx_dispatch_q2.cu
 cudaError_t launch_fused_q2(sbx_plan *p, int channels, const KernelArgs &a, uint64_t n_frames, cudaStream_t stream, Sequences seqs);      // P = 2, packed lanes
+bool q2_real_available(const sbx_plan *p);
+cudaError_t launch_real_q2(sbx_plan *p, const KernelArgs &a, uint64_t n_frames, cudaStream_t stream, Sequences seqs);                     // REAL geometry, P = 2
 bool wide_available(const sbx_plan *p);                                                                                 // sbx_dispatch_wide.cu
 cudaError_t launch_fused_wide(sbx_plan *p, const KernelArgs &a, cudaStream_t stream);                                   // one stereo frame
 sbx_status launch_colourise(sbx_plan *p, const float *d_mags, uint64_t n_frames, uint8_t *d_rgba, cudaStream_t stream);

@@ -73,8 +73,19 @@ static bool choose_q2(const sbx_plan *p, int channels)
     if (env && env[0] == '1') return true;
     // measured on a B200, M frames/s (fused_frames_kernel -> fused_q2_kernel): N = 4096 mono 58.6 -> 63.8, stereo 29.7 -> 32.7;
     // N = 2048 stereo 56.5 -> 57.6; N = 8192 stereo (one 512-thread CTA per SM either way) 12.6 -> 12.5
-    (void)channels;
-    return p->log2n <= 12;
+    // mono N = 2048 (hop 256, H 2048): 85.1 -> 82.6, so the 128-thread CTAs of N = 2048 are used for stereo PCM only
+    return p->log2n == 12 || (p->log2n == 11 && channels == 2);
+}
+
+static bool choose_q2_real(const sbx_plan *p)
+{
+    if (!q2_real_available(p)) return false;
+    const char *env = std::getenv("SBX_Q2");
+    if (env && env[0] == '0') return false;
+    if (env && env[0] == '1') return true;
+    // measured on a B200, M frames/s (classic real-sequence kernel -> q2): N = 8192 (cfg3) 29.9 -> 33.0; N = 4096 44.5 -> 42.4;
+    // N = 16384 (one 512-thread CTA per SM either way) 7.95 -> 7.96
+    return p->log2n == 13;
 }
 
 sbx_status launch_fused(sbx_plan *p, int channels, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba,
@@ -425,6 +436,7 @@ SBX_API sbx_status sbx_plan_create(const sbx_config *cfg, sbx_plan **out_plan)
     p->real_ok = t.real_ok;
     p->use_real = sbx::choose_real(t.real_ok, t.real_auto);
     for (int c = 1; c <= 2; ++c) p->use_q2[c - 1] = sbx::choose_q2(p, c);
+    p->use_q2_real = sbx::choose_q2_real(p);
     p->n_chunks = (uint32_t)t.chunks.size();
     if (!t.chunks.empty()) p->chunk0 = t.chunks[0];
     p->taps_clamped = t.taps_clamped ? 1 : 0;
@@ -483,7 +495,7 @@ SBX_API const char *sbx_kernel_path(const sbx_plan *p)
 {
     if (!p) return "";
     if (p->generic) return "generic";
-    if (p->channels == 1 && p->use_real && (p->hop & 1u) == 0) return "fused-real";
+    if (p->channels == 1 && p->use_real && (p->hop & 1u) == 0) return p->use_q2_real ? "fused-real-q2" : "fused-real";
     if (p->large) return "large";
     if (p->use_q2[p->channels - 1]) return p->channels == 1 ? "fused-pair-q2" : "fused-stereo-q2";
     return p->channels == 1 ? "fused-pair" : "fused-stereo";

@@ -336,6 +336,20 @@ __device__ __forceinline__ float2 ldg_stream(const float2 *p)
     float2 v; asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p)); return v;
 #endif
 }
+__device__ __forceinline__ float4 ldg_stream(const float4 *p)
+{
+#if defined(SBX_EMU) || SBX_Q2_STREAM_POLICY == 0
+    return ldg_tab(p);
+#elif SBX_Q2_STREAM_POLICY == 1
+    float4 v;
+    asm volatile("ld.global.nc.L1::evict_first.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+#else
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+#endif
+}
 __device__ __forceinline__ uint2 ldg_stream(const uint2 *p)
 {
 #if defined(SBX_EMU) || SBX_Q2_STREAM_POLICY == 0

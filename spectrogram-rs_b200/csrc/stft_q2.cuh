@@ -29,9 +29,13 @@
 
 namespace sbx {
 
-template <int LOG2N_, int CH_> struct Q2Geom {
+// REAL_: the complex sequence is the even/odd packing z[n] = x[2n] + i x[2n+1] of ONE mono frame of 2 N samples (the
+// real-sequence geometry of stft_kernels.cuh): CH_ = 2 (sample pairs), one frame per CTA.
+template <int LOG2N_, int CH_, bool REAL_ = false> struct Q2Geom {
     using GB = Geom<LOG2N_, 0, CH_>;                       // radix plan / digit reversal of the N-point sub-transform
     static constexpr int LOG2N = LOG2N_, CH = CH_, LOG2PAD = 1, PAD = 2;
+    static constexpr bool REAL = REAL_;
+    static_assert(!REAL_ || CH_ == 2, "the real-sequence packing reads sample pairs");
     static constexpr int N = 1 << LOG2N, M = 2 * N, LOG2M = LOG2N + 1;
     static constexpr int NPASS = GB::NPASS;
     static constexpr int THREADS = N / 16;                 // one radix-16 butterfly PAIR per thread and pass
@@ -115,10 +119,18 @@ __device__ __forceinline__ void q2_first_inputs(cpk (&v)[1 << G::log2r(0)], cons
             s.x = ldg_pcm(pa_lo + r * S);
             s.y = second_valid ? ldg_pcm(pb_lo + r * S) : 0.0f;
         }
-        const float wn = ldg_stream(win_lo + r * S);             // fft.rs:57-63 (complex * f32)
-        const float2 wc = ldg_stream(wtw_lo + r * S);
-        v[r].re = pk_make(s.x * wn, s.x * wc.x - s.y * wc.y);
-        v[r].im = pk_make(s.y * wn, s.x * wc.y + s.y * wc.x);
+        if constexpr (G::REAL) {
+            // s = (x[2n], x[2n+1]); A: each sample with its own window value; B: times W_(M)^n as well (wtw4, sbx_tables.h)
+            const float2 wn = ldg_stream(reinterpret_cast<const float2 *>(a.window) + lo + r * S);
+            const float4 f = ldg_stream(a.wtw4 + lo + r * S);
+            v[r].re = pk_make(s.x * wn.x, s.x * f.x - s.y * f.y);
+            v[r].im = pk_make(s.y * wn.y, s.x * f.z + s.y * f.w);
+        } else {
+            const float wn = ldg_stream(win_lo + r * S);         // fft.rs:57-63 (complex * f32)
+            const float2 wc = ldg_stream(wtw_lo + r * S);
+            v[r].re = pk_make(s.x * wn, s.x * wc.x - s.y * wc.y);
+            v[r].im = pk_make(s.y * wn, s.x * wc.y + s.y * wc.x);
+        }
     }
 }
 
@@ -254,6 +266,43 @@ __device__ __forceinline__ void q2_split_emit(float2 *mags, const float *pb, con
     }
 }
 
+// REAL: a = Z[kk], b = Z[M - kk] of the packed sequence, w = W_(2M)^kk.  With E, O the spectra of the even and odd
+// samples, a + conj b = 2 E, a - conj b = 2i O, X[kk] = E + w O and X[M - kk] = conj(E - w O) (split_pair_real).  One
+// magnitude per bin of the real spectrum, natural order, over the lower half of the buffer: zf[kk] = |X[kk]| * 2/N.
+// Thread 0 also owns the self-paired bin M/2 (its row's element 8, lane A): |X[M/2]| = |Z[M/2]|.
+template <class G>
+__device__ __forceinline__ void q2_split_emit_real(float *zf, const float *pb, const KernelArgs &a, const cpk (&v)[16])
+{
+    constexpr int NT = G::THREADS;
+    const int j = threadIdx.x;
+    const float hs = 0.5f * a.scale;
+    // W_(2M)^kk for kk = 2j (lane A), 2j + 1 (lane B); bins of digit d: times W_32^d
+    const float4 wt = ldg_tab(reinterpret_cast<const float4 *>(a.rtw) + j);
+    const cpk w0 = cpk_make(pk_make(wt.x, wt.z), pk_make(wt.y, wt.w));
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+        const pk yre = pk_make(pb[d * NT + j], pb[16 * NT + d * NT + j]);
+        const pk yim = pk_make(pb[8 * NT + d * NT + j], pb[24 * NT + d * NT + j]);
+        const cpk w = d == 0 ? w0 : pk_rot(w0, pk_dup(w32_cos(d)), pk_dup(w32_sin(d)));     // w0 * (cos - i sin)
+        const pk sx = pk_add(v[d].re, yre), sy = pk_sub(v[d].im, yim);     // a + conj b
+        const pk dx = pk_sub(v[d].re, yre), dy = pk_add(v[d].im, yim);     // a - conj b
+        const pk tx = pk_fma(w.re, dy, pk_mul(w.im, dx));                  // w * (-i d)
+        const pk ty = pk_fma(w.im, dy, pk_neg(pk_mul(w.re, dx)));
+        const pk ox = pk_add(sx, tx), oy = pk_add(sy, ty), px = pk_sub(sx, tx), py = pk_sub(sy, ty);
+        const pk o2 = pk_fma(ox, ox, pk_mul(oy, oy)), p2 = pk_fma(px, px, pk_mul(py, py));
+        const int kk = 2 * (j + NT * d);
+        // X[kk], X[kk + 1]; kk = 0 is DC (dropped, never read)
+        *reinterpret_cast<float2 *>(zf + kk) = make_float2(fast_sqrt(pk_lo(o2)) * hs, fast_sqrt(pk_hi(o2)) * hs);
+        // X[M - kk], X[M - kk - 1]; M - 0 is the Nyquist bin (dropped) and lies outside the magnitudes
+        if (d != 0 || j != 0) zf[G::M - kk] = fast_sqrt(pk_lo(p2)) * hs;
+        zf[G::M - kk - 1] = fast_sqrt(pk_hi(p2)) * hs;
+    }
+    if (j == 0) {
+        const float re = pk_lo(v[8].re), im = pk_lo(v[8].im);
+        zf[G::M / 2] = fast_sqrt(re * re + im * im) * a.scale;
+    }
+}
+
 #ifndef SBX_Q2_RESAMPLE_UNROLL
 #define SBX_Q2_RESAMPLE_UNROLL 8       // sample-table loads in flight per thread (128 registers to spend)
 #endif
@@ -285,10 +334,19 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) fused_q2_kernel(const
     __syncthreads();
     q2_partner_write<G>(pb, v);
     __syncthreads();
-    q2_split_emit<G>(z, pb, a, v);
+    if constexpr (G::REAL) q2_split_emit_real<G>(reinterpret_cast<float *>(smem_raw), pb, a, v);
+    else q2_split_emit<G>(z, pb, a, v);
     __syncthreads();
 
     const unsigned long long out_frame0 = seq * a.n_frames + frame0;
+    if constexpr (G::REAL) {
+        const float *zf = reinterpret_cast<const float *>(smem_raw);
+        if (a.mags_out != nullptr) {
+            float2 *out = reinterpret_cast<float2 *>(a.mags_out) + out_frame0 * a.k_out;
+            for (uint32_t j = threadIdx.x; j < a.k_out; j += G::THREADS) out[j] = make_float2(zf[j + 1], zf[j + 1]);
+        }
+        if (a.rgba != nullptr) resample_colour_single<G::LOG2M, G::THREADS>(z, a, out_frame0);
+    } else {
     if (a.mags_out != nullptr) {
         float2 *out = reinterpret_cast<float2 *>(a.mags_out) + out_frame0 * a.k_out;
         for (uint32_t j = threadIdx.x; j < a.k_out; j += G::THREADS) {
@@ -302,6 +360,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) fused_q2_kernel(const
         }
     }
     if (a.rgba != nullptr) pk_resample_colour<G::LOG2M, G::CH == 1, G::THREADS, SBX_Q2_RESAMPLE_UNROLL, SBX_Q2_COLOUR_ROWS>(z, a, out_frame0, second_valid);
+    }  // !REAL
     if (a.done_flag != nullptr) {
         __syncthreads();
         if (threadIdx.x == 0) {

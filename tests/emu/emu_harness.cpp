@@ -117,6 +117,25 @@ int emu_cta_q2(const sbx::KernelArgs &a, unsigned long long frame0, float *mags_
     for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::q2_last_load<G>(e.data(), rows[t].v); }
     for (float4 &x : e) x = make_float4(NAN, NAN, NAN, NAN);                      // the buffer is dead once every row is in registers
     for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::q2_partner_write<G>(pb, rows[t].v); }
+    if constexpr (G::REAL) {
+        float *zf = reinterpret_cast<float *>(e.data());
+        for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::q2_split_emit_real<G>(zf, pb, a, rows[t].v); }
+        if (mags_out) {
+            float *o = mags_out + (size_t)frame0 * a.k_out * 2;
+            for (uint32_t j = 0; j < a.k_out; ++j) { o[2 * j] = zf[j + 1]; o[2 * j + 1] = zf[j + 1]; }
+        }
+        if (rgba) {
+            sbx::KernelArgs b = a;
+            b.rgba = rgba;
+            float *scratch = zf + G::M;
+            for (uint32_t c = 0; c < a.n_chunks; ++c) {
+                const sbx::RowChunk ck = a.chunks[c];
+                for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::resample_samples<G::THREADS>(zf, scratch, b, ck); }
+                for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::colour_rows_single<G::THREADS>(scratch, b, ck, frame0); }
+            }
+        }
+        return 0;
+    }
     for (int t = 0; t < G::THREADS; ++t) { threadIdx.x = t; sbx::q2_split_emit<G>(z, pb, a, rows[t].v); }
     if (mags_out) {
         for (uint32_t j = 0; j < a.k_out; ++j) {
@@ -170,6 +189,12 @@ template <int LOG2NC, int LOG2PAD>
 int emu_real(const sbx::KernelArgs &a, unsigned long long frames, float *mags, uint8_t *rgba)
 {
     for (unsigned long long f = 0; f < frames; ++f) {
+        if constexpr (LOG2PAD == 1 && LOG2NC >= 9 && LOG2NC <= 13)
+            if (g_emu_q2) {
+                const int st = emu_cta_q2<sbx::Q2Geom<LOG2NC, 2, true>>(a, f, mags, rgba);
+                if (st != 0) return st;
+                continue;
+            }
         const int st = emu_cta<sbx::Geom<LOG2NC, LOG2PAD, 2, true>>(a, f, mags, rgba);
         if (st != 0) return st;
     }

@@ -226,3 +226,21 @@ def test_q2_packed_lane_phases_match_oracle(n, ch, hop, rows, interp):
     peak = np.abs(o_mags).max(axis=(1, 2), keepdims=True)
     assert (np.abs(mags - o_mags) / peak).max() <= 1e-5
     assert (rgba != o_rgba).any(axis=2).mean() <= 2e-3
+
+
+@pytest.mark.parametrize("n,hop,rows,interp", [(8192, 256, 1024, 0), (4096, 512, 512, 1), (16384, 1024, 256, 0), (8192, 1000, 300, 0)])
+def test_q2_real_sequence_phases_match_oracle(n, hop, rows, interp):
+    """stft_q2.cuh on the real-sequence geometry (one mono frame per CTA as N/2 sample pairs): the even/odd
+    recombination on packed lanes, the self-paired bin M/2 and the single-channel resample."""
+    lut = signals.lut("viridis")
+    frames = 4
+    ns = n + hop * (frames - 1) + 3
+    rng = np.random.Generator(np.random.PCG64(3))
+    pcm = (signals.log_sweep(ns) + 0.02 * rng.standard_normal(ns)).astype(np.float32)
+    cfg = emu.make_config(lut, window_n=n, pad_factor=2, hop=hop, rows_h=rows, channels=1, interp=interp)
+    mags, rgba = emu.batch(cfg, pcm, q2=True, real=True)
+    p = oracle.params(window_n=n, pad_factor=2, hop=hop, rows_h=rows, interp=interp)
+    o_rgba, o_mags = oracle.batch(p, pcm, 1, lut, want_mags=True)
+    peak = np.abs(o_mags).max(axis=(1, 2), keepdims=True)
+    assert (np.abs(mags - o_mags) / peak).max() <= 1e-5
+    assert (rgba != o_rgba).any(axis=2).mean() <= 2e-3

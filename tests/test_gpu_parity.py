@@ -706,3 +706,38 @@ def test_q2_packed_lane_kernel(sbx, magma, monkeypatch, n, ch, hop, rows, interp
             out[mode] = g_mags
     peak = np.abs(out["0"]).max(axis=(1, 2), keepdims=True)
     assert (np.abs(out["1"] - out["0"]) / peak).max() <= MAG_TOL
+
+
+@pytest.mark.parametrize("n,hop,rows,interp,scheme", [(8192, 256, 1024, 0, 0), (4096, 512, 512, 1, 0), (16384, 1024, 256, 0, 1),
+                                                       (8192, 1000, 300, 0, 0)])
+def test_q2_real_sequence_geometry(sbx, viridis, monkeypatch, n, hop, rows, interp, scheme):
+    """fused_q2_kernel<Q2Geom<.., REAL>> (one mono frame per CTA, both sub-transforms in packed lanes) against the oracle
+    and against the classic real-sequence kernel."""
+    import torch
+    frames = 9
+    n_samples = n + hop * (frames - 1) + 3
+    pcm = _pcm(1, n_samples, seed=13)
+    p = oracle.params(window_n=n, pad_factor=2, hop=hop, rows_h=rows, interp=interp, stereo_scheme=scheme)
+    o_rgba, o_mags = oracle.batch(p, pcm, 1, viridis, want_mags=True)
+    out = {}
+    monkeypatch.setenv("SBX_REAL", "1")
+    for mode in ("0", "1"):
+        monkeypatch.setenv("SBX_Q2", mode)
+        with sbx.Plan(window_n=n, pad_factor=2, hop=hop, rows_h=rows, channels=1, interp=interp, scheme=scheme, lut=viridis) as plan:
+            assert plan.kernel_path == ("fused-real-q2" if mode == "1" else "fused-real")
+            d_pcm = torch.from_numpy(pcm).cuda()
+            d_mags = torch.zeros((frames, plan.k, 2), dtype=torch.float32, device="cuda")
+            d_rgba = torch.zeros((frames, rows, 4), dtype=torch.uint8, device="cuda")
+            assert plan.magnitudes_batch_device(d_pcm, n_samples, d_mags, frames) == frames
+            assert plan.process_batch_device(d_pcm, n_samples, d_rgba, frames) == frames
+            plan.synchronize()
+            g_mags, g_rgba = d_mags.cpu().numpy(), d_rgba.cpu().numpy()
+            peak = np.abs(o_mags).max(axis=(1, 2), keepdims=True)
+            assert (np.abs(g_mags - o_mags) / peak).max() <= MAG_TOL
+            assert np.array_equal(g_mags[..., 0], g_mags[..., 1])                      # L == R for (s, s) input
+            assert np.array_equal(plan.colorize_magnitudes(g_mags), g_rgba)
+            assert np.array_equal(plan.process_batch(pcm), g_rgba)
+            assert (g_rgba != o_rgba).any(axis=2).mean() <= 2e-3
+            out[mode] = g_mags
+    peak = np.abs(out["0"]).max(axis=(1, 2), keepdims=True)
+    assert (np.abs(out["1"] - out["0"]) / peak).max() <= MAG_TOL

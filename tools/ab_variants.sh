@@ -1,9 +1,6 @@
-# A/B of library variants (tools/build_variant.sh) on the GPU box: label, then env assignments
-run() {
-  label=$1; shift
-  for c in $CFGS; do env "$@" python tools/profile_kernel.py --cfg $c --frames 262144 --iters 10 2>&1 | tail -1 | sed "s/^/$label /"; done
-}
-CFGS=${CFGS:-"1 2 8"}
-run main
-run sp1 SBX_LIB_PATH=variants/libsbx_sp1.so
-run sp2 SBX_LIB_PATH=variants/libsbx_sp2.so
+for q in 0 1; do
+  for n in 4096 16384; do
+    SBX_REAL=1 SBX_Q2=$q python tools/profile_kernel.py --n $n --pad 2 --hop $((n/16)) --frames 131072 --iters 5 2>&1 | tail -1 | sed "s/^/real Q2=$q /"
+  done
+  SBX_Q2=$q python tools/profile_kernel.py --n 2048 --pad 2 --hop 256 --frames 262144 --iters 5 2>&1 | tail -1 | sed "s/^/pair Q2=$q /"
+done

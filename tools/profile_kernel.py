@@ -24,10 +24,13 @@ ap.add_argument("--frames", type=int, default=32768)
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--mags", action="store_true", help="magnitude output instead of RGBA")
 ap.add_argument("--n", type=int, default=0, help="cfg5 sweep: window N with P = 4, hop = N/8, H = 2048")
+ap.add_argument("--pad", type=int, default=0, help="with --n: pad factor (default 4, the cfg5 sweep)")
+ap.add_argument("--hop", type=int, default=0)
+ap.add_argument("--ch", type=int, default=0)
 a = ap.parse_args()
 kw = dict(CFG[a.cfg])
 if a.n:
-    kw.update(window_n=a.n, pad_factor=4, hop=a.n // 8, rows_h=2048, channels=1)
+    kw.update(window_n=a.n, pad_factor=a.pad or 4, hop=a.hop or a.n // 8, rows_h=2048, channels=a.ch or 1)
 plan = sbx.Plan(**kw)
 s = torch.cuda.Stream()
 torch.cuda.set_stream(s)
