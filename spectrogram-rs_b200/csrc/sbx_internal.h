@@ -20,6 +20,7 @@ struct sbx_plan {
     std::vector<sbx::RowMap> h_rowmap;
     std::vector<float> h_thr_raw;       // [2][256] bare thresholds
     float guess_a[2] = {0, 0}, guess_b[2] = {0, 0};
+    float step_margin = 1.0f;
     uint32_t n_chunks = 0;
     sbx::RowChunk chunk0{};             // chunks[0], passed by value in the kernel arguments
 

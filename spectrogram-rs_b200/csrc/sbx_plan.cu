@@ -253,6 +253,7 @@ sbx::KernelArgs sbx_plan::base_args() const
     a.scale = scale;
     a.db_eps = cfg.db_eps;
     a.neg_zero = -0.0f;
+    a.step_margin = step_margin;
     for (int i = 0; i < 2; ++i) { a.guess_a[i] = guess_a[i]; a.guess_b[i] = guess_b[i]; }
     a.interp = (int)cfg.interp;
     a.scheme = (int)cfg.scheme;
@@ -441,6 +442,7 @@ SBX_API sbx_status sbx_plan_create(const sbx_config *cfg, sbx_plan **out_plan)
     if (!t.chunks.empty()) p->chunk0 = t.chunks[0];
     p->taps_clamped = t.taps_clamped ? 1 : 0;
     for (int i = 0; i < 2; ++i) { p->guess_a[i] = t.guess_a[i]; p->guess_b[i] = t.guess_b[i]; }
+    p->step_margin = t.step_margin;
 
 #define SBX_TRY(call)                                                                   \
     do {                                                                                \

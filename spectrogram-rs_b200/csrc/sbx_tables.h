@@ -2,6 +2,7 @@
 // Shared by sbx_plan.cu (the product) and tests/emu (host emulation of the kernel phases).
 // Each function cites the reference lines it restates (paths relative to the reference root).
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -111,6 +112,7 @@ struct HostTables {
     std::vector<float> thr;             // [2][256] pairs (ts[i], ts[i+1]), see step_index
     std::vector<float> thr_raw;         // [2][256] the bare thresholds (introspection)
     float guess_a[2], guess_b[2];
+    float step_margin = 1.0f;           // KernelArgs::step_margin (1: the guessed colour step is always checked)
     uint32_t lut[256];
     uint32_t ctab[1024];                // [256] {ts[i], ts[i+1], lut[i], 0} (colour step bracket + colour)
     bool ok = true;                     // false: a row has more samples than the scratch area holds
@@ -353,6 +355,36 @@ inline void build(const sbx_config &cfg, HostTables &t)
         const double levels = set == 0 ? 256.0 : 255.0;
         t.guess_a[set] = (float)(10.0 * std::log10(2.0) * levels / range);
         t.guess_b[set] = (float)(-(double)cfg.db_min * levels / range);
+    }
+
+    // How far the device's guess  g(p) = log2(p + eps) * a + b  can be from the point where the reference's step
+    // function actually changes, in steps.  Both follow T(p) = (10 log10(p + eps) - db_min) / range * 256:
+    //   * the reference chain (f32 log10f, subtract, divide, floor): measured here -- T at every exact threshold and
+    //     at the float just below it must straddle the integer it belongs to, to within err_ref;
+    //   * the device guess: p + eps rounded to f32 (|d log2| <= 1.8e-7), MUFU.LG2 (__log2f: 2 ulp of |log2| <= 128,
+    //     i.e. <= 3.1e-5 absolute), the FMA and the f32 roundings of a and b.
+    // A guess whose fractional part lies in (margin, 1 - margin) cannot be on the wrong side of a threshold.
+    {
+        const double range_d = (double)cfg.db_max - (double)cfg.db_min;
+        auto T = [&](float pw) {
+            const float sum = pw + cfg.db_eps;                                  // the f32 sum both sides start from
+            return (10.0 * std::log10((double)sum) - (double)cfg.db_min) / range_d * 256.0;
+        };
+        double err_ref = 0.0;
+        bool valid = true;
+        for (int i = 0; i < 255; ++i) {
+            const float th = t.thr_raw[i];
+            if (std::isnan(th)) continue;                                       // level never reached
+            if (!(th > 0.0f) || std::isinf(th)) { if (th != 0.0f) valid = false; continue; }
+            const float below = std::nextafterf(th, 0.0f);
+            const double hi = T(th) - (double)(i + 1), lo = T(below) - (double)(i + 1);
+            if (!std::isfinite(hi) || !std::isfinite(lo)) { valid = false; continue; }
+            err_ref = std::max(err_ref, std::max(std::fabs(hi), std::fabs(lo)));
+        }
+        const double a_abs = std::fabs((double)t.guess_a[0]);
+        const double err_dev = a_abs * (1.8e-7 + 3.1e-5) + 2.0 * 256.0 * 1.2e-7 + (a_abs * 128.0 + std::fabs((double)t.guess_b[0])) * 1.2e-7;
+        const double margin = 2.0 * (err_ref + err_dev);
+        t.step_margin = (valid && margin < 0.25) ? (float)std::max(margin, 1e-3) : 1.0f;
     }
 
     for (int i = 0; i < 256; ++i)

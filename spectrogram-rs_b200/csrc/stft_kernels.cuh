@@ -82,6 +82,7 @@ struct KernelArgs {
     float scale;                 // 2 / N     (fft.rs:92)
     float guess_a[2], guess_b[2];// step guess = log2(p + eps) * a + b   (colour, alpha)
     float db_eps;
+    float step_margin;           // colour step: the guess is final when its fractional part lies in (margin, 1 - margin); >= 0.5: never
     float neg_zero;              // -0.0f, opaque to the compiler: stft_q2.cuh writes exactly rounded products as fma(x, y, -0.0)
     int interp;                  // 0 cubic, 1 cosine
     int scheme;                  // 0 mono gradient, 1 stereo pan gradient
@@ -90,6 +91,9 @@ struct KernelArgs {
 
 #ifndef SBX_PK_RESAMPLE
 #define SBX_PK_RESAMPLE 0        // 1: the classic kernels resample / sum rows with packed (L, R) instructions too (pk_resample_colour)
+#endif
+#ifndef SBX_STEP_FAST
+#define SBX_STEP_FAST 1          // step_colour: accept the guessed step without the threshold load when it is clear of a boundary
 #endif
 #ifndef SBX_EPT_LOG2
 #define SBX_EPT_LOG2 4           // log2 of the transform points each thread owns per pass (4: M/16 threads, 5: M/32)
@@ -862,6 +866,15 @@ __device__ __forceinline__ int step_index(const float *ts, float p, float eps, f
 __device__ __forceinline__ uint32_t step_colour(const KernelArgs &a, float p)
 {
     const float t = fast_log2(p + a.db_eps) * a.guess_a[0] + a.guess_b[0];
+#if SBX_STEP_FAST
+    // The guess and the reference's f32 dB chain both follow T(p) = (10 log10(p + eps) - db_min) / (db_max - db_min) * 256
+    // to within a bound the plan has verified against every exact threshold (sbx_tables.h: step_margin): away from the
+    // integers by more than that, floor(guess) IS the step, and the pixel needs the 4-byte colour only.  NaN / inf
+    // guesses fail both comparisons and take the exact path below.
+    const float fl = floorf(t), fr = t - fl;
+    if (fr > a.step_margin && fr < 1.0f - a.step_margin)
+        return ldg_tab(a.lut + (int)fminf(fmaxf(fl, 0.0f), 255.0f));
+#endif
     const int idx = (int)fminf(fmaxf(t, 0.0f), 255.0f);      // NaN -> 0
     const uint4 e = ldg_tab(a.ctab + idx);
     if (p >= __uint_as_float(e.y) || p < __uint_as_float(e.x))

@@ -345,7 +345,7 @@ long long emu_batch(const sbx_config *cfg, const float *pcm, unsigned long long 
     a.ctab = reinterpret_cast<const uint4 *>(t.ctab);
     a.n_frames = frames;
     a.hop = cfg->hop; a.rows = t.rows; a.k_out = t.k_out;
-    a.scale = t.scale; a.db_eps = cfg->db_eps; a.neg_zero = -0.0f;
+    a.scale = t.scale; a.db_eps = cfg->db_eps; a.neg_zero = -0.0f; a.step_margin = t.step_margin;
     for (int i = 0; i < 2; ++i) { a.guess_a[i] = t.guess_a[i]; a.guess_b[i] = t.guess_b[i]; }
     a.interp = (int)cfg->interp; a.scheme = (int)cfg->scheme;
     const int ln = ilog2(t.n), lp = ilog2(t.pad), ch = (int)cfg->channels;
