@@ -20,6 +20,7 @@ sbx_status launch_real(sbx_plan *p, const float *d_pcm, uint64_t n_frames, uint8
     a.mags_out = d_mags;
     a.n_frames = n_frames;
     a.twp = p->d_twp_real;
+    a.wq = p->d_wq_real;
     a.hop = p->hop / 2;                                    // in sample pairs
     cudaError_t e = cudaErrorInvalidConfiguration;
     if (p->use_q2_real) {

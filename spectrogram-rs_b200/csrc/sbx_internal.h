@@ -28,6 +28,7 @@ struct sbx_plan {
     float *d_window = nullptr;
     float2 *d_wtw = nullptr;
     float2 *d_twp = nullptr;
+    float2 *d_wq = nullptr, *d_wq_real = nullptr;   // q2 kernels: W_M^lo (pass 0, lane B)
     sbx::RowMap *d_rowmap = nullptr;
     uint32_t *d_rowinfo = nullptr;
     sbx::RowChunk *d_chunks = nullptr;

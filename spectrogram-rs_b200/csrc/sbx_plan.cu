@@ -235,6 +235,7 @@ sbx::KernelArgs sbx_plan::base_args() const
     a.window = d_window;
     a.wtw = d_wtw;
     a.twp = d_twp;
+    a.wq = d_wq;
     a.wtw4 = d_wtw4;
     a.rtw = d_rtw;
     a.rowmap = d_rowmap;
@@ -339,7 +340,7 @@ SBX_API void sbx_plan_destroy(sbx_plan *p)
         cudaFree(s.d_pcm);
         cudaFree(s.d_rgba);
     }
-    cudaFree(p->d_window); cudaFree(p->d_wtw); cudaFree(p->d_twp); cudaFree(p->d_rowmap); cudaFree(p->d_rowinfo); cudaFree(p->d_chunks);
+    cudaFree(p->d_window); cudaFree(p->d_wtw); cudaFree(p->d_twp); cudaFree(p->d_wq); cudaFree(p->d_wq_real); cudaFree(p->d_rowmap); cudaFree(p->d_rowinfo); cudaFree(p->d_chunks);
     cudaFree(p->d_samp); cudaFree(p->d_f16_scratch); cudaFree(p->d_twm); cudaFree(p->d_twg); cudaFree(p->d_pos_tab); cudaFree(p->d_twp_block); cudaFree(p->d_zbuf); cudaFree(p->d_magbuf);
     cudaFree(p->d_thr); cudaFree(p->d_lut); cudaFree(p->d_ctab); cudaFree(p->d_twp_real); cudaFree(p->d_wtw4); cudaFree(p->d_rtw); cudaFree(p->d_frame); cudaFree(p->d_mags1); cudaFree(p->d_col);
     if (p->h_frame) cudaFreeHost(p->h_frame);
@@ -458,6 +459,8 @@ SBX_API sbx_status sbx_plan_create(const sbx_config *cfg, sbx_plan **out_plan)
     SBX_TRY(upload(&p->d_window, p->h_window.data(), p->n * sizeof(float)));
     SBX_TRY(upload(&p->d_wtw, t.wtw.data(), t.wtw.size() * sizeof(float)));
     SBX_TRY(upload(&p->d_twp, t.twp.data(), t.twp.size() * sizeof(float)));
+    SBX_TRY(upload(&p->d_wq, t.wq.data(), t.wq.size() * sizeof(float)));
+    SBX_TRY(upload(&p->d_wq_real, t.wq_real.data(), t.wq_real.size() * sizeof(float)));
     SBX_TRY(upload(&p->d_twp_real, t.twp_real.data(), t.twp_real.size() * sizeof(float)));
     SBX_TRY(upload(&p->d_wtw4, t.wtw4.data(), t.wtw4.size() * sizeof(float)));
     SBX_TRY(upload(&p->d_rtw, t.rtw.data(), t.rtw.size() * sizeof(float)));

@@ -90,6 +90,7 @@ struct HostTables {
     std::vector<float> window;          // [N]
     std::vector<float> wtw;             // [(P-1) N] x (re, im): window[n] * W_M^(n q0)
     std::vector<float> twp;             // per-pass twiddle planes x (re, im), see KernelArgs::twp
+    std::vector<float> wq, wq_real;     // q2 kernels: [S_0] x (re, im) W_M^lo, lo < N / R_0 (complex transform / real-sequence transform)
     std::vector<float> twp_block;       // large path: planes of the 4096-point block transform
     // REAL geometry (one mono frame per CTA as the even/odd packed sequence of N/2 pairs, M in {16384, 32768})
     bool real_ok = false;               // the tables below exist
@@ -222,6 +223,20 @@ inline void build(const sbx_config &cfg, HostTables &t)
         t.twp_block.clear();
     }
 
+    // q2 kernels (pad factor 2): W_M^lo for lo below the first pass's stride; lane B's pass-0 factor is W_M^lo times a constant
+    auto wq_table = [](int log2n_sub, uint32_t m_sub, std::vector<float> &dst) {
+        const RadixPlan r(log2n_sub);
+        const uint32_t s0 = 1u << r.log2stride(0);
+        dst.resize((size_t)s0 * 2);
+        for (uint32_t lo = 0; lo < s0; ++lo) {
+            const double ang = -2.0 * M_PI * (double)lo / (double)m_sub;
+            dst[2 * (size_t)lo] = (float)std::cos(ang);
+            dst[2 * (size_t)lo + 1] = (float)std::sin(ang);
+        }
+    };
+    t.wq.clear(); t.wq_real.clear();
+    if (!t.generic && !t.large && t.pad == 2) wq_table(log2n, t.m, t.wq);
+
     // REAL geometry: transform of the packed sequence z[n] = x[2n] + i x[2n+1], length M/2 with N/2 non-zero pairs
     t.real_ok = !t.generic && t.m >= REAL_MIN_M && t.m <= REAL_MAX_M && t.n >= 512;
     t.twp_real.clear(); t.wtw4.clear(); t.rtw.clear();
@@ -238,6 +253,7 @@ inline void build(const sbx_config &cfg, HostTables &t)
                 float *o = t.wtw4.data() + ((size_t)(q0 - 1) * nc + i) * 4;
                 o[0] = (float)(w0 * c); o[1] = (float)(w1 * sn); o[2] = (float)(w0 * sn); o[3] = (float)(w1 * c);
             }
+        if (t.pad == 2) wq_table(log2n - 1, mc, t.wq_real);
         t.rtw.resize((size_t)(t.m / 32) * 2);
         for (uint32_t k = 0; k < t.m / 32; ++k) {
             const double ang = -2.0 * M_PI * (double)k / (double)t.m;

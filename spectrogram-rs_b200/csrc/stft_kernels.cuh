@@ -56,6 +56,7 @@ struct KernelArgs {
     const float *window;         // [N] periodic Hann, f32, host-computed (fft.rs:59-63)
     const float2 *wtw;           // [(P-1) N] window[n] * W_M^(n q0), q0 = 1..P-1 (sub-transform premultiply)
     const float2 *twp;           // per DIF pass p: TW_PLANES planes of S_p entries, plane j = W_(S_p R_p)^(2^j lo)
+    const float2 *wq;            // q2 kernels: [S_0] W_M^lo (M = P N, the padded complex length), lo < the first pass's stride
     const float4 *wtw4;          // REAL: [(P-1) N/2] {w0 c, w1 s, w0 s, w1 c}: (w[2n], w[2n+1]) and (c, s) = W_(M/2)^(n q0)
     const float2 *rtw;           // REAL: [M/32] W_M^t, the even/odd recombination twiddle of bin t (M = real length)
     const RowMap *rowmap;        // [H] (host-side description; the kernels read rowinfo)

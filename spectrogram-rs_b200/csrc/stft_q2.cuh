@@ -23,6 +23,9 @@
 #include "sbx_pk.cuh"
 #include "stft_kernels.cuh"
 
+#ifndef SBX_Q2_WTW_COMPUTE
+#define SBX_Q2_WTW_COMPUTE 1           // pass 0: lane B's factor W_M^n from one table value per thread and constants (else the wtw table)
+#endif
 #ifndef SBX_Q2_THREAD_BUDGET
 #define SBX_Q2_THREAD_BUDGET 768        // 3 CTAs of 256 threads at 80 registers: measured 63.7 vs 58.1 M frames/s (cfg1) against 2 CTAs at 116
 #endif
@@ -92,6 +95,13 @@ template <int LOG2N_, int CH_, bool REAL_ = false> struct Q2Geom {
 // physical slot of element (base + off): `off` a compile-time multiple of 16 whose bits are clear in base, bx = qsw(base)
 #define SBX_QAT(G, bx, off) (((bx) ^ G::qkey(off)) + (off))
 
+// W_32^k = exp(-2 pi i k / 32), k = 0..15, as compile-time constants
+__host__ __device__ constexpr float2 w32_pow_c(int k)
+{
+    return k < 8 ? float2{w32_cos(k), -w32_sin(k)} : float2{-w32_sin(k - 8), -w32_cos(k - 8)};      // k >= 8: times -i
+}
+__device__ __forceinline__ float2 w32_pow(int k) { return make_float2(w32_pow_c(k).x, w32_pow_c(k).y); }
+
 // ---- pass 0: PCM -> window (A) / window * W_M^n (B) -> radix butterfly -> twiddle -> shared memory ----------------
 // SHIFT > 0 (mono pairs): hop == SHIFT * S, frame B's input r is frame A's input r + SHIFT (R + SHIFT loads, not 2 R)
 template <class G, int SHIFT>
@@ -100,7 +110,12 @@ __device__ __forceinline__ void q2_first_inputs(cpk (&v)[1 << G::log2r(0)], cons
 {
     constexpr int R = 1 << G::log2r(0), S = 1 << G::log2stride(0);
     const float *win_lo = a.window + lo;
+#if SBX_Q2_WTW_COMPUTE
+    const float2 wl = ldg_tab(a.wq + lo);                        // W_M^lo
+#else
+    const float2 wtw_lo_unused = make_float2(0.0f, 0.0f); (void)wtw_lo_unused;
     const float2 *wtw_lo = a.wtw + lo;                           // window[n] * W_M^n: the q0 = 1 factor
+#endif
     float xs[SHIFT > 0 ? R + SHIFT : 1];
     if constexpr (SHIFT > 0) {
 #pragma unroll
@@ -119,6 +134,21 @@ __device__ __forceinline__ void q2_first_inputs(cpk (&v)[1 << G::log2r(0)], cons
             s.x = ldg_pcm(pa_lo + r * S);
             s.y = second_valid ? ldg_pcm(pb_lo + r * S) : 0.0f;
         }
+#if SBX_Q2_WTW_COMPUTE
+        // lane A = the windowed sample, lane B = A * W_M^n with W_M^n = W_M^lo * W_(2R)^r: one table value per thread
+        // (wl) times compile-time constants instead of a 32-48 KB window * W table streamed through L1 by every CTA
+        float2 A;
+        if constexpr (G::REAL) {
+            const float2 wn = ldg_stream(reinterpret_cast<const float2 *>(a.window) + lo + r * S);
+            A = make_float2(s.x * wn.x, s.y * wn.y);             // each sample with its own window value
+        } else {
+            const float wn = ldg_stream(win_lo + r * S);         // fft.rs:57-63 (complex * f32)
+            A = make_float2(s.x * wn, s.y * wn);
+        }
+        const float2 wr = r == 0 ? wl : cmul(wl, w32_pow(r * (16 / R)));
+        v[r].re = pk_make(A.x, A.x * wr.x - A.y * wr.y);
+        v[r].im = pk_make(A.y, A.x * wr.y + A.y * wr.x);
+#else
         if constexpr (G::REAL) {
             // s = (x[2n], x[2n+1]); A: each sample with its own window value; B: times W_(M)^n as well (wtw4, sbx_tables.h)
             const float2 wn = ldg_stream(reinterpret_cast<const float2 *>(a.window) + lo + r * S);
@@ -131,6 +161,7 @@ __device__ __forceinline__ void q2_first_inputs(cpk (&v)[1 << G::log2r(0)], cons
             v[r].re = pk_make(s.x * wn, s.x * wc.x - s.y * wc.y);
             v[r].im = pk_make(s.y * wn, s.x * wc.y + s.y * wc.x);
         }
+#endif
     }
 }
 

@@ -333,6 +333,7 @@ long long emu_batch(const sbx_config *cfg, const float *pcm, unsigned long long 
     a.window = t.window.data();
     a.wtw = reinterpret_cast<const float2 *>(t.wtw.data());
     a.twp = reinterpret_cast<const float2 *>(t.twp.data());
+    a.wq = reinterpret_cast<const float2 *>(t.wq.data());
     a.rowmap = t.rowmap.data();
     a.rowinfo = t.rowinfo.data();
     a.chunks = t.chunks.data();
@@ -353,6 +354,7 @@ long long emu_batch(const sbx_config *cfg, const float *pcm, unsigned long long 
     if (ch == 1 && use_real && (cfg->hop & 1u) == 0) {
         sbx::KernelArgs r = a;
         r.twp = reinterpret_cast<const float2 *>(t.twp_real.data());
+        r.wq = reinterpret_cast<const float2 *>(t.wq_real.data());
         r.wtw4 = reinterpret_cast<const float4 *>(t.wtw4.data());
         r.rtw = reinterpret_cast<const float2 *>(t.rtw.data());
         r.hop = cfg->hop / 2;
