@@ -32,6 +32,7 @@ extern "C" {
 
 typedef struct sbx_plan sbx_plan;   /* opaque; owns device tables, scratch and a CUDA stream */
 typedef struct sbx_live sbx_live;   /* opaque; pinned ring + CUDA graph for one live stream */
+typedef struct sbx_multi sbx_multi; /* opaque; one plan per device of one box, for sharded host-pointer batches */
 typedef int32_t sbx_status;
 
 enum {
@@ -265,9 +266,48 @@ SBX_API uint32_t   sbx_live_buffered(const sbx_live *live);
 SBX_API sbx_status sbx_live_measure(sbx_live *live, const float *samples, uint32_t n_samples, uint32_t channels,
                                     uint32_t iters, float *latencies_us);
 
+/* ---- several devices: one HOST recording sharded over the GPUs of one box --------------------- */
+/* The reference transforms one stream on one thread (src/fourier/audio_transform.rs:34-42); frame f depends only on
+ * samples [f*hop, f*hop+N) (ibid. :37-41, src/fourier/fft.rs:48-50), so an offline recording shards without any
+ * exchange between devices: by time block -- device g of G transforms frames [F*g/G, F*(g+1)/G) and therefore reads
+ * its own samples plus a trailing halo of N - hop samples it shares with its neighbour -- or, for planar
+ * multi-channel input, by whole channels.  An sbx_multi owns one plan per device (identical tables) and drives each
+ * device from its own host thread with the chunk pipeline of sbx_process_batch; there is no collective and no
+ * device-to-device traffic.  Block boundaries of mono plans are rounded down to even frame numbers (frames 2c, 2c+1
+ * share one transform, see sbx_process_batch_device), so the sharded result equals the one-device result byte for
+ * byte.  An sbx_multi is not thread-safe (one caller at a time). */
+/* devices: n_devices distinct CUDA ordinals, or NULL for 0 .. n_devices-1.  cfg->device is ignored. */
+SBX_API sbx_status sbx_multi_create(const sbx_config *cfg, const int32_t *devices, uint32_t n_devices, sbx_multi **out_multi);
+SBX_API void       sbx_multi_destroy(sbx_multi *multi);
+/* Message of the last failing sbx_multi_* call (multi may be NULL: a failed sbx_multi_create on this thread). */
+SBX_API const char *sbx_multi_last_error(const sbx_multi *multi);
+SBX_API uint32_t   sbx_multi_device_count(const sbx_multi *multi);
+/* The plan of device `index` (owned by the sbx_multi; for the accessors, sbx_kernel_path, the device entry points). */
+SBX_API sbx_plan  *sbx_multi_plan(sbx_multi *multi, uint32_t index);
+/* The time block of device `index` for a recording of n_samples: frames [frame_lo, frame_hi), samples
+ * [sample_lo, sample_hi) including the halo.  Any output pointer may be NULL. */
+SBX_API sbx_status sbx_multi_time_block(const sbx_multi *multi, uint64_t n_samples, uint32_t index, uint64_t *frame_lo,
+                                        uint64_t *frame_hi, uint64_t *sample_lo, uint64_t *sample_hi);
+/* sbx_process_batch over all devices, time-block sharded.  pcm / rgba: HOST memory (pinned -- sbx_host_alloc,
+ * sbx_host_register -- for copies that overlap; pageable works, slowly). */
+SBX_API sbx_status sbx_multi_process_batch(sbx_multi *multi, const float *pcm, uint64_t n_samples, uint8_t *rgba,
+                                           uint64_t rgba_capacity_frames, uint64_t *frames_out);
+/* n_sequences equally long recordings (BASELINE cfg4: planar channels), whole sequences per device; arguments as
+ * sbx_process_batch_device_planar but HOST pointers: sequence s starts s * sequence_stride_samples samples into pcm,
+ * its columns land at rgba + s * frames * H * 4. */
+SBX_API sbx_status sbx_multi_process_batch_planar(sbx_multi *multi, const float *pcm, uint32_t n_sequences,
+                                                  uint64_t sequence_stride_samples, uint64_t n_samples_per_sequence,
+                                                  uint8_t *rgba, uint64_t rgba_capacity_frames,
+                                                  uint64_t *frames_per_sequence_out);
+/* Kernel launches of all its plans (see sbx_launch_count). */
+SBX_API uint64_t   sbx_multi_launch_count(const sbx_multi *multi);
+
 /* ---- pinned host memory helpers (for callers without a CUDA binding) --------------------- */
 SBX_API void *sbx_host_alloc(size_t bytes);
 SBX_API void  sbx_host_free(void *p);
+/* Page-locks / releases memory the caller already owns (a Rust Vec<f32>, an mmap), usable from every device. */
+SBX_API sbx_status sbx_host_register(void *ptr, size_t bytes);
+SBX_API sbx_status sbx_host_unregister(void *ptr);
 
 /* Library/ABI version and the SM architecture the kernels were compiled for ("sm_100a"). */
 SBX_API uint32_t    sbx_abi_version(void);

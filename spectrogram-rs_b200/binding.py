@@ -64,6 +64,17 @@ SYMBOLS = {
     "sbx_live_pop_magnitudes": (C.c_int32, [_vp, _vp]),
     "sbx_live_buffered": (C.c_uint32, [_vp]),
     "sbx_live_measure": (C.c_int32, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp]),
+    "sbx_multi_create": (C.c_int32, [C.POINTER(SbxConfig), C.POINTER(C.c_int32), C.c_uint32, C.POINTER(_vp)]),
+    "sbx_multi_destroy": (None, [_vp]),
+    "sbx_multi_last_error": (C.c_char_p, [_vp]),
+    "sbx_multi_device_count": (C.c_uint32, [_vp]),
+    "sbx_multi_plan": (_vp, [_vp, C.c_uint32]),
+    "sbx_multi_time_block": (C.c_int32, [_vp, C.c_uint64, C.c_uint32, _u64p, _u64p, _u64p, _u64p]),
+    "sbx_multi_process_batch": (C.c_int32, [_vp, _vp, C.c_uint64, _vp, C.c_uint64, _u64p]),
+    "sbx_multi_process_batch_planar": (C.c_int32, [_vp, _vp, C.c_uint32, C.c_uint64, C.c_uint64, _vp, C.c_uint64, _u64p]),
+    "sbx_multi_launch_count": (C.c_uint64, [_vp]),
+    "sbx_host_register": (C.c_int32, [_vp, C.c_size_t]),
+    "sbx_host_unregister": (C.c_int32, [_vp]),
     "sbx_host_alloc": (_vp, [C.c_size_t]),
     "sbx_host_free": (None, [_vp]),
     "sbx_abi_version": (C.c_uint32, []),

@@ -19,6 +19,7 @@ LIB = os.path.join(HERE, "libsbx_b200.so")
 UNITS = [
     ("plan", "sbx_plan.cu", []),
     ("live", "sbx_live.cu", []),
+    ("multi", "sbx_multi.cu", []),
     ("fused0", "sbx_dispatch_fused.cu", ["-DSBX_FUSED_PART=0"]),
     ("fused1", "sbx_dispatch_fused.cu", ["-DSBX_FUSED_PART=1"]),
     ("real", "sbx_dispatch_real.cu", []),

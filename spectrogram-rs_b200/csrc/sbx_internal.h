@@ -72,6 +72,10 @@ struct sbx_plan {
     float *d_mags1 = nullptr;           // K x 2
     uint8_t *d_col = nullptr;           // H x 4
 
+    float *d_cz_in = nullptr;           // sbx_colorize_magnitudes staging (grown on demand, kept)
+    uint8_t *d_cz_out = nullptr;
+    size_t cz_in_bytes = 0, cz_out_bytes = 0;
+
     float *d_f16_scratch = nullptr;     // f32 rows of one chunk, packed to binary16 by sbx_magnitudes_batch_device_f16
 
     // batch pipeline slots (host-pointer batch entry point)
@@ -101,6 +105,9 @@ namespace sbx {
 // equally long PCM sequences (planar channels) handled by one call: sequence s starts s * stride_floats into the PCM
 // buffer and writes frames [s * n_frames, (s + 1) * n_frames) of the output
 struct Sequences { uint32_t count = 1; unsigned long long stride_floats = 0; };
+// a run of `frames` frames of one recording in HOST memory and where its columns go (sbx_process_batch, sbx_multi_*)
+struct HostSegment { const float *pcm; uint64_t frames; uint8_t *rgba; };
+sbx_status batch_host_segments(sbx_plan *p, const HostSegment *segs, size_t n_segs);
 // launches the plan's kernel family for `channels`-layout PCM on `stream`
 sbx_status launch_fused(sbx_plan *p, int channels, const float *d_pcm, uint64_t n_frames, uint8_t *d_rgba,
                         float *d_mags, cudaStream_t stream, Sequences seqs = {});

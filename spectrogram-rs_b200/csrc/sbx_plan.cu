@@ -342,7 +342,7 @@ SBX_API void sbx_plan_destroy(sbx_plan *p)
     }
     cudaFree(p->d_window); cudaFree(p->d_wtw); cudaFree(p->d_twp); cudaFree(p->d_wq); cudaFree(p->d_wq_real); cudaFree(p->d_rowmap); cudaFree(p->d_rowinfo); cudaFree(p->d_chunks);
     cudaFree(p->d_samp); cudaFree(p->d_f16_scratch); cudaFree(p->d_twm); cudaFree(p->d_twg); cudaFree(p->d_pos_tab); cudaFree(p->d_twp_block); cudaFree(p->d_zbuf); cudaFree(p->d_magbuf);
-    cudaFree(p->d_thr); cudaFree(p->d_lut); cudaFree(p->d_ctab); cudaFree(p->d_twp_real); cudaFree(p->d_wtw4); cudaFree(p->d_rtw); cudaFree(p->d_frame); cudaFree(p->d_mags1); cudaFree(p->d_col);
+    cudaFree(p->d_thr); cudaFree(p->d_lut); cudaFree(p->d_ctab); cudaFree(p->d_twp_real); cudaFree(p->d_wtw4); cudaFree(p->d_rtw); cudaFree(p->d_cz_in); cudaFree(p->d_cz_out); cudaFree(p->d_frame); cudaFree(p->d_mags1); cudaFree(p->d_col);
     if (p->h_frame) cudaFreeHost(p->h_frame);
     if (p->h_col) cudaFreeHost(p->h_col);
     if (p->large_scratch_free) cudaEventDestroy(p->large_scratch_free);
@@ -567,18 +567,28 @@ SBX_API sbx_status sbx_colorize_magnitudes(sbx_plan *p, const float *mags_lr, ui
     SBX_CUDA(p, cudaSetDevice(p->cfg.device));
     cudaStream_t s = p->stream;
     const size_t in_bytes = (size_t)n_frames * p->k_out * 2 * sizeof(float), out_bytes = (size_t)n_frames * p->rows * 4;
-    float *d_in = nullptr;
-    uint8_t *d_out = nullptr;
-    cudaError_t e = cudaMalloc(&d_in, in_bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&d_out, out_bytes);
-    if (e != cudaSuccess) { cudaFree(d_in); return cuda_fail(p, e, "cudaMalloc(colourise buffers)"); }
+    // plan-owned staging, grown on demand and kept: no cudaMalloc / cudaFree (a device-wide synchronisation) per call
+    if (in_bytes > p->cz_in_bytes) {
+        cudaFree(p->d_cz_in);
+        p->d_cz_in = nullptr;
+        p->cz_in_bytes = 0;
+        const cudaError_t e = cudaMalloc(&p->d_cz_in, in_bytes);
+        if (e != cudaSuccess) return cuda_fail(p, e, "cudaMalloc(colourise input)");
+        p->cz_in_bytes = in_bytes;
+    }
+    if (out_bytes > p->cz_out_bytes) {
+        cudaFree(p->d_cz_out);
+        p->d_cz_out = nullptr;
+        p->cz_out_bytes = 0;
+        const cudaError_t e = cudaMalloc(&p->d_cz_out, out_bytes);
+        if (e != cudaSuccess) return cuda_fail(p, e, "cudaMalloc(colourise output)");
+        p->cz_out_bytes = out_bytes;
+    }
     sbx_status st = SBX_OK;
-    e = cudaMemcpyAsync(d_in, mags_lr, in_bytes, cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess) st = sbx::launch_colourise(p, d_in, n_frames, d_out, s);
-    if (e == cudaSuccess && st == SBX_OK) e = cudaMemcpyAsync(rgba, d_out, out_bytes, cudaMemcpyDeviceToHost, s);
-    cudaError_t e2 = cudaStreamSynchronize(s);
-    cudaFree(d_in);
-    cudaFree(d_out);
+    cudaError_t e = cudaMemcpyAsync(p->d_cz_in, mags_lr, in_bytes, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) st = sbx::launch_colourise(p, p->d_cz_in, n_frames, p->d_cz_out, s);
+    if (e == cudaSuccess && st == SBX_OK) e = cudaMemcpyAsync(rgba, p->d_cz_out, out_bytes, cudaMemcpyDeviceToHost, s);
+    const cudaError_t e2 = cudaStreamSynchronize(s);
     if (st != SBX_OK) return st;
     if (e != cudaSuccess) return cuda_fail(p, e, "colourise copy");
     if (e2 != cudaSuccess) return cuda_fail(p, e2, "colourise sync");
@@ -720,17 +730,15 @@ SBX_API sbx_status sbx_blit_columns_device(sbx_plan *p, const uint8_t *d_columns
 }
 
 // ---- batch, host buffers: chunked, H2D / kernel / D2H overlapped over kSlots streams -------------
-SBX_API sbx_status sbx_process_batch(sbx_plan *p, const float *pcm, uint64_t n_samples, uint8_t *rgba,
-                                     uint64_t rgba_capacity_frames, uint64_t *frames_out)
-{
-    if (frames_out) *frames_out = 0;
-    if (!p) return SBX_ERR_INVALID_ARGUMENT;
-    const uint64_t frames = sbx_num_frames(p, n_samples);
-    if (frames == 0) return SBX_OK;
-    if (!pcm || !rgba) return fail(p, SBX_ERR_INVALID_ARGUMENT, "NULL host buffer");
-    if (frames > rgba_capacity_frames) return fail(p, SBX_ERR_BUFFER_TOO_SMALL, "rgba capacity is smaller than the frame count");
-    SBX_CUDA(p, cudaSetDevice(p->cfg.device));
+}  // extern "C"
 
+namespace sbx {
+// The chunk pipeline behind sbx_process_batch and the sbx_multi_* calls: every segment is a run of frames of one
+// recording (HOST pointers); the chunks of all segments go round-robin over the plan's slot streams and only the
+// end of the call drains them, so the copies of one segment overlap the kernels of the next.
+sbx_status batch_host_segments(sbx_plan *p, const HostSegment *segs, size_t n_segs)
+{
+    SBX_CUDA(p, cudaSetDevice(p->cfg.device));
     if (p->chunk_frames == 0) {
         // at most ~32 MiB of RGBA (SBX_BATCH_CHUNK_MB) and ~64 MiB of PCM per chunk, even frame count (mono pairs),
         // at least 2 frames.  Measured end to end on a B200 (cfg1, 131072 frames per call): 8 / 32 / 128 MiB chunks
@@ -764,40 +772,62 @@ SBX_API sbx_status sbx_process_batch(sbx_plan *p, const float *pcm, uint64_t n_s
     const uint64_t cf = p->chunk_frames;
     uint64_t chunk = 0;
     sbx_status st = SBX_OK;
-    for (uint64_t f0 = 0; f0 < frames && st == SBX_OK; f0 += cf, ++chunk) {
-        sbx_plan::Slot &s = p->slots[chunk % sbx_plan::kSlots];
-        const uint64_t nf = frames - f0 < cf ? frames - f0 : cf;
-        const size_t samples = (size_t)(nf - 1) * p->hop + p->n;
-        cudaError_t e = cudaMemcpyAsync(s.d_pcm, pcm + (size_t)f0 * p->hop * p->channels,
-                                        samples * p->channels * sizeof(float), cudaMemcpyHostToDevice, s.stream);
-        if (e != cudaSuccess) { st = cuda_fail(p, e, "batch H2D copy"); break; }
-        // The multi-kernel path works in ONE plan-wide scratch (d_zbuf, d_magbuf): chunk k+1's kernels on the next
-        // slot stream must not start before chunk k's have finished with it.  Only the kernels are chained -- the
-        // H2D copy above and the D2H copy below still overlap with the neighbouring chunks' kernels.
-        if (p->large) {
-            if (!p->large_scratch_free) {
-                e = cudaEventCreateWithFlags(&p->large_scratch_free, cudaEventDisableTiming);
-                if (e != cudaSuccess) { st = cuda_fail(p, e, "cudaEventCreate(large scratch)"); break; }
-            } else {
-                e = cudaStreamWaitEvent(s.stream, p->large_scratch_free, 0);
-                if (e != cudaSuccess) { st = cuda_fail(p, e, "cudaStreamWaitEvent(large scratch)"); break; }
+    for (size_t g = 0; g < n_segs && st == SBX_OK; ++g) {
+        const float *pcm = segs[g].pcm;
+        uint8_t *rgba = segs[g].rgba;
+        const uint64_t frames = segs[g].frames;
+        for (uint64_t f0 = 0; f0 < frames && st == SBX_OK; f0 += cf, ++chunk) {
+            sbx_plan::Slot &s = p->slots[chunk % sbx_plan::kSlots];
+            const uint64_t nf = frames - f0 < cf ? frames - f0 : cf;
+            const size_t samples = (size_t)(nf - 1) * p->hop + p->n;
+            cudaError_t e = cudaMemcpyAsync(s.d_pcm, pcm + (size_t)f0 * p->hop * p->channels,
+                                            samples * p->channels * sizeof(float), cudaMemcpyHostToDevice, s.stream);
+            if (e != cudaSuccess) { st = cuda_fail(p, e, "batch H2D copy"); break; }
+            // The multi-kernel path works in ONE plan-wide scratch (d_zbuf, d_magbuf): chunk k+1's kernels on the next
+            // slot stream must not start before chunk k's have finished with it.  Only the kernels are chained -- the
+            // H2D copy above and the D2H copy below still overlap with the neighbouring chunks' kernels.
+            if (p->large) {
+                if (!p->large_scratch_free) {
+                    e = cudaEventCreateWithFlags(&p->large_scratch_free, cudaEventDisableTiming);
+                    if (e != cudaSuccess) { st = cuda_fail(p, e, "cudaEventCreate(large scratch)"); break; }
+                } else {
+                    e = cudaStreamWaitEvent(s.stream, p->large_scratch_free, 0);
+                    if (e != cudaSuccess) { st = cuda_fail(p, e, "cudaStreamWaitEvent(large scratch)"); break; }
+                }
             }
+            st = sbx::launch_fused(p, (int)p->channels, s.d_pcm, nf, s.d_rgba, nullptr, s.stream);
+            if (st != SBX_OK) break;
+            if (p->large) {
+                e = cudaEventRecord(p->large_scratch_free, s.stream);
+                if (e != cudaSuccess) { st = cuda_fail(p, e, "cudaEventRecord(large scratch)"); break; }
+            }
+            e = cudaMemcpyAsync(rgba + (size_t)f0 * p->rows * 4, s.d_rgba, (size_t)nf * p->rows * 4,
+                                cudaMemcpyDeviceToHost, s.stream);
+            if (e != cudaSuccess) st = cuda_fail(p, e, "batch D2H copy");
         }
-        st = sbx::launch_fused(p, (int)p->channels, s.d_pcm, nf, s.d_rgba, nullptr, s.stream);
-        if (st != SBX_OK) break;
-        if (p->large) {
-            e = cudaEventRecord(p->large_scratch_free, s.stream);
-            if (e != cudaSuccess) { st = cuda_fail(p, e, "cudaEventRecord(large scratch)"); break; }
-        }
-        e = cudaMemcpyAsync(rgba + (size_t)f0 * p->rows * 4, s.d_rgba, (size_t)nf * p->rows * 4,
-                            cudaMemcpyDeviceToHost, s.stream);
-        if (e != cudaSuccess) st = cuda_fail(p, e, "batch D2H copy");
     }
     // always drain: no copy into the caller's buffers may still be in flight when this returns, error or not
     for (auto &s : p->slots) {
         const cudaError_t e = cudaStreamSynchronize(s.stream);
         if (e != cudaSuccess && st == SBX_OK) st = cuda_fail(p, e, "batch stream synchronize");
     }
+    return st;
+}
+}  // namespace sbx
+
+extern "C" {
+
+SBX_API sbx_status sbx_process_batch(sbx_plan *p, const float *pcm, uint64_t n_samples, uint8_t *rgba,
+                                     uint64_t rgba_capacity_frames, uint64_t *frames_out)
+{
+    if (frames_out) *frames_out = 0;
+    if (!p) return SBX_ERR_INVALID_ARGUMENT;
+    const uint64_t frames = sbx_num_frames(p, n_samples);
+    if (frames == 0) return SBX_OK;
+    if (!pcm || !rgba) return fail(p, SBX_ERR_INVALID_ARGUMENT, "NULL host buffer");
+    if (frames > rgba_capacity_frames) return fail(p, SBX_ERR_BUFFER_TOO_SMALL, "rgba capacity is smaller than the frame count");
+    const sbx::HostSegment seg{pcm, frames, rgba};
+    const sbx_status st = sbx::batch_host_segments(p, &seg, 1);
     if (st != SBX_OK) return st;
     if (frames_out) *frames_out = frames;
     return SBX_OK;

@@ -109,6 +109,7 @@ struct HostTables {
     std::vector<uint32_t> rowinfo;      // [H] n | first scratch slot << 16 (what the kernels read)
     std::vector<RowChunk> chunks;       // rows grouped so that a chunk's samples fit the kernel's scratch area
     std::vector<uint32_t> samp;         // per (row, sample): {floor(x), weight bits}, see KernelArgs::samp
+    uint32_t bank_group = 16;           // lanes / rows served by one shared-memory request (see the sample table in build)
     bool taps_clamped = false;          // some cubic tap falls outside [0, K-1]
     std::vector<float> thr;             // [2][256] pairs (ts[i], ts[i+1]), see step_index
     std::vector<float> thr_raw;         // [2][256] the bare thresholds (introspection)
@@ -280,41 +281,78 @@ inline void build(const sbx_config &cfg, HostTables &t)
         total_samples += n;
         t.rowmap[py] = rm;
     }
-    // Row chunks and scratch slots.  A chunk is a run of rows whose interpolated samples fit the kernel's
-    // scratch area; row py's samples occupy slots aux .. aux+n-1 of its chunk, and rows with an even n >= 4 get
-    // one slot of padding so that the per-row stride is odd: the threads of colour_rows (one per row) then read
-    // different shared-memory banks at every step of their sequential sums (n = 2 is left at a 2-way conflict
-    // so that cfg1's 3893 samples still fit one chunk of M/2 = 4096 slots).
+    // Row chunks and scratch slots.  A chunk is a run of rows whose interpolated samples fit the kernel's scratch
+    // area; row py's samples occupy slots aux .. aux+n-1 of its chunk.  The threads of colour_rows (one per row) read
+    // slot aux + s at step s of their sequential sums, so the rows a shared-memory request serves together -- an
+    // aligned group of BANK_GROUP rows: 16 for the 8-byte (L,R) elements of the pair / stereo kernels (a half-warp per
+    // wavefront), 32 for the 4-byte elements of the real-sequence geometry -- must start in different residues modulo
+    // BANK_GROUP.  Three slot policies, the first that needs the fewest chunks wins:
+    //   GREEDY  a row starts at the next slot whose residue no earlier row of its group has taken (no padding at
+    //           all where n is odd or 1; one slot per 16/n rows where it is even);
+    //   ODD     rows with an even n >= 4 get one slot of padding (odd per-row stride; the round-1 rule);
+    //   DENSE   no padding.
     const uint32_t cap = t.large ? (uint32_t)LARGE_BLOCK : t.m / 2;
-    t.chunks.clear();
-    RowChunk ck = {0, 0, 0, 0};
-    uint32_t slot = 0;
-    for (uint32_t py = 0; py < t.rows; ++py) {
-        RowMap &rm = t.rowmap[py];
-        const uint32_t need = rm.n + (((rm.n & 1u) == 0 && rm.n >= 4) ? 1u : 0u);
-        if (cap > (1u << 15)) t.ok = false;                               // slots travel in 15 bits
-        if (need > cap) {
-            // a row too long for the scratch area (large path only: few rows over a very long transform) gets a
-            // chunk of its own, recognisable by samp_end - samp_begin > cap; the kernel resamples it in parts
-            if (!t.large) t.ok = false;
-            if (ck.row_end > ck.row_begin) t.chunks.push_back(ck);
-            rm.aux = 0;
-            t.chunks.push_back(RowChunk{py, py + 1, samp_first[py], samp_first[py] + rm.n});
-            ck = RowChunk{py + 1, py + 1, samp_first[py] + rm.n, samp_first[py] + rm.n};
-            slot = 0;
-            continue;
+    const bool real_likely = t.real_ok && !t.large && RadixPlan(log2n - 1).npass < RadixPlan(log2n).npass;
+    const uint32_t bank_group = real_likely ? 32u : 16u;
+    t.bank_group = bank_group;
+    if (cap >= 0x7fffu) t.ok = false;                                     // slots travel in 15 bits, 0x7fff = "no store"
+    enum SlotPolicy { GREEDY = 0, ODD = 1, DENSE = 2 };
+    auto assign_slots = [&](SlotPolicy policy, std::vector<RowChunk> &chunks, std::vector<uint32_t> &aux, bool &fits) {
+        chunks.clear();
+        aux.assign(t.rows, 0u);
+        fits = true;
+        RowChunk ck = {0, 0, 0, 0};
+        uint32_t slot = 0, used = 0;                                      // used: residues taken in the current row group
+        for (uint32_t py = 0; py < t.rows; ++py) {
+            const uint32_t n = t.rowmap[py].n;
+            if (n > cap) {
+                // a row too long for the scratch area (large path only: few rows over a very long transform) gets a
+                // chunk of its own, recognisable by samp_end - samp_begin > cap; the kernel resamples it in parts
+                if (!t.large) fits = false;
+                if (ck.row_end > ck.row_begin) chunks.push_back(ck);
+                chunks.push_back(RowChunk{py, py + 1, samp_first[py], samp_first[py] + n});
+                ck = RowChunk{py + 1, py + 1, samp_first[py] + n, samp_first[py] + n};
+                slot = 0;
+                continue;
+            }
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                if (ck.row_end == ck.row_begin) { ck.row_begin = py; ck.samp_begin = samp_first[py]; slot = 0; }
+                if ((py - ck.row_begin) % bank_group == 0) used = 0;
+                uint32_t first = slot, need = n;
+                if (policy == GREEDY)
+                    while (used & (1u << (first % bank_group))) ++first;
+                else if (policy == ODD && (n & 1u) == 0 && n >= 4)
+                    need = n + 1;
+                if (first + need > cap && ck.row_end > ck.row_begin) {    // close the chunk and place the row in a new one
+                    chunks.push_back(ck);
+                    ck = RowChunk{py, py, samp_first[py], samp_first[py]};
+                    continue;
+                }
+                aux[py] = first;
+                used |= 1u << (first % bank_group);
+                slot = first + need;
+                ck.row_end = py + 1;
+                ck.samp_end = samp_first[py] + n;
+                break;
+            }
         }
-        if (slot + need > cap && ck.row_end > ck.row_begin) {
-            t.chunks.push_back(ck);
-            ck.row_begin = py; ck.samp_begin = samp_first[py];
-            slot = 0;
+        if (ck.row_end > ck.row_begin) chunks.push_back(ck);
+    };
+    {
+        std::vector<RowChunk> best_chunks;
+        std::vector<uint32_t> best_aux;
+        bool have = false;
+        for (SlotPolicy policy : {GREEDY, ODD, DENSE}) {
+            std::vector<RowChunk> chunks;
+            std::vector<uint32_t> aux;
+            bool fits = true;
+            assign_slots(policy, chunks, aux, fits);
+            if (!fits) t.ok = false;
+            if (!have || chunks.size() < best_chunks.size()) { best_chunks.swap(chunks); best_aux.swap(aux); have = true; }
         }
-        rm.aux = slot;
-        slot += need;
-        ck.row_end = py + 1;
-        ck.samp_end = samp_first[py] + rm.n;
+        t.chunks.swap(best_chunks);
+        for (uint32_t py = 0; py < t.rows; ++py) t.rowmap[py].aux = best_aux[py];
     }
-    if (ck.row_end > ck.row_begin) t.chunks.push_back(ck);
     for (const RowChunk &c : t.chunks)
         if (c.samp_end - c.samp_begin > cap) t.real_ok = false;            // rows resampled in parts: large path only
     // Default choice between the frame-pair kernel and the real-sequence geometry for mono batches.  Measured on a
@@ -327,28 +365,50 @@ inline void build(const sbx_config &cfg, HostTables &t)
     for (uint32_t py = 0; py < t.rows; ++py) t.rowinfo[py] = t.rowmap[py].n | (t.rowmap[py].aux << 16);
 
     // per-sample table: x = index_of(lin_space(f0..f1, n)[s])  (ifs.rs:67-69, :24-31), stored as
-    //   word 0: floor(x) in bits 0..16, the sample's scratch slot in bits 17..31
+    //   word 0: floor(x) in bits 0..16, the sample's scratch slot in bits 17..31 (0x7fff: filler entry, nothing stored)
     //   word 1: the interpolation weight: mu = x - floor(x) (cubic, ifs.rs:90) or
     //           (1 - cos((x - low) * PI)) / 2 (cosine, ifs.rs:82-83; f32, host libm)
-    t.samp.resize(total_samples * 2);
+    // One lane handles one entry, and the lanes of one shared-memory request -- an aligned group of BANK_GROUP entries
+    // of a chunk -- read the taps at floor(x) + {-1, 0, 1, 2} and store to their slots: both are conflict-free when the
+    // group's bins and slots each span fewer than BANK_GROUP positions.  Rows average samples a little MORE than one
+    // bin apart, so a full group would span up to 1.5 BANK_GROUP bins; the table therefore closes a group early and
+    // fills it with entries that repeat the previous bin (a broadcast) and store nothing.  (Fused and mixed-radix
+    // paths; the four-kernel path reads its taps through L1 and keeps the dense table.)
+    t.samp.clear();
+    t.samp.reserve((size_t)total_samples * 2 + 64);
     t.taps_clamped = false;
     if (t.k_out >= (1u << 17)) t.ok = false;
     const float pi = 3.14159265358979323846f;
-    for (uint32_t py = 0; py < t.rows; ++py) {
-        const RowMap &rm = t.rowmap[py];
-        for (uint32_t s = 0; s < rm.n; ++s) {
-            const float fq = rm.f0 + (float)s * rm.step;
-            const float x = index_of(fq, t.period, t.k_out);
-            const float fl = std::floor(x);
-            const float off = x - fl;
-            const float w = cfg.interp == SBX_INTERP_COSINE ? (1.0f - cosf(off * pi)) / 2.0f : off;
-            const uint32_t x1 = (uint32_t)fl;
-            if (x1 < 1 || x1 + 2 > t.k_out - 1) t.taps_clamped = true;
-            uint32_t wbits;
-            std::memcpy(&wbits, &w, 4);
-            t.samp[2 * (size_t)(samp_first[py] + s)] = x1 | (((rm.aux + s) & 0x7fffu) << 17);   // big rows ignore the slot
-            t.samp[2 * (size_t)(samp_first[py] + s) + 1] = wbits;
+    const bool fill_groups = !t.large;
+    for (RowChunk &ck : t.chunks) {
+        const uint32_t begin = (uint32_t)(t.samp.size() / 2);
+        uint32_t group_x = 0, group_slot = 0, prev_x = 0;
+        for (uint32_t py = ck.row_begin; py < ck.row_end; ++py) {
+            const RowMap &rm = t.rowmap[py];
+            for (uint32_t s = 0; s < rm.n; ++s) {
+                const float fq = rm.f0 + (float)s * rm.step;
+                const float x = index_of(fq, t.period, t.k_out);
+                const float fl = std::floor(x);
+                const float off = x - fl;
+                const float w = cfg.interp == SBX_INTERP_COSINE ? (1.0f - cosf(off * pi)) / 2.0f : off;
+                const uint32_t x1 = (uint32_t)fl;
+                if (x1 < 1 || x1 + 2 > t.k_out - 1) t.taps_clamped = true;
+                uint32_t wbits;
+                std::memcpy(&wbits, &w, 4);
+                const uint32_t slot = (rm.aux + s) & 0x7fffu;                           // big rows ignore the slot
+                uint32_t pos = (uint32_t)(t.samp.size() / 2) - begin;
+                if (fill_groups && pos % bank_group != 0 &&
+                    (x1 < group_x || x1 - group_x >= bank_group || slot < group_slot || slot - group_slot >= bank_group)) {
+                    for (; pos % bank_group != 0; ++pos) { t.samp.push_back(prev_x | (0x7fffu << 17)); t.samp.push_back(0u); }
+                }
+                if (pos % bank_group == 0) { group_x = x1; group_slot = slot; }
+                t.samp.push_back(x1 | (slot << 17));
+                t.samp.push_back(wbits);
+                prev_x = x1;
+            }
         }
+        ck.samp_begin = begin;
+        ck.samp_end = (uint32_t)(t.samp.size() / 2);
     }
 
     t.thr_raw.resize(512);

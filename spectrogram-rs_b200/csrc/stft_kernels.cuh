@@ -110,6 +110,9 @@ constexpr int TW_PLANES = 4;     // twiddle planes stored per pass: W^(1,2,4,8 *
 #define SBX_TW_LOADS 2           // planes actually loaded per butterfly (1: W^lo; 2: + W^4lo; 4: all); rest by products
 #endif
 constexpr uint32_t REAL_MIN_M = 8192, REAL_MAX_M = 32768;   // real transform lengths the REAL geometry is built for
+// sample-table entries whose slot field is 0x7fff (sbx_tables.h: fillers that keep a lane group's taps inside one
+// wavefront) compute a value but store nothing; lanes past the end of the table take the same form
+constexpr uint32_t SAMP_NO_STORE = 0x7fffu << 17;
 constexpr int THR_STRIDE = 512;  // floats per threshold set: 256 pairs (ts[i], ts[i+1]), ts = [-inf, thr[0..254], +inf]
 
 // ----------------------------------------------------------------------------------------------
@@ -937,12 +940,11 @@ __device__ __forceinline__ void resample_samples_impl(const T *mags, T *scratch,
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const uint32_t g = g0 + i * THREADS;
-            sp[i] = g < count ? ldg_tab(tab + g) : make_uint2(0u, 0u);
+            sp[i] = g < count ? ldg_tab(tab + g) : make_uint2(SAMP_NO_STORE, 0u);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const uint32_t g = g0 + i * THREADS;
-            if (g < count)
+            if (sp[i].x < SAMP_NO_STORE)                                       // a real entry (not a filler, not past the end)
                 scratch[sp[i].x >> 17] = interp_sample<CLAMP>(mags, a, (int)(sp[i].x & 0x1ffffu), __uint_as_float(sp[i].y), k_last);
         }
     }
@@ -1127,12 +1129,11 @@ __device__ __forceinline__ void pk_resample_samples_impl(const float2 *mags, flo
 #pragma unroll
         for (int i = 0; i < UNROLL; ++i) {
             const uint32_t g = g0 + i * THREADS;
-            sp[i] = g < count ? ldg_stream(tab + g) : make_uint2(0u, 0u);
+            sp[i] = g < count ? ldg_stream(tab + g) : make_uint2(SAMP_NO_STORE, 0u);
         }
 #pragma unroll
         for (int i = 0; i < UNROLL; ++i) {
-            const uint32_t g = g0 + i * THREADS;
-            if (g < count)
+            if (sp[i].x < SAMP_NO_STORE)                                       // a real entry (not a filler, not past the end)
                 pk_st2(scratch + (sp[i].x >> 17),
                          pk_interp_sample<CLAMP>(mags, a, (int)(sp[i].x & 0x1ffffu), __uint_as_float(sp[i].y), k_last, negzero));
         }

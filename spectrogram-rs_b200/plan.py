@@ -226,6 +226,117 @@ class Plan:
         return LiveStream(self, ring_capacity)
 
 
+class _PlanView(Plan):
+    """A plan owned by an sbx_multi: same accessors and device entry points, no ownership."""
+
+    def __init__(self, lib, handle):                          # noqa: D401 -- deliberately skips Plan.__init__
+        self._lib, self._h = lib, C.c_void_p(handle)
+        self._live = weakref.WeakSet()
+        self.n = int(lib.sbx_num_input_samples(self._h))
+        self.k = int(lib.sbx_num_output_frequencies(self._h))
+        self.m = int(lib.sbx_fft_length(self._h))
+        self.rows = int(lib.sbx_rows(self._h))
+        self.hop = int(lib.sbx_hop(self._h))
+        self.channels = int(lib.sbx_channels(self._h))
+        self.sample_rate = float(lib.sbx_sample_rate(self._h))
+
+    def close(self):
+        self._h = None
+
+
+class MultiPlan:
+    """sbx_multi: one plan per device of one box; a HOST recording is sharded by time block (N - hop halo, no
+    exchange between devices) or, for planar channels, by whole channels (SURVEY.md 8e;
+    src/fourier/audio_transform.rs:37-41)."""
+
+    def __init__(self, devices, **plan_kwargs):
+        self._lib = binding.load()
+        self._h = None
+        lut = plan_kwargs.pop("lut", "magma")
+        cfg = SbxConfig()
+        self._lib.sbx_config_default(C.byref(cfg))
+        for key, val in plan_kwargs.items():
+            if not hasattr(cfg, key):
+                raise TypeError(f"unknown plan parameter {key!r}")
+            setattr(cfg, key, val)
+        lut_arr = builtin_lut(lut) if isinstance(lut, str) else np.ascontiguousarray(lut, dtype=np.uint8)
+        C.memmove(cfg.lut_rgb, lut_arr.ctypes.data, 768)
+        devs = list(range(devices)) if isinstance(devices, int) else [int(d) for d in devices]
+        arr = (C.c_int32 * len(devs))(*devs)
+        handle = C.c_void_p()
+        st = self._lib.sbx_multi_create(C.byref(cfg), arr, len(devs), C.byref(handle))
+        if st != binding.SBX_OK:
+            raise SbxError(st, self._lib.sbx_multi_last_error(None).decode())
+        self._h = handle
+        self.devices = devs
+        self.plans = [_PlanView(self._lib, self._lib.sbx_multi_plan(handle, i)) for i in range(len(devs))]
+        self.rows, self.hop, self.n, self.channels = self.plans[0].rows, self.plans[0].hop, self.plans[0].n, self.plans[0].channels
+
+    def close(self):
+        if self._h is not None:
+            for p in self.plans:
+                p.close()
+            self._lib.sbx_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, st):
+        if st < 0:
+            raise SbxError(st, self._lib.sbx_multi_last_error(self._h).decode())
+        return st
+
+    def num_frames(self, n_samples):
+        return self.plans[0].num_frames(n_samples)
+
+    def time_block(self, n_samples, index):
+        """(frame_lo, frame_hi, sample_lo, sample_hi) of device `index` -- sharding.time_blocks(frame_align=2 if mono)."""
+        v = [C.c_uint64() for _ in range(4)]
+        self._check(self._lib.sbx_multi_time_block(self._h, n_samples, index, *[C.byref(x) for x in v]))
+        return tuple(int(x.value) for x in v)
+
+    def process_batch_ptr(self, pcm_ptr, n_samples, rgba_ptr, capacity_frames):
+        got = C.c_uint64()
+        self._check(self._lib.sbx_multi_process_batch(self._h, _ptr(pcm_ptr), n_samples, _ptr(rgba_ptr), capacity_frames, C.byref(got)))
+        return int(got.value)
+
+    def process_batch(self, pcm, out=None):
+        pcm = np.ascontiguousarray(pcm, dtype=np.float32)
+        n_samples = pcm.shape[0]
+        if out is None:
+            out = np.empty((self.num_frames(n_samples), self.rows, 4), np.uint8)
+        return out[:self.process_batch_ptr(pcm.ctypes.data, n_samples, out.ctypes.data, out.shape[0])]
+
+    def process_batch_planar_ptr(self, pcm_ptr, n_sequences, sequence_stride_samples, n_samples_per_sequence, rgba_ptr, capacity_frames):
+        got = C.c_uint64()
+        self._check(self._lib.sbx_multi_process_batch_planar(self._h, _ptr(pcm_ptr), n_sequences, sequence_stride_samples,
+                                                             n_samples_per_sequence, _ptr(rgba_ptr), capacity_frames, C.byref(got)))
+        return int(got.value)
+
+    def process_batch_planar(self, pcm):
+        """(n_sequences, n_samples[, channels]) host array -> (n_sequences, frames, H, 4) uint8."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.float32)
+        n_seq, n_samples = pcm.shape[0], pcm.shape[1]
+        frames = self.num_frames(n_samples)
+        out = np.empty((n_seq, frames, self.rows, 4), np.uint8)
+        self.process_batch_planar_ptr(pcm.ctypes.data, n_seq, n_samples, n_samples, out.ctypes.data, n_seq * frames)
+        return out
+
+    @property
+    def launch_count(self):
+        return int(self._lib.sbx_multi_launch_count(self._h))
+
+
 class LiveStream:
     """sbx_live: pinned SPSC ring + hop cursor + one CUDA graph per frame."""
 

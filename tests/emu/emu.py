@@ -93,3 +93,23 @@ def tables(cfg):
     lib().emu_tables(C.byref(cfg), window.ctypes.data, f0.ctypes.data, step.ctypes.data, cnt.ctypes.data,
                      C.addressof(period), thr.ctypes.data)
     return dict(window=window, f0=f0, step=step, n=cnt, period=np.float32(period.value), thr=thr)
+
+
+def sample_table(cfg):
+    """The product's per-sample table: dict(samp (entries, 2) uint32, chunks (n, 4) = row_begin, row_end, samp_begin,
+    samp_end, rowinfo (H,), bank_group, ok)."""
+    cap = int(cfg.rows_h) * 64 + int(cfg.window_n) * int(cfg.pad_factor) * 2 + 4096
+    samp = np.empty((cap, 2), np.uint32)
+    chunks = np.empty((int(cfg.rows_h) + 8, 4), np.uint32)
+    rowinfo = np.empty(int(cfg.rows_h), np.uint32)
+    n_chunks, bank_group, ok = C.c_uint32(), C.c_uint32(), C.c_int()
+    fn = lib().emu_sample_table
+    fn.restype = C.c_longlong
+    fn.argtypes = [C.POINTER(binding.SbxConfig), C.c_void_p, C.c_ulonglong, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                   C.c_void_p, C.c_void_p]
+    got = fn(C.byref(cfg), samp.ctypes.data, cap, chunks.ctypes.data, chunks.shape[0], C.addressof(n_chunks),
+             rowinfo.ctypes.data, C.addressof(bank_group), C.addressof(ok))
+    if got < 0:
+        raise RuntimeError("emu_sample_table: buffers too small")
+    return dict(samp=samp[:got].copy(), chunks=chunks[:n_chunks.value].copy(), rowinfo=rowinfo, bank_group=int(bank_group.value),
+                ok=bool(ok.value))

@@ -444,4 +444,25 @@ int emu_tables(const sbx_config *cfg, float *window, float *f0, float *step, uin
     return 0;
 }
 
+// the per-sample table, row chunks and row info (n | first slot << 16) of the product, for the CPU test of the
+// shared-memory layout rules (conflict-free lane groups); returns the number of table entries, -1 if a buffer is small
+__attribute__((visibility("default")))
+long long emu_sample_table(const sbx_config *cfg, uint32_t *samp, unsigned long long samp_capacity_entries, uint32_t *chunks,
+                           uint32_t max_chunks, uint32_t *n_chunks, uint32_t *rowinfo, uint32_t *bank_group, int *ok)
+{
+    sbx::tables::HostTables t;
+    sbx::tables::build(*cfg, t);
+    if (t.samp.size() / 2 > samp_capacity_entries || t.chunks.size() > max_chunks) return -1;
+    memcpy(samp, t.samp.data(), t.samp.size() * sizeof(uint32_t));
+    for (size_t c = 0; c < t.chunks.size(); ++c) {
+        chunks[4 * c] = t.chunks[c].row_begin; chunks[4 * c + 1] = t.chunks[c].row_end;
+        chunks[4 * c + 2] = t.chunks[c].samp_begin; chunks[4 * c + 3] = t.chunks[c].samp_end;
+    }
+    *n_chunks = (uint32_t)t.chunks.size();
+    memcpy(rowinfo, t.rowinfo.data(), t.rows * sizeof(uint32_t));
+    *bank_group = t.bank_group;
+    *ok = t.ok ? 1 : 0;
+    return (long long)(t.samp.size() / 2);
+}
+
 }  // extern "C"

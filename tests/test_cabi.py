@@ -158,3 +158,67 @@ def test_cpp_host_mirror_compiles_and_fails_loudly_without_gpu(binding, tmp_path
         assert out.returncode == 0, out.stderr
     else:
         assert out.returncode == 2 and "no CPU fallback" in out.stderr
+
+
+# ---- INTEGRATION.md's Rust binding vs include/sbx.h --------------------------------------------------------------
+_C_TO_RUST = {"float": "f32", "double": "f64", "uint8_t": "u8", "uint16_t": "u16", "uint32_t": "u32", "uint64_t": "u64",
+              "int32_t": "i32", "sbx_status": "i32", "size_t": "usize", "void": "c_void", "char": "c_char",
+              "sbx_plan": "SbxPlan", "sbx_config": "SbxConfig", "sbx_multi": "SbxMulti", "sbx_live": "SbxLive"}
+
+
+def _rust_type_of_c(decl):
+    """'const float *pcm' -> '*const f32'; 'uint8_t lut_rgb[768]' -> '*mut u8'; 'uint32_t n' -> 'u32'."""
+    decl = decl.strip()
+    array = decl.endswith("]")
+    decl = re.sub(r"\[[^\]]*\]$", "", decl).strip()
+    stars = decl.count("*") + (1 if array else 0)
+    words = decl.replace("*", " ").split()
+    const = "const" in words
+    words = [w for w in words if w != "const"]
+    base = words[0]                                     # words[1:] is the parameter name (absent for `void`)
+    rust = _C_TO_RUST[base]
+    for level in range(stars):
+        rust = ("*const " if const and level == 0 else "*mut ") + rust
+    return rust
+
+
+def _header_signatures():
+    text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    sigs = {}
+    for ret, name, args in re.findall(r"SBX_API\s+([\w\s\*]+?)\b(sbx_\w+)\s*\(([^)]*)\)\s*;", text):
+        params = [] if args.strip() in ("", "void") else [_rust_type_of_c(a) for a in args.split(",")]
+        ret = ret.strip()
+        sigs[name] = (params, None if ret == "void" else _rust_type_of_c(ret + " _"))
+    return sigs
+
+
+def test_integration_md_rust_block_matches_the_header():
+    """The Rust shim cannot be compiled in this image (no rustc): keep its extern "C" block and its #[repr(C)]
+    config struct consistent with include/sbx.h by parsing both."""
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = re.search(r'extern "C" \{(.*?)\n\}', md, flags=re.S).group(1)
+    block = re.sub(r"//[^\n]*", "", block)
+    rust = {}
+    for name, args, ret in re.findall(r"fn\s+(sbx_\w+)\s*\(([^)]*)\)\s*(?:->\s*([^;]+))?;", block, flags=re.S):
+        params = [a.split(":", 1)[1].strip() for a in args.split(",") if a.strip()]
+        rust[name] = (params, ret.strip() if ret else None)
+    assert len(rust) >= 15
+    header = _header_signatures()
+    for name, sig in rust.items():
+        assert name in header, f"{name} is not declared in include/sbx.h"
+        assert sig == header[name], f"{name}: INTEGRATION.md {sig} vs sbx.h {header[name]}"
+    # every sbx_* call the shim makes is declared in its extern block
+    code = "\n".join(re.findall(r"```rust(.*?)```", md, flags=re.S))
+    assert set(re.findall(r"\b(sbx_\w+)\s*\(", code)) <= set(rust)
+    # struct SbxConfig: same fields, order and types as sbx_config
+    text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    body = re.search(r"typedef struct sbx_config \{(.*?)\} sbx_config;", text, flags=re.S).group(1)
+    c_fields = []
+    for ctype, names in re.findall(r"(\w+)\s+([^;]+);", body):
+        for nm in names.split(","):
+            nm = nm.strip()
+            m = re.match(r"(\w+)\[(\d+)\]", nm)
+            c_fields.append((m.group(1), f"[{_C_TO_RUST[ctype]}; {m.group(2)}]") if m else (nm, _C_TO_RUST[ctype]))
+    rs_body = re.search(r"pub struct SbxConfig \{(.*?)\n\}", md, flags=re.S).group(1)
+    rs_fields = [(n, t.strip()) for n, t in re.findall(r"(\w+)\s*:\s*([^,\n]+),", rs_body)]
+    assert rs_fields == c_fields

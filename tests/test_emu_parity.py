@@ -244,3 +244,64 @@ def test_q2_real_sequence_phases_match_oracle(n, hop, rows, interp):
     peak = np.abs(o_mags).max(axis=(1, 2), keepdims=True)
     assert (np.abs(mags - o_mags) / peak).max() <= 1e-5
     assert (rgba != o_rgba).any(axis=2).mean() <= 2e-3
+
+
+# ---- shared-memory layout rules of the resample tables (sbx_tables.h) ---------------------------------------------
+LAYOUT_CASES = [
+    # N, P, H, sample rate: cfg1/cfg4, cfg3 (real-sequence geometry: 4-byte elements, groups of 32), cfg2, cfg5, the app
+    (4096, 2, 1024, 48000.0), (8192, 2, 1024, 96000.0), (2048, 2, 1024, 48000.0), (4096, 4, 2048, 48000.0),
+    (512, 4, 2048, 48000.0), (2400, 2, 1024, 48000.0), (1024, 1, 333, 44100.0),
+]
+
+
+@pytest.mark.parametrize("n,pad,rows,sr", LAYOUT_CASES)
+def test_sample_table_lane_groups_are_conflict_free(magma, n, pad, rows, sr):
+    """One lane per table entry; an aligned group of `bank_group` entries is served by one shared-memory request.
+    Checked here: (1) the real entries, in order, are exactly the (row, sample) list of the bin map with the right
+    bin and slot; (2) within every group the bins span < bank_group (the four tap loads are conflict-free) and so do
+    the slots of the entries that store; (3) filler entries repeat a bin of their group and store nothing;
+    (4) the rows one request serves start at different residues, so the sequential row sums are conflict-free;
+    (5) no two samples of a chunk share a slot and every slot is inside the scratch area."""
+    cfg = emu.make_config(magma, sample_rate=sr, window_n=n, pad_factor=pad, hop=n // 8, rows_h=rows, channels=1)
+    tab = emu.sample_table(cfg)
+    assert tab["ok"]
+    g = tab["bank_group"]
+    assert g in (16, 32)
+    samp, chunks, rowinfo = tab["samp"], tab["chunks"], tab["rowinfo"]
+    x1, slot = samp[:, 0] & 0x1ffff, samp[:, 0] >> 17
+    filler = slot == 0x7fff
+    tb = emu.tables(cfg)
+    k_out = n * pad // 2 - 1
+    cap = n * pad // 2
+    n_rows = rowinfo & 0xffff
+    aux = rowinfo >> 16
+    assert np.array_equal(n_rows, tb["n"])
+    # (1) real entries == the bin map's samples, row by row
+    want_x, want_slot = [], []
+    for py in range(rows):
+        s = np.arange(n_rows[py], dtype=np.float32)
+        fq = tb["f0"][py] + s * tb["step"][py]
+        x = np.clip(fq * tb["period"], np.float32(0), np.float32(k_out - 1)).astype(np.float32)
+        want_x.append(np.floor(x).astype(np.uint32))
+        want_slot.append(aux[py] + np.arange(n_rows[py], dtype=np.uint32))
+    assert np.array_equal(x1[~filler], np.concatenate(want_x))
+    assert np.array_equal(slot[~filler], np.concatenate(want_slot))
+    fillers = 0
+    for row_begin, row_end, s_begin, s_end in chunks:
+        cx, cs, cf = x1[s_begin:s_end].astype(np.int64), slot[s_begin:s_end].astype(np.int64), filler[s_begin:s_end]
+        fillers += int(cf.sum())
+        for lo in range(0, len(cx), g):                                      # (2), (3)
+            gx, gs, gf = cx[lo:lo + g], cs[lo:lo + g], cf[lo:lo + g]
+            assert gx.max() - gx.min() < g, (lo, gx)
+            real = gs[~gf]
+            assert len(real) >= 1 and real.max() - real.min() < g and len(set(real)) == len(real)
+            assert set(gx[gf]) <= set(gx[~gf])
+        real_slots = cs[~cf]
+        assert len(set(real_slots)) == len(real_slots) and real_slots.max() < cap          # (5)
+        for lo in range(row_begin, row_end, g):                              # (4)
+            res = (aux[lo:min(lo + g, row_end)] % g).tolist()
+            assert len(set(res)) == len(res), (lo, res)
+    # the fillers cost at most a tenth more lanes, and the BASELINE geometries still need a single chunk
+    assert fillers <= 0.1 * (~filler).sum() + g
+    if (n, pad) in ((4096, 2), (8192, 2), (4096, 4)):
+        assert len(chunks) == 1
