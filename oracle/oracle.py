@@ -19,6 +19,9 @@ class OrcParams(C.Structure):
                 ("interp", C.c_uint32), ("stereo_scheme", C.c_uint32)]
 
 
+FAST_LIB_PATH = os.path.join(HERE, "liboracle_fast.so")
+
+
 def build(force=False):
     src = os.path.join(HERE, "stft_oracle.c")
     if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
@@ -26,7 +29,33 @@ def build(force=False):
     return LIB_PATH
 
 
+def build_fast():
+    """liboracle_fast.so: -O3 -march=native, for the TIMED CPU baseline only.  Always rebuilt on the machine that
+    times it (a library built for this container's CPU may not run on the GPU box's)."""
+    subprocess.run(["make", "-C", HERE, "-B", "liboracle_fast.so"], check=True, capture_output=True)
+    return FAST_LIB_PATH
+
+
 _lib = None
+_fast = None
+
+
+def fast_lib():
+    """The timed build with the entry points the baseline uses."""
+    global _fast
+    if _fast is None:
+        build_fast()
+        L = C.CDLL(FAST_LIB_PATH)
+        f32p, u8p = C.POINTER(C.c_float), C.POINTER(C.c_uint8)
+        L.orc_batch.restype = C.c_int64
+        L.orc_batch.argtypes = [C.POINTER(OrcParams), f32p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64,
+                                u8p, u8p, f32p, C.c_int]
+        L.orc_window_pad_batch.restype = C.c_int
+        L.orc_window_pad_batch.argtypes = [C.POINTER(OrcParams), f32p, C.c_uint32, C.c_uint64, C.c_uint64, f32p, C.c_int]
+        L.orc_split_colour_batch.restype = C.c_int
+        L.orc_split_colour_batch.argtypes = [C.POINTER(OrcParams), f32p, C.c_uint64, u8p, u8p, C.c_int]
+        _fast = L
+    return _fast
 
 
 def lib():
@@ -179,8 +208,9 @@ def num_frames(n_samples, n, hop):
     return int(lib().orc_num_frames(n_samples, n, hop))
 
 
-def batch(p, pcm, channels, lut_rgb, want_rgba=True, want_mags=False, frame_lo=0, frame_hi=None, threads=1):
-    """pcm: float32 (n_samples,) mono or (n_samples, 2).  Returns (rgba or None, mags or None)."""
+def batch(p, pcm, channels, lut_rgb, want_rgba=True, want_mags=False, frame_lo=0, frame_hi=None, threads=1, fast=False):
+    """pcm: float32 (n_samples,) mono or (n_samples, 2).  Returns (rgba or None, mags or None).
+    fast=True: the -O3 -march=native build (bench.py's timed baseline; same results)."""
     pcm = np.ascontiguousarray(pcm, dtype=np.float32)
     n_samples = pcm.shape[0]
     total = num_frames(n_samples, p.window_n, p.hop)
@@ -192,8 +222,9 @@ def batch(p, pcm, channels, lut_rgb, want_rgba=True, want_mags=False, frame_lo=0
     mags = np.empty((count, k, 2), np.float32) if want_mags else None
     lut_rgb = np.ascontiguousarray(lut_rgb, dtype=np.uint8)
     if count:
-        got = lib().orc_batch(C.byref(p), _f32(pcm), n_samples, channels, frame_lo, frame_hi, _u8(lut_rgb),
-                              _u8(rgba) if want_rgba else None, _f32(mags) if want_mags else None, threads)
+        L = fast_lib() if fast else lib()
+        got = L.orc_batch(C.byref(p), _f32(pcm), n_samples, channels, frame_lo, frame_hi, _u8(lut_rgb),
+                          _u8(rgba) if want_rgba else None, _f32(mags) if want_mags else None, threads)
         if got != count:
             raise RuntimeError(f"orc_batch returned {got}, expected {count}")
     return rgba, mags
@@ -203,32 +234,28 @@ def max_threads():
     return int(lib().orc_max_threads())
 
 
-def batch_pocketfft(p, pcm, channels, lut_rgb, threads=1, chunk_frames=2048):
+def batch_pocketfft(p, pcm, channels, lut_rgb, threads=1, chunk_frames=4096):
     """The same path with the FFT stage done by pocketfft (scipy.fft, complex64, `workers=threads`) instead of the
     oracle's own radix-2 FFT: the stand-in for the reference's FFTW call in the timed CPU baseline (FFTW is not
-    in this image).  Window/pack, L/R split and scale are numpy restatements of fft.rs:57-63 and :81-95; the
-    resample + colour stage is the C oracle, threaded over frames.  Returns rgba (frames, H, 4)."""
+    in this image).  Everything around the transform -- take N / pack / Hann / zero-pad (fft.rs:48-69) and split /
+    scale / resample / dB / gradient (fft.rs:81-98 onwards) -- is the C oracle (-O3 -march=native build), threaded
+    over frames like the transform itself.  Returns rgba (frames, H, 4)."""
     import scipy.fft
     pcm = np.ascontiguousarray(pcm, dtype=np.float32)
     n, pad, hop = p.window_n, p.pad_factor, p.hop
-    m, k = n * pad, num_output_frequencies(n, pad)
+    m = n * pad
     total = num_frames(pcm.shape[0], n, hop)
-    w = hann(n)
-    scale = np.float32(2.0) / np.float32(n)
     lut_rgb = np.ascontiguousarray(lut_rgb, dtype=np.uint8)
     rgba = np.empty((total, p.rows_h, 4), np.uint8)
+    L = fast_lib()
+    z = np.empty((min(chunk_frames, max(total, 1)), m), np.complex64)
     for f0 in range(0, total, chunk_frames):
         f1 = min(total, f0 + chunk_frames)
-        idx = (np.arange(f0, f1) * hop)[:, None] + np.arange(n)[None, :]
-        if channels == 1:
-            s = pcm[idx] * w
-            z = s + 1j * s                                   # (s, s) duplication, audio_input_list_model.rs:67
-        else:
-            z = pcm[idx, 0] * w + 1j * (pcm[idx, 1] * w)
-        zf = scipy.fft.fft(z.astype(np.complex64), n=m, axis=1, workers=threads)
-        a, b = zf[:, 1:k + 1], np.conj(zf[:, m - 1:m - 1 - k:-1])
-        mags = np.empty((f1 - f0, k, 2), np.float32)
-        mags[..., 0] = np.abs(a + b) / np.float32(2.0) * scale
-        mags[..., 1] = np.abs(a - b) / np.float32(2.0) * scale
-        lib().orc_colour_batch(C.byref(p), _f32(mags), f1 - f0, _u8(lut_rgb), _u8(rgba[f0:f1]), threads)
+        zc = z[:f1 - f0]
+        if L.orc_window_pad_batch(C.byref(p), _f32(pcm), channels, f0, f1 - f0, zc.ctypes.data_as(C.POINTER(C.c_float)), threads) != 0:
+            raise RuntimeError("orc_window_pad_batch failed")
+        zf = scipy.fft.fft(zc, axis=1, workers=threads, overwrite_x=True)
+        zf = np.ascontiguousarray(zf, dtype=np.complex64)
+        if L.orc_split_colour_batch(C.byref(p), zf.ctypes.data_as(C.POINTER(C.c_float)), f1 - f0, _u8(lut_rgb), _u8(rgba[f0:f1]), threads) != 0:
+            raise RuntimeError("orc_split_colour_batch failed")
     return rgba

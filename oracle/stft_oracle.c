@@ -29,6 +29,8 @@
  *
  * Build (see oracle/Makefile):  gcc -O2 -ffp-contract=off -fno-fast-math -pthread -shared -fPIC
  * -ffp-contract=off is REQUIRED: Rust never fuses a*b+c, GNU C does by default.
+ * liboracle.so (-O2, host-independent) is the checker; liboracle_fast.so (-O3 -march=native, same source, same
+ * results -- tests/test_oracle_kat.py compares the two) is what bench.py TIMES as the CPU baseline.
  */
 #include <math.h>
 #include <stdint.h>
@@ -541,6 +543,75 @@ ORC_API int orc_colour_batch(const orc_params *p, const float *mags_lr, uint64_t
     for (int t = 0; t < threads; ++t) if (started[t]) pthread_join(tid[t], NULL);
     free(jobs); free(tid); free(started);
     return 0;
+}
+
+/* The FFT stage handed to a library (timed CPU baseline only): everything of fft.rs:48-69 before the transform
+ * (take N, pack, Hann -- recomputed per frame as the reference does --, zero-pad) for a run of frames into
+ * z[frames][M], and everything after it (fft.rs:81-98 split + scale, then the column) from zf[frames][M].
+ * bench.py runs scipy.fft (pocketfft, complex64) between the two: FFTW itself is not in this image. */
+typedef struct { const orc_params *p; const float *pcm; uint32_t channels; uint64_t frame_lo, lo, hi;
+                 c32 *z; const uint8_t *lut; uint8_t *rgba; int err; } orc_sjob;
+static void *orc_window_worker(void *arg)
+{
+    orc_sjob *j = (orc_sjob *)arg;
+    uint32_t n = j->p->window_n, m = n * j->p->pad_factor;
+    float *lr = (float *)malloc(sizeof(float) * 2 * (size_t)n);
+    if (!lr) { j->err = 1; return NULL; }
+    for (uint64_t f = j->lo; f < j->hi; ++f) {
+        const float *src = j->pcm + (size_t)(j->frame_lo + f) * j->p->hop * j->channels;
+        if (j->channels == 1) for (uint32_t i = 0; i < n; ++i) { lr[2 * i] = src[i]; lr[2 * i + 1] = src[i]; }
+        else memcpy(lr, src, sizeof(float) * 2 * (size_t)n);
+        orc_window_pad(lr, n, j->p->pad_factor, j->z + (size_t)f * m);
+    }
+    free(lr);
+    return NULL;
+}
+static void *orc_split_colour_worker(void *arg)
+{
+    orc_sjob *j = (orc_sjob *)arg;
+    uint32_t n = j->p->window_n, m = n * j->p->pad_factor, k_out = orc_num_output_frequencies(n, j->p->pad_factor);
+    float *mags = (float *)malloc(sizeof(float) * 2 * (size_t)k_out);
+    if (!mags) { j->err = 1; return NULL; }
+    for (uint64_t f = j->lo; f < j->hi; ++f) {
+        orc_split_scale(j->z + (size_t)f * m, n, j->p->pad_factor, mags);
+        orc_column_from_magnitudes(j->p, mags, j->lut, j->rgba + (size_t)f * 4 * j->p->rows_h);
+    }
+    free(mags);
+    return NULL;
+}
+static int orc_run_sjobs(orc_sjob proto, uint64_t n_frames, int threads, void *(*worker)(void *))
+{
+    if (threads < 1) threads = 1;
+    if ((uint64_t)threads > n_frames) threads = (int)(n_frames ? n_frames : 1);
+    orc_sjob *jobs = (orc_sjob *)calloc((size_t)threads, sizeof(orc_sjob));
+    pthread_t *tid = (pthread_t *)calloc((size_t)threads, sizeof(pthread_t));
+    char *started = (char *)calloc((size_t)threads, 1);
+    if (!jobs || !tid || !started) { free(jobs); free(tid); free(started); return -1; }
+    for (int t = 0; t < threads; ++t) {
+        jobs[t] = proto;
+        jobs[t].lo = n_frames * (uint64_t)t / (uint64_t)threads;
+        jobs[t].hi = n_frames * (uint64_t)(t + 1) / (uint64_t)threads;
+        if (threads > 1 && pthread_create(&tid[t], NULL, worker, &jobs[t]) == 0) started[t] = 1;
+        else worker(&jobs[t]);
+    }
+    int err = 0;
+    for (int t = 0; t < threads; ++t) { if (started[t]) pthread_join(tid[t], NULL); err |= jobs[t].err; }
+    free(jobs); free(tid); free(started);
+    return err ? -1 : 0;
+}
+ORC_API int orc_window_pad_batch(const orc_params *p, const float *pcm, uint32_t channels, uint64_t frame_lo,
+                                 uint64_t n_frames, float *z, int threads)
+{
+    orc_sjob proto; memset(&proto, 0, sizeof proto);
+    proto.p = p; proto.pcm = pcm; proto.channels = channels; proto.frame_lo = frame_lo; proto.z = (c32 *)z;
+    return orc_run_sjobs(proto, n_frames, threads, orc_window_worker);
+}
+ORC_API int orc_split_colour_batch(const orc_params *p, const float *zf, uint64_t n_frames, const uint8_t *lut_rgb,
+                                   uint8_t *rgba, int threads)
+{
+    orc_sjob proto; memset(&proto, 0, sizeof proto);
+    proto.p = p; proto.z = (c32 *)zf; proto.lut = lut_rgb; proto.rgba = rgba;
+    return orc_run_sjobs(proto, n_frames, threads, orc_split_colour_worker);
 }
 
 ORC_API int orc_max_threads(void)

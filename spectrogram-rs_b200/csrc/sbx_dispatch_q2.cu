@@ -58,3 +58,16 @@ cudaError_t launch_real_q2(sbx_plan *p, const KernelArgs &a, uint64_t n_frames, 
 }
 
 }  // namespace sbx
+
+#ifdef SBX_PHASE_CLOCK
+// variant builds only (tools/phase_split.py): read and clear the per-phase cycle counters of fused_q2_kernel
+extern "C" __attribute__((visibility("default"))) int sbx_debug_phase_cycles(unsigned long long out[8], int clear)
+{
+    if (cudaMemcpyFromSymbol(out, sbx::g_phase_cycles, 8 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+    if (clear) {
+        const unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (cudaMemcpyToSymbol(sbx::g_phase_cycles, zero, sizeof(zero)) != cudaSuccess) return -1;
+    }
+    return 0;
+}
+#endif

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <vector>
@@ -342,7 +343,10 @@ inline void build(const sbx_config &cfg, HostTables &t)
         std::vector<RowChunk> best_chunks;
         std::vector<uint32_t> best_aux;
         bool have = false;
-        for (SlotPolicy policy : {GREEDY, ODD, DENSE}) {
+        const char *env_slots = std::getenv("SBX_TABLE_SLOTS");               // experiment knob: first policy tried
+        const int first_policy = env_slots ? std::atoi(env_slots) : 0;
+        for (int pi = 0; pi < 3; ++pi) {
+            const SlotPolicy policy = (SlotPolicy)((first_policy + pi) % 3);
             std::vector<RowChunk> chunks;
             std::vector<uint32_t> aux;
             bool fits = true;
@@ -379,10 +383,15 @@ inline void build(const sbx_config &cfg, HostTables &t)
     t.taps_clamped = false;
     if (t.k_out >= (1u << 17)) t.ok = false;
     const float pi = 3.14159265358979323846f;
-    const bool fill_groups = !t.large;
+    const char *env_fill = std::getenv("SBX_TABLE_FILL");                     // experiment knob
+    const int fill_mode = env_fill ? std::atoi(env_fill) : 0;                 // 0 none, 1 every group, 2 within the round budget
+    const bool fill_groups = !t.large && fill_mode != 0;
     for (RowChunk &ck : t.chunks) {
         const uint32_t begin = (uint32_t)(t.samp.size() / 2);
         uint32_t group_x = 0, group_slot = 0, prev_x = 0;
+        // the kernels take the table in rounds of 2048 entries (threads x loads in flight): fillers must not add a round
+        const uint32_t real_entries = ck.samp_end - ck.samp_begin;
+        uint32_t filler_budget = fill_mode == 2 ? (real_entries + 2047u) / 2048u * 2048u - real_entries : 0xffffffffu;
         for (uint32_t py = ck.row_begin; py < ck.row_end; ++py) {
             const RowMap &rm = t.rowmap[py];
             for (uint32_t s = 0; s < rm.n; ++s) {
@@ -397,8 +406,9 @@ inline void build(const sbx_config &cfg, HostTables &t)
                 std::memcpy(&wbits, &w, 4);
                 const uint32_t slot = (rm.aux + s) & 0x7fffu;                           // big rows ignore the slot
                 uint32_t pos = (uint32_t)(t.samp.size() / 2) - begin;
-                if (fill_groups && pos % bank_group != 0 &&
+                if (fill_groups && pos % bank_group != 0 && bank_group - pos % bank_group <= filler_budget &&
                     (x1 < group_x || x1 - group_x >= bank_group || slot < group_slot || slot - group_slot >= bank_group)) {
+                    filler_budget -= bank_group - pos % bank_group;
                     for (; pos % bank_group != 0; ++pos) { t.samp.push_back(prev_x | (0x7fffu << 17)); t.samp.push_back(0u); }
                 }
                 if (pos % bank_group == 0) { group_x = x1; group_slot = slot; }

@@ -342,9 +342,31 @@ __device__ __forceinline__ void q2_split_emit_real(float *zf, const float *pb, c
 #endif
 
 #ifndef SBX_EMU
+// -DSBX_PHASE_CLOCK (tools/phase_split.py builds that variant; never the shipped library): thread 0 of every CTA reads
+// the SM clock at the phase boundaries and adds the differences to g_phase_cycles -- the per-phase share of a CTA's
+// residency, profiles/phase_split_*.json.  [0] pass 0 (PCM + window loads, first radix pass), [1] shared-memory
+// passes, [2] last pass + partner exchange + L/R split, [3] resample (lane per sample), [4] row sums + colour + RGBA
+// stores, [5] magnitude output, [7] CTAs counted.
+#ifdef SBX_PHASE_CLOCK
+__device__ unsigned long long g_phase_cycles[8];
+#define SBX_PHASE_MARK(i)                                                                   \
+    do {                                                                                    \
+        if (threadIdx.x == 0) {                                                             \
+            const long long now__ = clock64();                                              \
+            atomicAdd(&g_phase_cycles[i], (unsigned long long)(now__ - phase_t__));         \
+            phase_t__ = now__;                                                              \
+        }                                                                                   \
+    } while (0)
+#define SBX_PHASE_BEGIN() long long phase_t__ = clock64()
+#else
+#define SBX_PHASE_MARK(i) do { } while (0)
+#define SBX_PHASE_BEGIN() do { } while (0)
+#endif
+
 template <class G>
 __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) fused_q2_kernel(const KernelArgs a)
 {
+    SBX_PHASE_BEGIN();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *e = reinterpret_cast<float4 *>(smem_raw);
     float2 *z = reinterpret_cast<float2 *>(smem_raw);
@@ -359,7 +381,9 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) fused_q2_kernel(const
     const bool second_valid = G::CH == 1 && frame0 + 1 < a.n_frames;
 
     q2_pass_first<G>(e, a, a.pcm + seq * a.seq_stride + frame0 * (unsigned long long)a.hop * G::CH, second_valid);
+    SBX_PHASE_MARK(0);
     Q2RunPasses<G, 1, G::NPASS - 1>::run(e, a);              // (each pass is preceded by its barrier; one more at the end)
+    SBX_PHASE_MARK(1);
     cpk v[16];
     q2_last_load<G>(e, v);
     __syncthreads();
@@ -368,6 +392,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) fused_q2_kernel(const
     if constexpr (G::REAL) q2_split_emit_real<G>(reinterpret_cast<float *>(smem_raw), pb, a, v);
     else q2_split_emit<G>(z, pb, a, v);
     __syncthreads();
+    SBX_PHASE_MARK(2);
 
     const unsigned long long out_frame0 = seq * a.n_frames + frame0;
     if constexpr (G::REAL) {
@@ -390,7 +415,28 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) fused_q2_kernel(const
             }
         }
     }
+    SBX_PHASE_MARK(5);
+#ifdef SBX_PHASE_CLOCK
+    if (a.rgba != nullptr) {                                   // pk_resample_colour, with a mark between its two phases
+        float2 *scratch = z + (1 << (G::LOG2M - 1));
+        for (uint32_t c = 0; c < a.n_chunks; ++c) {
+            RowChunk ck = a.chunk0;
+            if (c != 0) {
+                const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.chunks) + c);
+                ck = RowChunk{raw.x, raw.y, raw.z, raw.w};
+                __syncthreads();
+            }
+            pk_resample_samples<G::THREADS, SBX_Q2_RESAMPLE_UNROLL>(z, scratch, a, ck);
+            __syncthreads();
+            SBX_PHASE_MARK(3);
+            pk_colour_rows<G::CH == 1, G::THREADS, SBX_Q2_COLOUR_ROWS>(scratch, a, ck, out_frame0, second_valid);
+            SBX_PHASE_MARK(4);
+        }
+    }
+    if (threadIdx.x == 0) atomicAdd(&g_phase_cycles[7], 1ull);
+#else
     if (a.rgba != nullptr) pk_resample_colour<G::LOG2M, G::CH == 1, G::THREADS, SBX_Q2_RESAMPLE_UNROLL, SBX_Q2_COLOUR_ROWS>(z, a, out_frame0, second_valid);
+#endif
     }  // !REAL
     if (a.done_flag != nullptr) {
         __syncthreads();

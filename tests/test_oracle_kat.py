@@ -203,3 +203,23 @@ def test_threaded_batch_equals_serial(magma):
     assert np.array_equal(a, b) and np.array_equal(am, bm)
     c, _ = oracle.batch(p, x, 1, magma, frame_lo=10, frame_hi=20)
     assert np.array_equal(c, a[10:20])
+
+
+def test_fast_build_equals_the_checker():
+    """bench.py times liboracle_fast.so (-O3 -march=native, no fast-math, no contraction): same source, and the same
+    results as the -O2 checker build -- columns and magnitudes bit for bit; with pocketfft as the FFT stage the
+    columns agree to within a colour step on at most 0.1 % of the pixels (a different, equally valid f32 FFT)."""
+    from tests import signals
+    lut = signals.lut("viridis")
+    for ch, kw in ((1, dict(window_n=1024, pad_factor=2, hop=256, rows_h=256)),
+                   (2, dict(window_n=512, pad_factor=4, hop=100, rows_h=77, interp=1))):
+        p = oracle.params(**kw)
+        ns = kw["window_n"] + kw["hop"] * 40
+        x = signals.log_sweep(ns) if ch == 1 else signals.stereo_loopback(ns)
+        rgba, mags = oracle.batch(p, x, ch, lut, want_mags=True)
+        rgba_f, mags_f = oracle.batch(p, x, ch, lut, want_mags=True, fast=True, threads=3)
+        assert np.array_equal(rgba, rgba_f) and np.array_equal(mags, mags_f)
+        rgba_p = oracle.batch_pocketfft(p, x, ch, lut, threads=2, chunk_frames=16)
+        assert rgba_p.shape == rgba.shape
+        assert (rgba_p != rgba).any(axis=2).mean() <= 1e-3
+        assert np.abs(rgba_p.astype(int) - rgba.astype(int)).max() <= 40
