@@ -275,7 +275,9 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # a collective that cannot complete (a rank died) aborts after 5 minutes instead of hanging the box
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=300))
 
     import spectrogram_rs_b200 as sbx
     from tests import signals
@@ -288,7 +290,7 @@ def main():
     def max_over_ranks(x):
         if world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        t = torch.tensor([x], dtype=torch.float64, device=torch.device("cuda", local_rank))
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
@@ -386,6 +388,7 @@ def main():
                 del hm_pcm, hm_rgba
             except Exception as exc:                        # never lose the headline line
                 e2e_multi = {"error": repr(exc)}
+            torch.cuda.set_device(local_rank)
         barrier()
 
     peaks, peak_src = measured_peaks()
@@ -458,6 +461,9 @@ def main():
             sharded = sharded_extras(sbx, signals, torch, dist, rank, world, local_rank, barrier, max_over_ranks)
         except Exception as exc:
             sharded = {"error": repr(exc)}
+    if world > 1:                                            # the last collective: the rank-0-only legs below run alone
+        dist.barrier()
+        dist.destroy_process_group()
     if rank == 0 and not args.no_extras:
         try:
             out["extra"] = extras(sbx, signals, torch)
@@ -476,9 +482,6 @@ def main():
                                "by_fft_stage_and_threads": cpu_reference_rate.table, "build": "gcc -O3 -march=native -ffp-contract=off"}
     if rank == 0:
         emit(out)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
 
 
 def _checksum(torch, rgba):

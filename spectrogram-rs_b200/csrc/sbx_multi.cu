@@ -23,6 +23,15 @@ namespace {
 
 thread_local std::string g_multi_create_error;
 
+// The plans of an sbx_multi live on different devices and every plan entry point makes its device current: the
+// sbx_multi_* calls put the caller's current device back before they return (a host application -- or the CUDA
+// runtime user above it, e.g. torch -- must not find its device switched by a library call).
+struct DeviceGuard {
+    int saved = -1;
+    DeviceGuard() { if (cudaGetDevice(&saved) != cudaSuccess) { cudaGetLastError(); saved = -1; } }
+    ~DeviceGuard() { if (saved >= 0) cudaSetDevice(saved); }
+};
+
 sbx_status mfail(const sbx_multi *m, sbx_status st, const std::string &msg)
 {
     if (m) m->last_error = msg; else g_multi_create_error = msg;
@@ -69,6 +78,7 @@ SBX_API sbx_status sbx_multi_create(const sbx_config *cfg, const int32_t *device
             if (devices[i] == devices[j]) return mfail(nullptr, SBX_ERR_INVALID_ARGUMENT, "a device ordinal is listed twice");
     sbx_multi *m = new (std::nothrow) sbx_multi();
     if (!m) return mfail(nullptr, SBX_ERR_OUT_OF_MEMORY, "out of host memory");
+    DeviceGuard guard;
     m->mono = cfg->channels == 1;
     for (uint32_t i = 0; i < n_devices; ++i) {
         sbx_config c = *cfg;
@@ -89,6 +99,7 @@ SBX_API sbx_status sbx_multi_create(const sbx_config *cfg, const int32_t *device
 SBX_API void sbx_multi_destroy(sbx_multi *m)
 {
     if (!m) return;
+    DeviceGuard guard;
     for (sbx_plan *p : m->plans) sbx_plan_destroy(p);
     delete m;
 }
@@ -130,6 +141,7 @@ SBX_API sbx_status sbx_multi_process_batch(sbx_multi *m, const float *pcm, uint6
     if (!pcm || !rgba) return mfail(m, SBX_ERR_INVALID_ARGUMENT, "NULL host buffer");
     if (frames > rgba_capacity_frames) return mfail(m, SBX_ERR_BUFFER_TOO_SMALL, "rgba capacity is smaller than the frame count");
     const uint32_t G = (uint32_t)m->plans.size();
+    DeviceGuard guard;
     const sbx_status st = for_each_device(m, [&](size_t i) -> sbx_status {
         sbx_plan *p = m->plans[i];
         uint64_t lo, hi;
@@ -157,6 +169,7 @@ SBX_API sbx_status sbx_multi_process_batch_planar(sbx_multi *m, const float *pcm
     if (frames > rgba_capacity_frames / n_sequences)
         return mfail(m, SBX_ERR_BUFFER_TOO_SMALL, "output capacity is smaller than n_sequences * frames per sequence");
     const uint32_t G = (uint32_t)m->plans.size();
+    DeviceGuard guard;
     const sbx_status st = for_each_device(m, [&](size_t i) -> sbx_status {
         sbx_plan *p = m->plans[i];
         // whole sequences per device (sharding.channel_blocks), no halo

@@ -254,14 +254,17 @@ LAYOUT_CASES = [
 ]
 
 
+@pytest.mark.parametrize("fill", [0, 1])
 @pytest.mark.parametrize("n,pad,rows,sr", LAYOUT_CASES)
-def test_sample_table_lane_groups_are_conflict_free(magma, n, pad, rows, sr):
+def test_sample_table_lane_groups_are_conflict_free(magma, monkeypatch, n, pad, rows, sr, fill):
     """One lane per table entry; an aligned group of `bank_group` entries is served by one shared-memory request.
     Checked here: (1) the real entries, in order, are exactly the (row, sample) list of the bin map with the right
-    bin and slot; (2) within every group the bins span < bank_group (the four tap loads are conflict-free) and so do
-    the slots of the entries that store; (3) filler entries repeat a bin of their group and store nothing;
+    bin and slot; (2) with filler entries (SBX_TABLE_FILL=1; measured slower on a B200 and therefore off by default,
+    profiles/README.md) within every group the bins span < bank_group (the four tap loads are conflict-free) and so
+    do the slots of the entries that store; (3) filler entries repeat a bin of their group and store nothing;
     (4) the rows one request serves start at different residues, so the sequential row sums are conflict-free;
     (5) no two samples of a chunk share a slot and every slot is inside the scratch area."""
+    monkeypatch.setenv("SBX_TABLE_FILL", str(fill))
     cfg = emu.make_config(magma, sample_rate=sr, window_n=n, pad_factor=pad, hop=n // 8, rows_h=rows, channels=1)
     tab = emu.sample_table(cfg)
     assert tab["ok"]
@@ -292,9 +295,11 @@ def test_sample_table_lane_groups_are_conflict_free(magma, n, pad, rows, sr):
         fillers += int(cf.sum())
         for lo in range(0, len(cx), g):                                      # (2), (3)
             gx, gs, gf = cx[lo:lo + g], cs[lo:lo + g], cf[lo:lo + g]
-            assert gx.max() - gx.min() < g, (lo, gx)
             real = gs[~gf]
-            assert len(real) >= 1 and real.max() - real.min() < g and len(set(real)) == len(real)
+            assert len(real) >= 1 and len(set(real)) == len(real)
+            if fill:
+                assert gx.max() - gx.min() < g, (lo, gx)
+                assert real.max() - real.min() < g
             assert set(gx[gf]) <= set(gx[~gf])
         real_slots = cs[~cf]
         assert len(set(real_slots)) == len(real_slots) and real_slots.max() < cap          # (5)
@@ -302,6 +307,6 @@ def test_sample_table_lane_groups_are_conflict_free(magma, n, pad, rows, sr):
             res = (aux[lo:min(lo + g, row_end)] % g).tolist()
             assert len(set(res)) == len(res), (lo, res)
     # the fillers cost at most a tenth more lanes, and the BASELINE geometries still need a single chunk
-    assert fillers <= 0.1 * (~filler).sum() + g
+    assert fillers <= 0.1 * (~filler).sum() + g if fill else fillers == 0
     if (n, pad) in ((4096, 2), (8192, 2), (4096, 4)):
         assert len(chunks) == 1

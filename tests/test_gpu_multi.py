@@ -83,8 +83,11 @@ def test_multi_devices_equal_one_device(sbx, magma, monkeypatch, n, pad, ch, hop
     kw = dict(window_n=n, pad_factor=pad, hop=hop, rows_h=rows, channels=ch, lut=magma)
     with sbx.Plan(device=0, **kw) as plan:
         want = plan.process_batch(x)
+    import torch
+    torch.cuda.set_device(0)
     with sbx.MultiPlan(world, **kw) as multi:
         got = multi.process_batch(x)
+        assert torch.cuda.current_device() == 0                # the caller's current device is put back
         assert np.array_equal(got, want)
         # the last device alone, on its own block of samples (a real second device, not a shard on device 0)
         lo, hi, s_lo, s_hi = multi.time_block(x.shape[0], world - 1)
