@@ -54,7 +54,8 @@ enum { SBX_SCHEME_MONO = 0,       /* ColorScheme::new_mono: colour = gradient(dB
        SBX_SCHEME_STEREO = 1 };   /* ColorScheme::new_stereo: colour = gradient(l/(|l|+|r|)),
                                      alpha = normalised dB (src/colorscheme.rs:63-66).  The gradient is read as
                                      lut_rgb[clamp(floor(pan * 256))]: a 256-step quantisation of the reference's
-                                     continuous stereo gradients (see lut_rgb below) */
+                                     continuous stereo gradients (see lut_rgb below), or from the finer table of
+                                     sbx_plan_set_pan_gradient() */
 
 /*
  * Everything the reference hard-codes as literals (SURVEY.md section 5 "Config"), as one struct.
@@ -94,9 +95,20 @@ typedef struct sbx_config {
  * CUBIC, mono scheme, Magma, stereo PCM, device 0. */
 SBX_API void sbx_config_default(sbx_config *cfg);
 
-/* Built-in 256-entry ramps: "magma", "viridis", "inferno", "plasma"
- * (src/colorscheme.rs:131-132,138-139).  Returns SBX_ERR_INVALID_ARGUMENT for other names. */
+/* Built-in gradients: all 19 of default_color_schemes() (src/colorscheme.rs:129-149), by lower-case name of the
+ * colorous constant: "red_yellow_blue", "magma", "viridis", "red_blue", "spectral", "red_yellow_green", "pink_green",
+ * "purple_orange", "inferno", "plasma", "cividis", "cubehelix", "turbo", "cool", "reds", "blues", "greens", "greys",
+ * "oranges".  sbx_builtin_lut fills the 256-entry table of sbx_config::lut_rgb: table[i] = gradient((i + 0.5) / 256) --
+ * for the four ramps (magma, viridis, inferno, plasma) exactly colorous' table.  The definitions restate
+ * d3-scale-chromatic (colorous is its port and is not vendored with the reference; csrc/sbx_gradients.h); a Rust
+ * caller fills the tables from colorous itself.  SBX_ERR_INVALID_ARGUMENT for other names. */
 SBX_API sbx_status sbx_builtin_lut(const char *name, uint8_t lut_rgb[768]);
+/* The same gradient as a table of `entries` steps (1 .. 65536): rgb[3 i ..] = gradient((i + 0.5) / entries). */
+SBX_API sbx_status sbx_builtin_gradient(const char *name, uint32_t entries, uint8_t *rgb);
+/* Enumeration in the reference's list order: name of gradient `index` < sbx_builtin_gradient_count() (NULL beyond),
+ * *is_stereo_scheme (may be NULL) = 1 where the reference builds it with ColorScheme::new_stereo. */
+SBX_API uint32_t    sbx_builtin_gradient_count(void);
+SBX_API const char *sbx_builtin_gradient_name(uint32_t index, int32_t *is_stereo_scheme);
 
 /* (period * sample_rate) as usize -- src/fourier/fft.rs:19,41 -- and
  * (stride * sample_rate) as usize -- src/fourier/audio_transform.rs:35 (f32 multiply, truncation). */
@@ -113,6 +125,16 @@ SBX_API uint32_t sbx_samples_from_seconds(float seconds, float sample_rate);
  * dB-step thresholds) and uploads them; the kernels never evaluate exp / log / cos. */
 SBX_API sbx_status sbx_plan_create(const sbx_config *cfg, sbx_plan **out_plan);
 SBX_API void       sbx_plan_destroy(sbx_plan *plan);
+
+/* Stereo schemes (SBX_SCHEME_STEREO) colour a pixel with gradient.eval_continuous(pan), pan = l / (|l| + |r|)
+ * (src/colorscheme.rs:63-66), and every stereo gradient of the reference is a CONTINUOUS spline (the diverging
+ * ColorBrewer schemes), which the 256 steps of lut_rgb only approximate.  This installs a finer table for the pan
+ * lookup: rgb = entries x (r, g, b), entry i = gradient((i + 0.5) / entries), read as
+ * rgb[clamp(floor(pan * entries), 0, entries - 1)] (pan evaluated in f64 as the reference does).  With entries = 4096
+ * a channel differs from eval_continuous(pan) by at most 1 (tests/test_oracle_kat.py states the measured maximum per
+ * gradient and table size).  Alpha (the normalised dB) is unaffected.  Call before sbx_live_create: a live stream
+ * captures the table that is installed when it is created.  The table is copied. */
+SBX_API sbx_status sbx_plan_set_pan_gradient(sbx_plan *plan, const uint8_t *rgb, uint32_t entries);
 
 /* Message for the last failing call on this plan (plan may be NULL: last error of a failed
  * sbx_plan_create on this thread).  Never NULL. */

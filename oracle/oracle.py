@@ -16,7 +16,7 @@ class OrcParams(C.Structure):
     _fields_ = [("sample_rate", C.c_float), ("window_n", C.c_uint32), ("pad_factor", C.c_uint32),
                 ("hop", C.c_uint32), ("rows_h", C.c_uint32), ("f_min", C.c_double), ("f_max", C.c_double),
                 ("db_min", C.c_float), ("db_max", C.c_float), ("db_eps", C.c_float),
-                ("interp", C.c_uint32), ("stereo_scheme", C.c_uint32)]
+                ("interp", C.c_uint32), ("stereo_scheme", C.c_uint32), ("pan_levels", C.c_uint32)]
 
 
 FAST_LIB_PATH = os.path.join(HERE, "liboracle_fast.so")
@@ -122,9 +122,10 @@ def _u8(a):
 
 
 def params(sample_rate=48000.0, window_n=4096, pad_factor=2, hop=512, rows_h=1024, f_min=32.0, f_max=22030.0,
-           db_min=-70.0, db_max=-10.0, db_eps=1e-7, interp=INTERP_CUBIC, stereo_scheme=0):
+           db_min=-70.0, db_max=-10.0, db_eps=1e-7, interp=INTERP_CUBIC, stereo_scheme=0, pan_levels=0):
+    """pan_levels: stereo schemes only -- entries of the lut passed to batch / column_from_magnitudes (0 = 256)."""
     return OrcParams(sample_rate, window_n, pad_factor, hop, rows_h, f_min, f_max, db_min, db_max, db_eps,
-                     interp, stereo_scheme)
+                     interp, stereo_scheme, pan_levels)
 
 
 def num_output_frequencies(n, pad):

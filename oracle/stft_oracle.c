@@ -351,14 +351,23 @@ ORC_API uint32_t orc_color_index(float l, float r, float db_min, float db_max, f
 
 /* Stereo schemes (colorscheme.rs:63-66): colour = gradient(l/(|l|+|r|)) evaluated in f64,
  * alpha = normalised dB; put_pixel alpha = (alpha*255.0) as u8 (simple_spectrogram.rs:159). */
+ORC_API void orc_stereo_color_levels(float l, float r, float db_min, float db_max, float db_eps, uint32_t levels,
+                                     uint32_t *lut_index, uint8_t *alpha);
 ORC_API void orc_stereo_color(float l, float r, float db_min, float db_max, float db_eps,
                               uint32_t *lut_index, uint8_t *alpha)
+{
+    orc_stereo_color_levels(l, r, db_min, db_max, db_eps, 256u, lut_index, alpha);
+}
+/* `levels`: steps of the table standing in for the continuous diverging gradient (256 = the lut_rgb table; more
+ * with the product's sbx_plan_set_pan_gradient): index = clamp(floor(pan * levels), 0, levels - 1) [unvendored] */
+ORC_API void orc_stereo_color_levels(float l, float r, float db_min, float db_max, float db_eps, uint32_t levels,
+                                     uint32_t *lut_index, uint8_t *alpha)
 {
     float t = orc_normalised_db(l, r, db_min, db_max, db_eps);
     float l1 = fabsf(l) + fabsf(r);
     double pan = (double)l / (double)l1;
-    double v = floor(pan * 256.0);
-    *lut_index = !(v >= 0.0) ? 0u : (v > 255.0 ? 255u : (uint32_t)v);
+    double v = floor(pan * (double)levels);
+    *lut_index = !(v >= 0.0) ? 0u : (v > (double)(levels - 1u) ? levels - 1u : (uint32_t)v);
     float a = t * 255.0f;                                        /* Rust `as u8` saturates, NaN -> 0 */
     *alpha = !(a >= 0.0f) ? 0 : (a >= 255.0f ? 255 : (uint8_t)a);
 }
@@ -373,6 +382,7 @@ typedef struct {
     float db_min, db_max, db_eps;
     uint32_t interp;      /* ORC_INTERP_* */
     uint32_t stereo_scheme; /* 0 mono gradient (alpha 255), 1 stereo pan gradient */
+    uint32_t pan_levels;    /* stereo schemes: entries of lut_rgb, indexed by pan (0 = 256) */
 } orc_params;
 
 /* magnitudes (K x (L,R)) -> RGBA column of H rows; row 0 = top = highest frequency */
@@ -387,7 +397,8 @@ ORC_API void orc_column_from_magnitudes(const orc_params *p, const float *mags_l
         c32 m = orc_magnitude_in(d, k_out, period, f0, step, n, (int)p->interp);
         uint32_t row = p->rows_h - py - 1;                       /* :150 */
         uint32_t idx; uint8_t alpha = 255;
-        if (p->stereo_scheme) orc_stereo_color(m.re, m.im, p->db_min, p->db_max, p->db_eps, &idx, &alpha);
+        if (p->stereo_scheme) orc_stereo_color_levels(m.re, m.im, p->db_min, p->db_max, p->db_eps,
+                                                      p->pan_levels ? p->pan_levels : 256u, &idx, &alpha);
         else idx = orc_color_index(m.re, m.im, p->db_min, p->db_max, p->db_eps);
         rgba[4 * row + 0] = lut_rgb[3 * idx + 0];
         rgba[4 * row + 1] = lut_rgb[3 * idx + 1];

@@ -14,7 +14,7 @@ import collections
 import numpy as np
 
 from . import binding
-from .plan import Plan, builtin_lut, samples_from_seconds
+from .plan import Plan, builtin_gradient, builtin_lut, samples_from_seconds
 
 
 class AudioTransform:
@@ -123,10 +123,15 @@ class AudioStreamTransform:
 
 
 class ColorScheme:
-    """ColorScheme (src/colorscheme.rs:22-92) for the 256-entry ramp gradients."""
+    """ColorScheme (src/colorscheme.rs:22-92).  The gradient is held as a table: 256 entries for sbx_config::lut_rgb
+    and, for the stereo schemes (continuous diverging gradients indexed by pan), a finer one for
+    sbx_plan_set_pan_gradient."""
 
-    def __init__(self, lut_rgb, name, background=None):
+    PAN_ENTRIES = 4096
+
+    def __init__(self, lut_rgb, name, background=None, pan_rgb=None):
         self.lut = np.ascontiguousarray(lut_rgb, dtype=np.uint8).reshape(256, 3)
+        self.pan_gradient = None if pan_rgb is None else np.ascontiguousarray(pan_rgb, dtype=np.uint8).reshape(-1, 3)
         self.name = name
         self._background = background
 
@@ -136,7 +141,9 @@ class ColorScheme:
 
     @classmethod
     def new_stereo(cls, gradient, background, name):
-        return cls(builtin_lut(gradient) if isinstance(gradient, str) else gradient, name, tuple(background))
+        if isinstance(gradient, str):
+            return cls(builtin_lut(gradient), name, tuple(background), builtin_gradient(gradient, cls.PAN_ENTRIES))
+        return cls(gradient, name, tuple(background))
 
     @property
     def is_stereo(self):
@@ -150,9 +157,21 @@ class ColorScheme:
 
 
 def default_color_schemes():
-    """The table-type (256-entry ramp) subset of default_color_schemes() (src/colorscheme.rs:125-151)."""
-    return [ColorScheme.new_mono("magma", "Magma"), ColorScheme.new_mono("viridis", "Viridis"),
-            ColorScheme.new_mono("inferno", "Inferno"), ColorScheme.new_mono("plasma", "Plasma")]
+    """default_color_schemes() (src/colorscheme.rs:125-151): all 19, in the reference's order and with its names."""
+    black = (0, 0, 0)
+    return [ColorScheme.new_stereo("red_yellow_blue", black, "Blue-Yellow-Red (Stereo)"),
+            ColorScheme.new_mono("magma", "Magma"), ColorScheme.new_mono("viridis", "Viridis"),
+            ColorScheme.new_stereo("red_blue", black, "Blue-Red (Stereo)"),
+            ColorScheme.new_stereo("spectral", black, "Spectral (Stereo)"),
+            ColorScheme.new_stereo("red_yellow_green", black, "Green-Yellow-Red (Stereo)"),
+            ColorScheme.new_stereo("pink_green", black, "Green-Pink (Stereo)"),
+            ColorScheme.new_stereo("purple_orange", black, "Orange-Purple (Stereo)"),
+            ColorScheme.new_mono("inferno", "Inferno"), ColorScheme.new_mono("plasma", "Plasma"),
+            ColorScheme.new_mono("cividis", "Cividis"), ColorScheme.new_mono("cubehelix", "Cube-helix"),
+            ColorScheme.new_mono("turbo", "Turbo"), ColorScheme.new_mono("cool", "Cool"),
+            ColorScheme.new_mono("reds", "Reds"), ColorScheme.new_mono("blues", "Blues"),
+            ColorScheme.new_mono("greens", "Greens"), ColorScheme.new_mono("greys", "Greys"),
+            ColorScheme.new_mono("oranges", "Oranges")]
 
 
 class SpectrogramColumns:
@@ -184,6 +203,8 @@ class SpectrogramColumns:
         self.plan = Plan(sample_rate=sample_rate, window_n=n, pad_factor=self._pad, hop=hop, rows_h=self.height,
                          channels=2, lut=self.palette.lut, device=self._device,
                          scheme=binding.SCHEME_STEREO if self.palette.is_stereo else binding.SCHEME_MONO)
+        if self.palette.is_stereo and self.palette.pan_gradient is not None:
+            self.plan.set_pan_gradient(self.palette.pan_gradient)
 
     def set_sample_rate(self, sample_rate):
         n = self._window_n_override or samples_from_seconds(np.float32(self._period), np.float32(sample_rate))

@@ -28,6 +28,10 @@ _vp = C.c_void_p
 SYMBOLS = {
     "sbx_config_default": (None, [C.POINTER(SbxConfig)]),
     "sbx_builtin_lut": (C.c_int32, [C.c_char_p, _u8p]),
+    "sbx_builtin_gradient": (C.c_int32, [C.c_char_p, C.c_uint32, _vp]),
+    "sbx_builtin_gradient_count": (C.c_uint32, []),
+    "sbx_builtin_gradient_name": (C.c_char_p, [C.c_uint32, C.POINTER(C.c_int32)]),
+    "sbx_plan_set_pan_gradient": (C.c_int32, [_vp, _vp, C.c_uint32]),
     "sbx_samples_from_seconds": (C.c_uint32, [C.c_float, C.c_float]),
     "sbx_plan_create": (C.c_int32, [C.POINTER(SbxConfig), C.POINTER(_vp)]),
     "sbx_plan_destroy": (None, [_vp]),

@@ -12,6 +12,7 @@
 #include <new>
 
 #include "luts.inc"
+#include "sbx_gradients.h"
 #include "sbx_launch.h"
 #include "sbx_tables.h"
 
@@ -248,6 +249,8 @@ sbx::KernelArgs sbx_plan::base_args() const
     a.thr = d_thr;
     a.lut = d_lut;
     a.ctab = d_ctab;
+    a.pan_lut = d_pan_lut ? d_pan_lut : d_lut;
+    a.pan_levels = d_pan_lut ? pan_levels : 256u;
     a.hop = hop;
     a.rows = rows;
     a.k_out = k_out;
@@ -282,17 +285,27 @@ extern "C" {
 SBX_API uint32_t sbx_abi_version(void) { return SBX_ABI_VERSION; }
 SBX_API const char *sbx_build_arch(void) { return "sm_100a"; }
 
+SBX_API sbx_status sbx_builtin_gradient(const char *name, uint32_t entries, uint8_t *rgb)
+{
+    if (!name || !rgb || entries == 0 || entries > 65536u) return SBX_ERR_INVALID_ARGUMENT;
+    const sbx::gradients::Def *d = sbx::gradients::find(name);
+    if (!d) return SBX_ERR_INVALID_ARGUMENT;
+    sbx::gradients::table(*d, entries, rgb);
+    return SBX_OK;
+}
+
 SBX_API sbx_status sbx_builtin_lut(const char *name, uint8_t lut_rgb[768])
 {
-    if (!name || !lut_rgb) return SBX_ERR_INVALID_ARGUMENT;
-    const unsigned char *src = nullptr;
-    if (!std::strcmp(name, "magma")) src = SBX_LUT_MAGMA;
-    else if (!std::strcmp(name, "viridis")) src = SBX_LUT_VIRIDIS;
-    else if (!std::strcmp(name, "inferno")) src = SBX_LUT_INFERNO;
-    else if (!std::strcmp(name, "plasma")) src = SBX_LUT_PLASMA;
-    if (!src) return SBX_ERR_INVALID_ARGUMENT;
-    std::memcpy(lut_rgb, src, 768);
-    return SBX_OK;
+    return sbx_builtin_gradient(name, 256, lut_rgb);
+}
+
+SBX_API uint32_t sbx_builtin_gradient_count(void) { return 19; }
+
+SBX_API const char *sbx_builtin_gradient_name(uint32_t index, int32_t *is_stereo_scheme)
+{
+    if (index >= 19) return nullptr;
+    if (is_stereo_scheme) *is_stereo_scheme = sbx::gradients::kDefs[index].stereo ? 1 : 0;
+    return sbx::gradients::kDefs[index].name;
 }
 
 SBX_API void sbx_config_default(sbx_config *cfg)
@@ -342,7 +355,7 @@ SBX_API void sbx_plan_destroy(sbx_plan *p)
     }
     cudaFree(p->d_window); cudaFree(p->d_wtw); cudaFree(p->d_twp); cudaFree(p->d_wq); cudaFree(p->d_wq_real); cudaFree(p->d_rowmap); cudaFree(p->d_rowinfo); cudaFree(p->d_chunks);
     cudaFree(p->d_samp); cudaFree(p->d_f16_scratch); cudaFree(p->d_twm); cudaFree(p->d_twg); cudaFree(p->d_pos_tab); cudaFree(p->d_twp_block); cudaFree(p->d_zbuf); cudaFree(p->d_magbuf);
-    cudaFree(p->d_thr); cudaFree(p->d_lut); cudaFree(p->d_ctab); cudaFree(p->d_twp_real); cudaFree(p->d_wtw4); cudaFree(p->d_rtw); cudaFree(p->d_cz_in); cudaFree(p->d_cz_out); cudaFree(p->d_frame); cudaFree(p->d_mags1); cudaFree(p->d_col);
+    cudaFree(p->d_thr); cudaFree(p->d_lut); cudaFree(p->d_pan_lut); cudaFree(p->d_ctab); cudaFree(p->d_twp_real); cudaFree(p->d_wtw4); cudaFree(p->d_rtw); cudaFree(p->d_cz_in); cudaFree(p->d_cz_out); cudaFree(p->d_frame); cudaFree(p->d_mags1); cudaFree(p->d_col);
     if (p->h_frame) cudaFreeHost(p->h_frame);
     if (p->h_col) cudaFreeHost(p->h_col);
     if (p->large_scratch_free) cudaEventDestroy(p->large_scratch_free);
@@ -682,14 +695,38 @@ SBX_API sbx_status sbx_magnitudes_batch_device_f16(sbx_plan *p, const float *d_p
     return SBX_OK;
 }
 
+SBX_API sbx_status sbx_plan_set_pan_gradient(sbx_plan *p, const uint8_t *rgb, uint32_t entries)
+{
+    if (!p) return SBX_ERR_INVALID_ARGUMENT;
+    if (!rgb || entries < 2 || entries > 65536u) return fail(p, SBX_ERR_INVALID_ARGUMENT, "pan gradient: need rgb and 2 <= entries <= 65536");
+    SBX_CUDA(p, cudaSetDevice(p->cfg.device));
+    std::vector<uint32_t> packed(entries);
+    for (uint32_t i = 0; i < entries; ++i)
+        packed[i] = (uint32_t)rgb[3 * i] | ((uint32_t)rgb[3 * i + 1] << 8) | ((uint32_t)rgb[3 * i + 2] << 16) | (255u << 24);
+    SBX_CUDA(p, cudaStreamSynchronize(p->stream));           // no launch may still read the table being replaced
+    uint32_t *d_new = nullptr;
+    SBX_CUDA(p, cudaMalloc(&d_new, (size_t)entries * sizeof(uint32_t)));
+    const cudaError_t e = cudaMemcpy(d_new, packed.data(), (size_t)entries * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(d_new); return cuda_fail(p, e, "pan gradient upload"); }
+    cudaFree(p->d_pan_lut);
+    p->d_pan_lut = d_new;
+    p->pan_levels = entries;
+    p->h_pan_rgb.assign(rgb, rgb + (size_t)entries * 3);
+    return SBX_OK;
+}
+
 SBX_API sbx_status sbx_palette_table(const sbx_plan *p, uint32_t resolution, float *out)
 {
     if (!p || !out || resolution < 2) return SBX_ERR_INVALID_ARGUMENT;
-    // gradient.eval_continuous(t) for the 256-entry ramps: lut[clamp(floor(t * 256), 0, 255)]
-    auto eval = [p](double t, float rgb[3]) {
-        const double v = std::floor(t * 256.0);
-        const int idx = !(v >= 0.0) ? 0 : (v > 255.0 ? 255 : (int)v);
-        for (int c = 0; c < 3; ++c) rgb[c] = (float)p->cfg.lut_rgb[3 * idx + c] / 256.0f;      // colorscheme.rs:83,86
+    // gradient.eval_continuous(t) as a table of `levels` steps: table[clamp(floor(t * levels), 0, levels - 1)]
+    // (exact for the 256-entry ramps; the stereo schemes use the pan gradient where one is installed)
+    const bool pan_table = p->cfg.scheme == SBX_SCHEME_STEREO && !p->h_pan_rgb.empty();
+    const uint8_t *table = pan_table ? p->h_pan_rgb.data() : p->cfg.lut_rgb;
+    const double levels = pan_table ? (double)p->pan_levels : 256.0;
+    auto eval = [table, levels](double t, float rgb[3]) {
+        const double v = std::floor(t * levels);
+        const int idx = !(v >= 0.0) ? 0 : (v > levels - 1.0 ? (int)levels - 1 : (int)v);
+        for (int c = 0; c < 3; ++c) rgb[c] = (float)table[3 * idx + c] / 256.0f;               // colorscheme.rs:83,86
     };
     for (uint32_t i = 0; i < resolution; ++i)
         for (uint32_t j = 0; j < resolution; ++j) {

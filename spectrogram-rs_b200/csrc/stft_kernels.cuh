@@ -68,6 +68,9 @@ struct KernelArgs {
     const float *thr;            // [2][256] pairs (ts[i], ts[i+1]) of step thresholds with sentinels: colour index, alpha
     const uint32_t *lut;         // [256] packed r | g<<8 | b<<16 | 255<<24
     const uint4 *ctab;           // [256] {ts[i], ts[i+1], lut[i], 0}: the colour step and its colour in one 16-byte load
+    const uint32_t *pan_lut;     // stereo schemes: [pan_levels] packed r | g<<8 | b<<16, indexed by floor(pan * pan_levels);
+                                 //   = lut with 256 levels unless sbx_plan_set_pan_gradient installed a finer table
+    uint32_t pan_levels;
     unsigned long long n_frames; // frames per sequence
     // several equally long sequences (planar channels) in one launch: units_per_seq CTAs each, seq_stride FLOATS apart
     // in pcm; sequence s writes frames [s * n_frames, (s+1) * n_frames).  units_per_seq = 0: one sequence.
@@ -958,9 +961,10 @@ __device__ __forceinline__ void resample_samples(const T *mags, T *scratch, cons
 
 // Stereo-scheme gradient index of a mono pixel (l == r >= 0): floor(l / (|l| + |l|) * 256) with the reference's f32
 // sum -- 128 while l + l is finite, 0 once it overflows (l > FLT_MAX / 2: l / inf = 0) and for l = 0 or NaN (NaN -> 0)
-__device__ __forceinline__ uint32_t pan_index_equal(float l)
+__device__ __forceinline__ uint32_t pan_index_equal(float l, uint32_t levels)
 {
-    return (l > 0.0f && __fadd_rn(l, l) <= 3.402823466e+38f) ? 128u : 0u;
+    // floor(0.5 * levels) = levels >> 1 (clamped below levels for every levels >= 1)
+    return (l > 0.0f && __fadd_rn(l, l) <= 3.402823466e+38f) ? (levels >> 1) : 0u;
 }
 
 // Phase B: one thread per row: sequential mean of its samples (the reference's summation order,
@@ -988,10 +992,10 @@ __device__ __forceinline__ void colour_one_row(float ax, float ay, uint32_t n, u
         } else {
             // l == r: pan = l / (|l| + |r|) = 0.5 while the f32 sum l + l is finite (l <= FLT_MAX / 2); beyond that the
             // reference divides by inf -> pan 0, and l = 0 or NaN gives NaN -> index 0 as well
-            const uint32_t panA = pan_index_equal(ax), panB = pan_index_equal(ay);
-            outA[row] = (ldg_tab(lut + panA) & 0x00ffffffu) | ((uint32_t)step_index(thr_a, pA, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
+            const uint32_t panA = pan_index_equal(ax, a.pan_levels), panB = pan_index_equal(ay, a.pan_levels);
+            outA[row] = (ldg_tab(a.pan_lut + panA) & 0x00ffffffu) | ((uint32_t)step_index(thr_a, pA, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
             if (second_valid)
-                outB[row] = (ldg_tab(lut + panB) & 0x00ffffffu) | ((uint32_t)step_index(thr_a, pB, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
+                outB[row] = (ldg_tab(a.pan_lut + panB) & 0x00ffffffu) | ((uint32_t)step_index(thr_a, pB, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
         }
     } else {
         const float p = __fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay));    // norm_sqr
@@ -999,9 +1003,9 @@ __device__ __forceinline__ void colour_one_row(float ax, float ay, uint32_t n, u
             outA[row] = step_colour(a, p);
         } else {
             const double pan = (double)ax / (double)__fadd_rn(fabsf(ax), fabsf(ay));
-            const double v = floor(pan * 256.0);
-            const uint32_t idx = !(v >= 0.0) ? 0u : (v > 255.0 ? 255u : (uint32_t)v);
-            outA[row] = (ldg_tab(lut + idx) & 0x00ffffffu) | ((uint32_t)step_index(thr_a, p, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
+            const double v = floor(pan * (double)a.pan_levels);
+            const uint32_t idx = !(v >= 0.0) ? 0u : (v > (double)(a.pan_levels - 1u) ? a.pan_levels - 1u : (uint32_t)v);
+            outA[row] = (ldg_tab(a.pan_lut + idx) & 0x00ffffffu) | ((uint32_t)step_index(thr_a, p, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
         }
     }
 }
@@ -1015,8 +1019,8 @@ __device__ __forceinline__ void colour_one_row_single(float ax, uint32_t n, uint
     if (a.scheme == 0) {
         out[row] = step_colour(a, p);
     } else {
-        const uint32_t pan = pan_index_equal(ax);                            // l / (|l| + |l|), see colour_one_row
-        out[row] = (ldg_tab(a.lut + pan) & 0x00ffffffu) |
+        const uint32_t pan = pan_index_equal(ax, a.pan_levels);              // l / (|l| + |l|), see colour_one_row
+        out[row] = (ldg_tab(a.pan_lut + pan) & 0x00ffffffu) |
                    ((uint32_t)step_index(a.thr + THR_STRIDE, p, a.db_eps, a.guess_a[1], a.guess_b[1]) << 24);
     }
 }

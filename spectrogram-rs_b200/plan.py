@@ -15,13 +15,29 @@ class SbxError(RuntimeError):
         self.status = status
 
 
-def builtin_lut(name):
-    """256x3 uint8 ramp: 'magma' | 'viridis' | 'inferno' | 'plasma' (src/colorscheme.rs:131-139)."""
-    lut = np.empty(768, np.uint8)
-    st = binding.load().sbx_builtin_lut(name.encode(), lut.ctypes.data_as(C.POINTER(C.c_uint8)))
+def builtin_gradient(name, entries=256):
+    """(entries, 3) uint8 table of one of the reference's 19 gradients (src/colorscheme.rs:129-149), entry i =
+    gradient((i + 0.5) / entries): 'magma', 'viridis', 'red_yellow_blue', 'turbo', ... (builtin_gradient_names())."""
+    lut = np.empty(entries * 3, np.uint8)
+    st = binding.load().sbx_builtin_gradient(name.encode(), entries, lut.ctypes.data)
     if st != binding.SBX_OK:
-        raise SbxError(st, f"unknown built-in colour ramp {name!r}")
-    return lut.reshape(256, 3)
+        raise SbxError(st, f"unknown built-in gradient {name!r} (or entries outside 1..65536)")
+    return lut.reshape(entries, 3)
+
+
+def builtin_lut(name):
+    """256x3 uint8 table for sbx_config::lut_rgb."""
+    return builtin_gradient(name, 256)
+
+
+def builtin_gradient_names():
+    """[(name, is_stereo_scheme)] in the order of default_color_schemes() (src/colorscheme.rs:129-149)."""
+    lib = binding.load()
+    out = []
+    for i in range(lib.sbx_builtin_gradient_count()):
+        stereo = C.c_int32()
+        out.append((lib.sbx_builtin_gradient_name(i, C.byref(stereo)).decode(), bool(stereo.value)))
+    return out
 
 
 def samples_from_seconds(seconds, sample_rate):
@@ -185,6 +201,12 @@ class Plan:
         self._check(self._lib.sbx_blit_columns_device(self._h, _ptr(d_columns), n_frames, _ptr(d_image), width,
                                                       rowstride_bytes, first_column, C.byref(nxt)))
         return int(nxt.value)
+
+    def set_pan_gradient(self, rgb):
+        """Stereo schemes: a finer table for the pan lookup, (entries, 3) uint8 with entry i = gradient((i + 0.5) /
+        entries) (sbx_plan_set_pan_gradient); e.g. builtin_gradient('red_yellow_blue', 4096)."""
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8).reshape(-1, 3)
+        self._check(self._lib.sbx_plan_set_pan_gradient(self._h, rgb.ctypes.data, rgb.shape[0]))
 
     def set_stream(self, cuda_stream):
         self._check(self._lib.sbx_set_stream(self._h, cuda_stream))

@@ -113,3 +113,15 @@ def sample_table(cfg):
         raise RuntimeError("emu_sample_table: buffers too small")
     return dict(samp=samp[:got].copy(), chunks=chunks[:n_chunks.value].copy(), rowinfo=rowinfo, bank_group=int(bank_group.value),
                 ok=bool(ok.value))
+
+
+def set_pan_gradient(rgb):
+    """Stereo schemes: install (entries, 3) uint8 as the pan table of the emulated kernels; None restores the 256-entry lut."""
+    fn = lib().emu_set_pan_gradient
+    fn.restype = None
+    fn.argtypes = [C.c_void_p, C.c_uint32]
+    if rgb is None:
+        fn(None, 0)
+    else:
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8).reshape(-1, 3)
+        fn(rgb.ctypes.data, rgb.shape[0])

@@ -13,6 +13,7 @@ namespace {
 bool g_emu_staged = false;
 bool g_emu_wide = false;                // stereo frames on the WIDE (single-frame latency) geometries
 bool g_emu_q2 = false;                  // pad factor 2 on the packed-lane kernel of stft_q2.cuh
+std::vector<uint32_t> g_emu_pan_lut;    // stereo schemes: finer pan gradient (sbx_plan_set_pan_gradient), empty = the 256-entry lut
 int g_emu_real = 2;                     // mono batches on the REAL geometry: 0 never, 1 wherever its tables exist, 2 the product's default
 
 template <class G, int P, int END = G::NPASS> struct EmuPasses {
@@ -344,6 +345,8 @@ long long emu_batch(const sbx_config *cfg, const float *pcm, unsigned long long 
     a.thr = t.thr.data();
     a.lut = t.lut;
     a.ctab = reinterpret_cast<const uint4 *>(t.ctab);
+    a.pan_lut = g_emu_pan_lut.empty() ? t.lut : g_emu_pan_lut.data();
+    a.pan_levels = g_emu_pan_lut.empty() ? 256u : (uint32_t)g_emu_pan_lut.size();
     a.n_frames = frames;
     a.hop = cfg->hop; a.rows = t.rows; a.k_out = t.k_out;
     a.scale = t.scale; a.db_eps = cfg->db_eps; a.neg_zero = -0.0f; a.step_margin = t.step_margin;
@@ -426,6 +429,14 @@ void emu_set_wide(int wide) { g_emu_wide = wide != 0; }
 
 __attribute__((visibility("default")))
 void emu_set_q2(int q2) { g_emu_q2 = q2 != 0; }
+
+__attribute__((visibility("default")))
+void emu_set_pan_gradient(const uint8_t *rgb, uint32_t entries)
+{
+    g_emu_pan_lut.clear();
+    for (uint32_t i = 0; rgb && i < entries; ++i)
+        g_emu_pan_lut.push_back((uint32_t)rgb[3 * i] | ((uint32_t)rgb[3 * i + 1] << 8) | ((uint32_t)rgb[3 * i + 2] << 16) | (255u << 24));
+}
 
 // host tables of the product, exposed so CPU tests can compare them with the oracle bit for bit
 __attribute__((visibility("default")))

@@ -310,3 +310,27 @@ def test_sample_table_lane_groups_are_conflict_free(magma, monkeypatch, n, pad, 
     assert fillers <= 0.1 * (~filler).sum() + g if fill else fillers == 0
     if (n, pad) in ((4096, 2), (8192, 2), (4096, 4)):
         assert len(chunks) == 1
+
+
+@pytest.mark.parametrize("n,pad,ch,hop,rows,entries", [(1024, 2, 2, 256, 256, 4096), (512, 2, 1, 128, 100, 1024), (2400, 2, 2, 58, 128, 4096)])
+def test_stereo_scheme_with_a_finer_pan_gradient(n, pad, ch, hop, rows, entries):
+    """sbx_plan_set_pan_gradient: the pan lookup reads a table of `entries` steps of the continuous diverging
+    gradient instead of the 256 of lut_rgb; alpha is unchanged.  Bit-exact against the oracle given the GPU-side
+    (here: emulated) magnitudes."""
+    import spectrogram_rs_b200 as sbx
+    lut = sbx.builtin_lut("red_yellow_blue")
+    pan = sbx.builtin_gradient("red_yellow_blue", entries)
+    cfg = emu.make_config(lut, window_n=n, pad_factor=pad, hop=hop, rows_h=rows, channels=ch, scheme=1)
+    x = signals.stereo_loopback(n + hop * 4) if ch == 2 else signals.log_sweep(n + hop * 4)
+    emu.set_pan_gradient(pan)
+    try:
+        mags, rgba = emu.batch(cfg, x)
+    finally:
+        emu.set_pan_gradient(None)
+    p = oracle.params(window_n=n, pad_factor=pad, hop=hop, rows_h=rows, stereo_scheme=1, pan_levels=entries)
+    for f in range(mags.shape[0]):
+        assert np.array_equal(rgba[f], oracle.column_from_magnitudes(p, mags[f], pan)), f
+    # the finer table does change pixels relative to the 256-step one (it is not a no-op) for genuinely stereo input
+    if ch == 2:
+        _, coarse = emu.batch(cfg, x)
+        assert (coarse[..., :3] != rgba[..., :3]).any() and np.array_equal(coarse[..., 3], rgba[..., 3])

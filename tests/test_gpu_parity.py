@@ -741,3 +741,42 @@ def test_q2_real_sequence_geometry(sbx, viridis, monkeypatch, n, hop, rows, inte
             out[mode] = g_mags
     peak = np.abs(out["0"]).max(axis=(1, 2), keepdims=True)
     assert (np.abs(out["1"] - out["0"]) / peak).max() <= MAG_TOL
+
+
+@pytest.mark.parametrize("n,pad,ch,hop,rows,entries", [(1024, 2, 2, 256, 256, 4096), (4096, 2, 2, 512, 1024, 1024),
+                                                       (4096, 2, 1, 512, 512, 4096), (2400, 2, 2, 58, 128, 4096),
+                                                       (16384, 4, 2, 2048, 256, 4096)])
+def test_stereo_scheme_with_a_finer_pan_gradient(sbx, n, pad, ch, hop, rows, entries):
+    """sbx_plan_set_pan_gradient (all kernel families): the stereo schemes' continuous diverging gradient
+    (colorscheme.rs:63-66, RED_YELLOW_BLUE is the application's default) read from a table of `entries` steps.
+    Bit-exact with the oracle given identical magnitudes; the palette table follows the installed gradient."""
+    lut = sbx.builtin_lut("red_yellow_blue")
+    pan = sbx.builtin_gradient("red_yellow_blue", entries)
+    ns = n + hop * 4
+    pcm = signals.stereo_loopback(ns) if ch == 2 else signals.white_noise(ns)
+    if ch == 2:
+        pcm[:, 1] *= np.linspace(0, 2, ns).astype(np.float32)
+    p = oracle.params(window_n=n, pad_factor=pad, hop=hop, rows_h=rows, stereo_scheme=1, pan_levels=entries)
+    with sbx.Plan(window_n=n, pad_factor=pad, hop=hop, rows_h=rows, channels=ch, lut=lut, scheme=1) as plan:
+        coarse = plan.process_batch(pcm)
+        plan.set_pan_gradient(pan)
+        g = plan.process_batch(pcm)
+        o_rgba, o_mags = oracle.batch(p, pcm, ch, pan, want_mags=True)
+        assert np.array_equal(plan.colorize_magnitudes(o_mags), o_rgba)
+        assert (g != o_rgba).any(axis=2).mean() <= 2e-3
+        assert np.array_equal(g[..., 3], coarse[..., 3])                   # alpha does not depend on the gradient table
+        if ch == 2:
+            assert (g[..., :3] != coarse[..., :3]).any()
+            # a single frame through the single-frame and the live entry points reads the same table
+            lr = pcm[:n]
+            col = plan.process_column(lr)
+            assert np.array_equal(col, oracle.column_from_magnitudes(p, plan.process_magnitudes(lr), pan))
+            live = plan.live(max(4096, n))
+            live.push(lr)
+            assert np.array_equal(live.pop_column(), col)
+            live.close()
+        tab = plan.palette_table(8)
+        assert np.allclose(tab[0, 0, :3], pan[-1] / 256.0) and np.allclose(tab[0, -1, :3], pan[0] / 256.0)
+    with sbx.Plan(window_n=1024, lut=lut, scheme=1) as plan:
+        with pytest.raises(sbx.SbxError):
+            plan.set_pan_gradient(np.zeros((1, 3), np.uint8))

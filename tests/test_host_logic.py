@@ -82,8 +82,14 @@ def test_literal_conversions_match_oracle(sbx):
 
 def test_color_scheme_objects(sbx):
     schemes = sbx.default_color_schemes()
-    assert [s.name for s in schemes] == ["Magma", "Viridis", "Inferno", "Plasma"]
-    magma = schemes[0]
+    # default_color_schemes(), src/colorscheme.rs:129-149: all 19, in the reference's order and with its display names
+    assert [s.name for s in schemes] == [
+        "Blue-Yellow-Red (Stereo)", "Magma", "Viridis", "Blue-Red (Stereo)", "Spectral (Stereo)", "Green-Yellow-Red (Stereo)",
+        "Green-Pink (Stereo)", "Orange-Purple (Stereo)", "Inferno", "Plasma", "Cividis", "Cube-helix", "Turbo", "Cool", "Reds",
+        "Blues", "Greens", "Greys", "Oranges"]
+    assert [s.is_stereo for s in schemes] == [True, False, False] + [True] * 5 + [False] * 11
+    assert all(s.background() == (0, 0, 0) for s in schemes if s.is_stereo)            # Color { r: 0, g: 0, b: 0 }
+    magma = schemes[1]
     assert not magma.is_stereo and magma.background() == (0, 0, 4) and magma.foreground() == (252, 253, 191)
     st = sbx.ColorScheme.new_stereo("viridis", (0, 0, 0), "x")
     assert st.is_stereo and st.background() == (0, 0, 0) and st.foreground() == tuple(int(v) for v in st.lut[128])

@@ -223,3 +223,62 @@ def test_fast_build_equals_the_checker():
         assert rgba_p.shape == rgba.shape
         assert (rgba_p != rgba).any(axis=2).mean() <= 1e-3
         assert np.abs(rgba_p.astype(int) - rgba.astype(int)).max() <= 40
+
+
+# ---- the 19 gradients of default_color_schemes() (src/colorscheme.rs:129-149) ------------------------------------
+REFERENCE_SCHEMES = [  # (colorous constant lower-cased, stereo?) in the reference's list order
+    ("red_yellow_blue", True), ("magma", False), ("viridis", False), ("red_blue", True), ("spectral", True),
+    ("red_yellow_green", True), ("pink_green", True), ("purple_orange", True), ("inferno", False), ("plasma", False),
+    ("cividis", False), ("cubehelix", False), ("turbo", False), ("cool", False), ("reds", False), ("blues", False),
+    ("greens", False), ("greys", False), ("oranges", False)]
+
+
+def test_builtin_gradients_cover_the_reference_list():
+    """sbx_builtin_lut / sbx_builtin_gradient know every gradient the reference lists, in its order (host-side
+    functions of the product library: no GPU involved)."""
+    import re
+    import spectrogram_rs_b200 as sbx
+    assert sbx.builtin_gradient_names() == REFERENCE_SCHEMES
+    ref = "/root/reference/src/colorscheme.rs"
+    if os.path.exists(ref):                                   # in the build container only: the constants as written there
+        names = re.findall(r"ColorScheme::new_(mono|stereo)\((\w+),", open(ref).read())
+        assert [(n.lower(), kind == "stereo") for kind, n in names] == REFERENCE_SCHEMES
+    for name, _ in REFERENCE_SCHEMES:
+        t = sbx.builtin_lut(name)
+        assert t.shape == (256, 3) and len(np.unique(t, axis=0)) > 100
+    with pytest.raises(sbx.SbxError):
+        sbx.builtin_lut("jet")
+    py = sbx.default_color_schemes()
+    assert len(py) == 19 and [s.is_stereo for s in py] == [st for _, st in REFERENCE_SCHEMES]
+    assert py[0].name == "Blue-Yellow-Red (Stereo)" and py[0].pan_gradient.shape == (4096, 3)
+
+
+def test_builtin_gradients_against_second_sources():
+    """[unvendored] colorous is absent; what can be cross-checked here: the four ramps equal OpenCV's matplotlib
+    tables exactly; d3's polynomial Turbo / Cividis approximate the original tables OpenCV ships (their published
+    accuracy: a few levels on average); the ColorBrewer splines start and end on the scheme's first / last colour;
+    and a table of E steps deviates from the continuous gradient by <= 2 levels at E = 256 (6 for Turbo, whose
+    blue channel is steep) and <= 1 at E = 4096 -- the numbers include/sbx.h quotes for sbx_plan_set_pan_gradient."""
+    cv2 = pytest.importorskip("cv2")
+    import spectrogram_rs_b200 as sbx
+    ramp = np.arange(256, dtype=np.uint8).reshape(256, 1)
+    for name, code, max_tol, mean_tol in (("magma", cv2.COLORMAP_MAGMA, 0, 0), ("viridis", cv2.COLORMAP_VIRIDIS, 0, 0),
+                                          ("inferno", cv2.COLORMAP_INFERNO, 0, 0), ("plasma", cv2.COLORMAP_PLASMA, 0, 0),
+                                          ("turbo", cv2.COLORMAP_TURBO, 30, 7), ("cividis", cv2.COLORMAP_CIVIDIS, 20, 3)):
+        ref = cv2.applyColorMap(ramp, code).reshape(256, 3)[:, ::-1].astype(int)
+        d = np.abs(sbx.builtin_lut(name).astype(int) - ref)
+        assert d.max() <= max_tol and d.mean() <= mean_tol, (name, d.max(), d.mean())
+    ends = {"red_yellow_blue": (0xa50026, 0x313695), "red_blue": (0x67001f, 0x053061), "spectral": (0x9e0142, 0x5e4fa2),
+            "red_yellow_green": (0xa50026, 0x006837), "pink_green": (0x8e0152, 0x276419), "purple_orange": (0x2d004b, 0x7f3b08),
+            "reds": (0xfff5f0, 0x67000d), "blues": (0xf7fbff, 0x08306b), "greens": (0xf7fcf5, 0x00441b),
+            "greys": (0xffffff, 0x000000), "oranges": (0xfff5eb, 0x7f2704)}
+    for name, (first, last) in ends.items():
+        dense = sbx.builtin_gradient(name, 65536).astype(int)
+        for got, want in ((dense[0], first), (dense[-1], last)):
+            assert np.abs(got - [(want >> 16) & 255, (want >> 8) & 255, want & 255]).max() <= 1, name
+    for name, _ in REFERENCE_SCHEMES:
+        dense = sbx.builtin_gradient(name, 65536).astype(int)
+        for entries, tol in ((256, 6 if name == "turbo" else 2), (1024, 2), (4096, 1)):
+            tab = sbx.builtin_gradient(name, entries).astype(int)
+            idx = np.minimum((np.arange(65536) + 0.5) / 65536 * entries, entries - 1).astype(int)
+            assert np.abs(tab[idx] - dense).max() <= tol, (name, entries)
