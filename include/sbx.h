@@ -120,6 +120,8 @@ SBX_API uint32_t sbx_samples_from_seconds(float seconds, float sample_rate);
  *   - N a power of two, 256 .. 65536, P in {1, 2, 4}, M = P*N <= 262144 (M > 16384 needs N >= 8192);
  *   - N = 2^a 3^b 5^c 7^d otherwise (the application's 2400 / 2205 / 4800 / 9600, the widgets' N = 100),
  *     P in {1, 2, 4} with M even and 12*M bytes within one SM's shared memory (M <= 19370);
+ *   - any other N (a prime factor > 7: 1102 = 2*19*29 at 22.05 kHz, 551 at 11.025 kHz, primes) by Bluestein's
+ *     chirp-z over a power-of-two convolution, as long as N*(P+1) - 1 <= 16384 (N <= 5461 at P = 2), M even;
  *   - any hop >= 1, H in [1, 2^20], channels 1 or 2, both interpolators, both scheme kinds.
  * Plan creation computes every table on the host (window, twiddles, bin map, per-sample positions and weights,
  * dB-step thresholds) and uploads them; the kernels never evaluate exp / log / cos. */

@@ -19,12 +19,22 @@ sbx_status launch_generic(sbx_plan *p, int channels, const float *d_pcm, uint64_
     g.twm = p->d_twm;
     g.twg = p->d_twg;
     g.pos_tab = p->d_pos_tab;
-    const size_t smem = (size_t)p->m * 12;                      // transform [M] + magnitudes [M/2], float2
+    g.bl_a = p->d_bl_a;
+    g.bl_bf = p->d_bl_bf;
+    g.bl_c = p->d_bl_c;
+    // transform [M] (Bluestein: the convolution buffer [L]) + magnitudes [M/2], float2
+    const size_t smem = p->bluestein ? (size_t)p->bl_len * 8 + (size_t)p->m * 4 : (size_t)p->m * 12;
     const uint64_t ctas = channels == 1 ? (n_frames + 1) / 2 : n_frames;
     if (ctas > 0x7fffffffull) return fail(p, SBX_ERR_INVALID_ARGUMENT, "too many frames in one launch");
-    static std::atomic<bool> configured1[kMaxDevices], configured2[kMaxDevices];
+    static std::atomic<bool> configured1[kMaxDevices], configured2[kMaxDevices], configured1b[kMaxDevices], configured2b[kMaxDevices];
     cudaError_t e;
-    if (channels == 1) {
+    if (p->bluestein && channels == 1) {
+        e = allow_smem(generic_frames_kernel<1, true>, kMaxSmemOptIn, configured1b);
+        if (e == cudaSuccess) { generic_frames_kernel<1, true><<<(unsigned)ctas, GENERIC_THREADS, smem, stream>>>(g); e = cudaGetLastError(); }
+    } else if (p->bluestein) {
+        e = allow_smem(generic_frames_kernel<2, true>, kMaxSmemOptIn, configured2b);
+        if (e == cudaSuccess) { generic_frames_kernel<2, true><<<(unsigned)ctas, GENERIC_THREADS, smem, stream>>>(g); e = cudaGetLastError(); }
+    } else if (channels == 1) {
         e = allow_smem(generic_frames_kernel<1>, kMaxSmemOptIn, configured1);
         if (e == cudaSuccess) { generic_frames_kernel<1><<<(unsigned)ctas, GENERIC_THREADS, smem, stream>>>(g); e = cudaGetLastError(); }
     } else {

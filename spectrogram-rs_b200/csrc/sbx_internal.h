@@ -42,6 +42,10 @@ struct sbx_plan {
     std::vector<uint32_t> radix, stride;
     sbx::GenericArgs generic_passes{};  // pass description (radices, strides, table offsets), filled at plan creation
     float2 *d_twg = nullptr;            // per-pass twiddle planes
+    // Bluestein (generic windows with a prime factor > 7): chirp tables, convolution length
+    bool bluestein = false;
+    uint32_t bl_len = 0;
+    float2 *d_bl_a = nullptr, *d_bl_bf = nullptr, *d_bl_c = nullptr;
 
     // REAL geometry (mono batches of long windows, one frame per CTA): tables of the half-length packed transform
     bool real_ok = false;               // tables exist

@@ -354,7 +354,7 @@ SBX_API void sbx_plan_destroy(sbx_plan *p)
         cudaFree(s.d_rgba);
     }
     cudaFree(p->d_window); cudaFree(p->d_wtw); cudaFree(p->d_twp); cudaFree(p->d_wq); cudaFree(p->d_wq_real); cudaFree(p->d_rowmap); cudaFree(p->d_rowinfo); cudaFree(p->d_chunks);
-    cudaFree(p->d_samp); cudaFree(p->d_f16_scratch); cudaFree(p->d_twm); cudaFree(p->d_twg); cudaFree(p->d_pos_tab); cudaFree(p->d_twp_block); cudaFree(p->d_zbuf); cudaFree(p->d_magbuf);
+    cudaFree(p->d_samp); cudaFree(p->d_f16_scratch); cudaFree(p->d_twm); cudaFree(p->d_bl_a); cudaFree(p->d_bl_bf); cudaFree(p->d_bl_c); cudaFree(p->d_twg); cudaFree(p->d_pos_tab); cudaFree(p->d_twp_block); cudaFree(p->d_zbuf); cudaFree(p->d_magbuf);
     cudaFree(p->d_thr); cudaFree(p->d_lut); cudaFree(p->d_pan_lut); cudaFree(p->d_ctab); cudaFree(p->d_twp_real); cudaFree(p->d_wtw4); cudaFree(p->d_rtw); cudaFree(p->d_cz_in); cudaFree(p->d_cz_out); cudaFree(p->d_frame); cudaFree(p->d_mags1); cudaFree(p->d_col);
     if (p->h_frame) cudaFreeHost(p->h_frame);
     if (p->h_col) cudaFreeHost(p->h_col);
@@ -376,8 +376,6 @@ SBX_API sbx_status sbx_plan_create(const sbx_config *cfg, sbx_plan **out_plan)
     const bool generic = log2n < (int)kMinLog2N;                  // not a power of two, or a tiny one
     if (generic) {
         log2n = -1;
-        if ((uint64_t)cfg->window_n * cfg->pad_factor * 12 > sbx::kMaxSmemOptIn)
-            return fail(nullptr, SBX_ERR_UNSUPPORTED, "non-power-of-two windows need window_n * pad_factor <= 19370 (one SM's shared memory)");
         if (((cfg->window_n * cfg->pad_factor) & 1u) != 0)
             return fail(nullptr, SBX_ERR_UNSUPPORTED, "window_n * pad_factor must be even");
         if (cfg->window_n * cfg->pad_factor < 8)
@@ -385,8 +383,14 @@ SBX_API sbx_status sbx_plan_create(const sbx_config *cfg, sbx_plan **out_plan)
         uint32_t rest = cfg->window_n;
         for (uint32_t f : {2u, 3u, 5u, 7u})
             while (rest % f == 0) rest /= f;
-        if (rest != 1)
-            return fail(nullptr, SBX_ERR_UNSUPPORTED, "window_n has a prime factor larger than 7 (supported radices: 2, 3, 4, 5, 7, 8, 16)");
+        if (rest != 1) {
+            // a prime factor > 7: Bluestein, a circular convolution of power-of-two length >= N + M - 1 in shared memory
+            if ((uint64_t)cfg->window_n * (cfg->pad_factor + 1) - 1 > sbx::BLUESTEIN_MAX_LEN)
+                return fail(nullptr, SBX_ERR_UNSUPPORTED, "window_n has a prime factor larger than 7 and window_n * (pad_factor + 1) - 1 exceeds 16384 "
+                                                          "(the Bluestein path's convolution length)");
+        } else if ((uint64_t)cfg->window_n * cfg->pad_factor * 12 > sbx::kMaxSmemOptIn) {
+            return fail(nullptr, SBX_ERR_UNSUPPORTED, "non-power-of-two windows need window_n * pad_factor <= 19370 (one SM's shared memory)");
+        }
     } else {
         if (log2n > (int)kMaxLog2NLarge) return fail(nullptr, SBX_ERR_UNSUPPORTED, "window_n must be <= 65536");
         if (log2n + log2pad > (int)kMaxLog2MLarge)
@@ -478,6 +482,11 @@ SBX_API sbx_status sbx_plan_create(const sbx_config *cfg, sbx_plan **out_plan)
     SBX_TRY(upload(&p->d_wtw4, t.wtw4.data(), t.wtw4.size() * sizeof(float)));
     SBX_TRY(upload(&p->d_rtw, t.rtw.data(), t.rtw.size() * sizeof(float)));
     SBX_TRY(upload(&p->d_twm, t.twm.data(), t.twm.size() * sizeof(float)));
+    p->bluestein = t.bluestein;
+    p->bl_len = t.bl_len;
+    SBX_TRY(upload(&p->d_bl_a, t.bl_a.data(), t.bl_a.size() * sizeof(float)));
+    SBX_TRY(upload(&p->d_bl_bf, t.bl_bf.data(), t.bl_bf.size() * sizeof(float)));
+    SBX_TRY(upload(&p->d_bl_c, t.bl_c.data(), t.bl_c.size() * sizeof(float)));
     SBX_TRY(upload(&p->d_twg, t.twg.data(), t.twg.size() * sizeof(float)));
     SBX_TRY(upload(&p->d_pos_tab, t.pos_tab.data(), t.pos_tab.size() * sizeof(uint32_t)));
     SBX_TRY(upload(&p->d_twp_block, t.twp_block.data(), t.twp_block.size() * sizeof(float)));
@@ -512,7 +521,7 @@ SBX_API uint64_t sbx_launch_count(const sbx_plan *p) { return p ? p->launches : 
 SBX_API const char *sbx_kernel_path(const sbx_plan *p)
 {
     if (!p) return "";
-    if (p->generic) return "generic";
+    if (p->generic) return p->bluestein ? "bluestein" : "generic";
     if (p->channels == 1 && p->use_real && (p->hop & 1u) == 0) return p->use_q2_real ? "fused-real-q2" : "fused-real";
     if (p->large) return "large";
     if (p->use_q2[p->channels - 1]) return p->channels == 1 ? "fused-pair-q2" : "fused-stereo-q2";

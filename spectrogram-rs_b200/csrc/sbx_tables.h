@@ -106,6 +106,13 @@ struct HostTables {
     std::vector<uint32_t> radix, stride;// generic: per-pass radix and butterfly stride
     std::vector<float> twg;             // generic: per-pass twiddle planes, see GenericArgs::twg
     std::vector<uint32_t> tw_off;       // generic: first entry of each pass in twg
+    // Bluestein (generic windows with a prime factor > 7): radix / stride / twg / tw_off / pos_tab describe the
+    // power-of-two convolution length bl_len instead of N
+    bool bluestein = false;
+    uint32_t bl_len = 0;
+    std::vector<float> bl_a;            // [N] x (re, im): window[n] * conj(b[n]), b[j] = exp(+i pi j^2 / M)
+    std::vector<float> bl_bf;           // [L] x (re, im): FFT_L(b wrapped mod L) / L, stored at the position of each bin
+    std::vector<float> bl_c;            // [M] x (re, im): conj(b[k])
     std::vector<RowMap> rowmap;         // [H]
     std::vector<uint32_t> rowinfo;      // [H] n | first scratch slot << 16 (what the kernels read)
     std::vector<RowChunk> chunks;       // rows grouped so that a chunk's samples fit the kernel's scratch area
@@ -167,8 +174,24 @@ inline void build(const sbx_config &cfg, HostTables &t)
         const uint32_t cand[] = {16, 8, 4, 2, 3, 5, 7};
         for (uint32_t r : cand)
             while (rest % r == 0 && rest > 1) { t.radix.push_back(r); rest /= r; }
-        if (rest != 1 || t.radix.size() > (size_t)GENERIC_MAX_PASSES || (t.m & 1u) || t.m < 8) { t.radix.clear(); t.ok = false; return; }
-        uint32_t s = t.n;
+        if ((t.m & 1u) || t.m < 8) { t.radix.clear(); t.ok = false; return; }
+        uint32_t fft_len = t.n;                                  // length the passes transform (P sub-transforms of N)
+        if (rest != 1 || t.radix.size() > (size_t)GENERIC_MAX_PASSES) {
+            // a prime factor > 7 (N = 1102 = 2 * 19 * 29 at 22.05 kHz, 551, ...): Bluestein over a power-of-two
+            // circular convolution of length L >= N + M - 1, which must fit one SM's shared memory beside the magnitudes
+            uint32_t len = 8;
+            while (len < t.n + t.m - 1) len <<= 1;
+            if (len > BLUESTEIN_MAX_LEN) { t.radix.clear(); t.ok = false; return; }
+            t.bluestein = true;
+            t.bl_len = fft_len = len;
+            t.radix.clear();
+            for (uint32_t rest2 = len; rest2 > 1;) {
+                const uint32_t r = rest2 % 16 == 0 ? 16u : (rest2 % 8 == 0 ? 8u : (rest2 % 4 == 0 ? 4u : 2u));
+                t.radix.push_back(r);
+                rest2 /= r;
+            }
+        }
+        uint32_t s = fft_len;
         for (uint32_t r : t.radix) { s /= r; t.stride.push_back(s); }
         t.twm.resize((size_t)t.m * 2);
         for (uint32_t k = 0; k < t.m; ++k) {
@@ -190,11 +213,61 @@ inline void build(const sbx_config &cfg, HostTables &t)
                 }
         }
         // bin kk = P k + q0, k = sum d_p (R_0 .. R_(p-1))  ->  position q0 N + sum d_p S_p
-        t.pos_tab.resize(t.m);
-        for (uint32_t kk = 0; kk < t.m; ++kk) {
-            uint32_t k = kk / t.pad, pos = (kk % t.pad) * t.n;
+        const uint32_t tab_len = t.bluestein ? t.bl_len : t.m, tab_pad = t.bluestein ? 1u : t.pad, tab_n = t.bluestein ? t.bl_len : t.n;
+        t.pos_tab.resize(tab_len);
+        for (uint32_t kk = 0; kk < tab_len; ++kk) {
+            uint32_t k = kk / tab_pad, pos = (kk % tab_pad) * tab_n;
             for (size_t p = 0; p < t.radix.size(); ++p) { pos += (k % t.radix[p]) * t.stride[p]; k /= t.radix[p]; }
             t.pos_tab[kk] = pos;
+        }
+        if (t.bluestein) {
+            const uint32_t len = t.bl_len;
+            // b[j] = exp(+i pi j^2 / M): the angle from j^2 mod 2M, exactly (integers), then f64 cos / sin
+            auto chirp = [&](uint64_t j, double &re, double &im) {
+                const uint64_t r = (j * j) % (2ull * t.m);
+                const double ang = M_PI * (double)r / (double)t.m;
+                re = std::cos(ang); im = std::sin(ang);
+            };
+            t.bl_a.resize((size_t)t.n * 2);
+            for (uint32_t i = 0; i < t.n; ++i) {
+                double re, im;
+                chirp(i, re, im);
+                t.bl_a[2 * (size_t)i] = (float)((double)t.window[i] * re);
+                t.bl_a[2 * (size_t)i + 1] = (float)(-(double)t.window[i] * im);
+            }
+            t.bl_c.resize((size_t)t.m * 2);
+            for (uint32_t k = 0; k < t.m; ++k) {
+                double re, im;
+                chirp(k, re, im);
+                t.bl_c[2 * (size_t)k] = (float)re;
+                t.bl_c[2 * (size_t)k + 1] = (float)(-im);
+            }
+            // h[j mod L] = b[j] for j in [-(N-1), M-1]; its L-point DFT in f64 (iterative radix 2), scaled by 1 / L
+            std::vector<double> hr(len, 0.0), hi(len, 0.0);
+            for (uint32_t j = 0; j < t.m; ++j) chirp(j, hr[j], hi[j]);
+            for (uint32_t j = 1; j < t.n; ++j) chirp(j, hr[len - j], hi[len - j]);
+            for (uint32_t i = 1, j = 0; i < len; ++i) {                      // bit reversal
+                uint32_t bit = len >> 1;
+                for (; j & bit; bit >>= 1) j ^= bit;
+                j ^= bit;
+                if (i < j) { std::swap(hr[i], hr[j]); std::swap(hi[i], hi[j]); }
+            }
+            for (uint32_t span = 2; span <= len; span <<= 1) {
+                const uint32_t half = span >> 1;
+                for (uint32_t base = 0; base < len; base += span)
+                    for (uint32_t j = 0; j < half; ++j) {
+                        const double ang = -2.0 * M_PI * (double)j / (double)span, wr = std::cos(ang), wi = std::sin(ang);
+                        const double xr = hr[base + j + half] * wr - hi[base + j + half] * wi;
+                        const double xi = hr[base + j + half] * wi + hi[base + j + half] * wr;
+                        hr[base + j + half] = hr[base + j] - xr; hi[base + j + half] = hi[base + j] - xi;
+                        hr[base + j] += xr; hi[base + j] += xi;
+                    }
+            }
+            t.bl_bf.resize((size_t)len * 2);
+            for (uint32_t k = 0; k < len; ++k) {
+                t.bl_bf[2 * (size_t)t.pos_tab[k]] = (float)(hr[k] / (double)len);
+                t.bl_bf[2 * (size_t)t.pos_tab[k] + 1] = (float)(hi[k] / (double)len);
+            }
         }
     }
     // per-pass twiddle planes: plane j of pass p holds W_(S_p R_p)^(2^j lo), lo < S_p
@@ -487,11 +560,13 @@ inline void build(const sbx_config &cfg, HostTables &t)
 inline void fill_generic_passes(const HostTables &t, GenericArgs &g)
 {
     g.n = t.n; g.pad = t.pad; g.m = t.m;
+    g.bl_n = t.n; g.bl_m = t.m;
+    if (t.bluestein) { g.n = g.m = t.bl_len; g.pad = 1; }     // the passes transform ONE sequence of length L
     g.npass = (uint32_t)t.radix.size();
     for (size_t i = 0; i < t.radix.size(); ++i) {
         g.radix[i] = t.radix[i];
         g.stride[i] = t.stride[i];
-        g.per_sub[i] = t.n / t.radix[i];
+        g.per_sub[i] = g.n / t.radix[i];
         g.tw_off[i] = t.tw_off[i];
         g.inv_stride[i] = (uint32_t)((1ull << 32) / t.stride[i]) + 1u;      // unused (and wraps) for S = 1
     }

@@ -22,6 +22,7 @@ namespace sbx {
 #endif
 constexpr int GENERIC_THREADS = SBX_GENERIC_THREADS;
 constexpr int GENERIC_MAX_PASSES = 12;
+constexpr uint32_t BLUESTEIN_MAX_LEN = 16384;   // Bluestein convolution length L (128 KB of float2 in shared memory)
 
 struct GenericArgs {
     KernelArgs k;                 // window, rowmap, chunks, samp, thr, lut, rgba, mags_out, pcm ... (wtw/twp unused)
@@ -34,6 +35,11 @@ struct GenericArgs {
     uint32_t per_sub[GENERIC_MAX_PASSES];  // butterflies per sub-transform: N / R_p
     uint32_t tw_off[GENERIC_MAX_PASSES];   // first entry of pass p in twg
     uint32_t inv_stride[GENERIC_MAX_PASSES];   // floor(2^32 / S_p) + 1: u / S_p == __umulhi(u, inv) for u < 2^16, S_p < 2^15
+    // Bluestein (window with a prime factor > 7): n = m = the power-of-two convolution length L, pad = 1, and
+    const float2 *bl_a;           // [N]  window[n] * conj(b[n]),  b[j] = exp(+i pi j^2 / M)
+    const float2 *bl_bf;          // [L]  FFT_L(h) / L at the POSITION of each bin (digit-reversed order), h = b wrapped mod L
+    const float2 *bl_c;           // [M]  conj(b[k])
+    uint32_t bl_n, bl_m;          // the window N and the padded transform length M = P N
 };
 
 // which of the (at most four) equal runs of length `len` holds u, without a division: u in [0, pad * len)
@@ -143,6 +149,92 @@ __device__ __forceinline__ void generic_pass_dispatch(float2 *z, const GenericAr
     }
 }
 
+// ---- Bluestein (chirp-z) for windows the radix list cannot factor: N = 1102 = 2 * 19 * 29 (22.05 kHz), 551, primes ----
+// W_M^(n k) = conj(b[n]) conj(b[k]) b[k - n] with b[j] = exp(+i pi j^2 / M), so the M-point DFT of the N windowed samples
+// is X[k] = conj(b[k]) * sum_n (z[n] conj(b[n])) b[k - n]: a convolution, done as a circular one of power-of-two
+// length L >= N + M - 1 with the passes above: forward DIF (natural order in, digit-reversed out), a pointwise product
+// with the transformed chirp stored in that same digit-reversed order, and the inverse as the exact reverse of the
+// forward passes (decimation in time: digit-reversed in, natural order out) -- no reordering pass at all.
+
+// one in-place inverse pass: undoes generic_pass<R>(p): conjugate twiddles on the way in, then the inverse R-point DFT
+template <int R>
+__device__ __forceinline__ void generic_pass_inverse(float2 *z, const GenericArgs &g, uint32_t p, bool last)
+{
+    const uint32_t S = g.stride[p], per_sub = g.per_sub[p];
+    const float2 *tw = g.twg + g.tw_off[p];
+    const uint32_t inv = g.inv_stride[p];
+    for (uint32_t u = threadIdx.x; u < per_sub; u += GENERIC_THREADS) {
+        const uint32_t hi = S == 1 ? u : mulhi_u32(u, inv), lo = u - hi * S;
+        float2 *b = z + (size_t)hi * S * R + lo;
+        float2 v[R];
+        v[0] = b[0];
+        v[0].y = -v[0].y;
+#pragma unroll
+        for (int q = 1; q < R; ++q) {
+            float2 x = b[(size_t)q * S];
+            if (!last) {
+                const float2 w = __ldg(tw + (size_t)(q - 1) * S + lo);
+                x = cmul(x, make_float2(w.x, -w.y));
+            }
+            v[q] = make_float2(x.x, -x.y);                   // conj in, forward butterfly, conj out = inverse DFT (unscaled)
+        }
+        Butterfly<R>::run(v);
+#pragma unroll
+        for (int r = 0; r < R; ++r) b[(size_t)r * S] = make_float2(v[r].x, -v[r].y);
+    }
+}
+
+__device__ __forceinline__ void generic_pass_inverse_dispatch(float2 *z, const GenericArgs &g, uint32_t p)
+{
+    const bool last = p + 1 == g.npass;
+    switch (g.radix[p]) {                                    // L is a power of two
+        case 2: generic_pass_inverse<2>(z, g, p, last); break;
+        case 4: generic_pass_inverse<4>(z, g, p, last); break;
+        case 8: generic_pass_inverse<8>(z, g, p, last); break;
+        case 16: generic_pass_inverse<16>(z, g, p, last); break;
+        default: break;
+    }
+}
+
+// phase 0: PCM -> window * conj(chirp) -> shared memory, zero beyond N
+template <int CH>
+__device__ __forceinline__ void bluestein_load(float2 *z, const GenericArgs &g, unsigned long long frame0, bool second_valid)
+{
+    const KernelArgs &a = g.k;
+    const float *pa = a.pcm + frame0 * (unsigned long long)a.hop * CH;
+    const float *pb = pa + a.hop;
+    for (uint32_t n = threadIdx.x; n < g.m; n += GENERIC_THREADS) {
+        float2 v = make_float2(0.0f, 0.0f);
+        if (n < g.bl_n) {
+            float2 s;
+            if constexpr (CH == 2) {
+                s = __ldg(reinterpret_cast<const float2 *>(pa) + n);
+            } else {
+                s.x = __ldg(pa + n);
+                s.y = second_valid ? __ldg(pb + n) : 0.0f;
+            }
+            v = cmul(s, __ldg(g.bl_a + n));                  // fft.rs:57-63 (window) folded into the chirp factor
+        }
+        z[n] = v;
+    }
+}
+
+// pointwise product with the transformed chirp (both in position order)
+__device__ __forceinline__ void bluestein_multiply(float2 *z, const GenericArgs &g)
+{
+    for (uint32_t i = threadIdx.x; i < g.m; i += GENERIC_THREADS) z[i] = cmul(z[i], __ldg(g.bl_bf + i));
+}
+
+// X[k] = conj(b[k]) y[k], then the L/R split of fft.rs:81-95 into the magnitude array indexed by bin kk
+__device__ __forceinline__ void bluestein_split(const float2 *z, float2 *mags, const GenericArgs &g)
+{
+    for (uint32_t kk = 1 + threadIdx.x; kk < g.bl_m / 2; kk += GENERIC_THREADS) {
+        const float2 x1 = cmul(z[kk], __ldg(g.bl_c + kk));
+        const float2 x2 = cmul(z[g.bl_m - kk], __ldg(g.bl_c + (g.bl_m - kk)));
+        mags[kk] = split_pair(x1, x2, g.k.scale);
+    }
+}
+
 // L/R split (fft.rs:81-95) into a separate magnitude array indexed by bin kk
 __device__ __forceinline__ void generic_split(const float2 *z, float2 *mags, const GenericArgs &g)
 {
@@ -151,22 +243,33 @@ __device__ __forceinline__ void generic_split(const float2 *z, float2 *mags, con
 }
 
 #ifndef SBX_EMU
-template <int CH>
+template <int CH, bool BLUESTEIN = false>
 __global__ void __launch_bounds__(GENERIC_THREADS) generic_frames_kernel(const GenericArgs g)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2 *z = reinterpret_cast<float2 *>(smem_raw);                    // [M]; reused as resample scratch
+    float2 *z = reinterpret_cast<float2 *>(smem_raw);                    // [M] ([L] for Bluestein); reused as resample scratch
     float2 *mags = z + g.m;                                               // [M/2]
     const KernelArgs &a = g.k;
     const unsigned long long frame0 = (unsigned long long)blockIdx.x * (CH == 1 ? 2 : 1);
     const bool second_valid = CH == 1 && frame0 + 1 < a.n_frames;
-    generic_load<CH>(z, g, frame0, second_valid);
+    if constexpr (BLUESTEIN) bluestein_load<CH>(z, g, frame0, second_valid);
+    else generic_load<CH>(z, g, frame0, second_valid);
     for (uint32_t p = 0; p < g.npass; ++p) {
         __syncthreads();
         generic_pass_dispatch(z, g, p);
     }
     __syncthreads();
-    generic_split(z, mags, g);
+    if constexpr (BLUESTEIN) {
+        bluestein_multiply(z, g);
+        for (uint32_t p = g.npass; p-- > 0;) {
+            __syncthreads();
+            generic_pass_inverse_dispatch(z, g, p);
+        }
+        __syncthreads();
+        bluestein_split(z, mags, g);
+    } else {
+        generic_split(z, mags, g);
+    }
     __syncthreads();
     if (a.mags_out != nullptr) {
         float2 *out = reinterpret_cast<float2 *>(a.mags_out) + frame0 * a.k_out;

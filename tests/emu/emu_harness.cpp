@@ -285,12 +285,24 @@ int emu_generic(const sbx::GenericArgs &g0, unsigned long long frames, float *ma
     g.k.rgba = rgba;
     const int per = CH == 1 ? 2 : 1;
     for (unsigned long long frame0 = 0; frame0 < frames; frame0 += per) {
-        std::vector<float2> z(g.m), mags(g.m / 2);
+        std::vector<float2> z(g.m), mags(g.bl_m / 2);
         const bool second_valid = CH == 1 && frame0 + 1 < frames;
-        for (int t = 0; t < sbx::GENERIC_THREADS; ++t) { threadIdx.x = t; sbx::generic_load<CH>(z.data(), g, frame0, second_valid); }
+        const bool bluestein = g.bl_bf != nullptr;
+        for (int t = 0; t < sbx::GENERIC_THREADS; ++t) {
+            threadIdx.x = t;
+            if (bluestein) sbx::bluestein_load<CH>(z.data(), g, frame0, second_valid);
+            else sbx::generic_load<CH>(z.data(), g, frame0, second_valid);
+        }
         for (uint32_t p = 0; p < g.npass; ++p)
             for (int t = 0; t < sbx::GENERIC_THREADS; ++t) { threadIdx.x = t; sbx::generic_pass_dispatch(z.data(), g, p); }
-        for (int t = 0; t < sbx::GENERIC_THREADS; ++t) { threadIdx.x = t; sbx::generic_split(z.data(), mags.data(), g); }
+        if (bluestein) {
+            for (int t = 0; t < sbx::GENERIC_THREADS; ++t) { threadIdx.x = t; sbx::bluestein_multiply(z.data(), g); }
+            for (uint32_t p = g.npass; p-- > 0;)
+                for (int t = 0; t < sbx::GENERIC_THREADS; ++t) { threadIdx.x = t; sbx::generic_pass_inverse_dispatch(z.data(), g, p); }
+            for (int t = 0; t < sbx::GENERIC_THREADS; ++t) { threadIdx.x = t; sbx::bluestein_split(z.data(), mags.data(), g); }
+        } else {
+            for (int t = 0; t < sbx::GENERIC_THREADS; ++t) { threadIdx.x = t; sbx::generic_split(z.data(), mags.data(), g); }
+        }
         if (mags_out) {
             float *o = mags_out + (size_t)frame0 * g.k.k_out * 2;
             for (uint32_t j = 0; j < g.k.k_out; ++j) {
@@ -382,6 +394,11 @@ long long emu_batch(const sbx_config *cfg, const float *pcm, unsigned long long 
         g.pos_tab = t.pos_tab.data();
         sbx::tables::fill_generic_passes(t, g);
         g.twg = reinterpret_cast<const float2 *>(t.twg.data());
+        if (t.bluestein) {
+            g.bl_a = reinterpret_cast<const float2 *>(t.bl_a.data());
+            g.bl_bf = reinterpret_cast<const float2 *>(t.bl_bf.data());
+            g.bl_c = reinterpret_cast<const float2 *>(t.bl_c.data());
+        }
         const int st = ch == 1 ? emu_generic<1>(g, frames, mags_lr, rgba) : emu_generic<2>(g, frames, mags_lr, rgba);
         return st != 0 ? st : (long long)frames;
     }

@@ -102,7 +102,7 @@ def test_null_and_invalid_arguments_return_codes(binding):
     assert lib.sbx_plan_create(C.byref(cfg), C.byref(h)) == -1 and not h.value
     assert b"size/version" in lib.sbx_last_error(None)
     lib.sbx_config_default(C.byref(cfg))
-    cfg.window_n = 2402                                                       # 2 * 1201: a prime factor > 7
+    cfg.window_n = 5462                                                       # 2 * 2731: a prime factor > 7, too long for Bluestein
     assert lib.sbx_plan_create(C.byref(cfg), C.byref(h)) == -2 and b"prime factor" in lib.sbx_last_error(None)
     lib.sbx_config_default(C.byref(cfg))
     cfg.window_n = 131072

@@ -334,3 +334,23 @@ def test_stereo_scheme_with_a_finer_pan_gradient(n, pad, ch, hop, rows, entries)
     if ch == 2:
         _, coarse = emu.batch(cfg, x)
         assert (coarse[..., :3] != rgba[..., :3]).any() and np.array_equal(coarse[..., 3], rgba[..., 3])
+
+
+@pytest.mark.parametrize("n,pad,ch,hop,rows,interp", [(1102, 2, 2, 43, 256, 0), (551, 2, 1, 21, 128, 1), (1103, 2, 1, 100, 64, 0),
+                                                      (347, 4, 2, 50, 64, 0), (5461, 2, 2, 700, 64, 0), (94, 2, 2, 9, 32, 0)])
+def test_bluestein_windows_match_oracle(magma, n, pad, ch, hop, rows, interp):
+    """Windows with a prime factor > 7 (cpal devices at 22.05 / 11.025 kHz: N = (0.05 s * sr) as usize = 1102, 551;
+    fft.rs:19-21 takes any N): chirp-z over a power-of-two circular convolution, forward DIF -> product with the
+    transformed chirp in digit-reversed order -> inverse as the reversed passes.  Against the oracle's f64 DFT."""
+    cfg = emu.make_config(magma, sample_rate=22050.0, window_n=n, pad_factor=pad, hop=hop, rows_h=rows, channels=ch, interp=interp)
+    ns = n + hop * 3
+    lr = signals.stereo_loopback(ns, 22050.0)
+    x = lr if ch == 2 else lr[:, 0].copy()
+    mags, rgba = emu.batch(cfg, x)
+    p = oracle.params(sample_rate=22050.0, window_n=n, pad_factor=pad, hop=hop, rows_h=rows, interp=interp)
+    o_rgba, o_mags = oracle.batch(p, x, ch, magma, want_mags=True)
+    err = (np.abs(mags - o_mags) / np.abs(o_mags).max(axis=(1, 2), keepdims=True)).max()
+    assert err <= 1e-5, err
+    assert (rgba != o_rgba).any(axis=2).mean() <= 2e-3
+    for f in range(mags.shape[0]):
+        assert np.array_equal(rgba[f], oracle.column_from_magnitudes(p, mags[f], magma))

@@ -117,7 +117,7 @@ def test_multi_errors(sbx, magma):
     with pytest.raises(sbx.SbxError):
         sbx.MultiPlan([_n_devices()], window_n=1024, lut=magma)              # ordinal out of range
     with pytest.raises(sbx.SbxError):
-        sbx.MultiPlan([0], window_n=2402, lut=magma)                         # unsupported window: plan error surfaces
+        sbx.MultiPlan([0], window_n=5462, lut=magma)                         # unsupported window: plan error surfaces
     with sbx.MultiPlan([0], window_n=1024, hop=256, rows_h=64, lut=magma) as multi:
         x = signals.stereo_loopback(1024 * 8)
         small = np.empty((3, 64, 4), np.uint8)

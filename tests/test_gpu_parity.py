@@ -58,6 +58,12 @@ CASES = [
     (1600, 4, 1, 200, 256, 0),
     (100, 2, 2, 10, 64, 0),            # the dummy transform the widgets start with (gpu_spectrogram.rs:80)
     (4800, 2, 2, 512, 1024, 0),        # 96 kHz
+    # windows with a prime factor > 7: Bluestein over a power-of-two convolution (22.05 kHz: N = 1102 = 2 * 19 * 29)
+    (1102, 2, 2, 43, 1024, 0),
+    (551, 2, 1, 21, 512, 1),           # 11.025 kHz, mono pairs
+    (1103, 2, 2, 100, 256, 0),         # a prime window
+    (347, 4, 1, 50, 128, 0),
+    (5461, 2, 2, 1000, 256, 0),        # the longest: N + M - 1 = 16382 <= 16384
     # M > 16384: the multi-kernel path (cfg5's larger sizes)
     (8192, 4, 1, 1024, 2048, 0),
     (16384, 2, 2, 2048, 512, 1),
@@ -212,7 +218,7 @@ def test_live_ring_semantics(sbx, magma):
 
 def test_errors_do_not_abort(sbx, magma):
     with pytest.raises(sbx.SbxError) as e:
-        sbx.Plan(window_n=2402, lut=magma)                          # 2 * 1201: prime factor > 7
+        sbx.Plan(window_n=5462, lut=magma)                          # 2 * 2731: prime factor > 7 and too long for Bluestein
     assert e.value.status == -2
     with pytest.raises(sbx.SbxError):
         sbx.Plan(window_n=131072, pad_factor=2, lut=magma)

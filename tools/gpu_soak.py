@@ -24,7 +24,8 @@ a = ap.parse_args()
 rng = np.random.Generator(np.random.PCG64(a.seed))
 lut = signals.lut("magma")
 pow2 = [256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536]
-mixed = [100, 120, 300, 441, 600, 1000, 1470, 2205, 2400, 4800, 9600]
+mixed = [100, 120, 300, 441, 600, 1000, 1470, 2205, 2400, 4800, 9600,
+         551, 1102, 1103, 94, 347, 2731, 4099]             # the last row: a prime factor > 7 (Bluestein path)
 t0, done, worst, paths = time.time(), 0, 0.0, {}
 for case in range(a.cases):
     if time.time() - t0 > a.seconds:
@@ -33,6 +34,8 @@ for case in range(a.cases):
         n, pad = int(rng.choice(mixed)), int(rng.choice([2, 4]))
         if n * pad * 12 > 227 * 1024:
             pad = 2
+        if n in (551, 1102, 1103, 94, 347, 2731, 4099) and n * (pad + 1) - 1 > 16384:
+            pad = 2 if n * 3 - 1 <= 16384 else 1
     else:
         n = int(rng.choice(pow2))
         pads = [p for p in (1, 2, 4) if n * p <= 262144 and (n * p <= 16384 or n >= 8192)]
