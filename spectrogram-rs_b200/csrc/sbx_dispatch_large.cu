@@ -46,11 +46,55 @@ sbx_status launch_generic(sbx_plan *p, int channels, const float *d_pcm, uint64_
     return SBX_OK;
 }
 
-// ---- large path (M > 16384): four kernels per chunk of units --------------------------------------
+// ---- large path (M > 16384): the cluster kernel + colour, or four kernels per chunk of units ----------
+// Measured on a B200 (cfg5 geometries, M frames/s, four kernels vs cluster kernel + colour; profiles/README.md):
+//   2-CTA clusters (M = 32768, stereo N 16384 P 2): 3.31 vs 3.55-3.67  -> cluster path by default
+//   4-CTA clusters (M = 65536, mono N 16384 P 4):   3.36 vs 2.76;  stereo N 16384 P 4: 1.72 vs 1.34
+//   8-CTA clusters (M = 131072, mono N 32768 P 4):  1.73 vs 1.28
+// One 1024-thread CTA owns an SM (128 KB of shared memory), so nothing overlaps its load, barrier and store phases, and
+// clusters of 4 / 8 leave 16 / 20 of the 148 SMs without work; the four-kernel path stays the default there.
+// SBX_LARGE_CLUSTER=1 / 0 forces the cluster kernel wherever it exists (M <= 131072) / nowhere.
+static bool cluster_path_enabled(int ctas)
+{
+    const char *e = std::getenv("SBX_LARGE_CLUSTER");           // read per launch: the tests compare both paths in one process
+    if (e && e[0] == '0') return false;
+    if (e && e[0] == '1') return true;
+    return ctas == 2;
+}
+
+template <int LOG2N, int LOG2PAD, int CH>
+cudaError_t launch_large_cluster(const LargeArgs &la, bool want_rgba, cudaStream_t stream)
+{
+    using GC = GeomC<LOG2N, LOG2PAD>;
+    static std::atomic<bool> configured[kMaxDevices];
+    cudaError_t e = allow_smem(large_cluster_kernel<LOG2N, LOG2PAD, CH>, GC::SMEM_BYTES, configured);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(la.units * GC::CTAS);
+    cfg.blockDim = dim3(CLUSTER_THREADS);
+    cfg.dynamicSmemBytes = GC::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = GC::CTAS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, large_cluster_kernel<LOG2N, LOG2PAD, CH>, la);
+    if (e != cudaSuccess) return e;
+    if (want_rgba)
+        large_colour_kernel<CH == 1><<<dim3(la.units, la.k.n_chunks), LARGE_THREADS, 0, stream>>>(la, la.magbuf, (size_t)GeomL<LOG2N, LOG2PAD>::M / 2);
+    return cudaGetLastError();
+}
+
 template <int LOG2N, int LOG2PAD, int CH>
 cudaError_t launch_large_one(const LargeArgs &la, bool want_rgba, cudaStream_t stream)
 {
     using GL = GeomL<LOG2N, LOG2PAD>;
+    if constexpr (GL::Q / 4 <= 8) {
+        if (cluster_path_enabled(GL::Q / 4)) return launch_large_cluster<LOG2N, LOG2PAD, CH>(la, want_rgba, stream);
+    }
     const unsigned units = la.units;
     large_first_kernel<LOG2N, LOG2PAD, CH><<<units * GL::PAD * (LARGE_BLOCK / LARGE_THREADS), LARGE_THREADS, 0, stream>>>(la);
     large_block_kernel<<<units * (GL::M / LARGE_BLOCK), LARGE_THREADS, 0, stream>>>(la);

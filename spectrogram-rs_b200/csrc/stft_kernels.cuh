@@ -607,13 +607,15 @@ __device__ __forceinline__ void pass_first(float2 *z, const KernelArgs &a, const
 
 // Pass P >= 1: in-place radix-16 butterflies at stride S = 2^LS; the last pass (S = 1) moves whole
 // 128-byte rows with float4 accesses
+// (tid: the thread's index within the G::THREADS threads that share the transform buffer z -- threadIdx.x, or the
+// index within a thread group where one CTA holds several independent buffers, stft_large.cuh)
 template <class G, int P>
-__device__ __forceinline__ void pass_inplace(float2 *z, const KernelArgs &a)
+__device__ __forceinline__ void pass_inplace_t(float2 *z, const KernelArgs &a, int tid)
 {
     constexpr int LS = G::log2stride(P), S = 1 << LS;
     constexpr int COUNT = G::M / 16;
     constexpr int PER_SUB_LOG2 = G::LOG2N - 4;
-    for (int w = threadIdx.x; w < COUNT; w += G::THREADS) {
+    for (int w = tid; w < COUNT; w += G::THREADS) {
         float2 v[16];
         if constexpr (S == 1) {
             // row w holds elements 16w .. 16w+15
@@ -641,6 +643,11 @@ __device__ __forceinline__ void pass_inplace(float2 *z, const KernelArgs &a)
             for (int q = 0; q < 16; ++q) z[SBX_ZAT(G, bx, q * S)] = v[q];
         }
     }
+}
+template <class G, int P>
+__device__ __forceinline__ void pass_inplace(float2 *z, const KernelArgs &a)
+{
+    pass_inplace_t<G, P>(z, a, (int)threadIdx.x);
 }
 
 // passes P .. END-1, each followed by a barrier

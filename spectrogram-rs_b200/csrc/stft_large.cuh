@@ -202,6 +202,170 @@ __global__ void __launch_bounds__(LARGE_THREADS) large_split_kernel(const LargeA
     large_split_emit<LOG2N, LOG2PAD, CH>(la, blockIdx.x, own, par);
 }
 
+// ---- cluster path: the whole transform of a unit in the distributed shared memory of one thread-block cluster ------
+// M = 32768 .. 131072 (Q = M / 4096 = 8, 16, 32 blocks of 32 KB): a cluster of C = Q / 4 CTAs, four blocks (128 KB) each.
+// The three trips through the global scratch of the four-kernel path (Y out, Y in / Z out, Z in) become
+//   phase A  every CTA takes an equal share of the radix-R0 first-pass butterflies (PCM -> window -> premultiply ->
+//            butterfly -> W_N^(lo q)) and SCATTERS each output into the block it belongs to -- a st.shared::cluster
+//            into the owning CTA's shared memory, already at its swizzled slot;
+//   -------- barrier.cluster --------
+//   phase B  the four local 4096-point blocks: three in-place radix-16 passes each, four thread groups in lock step;
+//   phase C  the L/R split, LOCAL: bin kk = k Q + c pairs with M - kk = (4095 - k) Q + (Q - c), and columns c and
+//            Q - c are assigned to the same CTA (0 and Q / 2 pair with themselves), so no second exchange is needed;
+//            magnitudes go to the global array large_colour_kernel reads.
+// HBM scratch per unit: M/2 magnitudes written once and read once, instead of 5 M + the same.
+constexpr int CLUSTER_THREADS = 1024;                          // 4 groups of G12::THREADS = 256, one per local block
+
+template <int LOG2N, int LOG2PAD> struct GeomC : GeomL<LOG2N, LOG2PAD> {
+    using GL = GeomL<LOG2N, LOG2PAD>;
+    static constexpr int CTAS = GL::Q / 4;                     // cluster size: 2, 4 or 8
+    static_assert(CTAS >= 2 && CTAS <= 8, "portable cluster sizes");
+    static constexpr int SMEM_BYTES = 4 * LARGE_BLOCK * 8;     // 128 KB
+    static constexpr int BFLY_PER_CTA = GL::PAD * LARGE_BLOCK / CTAS;
+    // columns in pair order: entry 0 = {0, Q/2}, entry e = {e, Q - e}; CTA j holds entries 2j and 2j+1
+    static __host__ __device__ constexpr int entry_of_column(int c) { return (c == 0 || c == GL::Q / 2) ? 0 : (c < GL::Q / 2 ? c : GL::Q - c); }
+    static __host__ __device__ constexpr int owner_of_column(int c) { return entry_of_column(c) >> 1; }
+    static __host__ __device__ constexpr int slot_of_column(int c)
+    {
+        const int e = entry_of_column(c);
+        const int second = e == 0 ? (c == 0 ? 0 : 1) : (c == e ? 0 : 1);
+        return ((e & 1) << 1) + second;
+    }
+    static __host__ __device__ constexpr int column_of_slot(int rank, int slot)
+    {
+        const int e = 2 * rank + (slot >> 1);
+        return e == 0 ? ((slot & 1) ? GL::Q / 2 : 0) : ((slot & 1) ? GL::Q - e : e);
+    }
+};
+
+#ifndef SBX_EMU
+__device__ __forceinline__ unsigned int cluster_ctarank()
+{
+    unsigned int r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_smem_addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ unsigned int cluster_map(unsigned int local_smem_addr, unsigned int rank)
+{
+    unsigned int r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_store(unsigned int cluster_addr, float2 v)
+{
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" :: "r"(cluster_addr), "f"(v.x), "f"(v.y) : "memory");
+}
+
+// grid = units * CTAS (cluster dimension CTAS), CLUSTER_THREADS threads, dynamic shared memory = GeomC::SMEM_BYTES
+template <int LOG2N, int LOG2PAD, int CH>
+__global__ void __launch_bounds__(CLUSTER_THREADS, 1) large_cluster_kernel(const LargeArgs la)
+{
+    using GC = GeomC<LOG2N, LOG2PAD>;
+    using GL = GeomL<LOG2N, LOG2PAD>;
+    constexpr int R = GL::R0;
+    extern __shared__ __align__(16) unsigned char cluster_smem[];
+    float2 *zb = reinterpret_cast<float2 *>(cluster_smem);                    // [4][4096]
+    const KernelArgs &a = la.k;
+    const unsigned int rank = cluster_ctarank();
+    const unsigned int unit = blockIdx.x / GC::CTAS;
+    const unsigned long long frame0 = la.frame_base + (unsigned long long)unit * (CH == 1 ? 2 : 1);
+    const bool second_valid = CH == 1 && frame0 + 1 < a.n_frames;
+
+    // ---- phase A: first-pass butterflies, outputs scattered over the cluster ------------------------------------
+    {
+        const float *pa = a.pcm + frame0 * (unsigned long long)a.hop * CH;
+        const float *pb = pa + a.hop;
+        const unsigned int smem_base = (unsigned int)__cvta_generic_to_shared(zb);
+        // BFLY_PER_CTA / CLUSTER_THREADS butterflies of R inputs per thread = 16 inputs in every geometry: all loads
+        // are issued before the first butterfly (one CTA owns the SM here, nothing else hides their latency)
+        constexpr int PER_THREAD = GC::BFLY_PER_CTA / CLUSTER_THREADS;
+        static_assert(PER_THREAD * CLUSTER_THREADS == GC::BFLY_PER_CTA && PER_THREAD * R == 16, "16 inputs per thread");
+        float2 v[PER_THREAD][R];
+#pragma unroll
+        for (int t = 0; t < PER_THREAD; ++t) {
+            const int b = (int)rank * GC::BFLY_PER_CTA + t * CLUSTER_THREADS + (int)threadIdx.x;
+            const int q0 = b >> LARGE_LOG2_BLOCK, lo = b & (LARGE_BLOCK - 1);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int n = lo + r * LARGE_BLOCK;
+                float2 s;
+                if constexpr (CH == 2) {
+                    s = __ldg(reinterpret_cast<const float2 *>(pa) + n);
+                } else {
+                    s.x = __ldg(pa + n);
+                    s.y = second_valid ? __ldg(pb + n) : 0.0f;
+                }
+                // q0 = 0: the plain window (fft.rs:57-63); q0 > 0: window * W_M^(n q0) from one table
+                const float2 w = q0 == 0 ? make_float2(__ldg(a.window + n), 0.0f) : __ldg(a.wtw + (size_t)(q0 - 1) * GL::N + n);
+                v[t][r] = q0 == 0 ? make_float2(s.x * w.x, s.y * w.x) : cmul(s, w);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < PER_THREAD; ++t) {
+            const int b = (int)rank * GC::BFLY_PER_CTA + t * CLUSTER_THREADS + (int)threadIdx.x;
+            const int q0 = b >> LARGE_LOG2_BLOCK, lo = b & (LARGE_BLOCK - 1);
+            Butterfly<R>::run(v[t]);
+            apply_twiddles<R>(v[t], a.twp + lo, LARGE_BLOCK);                 // W_N^(lo q)
+            const unsigned int slot_off = (unsigned int)G12::zsw(lo) * 8u;
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int c = q * GL::PAD + q0;                               // column of output d0 = q: bins kk = k Q + c
+                const int e = (c == 0 || c == GL::Q / 2) ? 0 : (c < GL::Q / 2 ? c : GL::Q - c);
+                const int slot = ((e & 1) << 1) + (e == 0 ? (c == 0 ? 0 : 1) : (c == e ? 0 : 1));
+                cluster_store(cluster_map(smem_base, (unsigned int)(e >> 1)) + (unsigned int)slot * (LARGE_BLOCK * 8u) + slot_off, v[t][q]);
+            }
+        }
+    }
+    cluster_sync_all();
+
+    // ---- phase B: four local 4096-point blocks, one thread group each -----------------------------------------
+    {
+        KernelArgs ab = a;
+        ab.twp = la.twp_block;
+        const int group = threadIdx.x >> 8, tid = threadIdx.x & 255;
+        float2 *z = zb + group * LARGE_BLOCK;
+        pass_inplace_t<G12, 0>(z, ab, tid);
+        __syncthreads();
+        pass_inplace_t<G12, 1>(z, ab, tid);
+        __syncthreads();
+        pass_inplace_t<G12, 2>(z, ab, tid);
+        __syncthreads();
+    }
+
+    // ---- phase C: local L/R split -> global magnitudes by bin kk --------------------------------------------------
+    {
+        float2 *mag_u = la.magbuf + (size_t)unit * (GL::M / 2);
+        for (int i = threadIdx.x; i < 4 * (LARGE_BLOCK / 2); i += CLUSTER_THREADS) {
+            const int slot = i >> (LARGE_LOG2_BLOCK - 1), k = i & (LARGE_BLOCK / 2 - 1);
+            const int c = GC::column_of_slot((int)rank, slot);
+            const int kk = k * GL::Q + c;
+            if (kk == 0) continue;                                            // DC is dropped (fft.rs:81)
+            const bool self = (c == 0 || c == GL::Q / 2);
+            const int pslot = self ? slot : (slot ^ 1);
+            const int kp = c != 0 ? LARGE_BLOCK - 1 - k : LARGE_BLOCK - k;    // partner index in block Q - c (c = 0: 4096 - k)
+            const float2 own = zb[slot * LARGE_BLOCK + G12::zsw(G12::pos_of_bin(k))];
+            const float2 par = zb[pslot * LARGE_BLOCK + G12::zsw(G12::pos_of_bin(kp))];
+            const float2 m = split_pair(own, par, a.scale);
+            mag_u[kk] = m;
+            if (a.mags_out != nullptr) {
+                float2 *out = reinterpret_cast<float2 *>(a.mags_out) + frame0 * a.k_out + (kk - 1);
+                if constexpr (CH == 1) {
+                    out[0] = make_float2(m.x, m.x);
+                    if (second_valid) out[a.k_out] = make_float2(m.y, m.y);
+                } else {
+                    out[0] = m;
+                }
+            }
+        }
+    }
+}
+#endif  // SBX_EMU
+
 // grid = (units, row chunks): row chunks are independent, so each CTA resamples and colours one chunk of one
 // unit; mags by bin kk from global memory (magbuf, or a caller's K x (L,R) array shifted by one)
 template <bool PAIR>

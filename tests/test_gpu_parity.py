@@ -786,3 +786,38 @@ def test_stereo_scheme_with_a_finer_pan_gradient(sbx, n, pad, ch, hop, rows, ent
     with sbx.Plan(window_n=1024, lut=lut, scheme=1) as plan:
         with pytest.raises(sbx.SbxError):
             plan.set_pan_gradient(np.zeros((1, 3), np.uint8))
+
+
+@pytest.mark.parametrize("n,pad,ch,hop,rows", [(16384, 2, 2, 2048, 512), (16384, 4, 1, 2048, 2048), (16384, 4, 1, 2047, 256),
+                                               (32768, 1, 2, 4096, 256), (32768, 2, 1, 4096, 1024), (32768, 4, 2, 4096, 1024),
+                                               (32768, 4, 1, 4096, 2048), (65536, 1, 2, 8192, 128), (65536, 2, 1, 8192, 2048)])
+def test_cluster_path_equals_four_kernel_path(sbx, magma, monkeypatch, n, pad, ch, hop, rows):
+    """M = 32768 .. 131072: the transform held in the distributed shared memory of a 2 / 4 / 8-CTA cluster
+    (large_cluster_kernel) against the four-kernel path through global scratch (SBX_LARGE_CLUSTER=0) -- the same
+    butterflies in the same order -- and against the oracle."""
+    import torch
+    frames = 9
+    ns = n + hop * (frames - 1) + 3
+    pcm = _pcm(ch, ns, seed=11)
+    p = oracle.params(window_n=n, pad_factor=pad, hop=hop, rows_h=rows)
+    o_rgba, o_mags = oracle.batch(p, pcm, ch, magma, want_mags=True)
+    got = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("SBX_LARGE_CLUSTER", mode)
+        with sbx.Plan(window_n=n, pad_factor=pad, hop=hop, rows_h=rows, channels=ch, lut=magma) as plan:
+            assert plan.kernel_path == "large"
+            d_x = torch.from_numpy(pcm).cuda()
+            d_rgba = torch.zeros((frames, rows, 4), dtype=torch.uint8, device="cuda")
+            d_mags = torch.zeros((frames, plan.k, 2), dtype=torch.float32, device="cuda")
+            assert plan.process_batch_device(d_x, ns, d_rgba, frames) == frames
+            assert plan.magnitudes_batch_device(d_x, ns, d_mags, frames) == frames
+            plan.synchronize()
+            got[mode] = (d_rgba.cpu().numpy(), d_mags.cpu().numpy())
+    # same algorithm, separately compiled (FMA contraction differs): equal to a few ulp of the frame peak, not bit for bit
+    peak = np.abs(got["0"][1]).max(axis=(1, 2), keepdims=True)
+    assert float((np.abs(got["0"][1] - got["1"][1]) / peak).max()) <= 2e-6
+    assert (got["0"][0] != got["1"][0]).any(axis=2).mean() <= 2e-3
+    g_rgba, g_mags = got["1"]
+    err = float((np.abs(g_mags - o_mags) / np.abs(o_mags).max(axis=(1, 2), keepdims=True)).max())
+    assert err <= MAG_TOL, err
+    assert (g_rgba != o_rgba).any(axis=2).mean() <= 2e-3
