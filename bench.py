@@ -360,6 +360,33 @@ def main():
     assert got == Fe and torch.equal(h_rgba[:64].cuda(), rgba[:64])
     plan.set_stream(stream.cuda_stream)
 
+    # ---- the copy ceiling of this run: the SAME pinned buffers, bytes, chunking (32 MiB of RGBA per chunk, three
+    # streams) and ranks as the end-to-end leg, but no kernels -- what the host<->device path alone allows -------------
+    CH_F = 8192
+    cstreams = [torch.cuda.Stream() for _ in range(3)]
+    d_cin = [torch.empty(CH_F * HOP, dtype=torch.float32, device="cuda") for _ in range(3)]
+    d_cout = [torch.empty((CH_F, ROWS, 4), dtype=torch.uint8, device="cuda") for _ in range(3)]
+
+    def copy_only_step():
+        for c, f0 in enumerate(range(0, Fe, CH_F)):
+            nf = min(CH_F, Fe - f0)
+            with torch.cuda.stream(cstreams[c % 3]):
+                d_cin[c % 3][:nf * HOP].copy_(h_pcm[f0 * HOP:(f0 + nf) * HOP], non_blocking=True)
+                h_rgba[f0:f0 + nf].copy_(d_cout[c % 3][:nf], non_blocking=True)
+        for cs in cstreams:
+            cs.synchronize()
+
+    for _ in range(2):
+        copy_only_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        copy_only_step()
+    barrier()
+    copy_s = max_over_ranks(time.perf_counter() - t0)
+    copy_ceiling = world * Fe * e2e_steps / copy_s
+    del d_cin, d_cout
+
     # ---- the same call over ALL devices from one process: sbx_multi_process_batch (rank 0 drives every GPU from its
     # own host threads while the other ranks wait at the barrier): one host recording of world * Fe frames ------------
     e2e_multi = None
@@ -442,6 +469,9 @@ def main():
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": ns_e * 4 * world, "d2h_bytes_per_step": Fe * ROWS * 4 * world,
                 "frames_per_gpu_per_step": Fe, "steps": e2e_steps, "api": "sbx_process_batch (host pointers, pinned), one process per GPU", "numa": numa,
                 "d2h_gbs_per_gpu": e2e_value / world * ROWS * 4 / 1e9, "h2d_gbs_per_gpu": e2e_value / world * HOP * 4 / 1e9,
+                "copy_ceiling": {"frames_per_s": copy_ceiling, "frac": e2e_value / copy_ceiling,
+                                 "what": "the same pinned buffers, bytes per frame (2 KB in, 4 KB out), chunking and ranks with NO kernels, "
+                                         "timed right after the end-to-end leg: the host<->device path's own limit in this run"},
                 "note": "bound by the PCIe D2H of the RGBA output (4 KB per frame): chunked, three streams, H2D/kernel/D2H overlapped"
                         + ("; with several GPUs the ranks share the host's PCIe / memory path (DESIGN.md section 6, profiles/copy_ceiling_r02.json)" if world > 1 else "")},
         "gpu_launches": launches * world,
@@ -452,6 +482,7 @@ def main():
         out["e2e"]["one_process_multi_device"] = e2e_multi
         out["e2e"]["one_process_per_gpu"] = {"value": e2e_value, "api": out["e2e"]["api"]}
         if e2e_multi.get("value", 0.0) > e2e_value:          # the headline is the better of the two public calls
+            out["e2e"]["copy_ceiling"]["frac"] = e2e_multi["value"] / copy_ceiling
             out["e2e"].update(value=e2e_multi["value"], api=e2e_multi["api"], frames_per_gpu_per_step=Fe,
                               d2h_gbs_per_gpu=e2e_multi["value"] / world * ROWS * 4 / 1e9,
                               h2d_gbs_per_gpu=e2e_multi["value"] / world * HOP * 4 / 1e9)
