@@ -680,6 +680,22 @@ def extras(sbx, signals, torch):
     plan.close()
     del x, out, img
 
+    # sbx_process_batch from PAGEABLE host memory (a plain numpy array, what a caller without pinned buffers passes):
+    # the runtime stages every copy through its own pinned buffer, so the copies do not overlap the kernels
+    plan = sbx.Plan(sample_rate=SR, window_n=N, pad_factor=PAD, hop=HOP, rows_h=ROWS, channels=1, lut="magma",
+                    device=torch.cuda.current_device())
+    Fp = 1 << 15
+    xp = np.resize(signals.log_sweep(int(SR * 60)), (Fp - 1) * HOP + N)
+    outp = np.empty((Fp, ROWS, 4), np.uint8)
+    plan.process_batch(xp, outp)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        plan.process_batch(xp, outp)
+    res["e2e_pageable_frames_per_s"] = {"value": 3 * Fp / (time.perf_counter() - t0), "frames_per_step": Fp,
+                                        "what": "sbx_process_batch with pageable (numpy) input and output buffers, cfg1, 1 GPU"}
+    plan.close()
+    del xp, outp
+
     # cfg2: live single stream, 48 kHz stereo, 2048-pt frames pushed one at a time through the pinned ring
     plan = sbx.Plan(sample_rate=48000.0, window_n=2048, pad_factor=2, hop=2048, rows_h=1024, channels=2, lut="magma",
                     device=torch.cuda.current_device())
