@@ -169,11 +169,55 @@ inline void build(const sbx_config &cfg, HostTables &t)
     // ---- transform tables ----------------------------------------------------------------------
     t.twm.clear(); t.pos_tab.clear(); t.radix.clear(); t.stride.clear(); t.twg.clear(); t.tw_off.clear();
     if (t.generic) {
-        // radix list from {16, 8, 4, 2, 3, 5, 7}; a left-over factor means a prime > 7: unsupported
+        // radix list from {16, 15, 12, 10, 9, 8, 7, 6, 5, 4, 3, 2}: the factorisation with the FEWEST passes (every pass
+        // is a barrier-separated trip through shared memory), larger radices first; a left-over factor means a
+        // prime > 7.  SBX_GENERIC_PRIME_RADICES=1 restores round 1's {16, 8, 4, 2, 3, 5, 7} list (A/B measurements).
         uint32_t rest = t.n;
-        const uint32_t cand[] = {16, 8, 4, 2, 3, 5, 7};
-        for (uint32_t r : cand)
-            while (rest % r == 0 && rest > 1) { t.radix.push_back(r); rest /= r; }
+        for (uint32_t f : {2u, 3u, 5u, 7u})
+            while (rest % f == 0) rest /= f;
+        const char *env_prime = std::getenv("SBX_GENERIC_PRIME_RADICES");
+        if (rest == 1 && !(env_prime && env_prime[0] == '1')) {
+            const uint32_t cand[] = {16, 15, 12, 10, 9, 8, 7, 6, 5, 4, 3, 2};
+            std::vector<uint32_t> cur, best;
+            // depth-limited search, non-increasing factors
+            struct Search {
+                static bool go(uint32_t n, size_t max_r, int left, const uint32_t *cand, std::vector<uint32_t> &cur)
+                {
+                    if (n == 1) return true;
+                    if (left == 0) return false;
+                    for (size_t i = max_r; i < 12; ++i) {
+                        if (n % cand[i] != 0) continue;
+                        cur.push_back(cand[i]);
+                        if (go(n / cand[i], i, left - 1, cand, cur)) return true;
+                        cur.pop_back();
+                    }
+                    return false;
+                }
+            };
+            for (int depth = 1; depth <= GENERIC_MAX_PASSES && best.empty(); ++depth) {
+                cur.clear();
+                if (Search::go(t.n, 0, depth, cand, cur)) best = cur;
+            }
+            // The LAST pass has stride 1: a thread owns R consecutive elements, so the 16 lanes of a shared-memory
+            // request sit R elements apart -- conflict-free when R is odd, gcd(R, 16)-way conflicted otherwise
+            // (16-way for R = 16).  Put the radix with the smallest gcd(R, 16) last (ties: the larger one).
+            if (best.size() > 1) {
+                auto g16 = [](uint32_t r) { uint32_t g = 1; while (g < 16 && r % (2 * g) == 0) g *= 2; return g; };
+                size_t pick = 0;
+                for (size_t i = 1; i < best.size(); ++i)
+                    if (g16(best[i]) < g16(best[pick]) || (g16(best[i]) == g16(best[pick]) && best[i] > best[pick])) pick = i;
+                const uint32_t last = best[pick];
+                best.erase(best.begin() + (long)pick);
+                best.push_back(last);
+            }
+            t.radix = best;
+            rest = best.empty() ? t.n : 1;
+        } else {
+            rest = t.n;
+            const uint32_t cand[] = {16, 8, 4, 2, 3, 5, 7};
+            for (uint32_t r : cand)
+                while (rest % r == 0 && rest > 1) { t.radix.push_back(r); rest /= r; }
+        }
         if ((t.m & 1u) || t.m < 8) { t.radix.clear(); t.ok = false; return; }
         uint32_t fft_len = t.n;                                  // length the passes transform (P sub-transforms of N)
         if (rest != 1 || t.radix.size() > (size_t)GENERIC_MAX_PASSES) {

@@ -3,15 +3,18 @@
 //
 // Same structure as the fused kernel -- P premultiplied sub-transforms of length N, in-place DIF,
 // digit-reversed output, conjugate-symmetry split, tabulated resample, threshold dB step -- with the
-// radix list chosen at run time from {16, 8, 4, 2, 3, 5, 7}: N = 2400 = 16*2*3*5*5, 2205 = 3*3*5*7*7.
+// radix list chosen at run time from {16, 15, 12, 10, 9, 8, 7, 6, 5, 4, 3, 2}: the fewest passes, the radix with the
+// smallest gcd(R, 16) last (N = 2400 = 16*10*15, 2205 = 15*7*7*3).
 // This is the low-rate live path (819 frames/s in the reference), so it trades the fused kernel's
 // swizzles and compile-time index math for generality: bin -> position comes from a host table, twiddles
 // from per-pass planes (contiguous in the butterfly index), divisions by host-computed reciprocals.
-// Measured on a B200, N = 2400 stereo: 18.3 M frames/s in batch, 27 us per live frame (12.0 M / 41 us with
-// strided loads from the full W_M table and run-time divisions).  Composite radices evaluated in registers
-// (20, 21, 15, ...: 2400 = 20*20*6, three passes instead of five) were measured and rejected: 128 registers halve
-// the occupancy and the batch rate drops to 12.8 M frames/s, with no gain for the single live frame.  One CTA per frame (stereo) or frame pair (mono); the transform (M float2)
-// and the magnitudes (M/2 float2) live in shared memory: M <= 16384.
+// Measured on a B200, N = 2400 stereo: 24.0 M frames/s in batch, 24.6 us per live frame.  History: 12.0 M / 41 us with
+// strided loads from the full W_M table and run-time divisions; 18.5 M / 26.6 us with five prime-radix passes
+// (16*2*3*5*5); 20.6 M with literal-constant 3- and 5-point DFTs; 23.1 M with composite radices 6 / 9 / 10 / 12 / 15
+// in registers (three passes); 24.0 M with the odd radix last (the stride-1 pass conflict-free).  Radices of 20 / 21
+// in registers were measured in round 1 and rejected: 128 registers halve the occupancy (12.8 M frames/s).
+// One CTA per frame (stereo) or frame pair (mono); the transform (M float2) and the magnitudes (M/2 float2) live
+// in shared memory: M <= 19370.  Windows with a prime factor > 7 take the Bluestein form further down.
 #pragma once
 #include "stft_kernels.cuh"
 
@@ -58,14 +61,137 @@ __device__ __forceinline__ uint32_t mulhi_u32(uint32_t a, uint32_t b)
 #endif
 }
 
-// R-point DFT, natural order in and out.  Powers of two reuse the fused kernel's butterflies; 3, 5 and 7
-// are evaluated directly from the table (w[j] = W_R^j).
+// W_R^j = exp(-2 pi i j / R) for the composite radices, as literals: after unrolling every index is a compile-time
+// constant and the values become instruction immediates
+__device__ __forceinline__ float2 wconst6(int j)
+{
+    constexpr float re[6] = {1.0f, 0.5f, -0.5f, -1.0f, -0.5f, 0.5f};
+    constexpr float im[6] = {0.0f, -0.866025404f, -0.866025404f, 0.0f, 0.866025404f, 0.866025404f};
+    return make_float2(re[j], im[j]);
+}
+__device__ __forceinline__ float2 wconst9(int j)
+{
+    constexpr float re[9] = {1.0f, 0.766044443f, 0.173648178f, -0.5f, -0.939692621f, -0.939692621f, -0.5f, 0.173648178f, 0.766044443f};
+    constexpr float im[9] = {0.0f, -0.64278761f, -0.984807753f, -0.866025404f, -0.342020143f, 0.342020143f, 0.866025404f, 0.984807753f, 0.64278761f};
+    return make_float2(re[j], im[j]);
+}
+__device__ __forceinline__ float2 wconst10(int j)
+{
+    constexpr float re[10] = {1.0f, 0.809016994f, 0.309016994f, -0.309016994f, -0.809016994f, -1.0f, -0.809016994f, -0.309016994f, 0.309016994f, 0.809016994f};
+    constexpr float im[10] = {0.0f, -0.587785252f, -0.951056516f, -0.951056516f, -0.587785252f, 0.0f, 0.587785252f, 0.951056516f, 0.951056516f, 0.587785252f};
+    return make_float2(re[j], im[j]);
+}
+__device__ __forceinline__ float2 wconst12(int j)
+{
+    constexpr float re[12] = {1.0f, 0.866025404f, 0.5f, 0.0f, -0.5f, -0.866025404f, -1.0f, -0.866025404f, -0.5f, 0.0f, 0.5f, 0.866025404f};
+    constexpr float im[12] = {0.0f, -0.5f, -0.866025404f, -1.0f, -0.866025404f, -0.5f, 0.0f, 0.5f, 0.866025404f, 1.0f, 0.866025404f, 0.5f};
+    return make_float2(re[j], im[j]);
+}
+__device__ __forceinline__ float2 wconst15(int j)
+{
+    constexpr float re[15] = {1.0f, 0.913545458f, 0.669130606f, 0.309016994f, -0.104528463f, -0.5f, -0.809016994f, -0.978147601f,
+                              -0.978147601f, -0.809016994f, -0.5f, -0.104528463f, 0.309016994f, 0.669130606f, 0.913545458f};
+    constexpr float im[15] = {0.0f, -0.406736643f, -0.743144825f, -0.951056516f, -0.994521895f, -0.866025404f, -0.587785252f, -0.207911691f,
+                              0.207911691f, 0.587785252f, 0.866025404f, 0.994521895f, 0.951056516f, 0.743144825f, 0.406736643f};
+    return make_float2(re[j], im[j]);
+}
+template <int R> __device__ __forceinline__ float2 wconst(int j)
+{
+    if constexpr (R == 6) return wconst6(j);
+    else if constexpr (R == 9) return wconst9(j);
+    else if constexpr (R == 10) return wconst10(j);
+    else if constexpr (R == 12) return wconst12(j);
+    else return wconst15(j);
+}
+
+// prime-length DFTs with literal constants, natural order in and out
+template <int R> struct PrimDft;
+template <> struct PrimDft<2> { static __device__ __forceinline__ void run(float2 (&v)[2]) { Butterfly<2>::run(v); } };
+template <> struct PrimDft<4> { static __device__ __forceinline__ void run(float2 (&v)[4]) { Butterfly<4>::run(v); } };
+template <> struct PrimDft<3> {
+    static __device__ __forceinline__ void run(float2 (&v)[3])
+    {
+        // W_3 = -1/2 - i sqrt(3)/2:  X1 = a - s/2 - i (sqrt3/2) d,  X2 = a - s/2 + i (sqrt3/2) d,  s = b + c, d = b - c
+        const float2 s = cadd(v[1], v[2]), d = csub(v[1], v[2]);
+        const float2 m = make_float2(v[0].x - 0.5f * s.x, v[0].y - 0.5f * s.y);
+        const float2 e = make_float2(0.866025404f * d.y, -0.866025404f * d.x);      // -i (sqrt3/2) d
+        v[0] = cadd(v[0], s);
+        v[1] = cadd(m, e);
+        v[2] = csub(m, e);
+    }
+};
+template <> struct PrimDft<5> {
+    static __device__ __forceinline__ void run(float2 (&v)[5])
+    {
+        constexpr float c1 = 0.309016994f, c2 = -0.809016994f, s1 = 0.951056516f, s2 = 0.587785252f;
+        const float2 t1 = cadd(v[1], v[4]), t2 = cadd(v[2], v[3]), t3 = csub(v[1], v[4]), t4 = csub(v[2], v[3]);
+        const float2 a1 = make_float2(v[0].x + c1 * t1.x + c2 * t2.x, v[0].y + c1 * t1.y + c2 * t2.y);
+        const float2 a2 = make_float2(v[0].x + c2 * t1.x + c1 * t2.x, v[0].y + c2 * t1.y + c1 * t2.y);
+        const float2 b1 = make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
+        const float2 b2 = make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
+        v[0] = cadd(v[0], cadd(t1, t2));
+        v[1] = make_float2(a1.x + b1.y, a1.y - b1.x);                                // a1 - i b1
+        v[4] = make_float2(a1.x - b1.y, a1.y + b1.x);                                // a1 + i b1
+        v[2] = make_float2(a2.x + b2.y, a2.y - b2.x);
+        v[3] = make_float2(a2.x - b2.y, a2.y + b2.x);
+    }
+};
+
+// R = R1 R2 by one Cooley-Tukey step in registers: n = R2 n1 + n2, k = k1 + R1 k2,
+// W_R^(n k) = W_R1^(n1 k1) W_R^(n2 k1) W_R2^(n2 k2)
+template <int R1, int R2> struct CompositeDft {
+    static constexpr int R = R1 * R2;
+    static __device__ __forceinline__ void run(float2 (&v)[R])
+    {
+        float2 t[R1][R2];
+#pragma unroll
+        for (int n2 = 0; n2 < R2; ++n2) {
+            float2 a[R1];
+#pragma unroll
+            for (int n1 = 0; n1 < R1; ++n1) a[n1] = v[R2 * n1 + n2];
+            PrimDft<R1>::run(a);
+#pragma unroll
+            for (int k1 = 0; k1 < R1; ++k1) t[k1][n2] = a[k1];
+        }
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) {
+            float2 b[R2];
+#pragma unroll
+            for (int n2 = 0; n2 < R2; ++n2) b[n2] = (k1 * n2) % R == 0 ? t[k1][n2] : cmul(t[k1][n2], wconst<R>((k1 * n2) % R));
+            PrimDft<R2>::run(b);
+#pragma unroll
+            for (int k2 = 0; k2 < R2; ++k2) v[k1 + R1 * k2] = b[k2];
+        }
+    }
+};
+
+// R-point DFT, natural order in and out.  Powers of two reuse the fused kernel's butterflies; 3 and 5 use literal
+// constants; 6, 9, 10, 12 and 15 are one Cooley-Tukey step of those in registers (fewer barrier-separated passes:
+// 2400 = 16 x 15 x 10 instead of 16 x 2 x 3 x 5 x 5); 7 is evaluated directly from the table (w[j] = W_7^j).
 template <int R> struct SmallDft {
     static __device__ __forceinline__ void run(float2 (&v)[R], const float2 *twm, uint32_t m)
     {
         if constexpr (R == 2 || R == 4 || R == 8 || R == 16) {
             (void)twm; (void)m;
             Butterfly<R>::run(v);
+        } else if constexpr (R == 3 || R == 5) {
+            (void)twm; (void)m;
+            PrimDft<R>::run(v);
+        } else if constexpr (R == 6) {
+            (void)twm; (void)m;
+            CompositeDft<2, 3>::run(v);
+        } else if constexpr (R == 9) {
+            (void)twm; (void)m;
+            CompositeDft<3, 3>::run(v);
+        } else if constexpr (R == 10) {
+            (void)twm; (void)m;
+            CompositeDft<2, 5>::run(v);
+        } else if constexpr (R == 12) {
+            (void)twm; (void)m;
+            CompositeDft<4, 3>::run(v);
+        } else if constexpr (R == 15) {
+            (void)twm; (void)m;
+            CompositeDft<3, 5>::run(v);
         } else {
             float2 w[R];
 #pragma unroll
@@ -142,8 +268,13 @@ __device__ __forceinline__ void generic_pass_dispatch(float2 *z, const GenericAr
         case 3: generic_pass<3>(z, g, p, last); break;
         case 4: generic_pass<4>(z, g, p, last); break;
         case 5: generic_pass<5>(z, g, p, last); break;
+        case 6: generic_pass<6>(z, g, p, last); break;
         case 7: generic_pass<7>(z, g, p, last); break;
         case 8: generic_pass<8>(z, g, p, last); break;
+        case 9: generic_pass<9>(z, g, p, last); break;
+        case 10: generic_pass<10>(z, g, p, last); break;
+        case 12: generic_pass<12>(z, g, p, last); break;
+        case 15: generic_pass<15>(z, g, p, last); break;
         case 16: generic_pass<16>(z, g, p, last); break;
         default: break;
     }
