@@ -939,31 +939,31 @@ __device__ __forceinline__ T interp_sample(const T *mags, const KernelArgs &a, i
 
 // Phase A of a row chunk: one lane per (row, sample); consecutive lanes read consecutive bins.
 // The sample-table loads of four iterations are issued together (latency hiding).
-template <int THREADS, bool CLAMP, class T>
+template <int THREADS, bool CLAMP, class T, int UNROLL = 4>
 __device__ __forceinline__ void resample_samples_impl(const T *mags, T *scratch, const KernelArgs &a, const RowChunk ck)
 {
     const int k_last = (int)a.k_out - 1;
     const uint32_t count = ck.samp_end - ck.samp_begin;
     const uint2 *tab = a.samp + ck.samp_begin;
-    for (uint32_t g0 = threadIdx.x; g0 < count; g0 += 4 * THREADS) {
-        uint2 sp[4];
+    for (uint32_t g0 = threadIdx.x; g0 < count; g0 += UNROLL * THREADS) {
+        uint2 sp[UNROLL];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < UNROLL; ++i) {
             const uint32_t g = g0 + i * THREADS;
             sp[i] = g < count ? ldg_tab(tab + g) : make_uint2(SAMP_NO_STORE, 0u);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < UNROLL; ++i) {
             if (sp[i].x < SAMP_NO_STORE)                                       // a real entry (not a filler, not past the end)
                 scratch[sp[i].x >> 17] = interp_sample<CLAMP>(mags, a, (int)(sp[i].x & 0x1ffffu), __uint_as_float(sp[i].y), k_last);
         }
     }
 }
-template <int THREADS, class T>
+template <int THREADS, class T, int UNROLL = 4>
 __device__ __forceinline__ void resample_samples(const T *mags, T *scratch, const KernelArgs &a, const RowChunk ck)
 {
-    if (a.taps_clamped) resample_samples_impl<THREADS, true>(mags, scratch, a, ck);
-    else resample_samples_impl<THREADS, false>(mags, scratch, a, ck);
+    if (a.taps_clamped) resample_samples_impl<THREADS, true, T, UNROLL>(mags, scratch, a, ck);
+    else resample_samples_impl<THREADS, false, T, UNROLL>(mags, scratch, a, ck);
 }
 
 // Stereo-scheme gradient index of a mono pixel (l == r >= 0): floor(l / (|l| + |l|) * 256) with the reference's f32
@@ -1032,24 +1032,31 @@ __device__ __forceinline__ void colour_one_row_single(float ax, uint32_t n, uint
     }
 }
 
-template <int THREADS>
+template <int THREADS, int ROWS = 2>
 __device__ __forceinline__ void colour_rows_single(const float *scratch, const KernelArgs &a, const RowChunk ck, unsigned long long frame)
 {
     uint32_t *out = reinterpret_cast<uint32_t *>(a.rgba) + frame * a.rows;
-    for (uint32_t py0 = ck.row_begin + threadIdx.x; py0 < ck.row_end; py0 += 2 * THREADS) {
-        const uint32_t py1 = py0 + THREADS;
-        const bool has1 = py1 < ck.row_end;
-        const uint32_t r0 = ldg_tab(a.rowinfo + py0), r1 = has1 ? ldg_tab(a.rowinfo + py1) : 0u;
-        const uint32_t n0 = r0 & 0xffffu, n1 = r1 & 0xffffu;
-        const float *m0 = scratch + (r0 >> 16), *m1 = scratch + (r1 >> 16);
-        float a0 = 0.0f, a1 = 0.0f;
-        const uint32_t nmax = n0 > n1 ? n0 : n1;
-        for (uint32_t s = 0; s < nmax; ++s) {
-            if (s < n0) a0 = __fadd_rn(a0, m0[s]);
-            if (s < n1) a1 = __fadd_rn(a1, m1[s]);
+    for (uint32_t py0 = ck.row_begin + threadIdx.x; py0 < ck.row_end; py0 += ROWS * THREADS) {
+        uint32_t n[ROWS], nmax = 0;
+        const float *m[ROWS];
+        float acc[ROWS];
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) {
+            const uint32_t py = py0 + i * THREADS;
+            const uint32_t r = py < ck.row_end ? ldg_tab(a.rowinfo + py) : 0u;       // n = 0: row absent
+            n[i] = r & 0xffffu;
+            m[i] = scratch + (r >> 16);
+            acc[i] = 0.0f;
+            nmax = n[i] > nmax ? n[i] : nmax;
         }
-        colour_one_row_single(a0, n0, py0, a, out);
-        if (has1) colour_one_row_single(a1, n1, py1, a, out);
+        for (uint32_t s = 0; s < nmax; ++s) {
+#pragma unroll
+            for (int i = 0; i < ROWS; ++i)
+                if (s < n[i]) acc[i] = __fadd_rn(acc[i], m[i][s]);
+        }
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i)
+            if (n[i] != 0) colour_one_row_single(acc[i], n[i], py0 + i * THREADS, a, out);
     }
 }
 
@@ -1266,7 +1273,7 @@ __device__ __forceinline__ void resample_colour(float2 *z, const KernelArgs &a, 
     }
 }
 
-template <int LOG2M, int THREADS>
+template <int LOG2M, int THREADS, int UNROLL = 4, int ROWS = 2>
 __device__ __forceinline__ void resample_colour_single(float2 *z, const KernelArgs &a, unsigned long long frame)
 {
     const float *mags = reinterpret_cast<const float *>(z);   // M floats: the lower half of the buffer
@@ -1275,9 +1282,9 @@ __device__ __forceinline__ void resample_colour_single(float2 *z, const KernelAr
         const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.chunks) + c);
         const RowChunk ck = {raw.x, raw.y, raw.z, raw.w};
         if (c != 0) __syncthreads();
-        resample_samples<THREADS>(mags, scratch, a, ck);
+        resample_samples<THREADS, float, UNROLL>(mags, scratch, a, ck);
         __syncthreads();
-        colour_rows_single<THREADS>(scratch, a, ck, frame);
+        colour_rows_single<THREADS, ROWS>(scratch, a, ck, frame);
     }
 }
 

@@ -341,6 +341,13 @@ __device__ __forceinline__ void q2_split_emit_real(float *zf, const float *pb, c
 #define SBX_Q2_COLOUR_ROWS 4           // rows in flight per thread in the colour phase
 #endif
 
+#ifndef SBX_Q2_SINGLE_UNROLL
+#define SBX_Q2_SINGLE_UNROLL 8         // real-sequence geometry (one float per bin): sample-table loads in flight per thread
+#endif
+#ifndef SBX_Q2_SINGLE_ROWS
+#define SBX_Q2_SINGLE_ROWS 2           // ... and rows in flight per thread in its colour phase (B200, cfg3: (4,2) 34.38, (8,2) 34.63, (8,4) 34.14 M frames/s: 4 rows spill)
+#endif
+
 #ifndef SBX_EMU
 // -DSBX_PHASE_CLOCK (tools/phase_split.py builds that variant; never the shipped library): thread 0 of every CTA reads
 // the SM clock at the phase boundaries and adds the differences to g_phase_cycles -- the per-phase share of a CTA's
@@ -401,7 +408,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) fused_q2_kernel(const
             float2 *out = reinterpret_cast<float2 *>(a.mags_out) + out_frame0 * a.k_out;
             for (uint32_t j = threadIdx.x; j < a.k_out; j += G::THREADS) out[j] = make_float2(zf[j + 1], zf[j + 1]);
         }
-        if (a.rgba != nullptr) resample_colour_single<G::LOG2M, G::THREADS>(z, a, out_frame0);
+        if (a.rgba != nullptr) resample_colour_single<G::LOG2M, G::THREADS, SBX_Q2_SINGLE_UNROLL, SBX_Q2_SINGLE_ROWS>(z, a, out_frame0);
     } else {
     if (a.mags_out != nullptr) {
         float2 *out = reinterpret_cast<float2 *>(a.mags_out) + out_frame0 * a.k_out;
