@@ -185,4 +185,38 @@ struct ColumnStore {
     }
 };
 
+// A whole recording on every GPU of the box through ONE call (no reference counterpart: the application is live-only;
+// frames are independent, src/fourier/audio_transform.rs:37-41): time blocks with an N - hop halo, or whole planar
+// channels, one plan and one host thread per device inside the library (sbx_multi_*).
+class OfflineSpectrogram {
+public:
+    // devices: CUDA ordinals; empty = 0 .. n_devices-1
+    OfflineSpectrogram(const sbx_config &cfg, uint32_t n_devices, const std::vector<int32_t> &devices = {})
+    {
+        const sbx_status st = sbx_multi_create(&cfg, devices.empty() ? nullptr : devices.data(), n_devices, &multi_);
+        if (st != SBX_OK) throw Error(st, std::string("sbx_multi_create: ") + sbx_multi_last_error(nullptr));
+        rows_ = sbx_rows(sbx_multi_plan(multi_, 0));
+    }
+    ~OfflineSpectrogram() { sbx_multi_destroy(multi_); }
+    OfflineSpectrogram(const OfflineSpectrogram &) = delete;
+    OfflineSpectrogram &operator=(const OfflineSpectrogram &) = delete;
+
+    uint64_t num_frames(uint64_t n_samples) const { return sbx_num_frames(sbx_multi_plan(multi_, 0), n_samples); }
+
+    // pcm: n_samples x channels (host; pinned or sbx_host_register'ed for overlapping copies) -> frames x H x 4 RGBA
+    std::vector<uint8_t> process(const float *pcm, uint64_t n_samples)
+    {
+        std::vector<uint8_t> rgba((size_t)num_frames(n_samples) * rows_ * 4);
+        uint64_t frames = 0;
+        const sbx_status st = sbx_multi_process_batch(multi_, pcm, n_samples, rgba.data(), num_frames(n_samples), &frames);
+        if (st != SBX_OK) throw Error(st, std::string("sbx_multi_process_batch: ") + sbx_multi_last_error(multi_));
+        rgba.resize((size_t)frames * rows_ * 4);
+        return rgba;
+    }
+
+private:
+    sbx_multi *multi_ = nullptr;
+    uint32_t rows_ = 0;
+};
+
 }  // namespace sbx

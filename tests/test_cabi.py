@@ -126,6 +126,15 @@ def test_no_cpu_fallback_without_a_gpu():
     with pytest.raises(s.SbxError) as e:
         s.Plan()
     assert e.value.status == -3 and "no CPU fallback" in str(e.value)
+    with pytest.raises(s.SbxError) as e:                                      # the several-device entry point likewise
+        s.MultiPlan(2)
+    assert e.value.status == -3 and "no CPU fallback" in str(e.value) and "device 0" in str(e.value)
+    lib = s.binding.load()
+    assert lib.sbx_multi_device_count(None) == 0 and lib.sbx_multi_plan(None, 0) is None
+    assert lib.sbx_multi_process_batch(None, None, 0, None, 0, None) == -1
+    assert lib.sbx_multi_last_error(None) is not None
+    # the built-in gradients are host functions: available without a GPU
+    assert s.builtin_lut("turbo").shape == (256, 3) and s.builtin_gradient("red_blue", 1024).shape == (1024, 3)
 
 
 def test_product_does_not_reference_the_oracle():

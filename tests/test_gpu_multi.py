@@ -216,3 +216,24 @@ def test_live_push_abort_regression(sbx, magma):
                 if len(model) < n:
                     break
             live.close()
+
+
+def test_host_register_makes_caller_memory_usable(sbx, magma):
+    """sbx_host_register / sbx_host_unregister: page-lock memory the caller already owns (a Rust Vec<f32>, here numpy
+    arrays) and run the host-pointer batch on it; results equal the pageable call."""
+    lib = sbx.binding.load()
+    n, hop, rows, frames = 2048, 512, 128, 700
+    x = _recording(1, n + hop * (frames - 1))
+    out = np.zeros((frames, rows, 4), np.uint8)
+    with sbx.Plan(window_n=n, hop=hop, rows_h=rows, channels=1, lut=magma) as plan:
+        want = plan.process_batch(x)
+        assert lib.sbx_host_register(x.ctypes.data, x.nbytes) == 0
+        assert lib.sbx_host_register(out.ctypes.data, out.nbytes) == 0
+        try:
+            assert plan.process_batch_ptr(x.ctypes.data, x.shape[0], out.ctypes.data, frames) == frames
+        finally:
+            assert lib.sbx_host_unregister(out.ctypes.data) == 0
+            assert lib.sbx_host_unregister(x.ctypes.data) == 0
+        assert np.array_equal(out, want)
+    assert lib.sbx_host_register(None, 16) == -1 and lib.sbx_host_unregister(None) == -1
+    assert lib.sbx_host_unregister(x.ctypes.data) == -3                     # not registered (any more)
