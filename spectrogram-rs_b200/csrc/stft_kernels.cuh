@@ -93,6 +93,16 @@ struct KernelArgs {
     int taps_clamped;            // 1 if any cubic tap index needs clamping to [0, K-1] (spectrum edges)
 };
 
+#ifndef SBX_ROWSUM_PER_ROW
+#define SBX_ROWSUM_PER_ROW 1     // colour phase: every row of a thread is summed with ITS OWN trip count (1), instead of all the
+                                 // thread's rows in one loop of max(n) steps with predicated adds (0: round 1).  A thread's rows
+                                 // are H/ROWS apart -- n = 1 in the low rows, up to 23 in the top ones -- so the fused loop spent
+                                 // three of four slots predicated off; lanes of a warp hold ADJACENT rows, so per-row trip counts
+                                 // barely diverge.  Same additions in the same order: bit-identical sums.
+#endif
+#ifndef SBX_ROWSUM_PER_ROW_CLASSIC
+#define SBX_ROWSUM_PER_ROW_CLASSIC 0   // the same choice for colour_rows of the classic / mixed-radix / multi-kernel paths (two rows per thread)
+#endif
 #ifndef SBX_PK_RESAMPLE
 #define SBX_PK_RESAMPLE 0        // 1: the classic kernels resample / sum rows with packed (L, R) instructions too (pk_resample_colour)
 #endif
@@ -1049,11 +1059,22 @@ __device__ __forceinline__ void colour_rows_single(const float *scratch, const K
             acc[i] = 0.0f;
             nmax = n[i] > nmax ? n[i] : nmax;
         }
+#if SBX_ROWSUM_PER_ROW
+        (void)nmax;
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) {
+            float sum = 0.0f;
+            const float *mi = m[i];
+            for (uint32_t s = 0; s < n[i]; ++s) sum = __fadd_rn(sum, mi[s]);
+            acc[i] = sum;
+        }
+#else
         for (uint32_t s = 0; s < nmax; ++s) {
 #pragma unroll
             for (int i = 0; i < ROWS; ++i)
                 if (s < n[i]) acc[i] = __fadd_rn(acc[i], m[i][s]);
         }
+#endif
 #pragma unroll
         for (int i = 0; i < ROWS; ++i)
             if (n[i] != 0) colour_one_row_single(acc[i], n[i], py0 + i * THREADS, a, out);
@@ -1073,11 +1094,16 @@ __device__ __forceinline__ void colour_rows(const float2 *scratch, const float *
         const uint32_t n0 = r0 & 0xffffu, n1 = r1 & 0xffffu;                 // n1 == 0 when the second row is absent
         const float2 *m0 = scratch + (r0 >> 16), *m1 = scratch + (r1 >> 16); // odd stride between rows
         float ax0 = 0.0f, ay0 = 0.0f, ax1 = 0.0f, ay1 = 0.0f;
+#if SBX_ROWSUM_PER_ROW_CLASSIC
+        for (uint32_t s = 0; s < n0; ++s) { const float2 v = m0[s]; ax0 = __fadd_rn(ax0, v.x); ay0 = __fadd_rn(ay0, v.y); }
+        for (uint32_t s = 0; s < n1; ++s) { const float2 v = m1[s]; ax1 = __fadd_rn(ax1, v.x); ay1 = __fadd_rn(ay1, v.y); }
+#else
         const uint32_t nmax = n0 > n1 ? n0 : n1;
         for (uint32_t s = 0; s < nmax; ++s) {
             if (s < n0) { const float2 v = m0[s]; ax0 = __fadd_rn(ax0, v.x); ay0 = __fadd_rn(ay0, v.y); }
             if (s < n1) { const float2 v = m1[s]; ax1 = __fadd_rn(ax1, v.x); ay1 = __fadd_rn(ay1, v.y); }
         }
+#endif
         colour_one_row<PAIR>(ax0, ay0, n0, py0, thr, lut, a, outA, outB, second_valid);
         if (has1) colour_one_row<PAIR>(ax1, ay1, n1, py1, thr, lut, a, outA, outB, second_valid);
     }
@@ -1184,10 +1210,22 @@ __device__ __forceinline__ void pk_colour_rows(const float2 *scratch, const Kern
             acc[i] = pk_make(0.0f, 0.0f);
             nmax = n[i] > nmax ? n[i] : nmax;
         }
-        for (uint32_t s = 0; s < nmax; ++s) {
+        // measured on a B200 (M frames/s, fused loop -> per-row loops): cfg1 67.4 -> 69.25, cfg1 geometry stereo 34.5 -> 35.7,
+        // cfg3 34.65 -> 34.94; but cfg2 (N = 2048: 128-thread CTAs, eight rows per thread) 58.2 -> 57.1: per row from 256 threads up
+        if constexpr (SBX_ROWSUM_PER_ROW != 0 && THREADS >= 256) {
 #pragma unroll
-            for (int i = 0; i < ROWS; ++i)
-                if (s < n[i]) acc[i] = pk_add(acc[i], pk_ld2(m[i] + s));
+            for (int i = 0; i < ROWS; ++i) {
+                pk sum = pk_make(0.0f, 0.0f);
+                const float2 *mi = m[i];
+                for (uint32_t s = 0; s < n[i]; ++s) sum = pk_add(sum, pk_ld2(mi + s));
+                acc[i] = sum;
+            }
+        } else {
+            for (uint32_t s = 0; s < nmax; ++s) {
+#pragma unroll
+                for (int i = 0; i < ROWS; ++i)
+                    if (s < n[i]) acc[i] = pk_add(acc[i], pk_ld2(m[i] + s));
+            }
         }
 #pragma unroll
         for (int i = 0; i < ROWS; ++i)
