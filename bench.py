@@ -464,7 +464,7 @@ def main():
                      "secondary": secondary,
                      "note": "the HBM fraction is the mandated figure (algorithmic bytes hop*4 + H*4 per frame against the measured copy "
                              "bandwidth); the path does 44-87 flop per compulsory byte against a 12 flop/B ridge (SURVEY.md D6), so what "
-                             "binds it is the SM: ncu (profiles/ncu_r02_cfg1_*) L1/shared pipe 78 %, issue slots 62 %, FMA pipe 55 %, "
+                             "binds it is the SM: ncu (profiles/ncu_r02_cfg1_*) L1/shared pipe 75.5 %, issue slots 61 %, FMA pipe 56 %, "
                              "DRAM traffic = 0.98 x the algorithmic bytes"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": ns_e * 4 * world, "d2h_bytes_per_step": Fe * ROWS * 4 * world,
                 "frames_per_gpu_per_step": Fe, "steps": e2e_steps, "api": "sbx_process_batch (host pointers, pinned), one process per GPU", "numa": numa,
