@@ -100,6 +100,9 @@ struct KernelArgs {
                                  // three of four slots predicated off; lanes of a warp hold ADJACENT rows, so per-row trip counts
                                  // barely diverge.  Same additions in the same order: bit-identical sums.
 #endif
+#ifndef SBX_ROWSUM_UNROLL
+#define SBX_ROWSUM_UNROLL 4      // unroll factor of the per-row sum loops (loads issued ahead of the dependent adds)
+#endif
 #ifndef SBX_ROWSUM_PER_ROW_CLASSIC
 #define SBX_ROWSUM_PER_ROW_CLASSIC 0   // the same choice for colour_rows of the classic / mixed-radix / multi-kernel paths (two rows per thread)
 #endif
@@ -126,6 +129,7 @@ constexpr uint32_t REAL_MIN_M = 8192, REAL_MAX_M = 32768;   // real transform le
 // sample-table entries whose slot field is 0x7fff (sbx_tables.h: fillers that keep a lane group's taps inside one
 // wavefront) compute a value but store nothing; lanes past the end of the table take the same form
 constexpr uint32_t SAMP_NO_STORE = 0x7fffu << 17;
+constexpr int ROWSUM_UNROLL = SBX_ROWSUM_UNROLL;
 constexpr int THR_STRIDE = 512;  // floats per threshold set: 256 pairs (ts[i], ts[i+1]), ts = [-inf, thr[0..254], +inf]
 
 // ----------------------------------------------------------------------------------------------
@@ -1065,6 +1069,7 @@ __device__ __forceinline__ void colour_rows_single(const float *scratch, const K
         for (int i = 0; i < ROWS; ++i) {
             float sum = 0.0f;
             const float *mi = m[i];
+#pragma unroll ROWSUM_UNROLL
             for (uint32_t s = 0; s < n[i]; ++s) sum = __fadd_rn(sum, mi[s]);
             acc[i] = sum;
         }
@@ -1217,6 +1222,7 @@ __device__ __forceinline__ void pk_colour_rows(const float2 *scratch, const Kern
             for (int i = 0; i < ROWS; ++i) {
                 pk sum = pk_make(0.0f, 0.0f);
                 const float2 *mi = m[i];
+#pragma unroll ROWSUM_UNROLL
                 for (uint32_t s = 0; s < n[i]; ++s) sum = pk_add(sum, pk_ld2(mi + s));
                 acc[i] = sum;
             }
