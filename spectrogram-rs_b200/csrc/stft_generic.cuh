@@ -24,6 +24,9 @@ namespace sbx {
 #define SBX_GENERIC_THREADS 512     // measured on a B200, N = 2400: live p50 43.2 / 40.9 / 40.9 us and batch 12.0 / 12.1 / 8.8 M frames/s at 256 / 512 / 1024
 #endif
 constexpr int GENERIC_THREADS = SBX_GENERIC_THREADS;
+#ifndef SBX_GENERIC_PK_EPILOGUE
+#define SBX_GENERIC_PK_EPILOGUE 0   // 1: resample / row sums on packed (L, R) pairs as in the q2 kernels
+#endif
 constexpr int GENERIC_MAX_PASSES = 12;
 constexpr uint32_t BLUESTEIN_MAX_LEN = 16384;   // Bluestein convolution length L (128 KB of float2 in shared memory)
 
@@ -419,9 +422,16 @@ __global__ void __launch_bounds__(GENERIC_THREADS) generic_frames_kernel(const G
             const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.chunks) + c);
             const RowChunk ck = {raw.x, raw.y, raw.z, raw.w};
             if (c != 0) __syncthreads();
+#if SBX_GENERIC_PK_EPILOGUE
+            // the packed (L, R) epilogue of the q2 kernels: same operations, same roundings (stft_kernels.cuh)
+            pk_resample_samples<GENERIC_THREADS, 4>(mags, z, a, ck);
+            __syncthreads();
+            pk_colour_rows<CH == 1, GENERIC_THREADS, 2>(z, a, ck, frame0, second_valid);
+#else
             resample_samples<GENERIC_THREADS>(mags, z, a, ck);
             __syncthreads();
             colour_rows<CH == 1, GENERIC_THREADS>(z, a.thr, a.lut, a, ck, frame0, second_valid);
+#endif
         }
     }
     if (a.done_flag != nullptr) {                                         // live single frame, see fused_frames_kernel

@@ -107,7 +107,10 @@ struct KernelArgs {
 #define SBX_ROWSUM_PER_ROW_CLASSIC 0   // the same choice for colour_rows of the classic / mixed-radix / multi-kernel paths (two rows per thread)
 #endif
 #ifndef SBX_PK_RESAMPLE
-#define SBX_PK_RESAMPLE 0        // 1: the classic kernels resample / sum rows with packed (L, R) instructions too (pk_resample_colour)
+#define SBX_PK_RESAMPLE 1        // 1: the classic kernels resample / sum rows with packed (L, R) instructions too (pk_resample_colour).
+                                 // Measured on a B200 with the per-row unrolled row sums (M frames/s, 0 -> 1): cfg5 N = 512 / 1024 /
+                                 // 2048 / 4096 at P = 4: 113.3 -> 114.2, 84.0 -> 89.7, 48.7 -> 49.2, 25.0 -> 26.2; stereo N 4096 P 1:
+                                 // 47.6 -> 49.6 (with the round-1 fused row-sum loop it lost, which is why it was off)
 #endif
 #ifndef SBX_STEP_FAST
 #define SBX_STEP_FAST 1          // step_colour: accept the guessed step without the threshold load when it is clear of a boundary
