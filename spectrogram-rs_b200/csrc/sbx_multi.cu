@@ -49,15 +49,37 @@ void frame_block(uint64_t total, uint32_t g, uint32_t G, uint64_t align, uint64_
 }
 
 // runs fn(i) for every plan on its own host thread and returns the first failing status
+template <class F> sbx_status for_each_device_impl(sbx_multi *m, F fn);
 template <class F> sbx_status for_each_device(sbx_multi *m, F fn)
+{
+    try {
+        return for_each_device_impl(m, fn);
+    } catch (...) {                                             // bookkeeping allocations: report, never throw across the C ABI
+        return mfail(m, SBX_ERR_OUT_OF_MEMORY, "out of host memory");
+    }
+}
+template <class F> sbx_status for_each_device_impl(sbx_multi *m, F fn)
 {
     const size_t G = m->plans.size();
     std::vector<sbx_status> st(G, SBX_OK);
     std::vector<std::thread> threads;
     threads.reserve(G);
-    for (size_t i = 1; i < G; ++i) threads.emplace_back([&, i] { st[i] = fn(i); });
-    st[0] = fn(0);                                              // the caller's thread drives device 0
+    std::vector<char> spawned(G, 0);
+    for (size_t i = 1; i < G; ++i) {
+        try {
+            threads.emplace_back([&, i] {
+                try { st[i] = fn(i); } catch (...) { st[i] = SBX_ERR_OUT_OF_MEMORY; }
+            });
+            spawned[i] = 1;
+        } catch (...) {                                         // no thread to be had: nothing may throw across the C ABI
+        }
+    }
+    try { st[0] = fn(0); } catch (...) { st[0] = SBX_ERR_OUT_OF_MEMORY; }      // the caller's thread drives device 0
     for (auto &t : threads) t.join();
+    for (size_t i = 1; i < G; ++i)
+        if (!spawned[i]) {                                      // ... that device's block runs on the caller's thread instead
+            try { st[i] = fn(i); } catch (...) { st[i] = SBX_ERR_OUT_OF_MEMORY; }
+        }
     for (size_t i = 0; i < G; ++i)
         if (st[i] != SBX_OK)
             return mfail(m, st[i], "device " + std::to_string(m->plans[i]->cfg.device) + ": " + sbx_last_error(m->plans[i]));
@@ -79,6 +101,12 @@ SBX_API sbx_status sbx_multi_create(const sbx_config *cfg, const int32_t *device
     sbx_multi *m = new (std::nothrow) sbx_multi();
     if (!m) return mfail(nullptr, SBX_ERR_OUT_OF_MEMORY, "out of host memory");
     DeviceGuard guard;
+    try {
+        m->plans.reserve(n_devices);
+    } catch (...) {
+        delete m;
+        return mfail(nullptr, SBX_ERR_OUT_OF_MEMORY, "out of host memory");
+    }
     m->mono = cfg->channels == 1;
     for (uint32_t i = 0; i < n_devices; ++i) {
         sbx_config c = *cfg;
