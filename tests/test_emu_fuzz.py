@@ -1,6 +1,6 @@
 """CPU: randomised configurations (hypothesis) through the host-emulated kernel phases against the oracle:
 odd hops, hops larger than the window, tiny and huge frequency ranges (indices clamped at both spectrum
-edges), one-row images, both interpolators, both colour schemes, power-of-two / mixed-radix / large paths."""
+edges), one-row images, both interpolators, both colour schemes, power-of-two / mixed-radix / Bluestein / large paths."""
 import numpy as np
 from hypothesis import HealthCheck, given, settings, strategies as st
 
@@ -12,17 +12,21 @@ LUT = signals.lut("magma")
 
 pow2_small = st.sampled_from([256, 512, 1024, 2048])
 generic_n = st.sampled_from([100, 120, 300, 441, 600, 1000, 1470, 2205, 2400])
+bluestein_n = st.sampled_from([22, 94, 347, 551, 1102, 1103, 2731])     # a prime factor > 7 (2731 at P = 2: L = 8192)
 
 
 @st.composite
 def configs(draw):
-    kind = draw(st.sampled_from(["fused", "fused", "generic", "large", "real"]))
+    kind = draw(st.sampled_from(["fused", "fused", "generic", "large", "real", "bluestein"]))
     if kind == "fused":
         n, pad = draw(pow2_small), draw(st.sampled_from([1, 2, 4]))
     elif kind == "real":                 # mono, real transform length 8192 .. 32768: one frame per CTA (even hops)
         n, pad = draw(st.sampled_from([(2048, 4), (4096, 2), (8192, 1), (8192, 2), (4096, 4)]))
     elif kind == "generic":
         n, pad = draw(generic_n), draw(st.sampled_from([2, 4]))
+    elif kind == "bluestein":
+        n = draw(bluestein_n)
+        pad = draw(st.sampled_from([1, 2, 4] if n % 2 == 0 else [2, 4]))     # M = P N must be even
     else:
         n, pad = 8192, 4
     sr = draw(st.sampled_from([8000.0, 22050.0, 44100.0, 48000.0, 96000.0]))
