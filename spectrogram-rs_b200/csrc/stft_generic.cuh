@@ -8,10 +8,11 @@
 // This is the low-rate live path (819 frames/s in the reference), so it trades the fused kernel's
 // swizzles and compile-time index math for generality: bin -> position comes from a host table, twiddles
 // from per-pass planes (contiguous in the butterfly index), divisions by host-computed reciprocals.
-// Measured on a B200, N = 2400 stereo: 24.0 M frames/s in batch, 24.6 us per live frame.  History: 12.0 M / 41 us with
+// Measured on a B200, N = 2400 stereo: 25.4 M frames/s in batch, 24 us per live frame.  History: 12.0 M / 41 us with
 // strided loads from the full W_M table and run-time divisions; 18.5 M / 26.6 us with five prime-radix passes
 // (16*2*3*5*5); 20.6 M with literal-constant 3- and 5-point DFTs; 23.1 M with composite radices 6 / 9 / 10 / 12 / 15
-// in registers (three passes); 24.0 M with the odd radix last (the stride-1 pass conflict-free).  Radices of 20 / 21
+// in registers (three passes); 24.0 M with the odd radix last (the stride-1 pass conflict-free); 25.4 M with pass 0
+// reading the PCM itself (batches only).  Radices of 20 / 21
 // in registers were measured in round 1 and rejected: 128 registers halve the occupancy (12.8 M frames/s).
 // One CTA per frame (stereo) or frame pair (mono); the transform (M float2) and the magnitudes (M/2 float2) live
 // in shared memory: M <= 19370.  Windows with a prime factor > 7 take the Bluestein form further down.
@@ -24,6 +25,9 @@ namespace sbx {
 #define SBX_GENERIC_THREADS 512     // measured on a B200, N = 2400: live p50 43.2 / 40.9 / 40.9 us and batch 12.0 / 12.1 / 8.8 M frames/s at 256 / 512 / 1024
 #endif
 constexpr int GENERIC_THREADS = SBX_GENERIC_THREADS;
+#ifndef SBX_GENERIC_FUSED_FIRST_PASS
+#define SBX_GENERIC_FUSED_FIRST_PASS 1   // pass 0 reads the PCM itself (generic_first_pass) instead of a staged copy
+#endif
 #ifndef SBX_GENERIC_PK_EPILOGUE
 #define SBX_GENERIC_PK_EPILOGUE 0   // 1: resample / row sums on packed (L, R) pairs as in the q2 kernels
 #endif
@@ -263,6 +267,69 @@ __device__ __forceinline__ void generic_pass(float2 *z, const GenericArgs &g, ui
     }
 }
 
+// pass 0 fused with the load: the first radix pass has stride S = N / R_0 over the WHOLE sub-transform, so butterfly lo
+// takes the samples n = lo + r S straight from the PCM (window, and W_M^(n q0) for the sub-transforms q0 > 0, applied
+// on the way) and nothing is staged in shared memory first -- one trip through the buffer and one barrier fewer.  The
+// P sub-transforms of a butterfly re-read its samples (L1 hits), each as a work item of its own: N / R_0 butterflies
+// alone would leave most of the CTA idle (150 at N = 2400).
+template <int R, int CH>
+__device__ __forceinline__ void generic_first_pass(float2 *z, const GenericArgs &g, unsigned long long frame0, bool second_valid)
+{
+    const KernelArgs &a = g.k;
+    const float *pa = a.pcm + frame0 * (unsigned long long)a.hop * CH;
+    const float *pb = pa + a.hop;
+    const uint32_t S = g.stride[0];                                       // = N / R
+    const bool last = g.npass == 1;
+    const float2 *tw = g.twg + g.tw_off[0];
+    for (uint32_t u = threadIdx.x; u < g.pad * S; u += GENERIC_THREADS) {   // one butterfly of one sub-transform per item
+        uint32_t lo;
+        const uint32_t q0 = run_of(u, S, lo);
+        {
+            float2 v[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint32_t n = lo + (uint32_t)r * S;
+                float2 s;
+                if constexpr (CH == 2) {
+                    s = __ldg(reinterpret_cast<const float2 *>(pa) + n);
+                } else {
+                    s.x = __ldg(pa + n);
+                    s.y = second_valid ? __ldg(pb + n) : 0.0f;
+                }
+                const float wn = __ldg(a.window + n);
+                s.x *= wn;  s.y *= wn;                                    // fft.rs:57-63
+                v[r] = q0 == 0 ? s : cmul(s, __ldg(g.twm + n * q0));      // n q0 < N P = M
+            }
+            SmallDft<R>::run(v, g.twm, g.m);
+            float2 *b = z + (size_t)q0 * g.n + lo;
+            b[0] = v[0];
+#pragma unroll
+            for (int q = 1; q < R; ++q)
+                b[(size_t)q * S] = last ? v[q] : cmul(v[q], __ldg(tw + (size_t)(q - 1) * S + lo));
+        }
+    }
+}
+
+template <int CH>
+__device__ __forceinline__ void generic_first_pass_dispatch(float2 *z, const GenericArgs &g, unsigned long long frame0, bool second_valid)
+{
+    switch (g.radix[0]) {
+        case 2: generic_first_pass<2, CH>(z, g, frame0, second_valid); break;
+        case 3: generic_first_pass<3, CH>(z, g, frame0, second_valid); break;
+        case 4: generic_first_pass<4, CH>(z, g, frame0, second_valid); break;
+        case 5: generic_first_pass<5, CH>(z, g, frame0, second_valid); break;
+        case 6: generic_first_pass<6, CH>(z, g, frame0, second_valid); break;
+        case 7: generic_first_pass<7, CH>(z, g, frame0, second_valid); break;
+        case 8: generic_first_pass<8, CH>(z, g, frame0, second_valid); break;
+        case 9: generic_first_pass<9, CH>(z, g, frame0, second_valid); break;
+        case 10: generic_first_pass<10, CH>(z, g, frame0, second_valid); break;
+        case 12: generic_first_pass<12, CH>(z, g, frame0, second_valid); break;
+        case 15: generic_first_pass<15, CH>(z, g, frame0, second_valid); break;
+        case 16: generic_first_pass<16, CH>(z, g, frame0, second_valid); break;
+        default: break;
+    }
+}
+
 __device__ __forceinline__ void generic_pass_dispatch(float2 *z, const GenericArgs &g, uint32_t p)
 {
     const bool last = p + 1 == g.npass;
@@ -378,7 +445,7 @@ __device__ __forceinline__ void generic_split(const float2 *z, float2 *mags, con
 
 #ifndef SBX_EMU
 template <int CH, bool BLUESTEIN = false>
-__global__ void __launch_bounds__(GENERIC_THREADS) generic_frames_kernel(const GenericArgs g)
+__global__ void __launch_bounds__(GENERIC_THREADS, 2) generic_frames_kernel(const GenericArgs g)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *z = reinterpret_cast<float2 *>(smem_raw);                    // [M] ([L] for Bluestein); reused as resample scratch
@@ -386,9 +453,18 @@ __global__ void __launch_bounds__(GENERIC_THREADS) generic_frames_kernel(const G
     const KernelArgs &a = g.k;
     const unsigned long long frame0 = (unsigned long long)blockIdx.x * (CH == 1 ? 2 : 1);
     const bool second_valid = CH == 1 && frame0 + 1 < a.n_frames;
-    if constexpr (BLUESTEIN) bluestein_load<CH>(z, g, frame0, second_valid);
-    else generic_load<CH>(z, g, frame0, second_valid);
-    for (uint32_t p = 0; p < g.npass; ++p) {
+    // A live single frame (done_flag set: the zero-copy graph) reads its window from PINNED HOST memory: every sample
+    // is fetched once and staged (generic_load); batches read device memory and fuse the load into pass 0.
+    // Measured on a B200: batch N = 2400 24.1 -> 25.4, N = 2205 19.4 -> 20.2, N = 4800 11.0 -> 11.7 M frames/s; live p50
+    // 24.4 us staged vs 25.1 us fused.
+    const bool fused_first = !BLUESTEIN && SBX_GENERIC_FUSED_FIRST_PASS && a.done_flag == nullptr;
+    if constexpr (BLUESTEIN) {
+        bluestein_load<CH>(z, g, frame0, second_valid);
+    } else {
+        if (fused_first) generic_first_pass_dispatch<CH>(z, g, frame0, second_valid);
+        else generic_load<CH>(z, g, frame0, second_valid);
+    }
+    for (uint32_t p = fused_first ? 1u : 0u; p < g.npass; ++p) {
         __syncthreads();
         generic_pass_dispatch(z, g, p);
     }

@@ -288,12 +288,14 @@ int emu_generic(const sbx::GenericArgs &g0, unsigned long long frames, float *ma
         std::vector<float2> z(g.m), mags(g.bl_m / 2);
         const bool second_valid = CH == 1 && frame0 + 1 < frames;
         const bool bluestein = g.bl_bf != nullptr;
+        const bool fused_first = !bluestein && SBX_GENERIC_FUSED_FIRST_PASS && (frame0 & 2) == 0;   // both variants get exercised
         for (int t = 0; t < sbx::GENERIC_THREADS; ++t) {
             threadIdx.x = t;
             if (bluestein) sbx::bluestein_load<CH>(z.data(), g, frame0, second_valid);
+            else if (fused_first) sbx::generic_first_pass_dispatch<CH>(z.data(), g, frame0, second_valid);
             else sbx::generic_load<CH>(z.data(), g, frame0, second_valid);
         }
-        for (uint32_t p = 0; p < g.npass; ++p)
+        for (uint32_t p = fused_first ? 1u : 0u; p < g.npass; ++p)
             for (int t = 0; t < sbx::GENERIC_THREADS; ++t) { threadIdx.x = t; sbx::generic_pass_dispatch(z.data(), g, p); }
         if (bluestein) {
             for (int t = 0; t < sbx::GENERIC_THREADS; ++t) { threadIdx.x = t; sbx::bluestein_multiply(z.data(), g); }
