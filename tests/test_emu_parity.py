@@ -354,3 +354,20 @@ def test_bluestein_windows_match_oracle(magma, n, pad, ch, hop, rows, interp):
     assert (rgba != o_rgba).any(axis=2).mean() <= 2e-3
     for f in range(mags.shape[0]):
         assert np.array_equal(rgba[f], oracle.column_from_magnitudes(p, mags[f], magma))
+
+
+@pytest.mark.parametrize("n,pad,rows,sr", LAYOUT_CASES)
+def test_budgeted_fillers_never_add_a_table_round(magma, monkeypatch, n, pad, rows, sr):
+    """SBX_TABLE_FILL=2: fillers are spent only while the chunk's table stays within the rounds of 2048 entries
+    (threads x loads in flight) its real entries need anyway; the real entries are untouched."""
+    cfg = emu.make_config(magma, sample_rate=sr, window_n=n, pad_factor=pad, hop=n // 8, rows_h=rows, channels=1)
+    monkeypatch.setenv("SBX_TABLE_FILL", "0")
+    dense = emu.sample_table(cfg)
+    monkeypatch.setenv("SBX_TABLE_FILL", "2")
+    tab = emu.sample_table(cfg)
+    assert tab["ok"] and len(tab["chunks"]) == len(dense["chunks"])
+    real = (tab["samp"][:, 0] >> 17) != 0x7fff
+    assert np.array_equal(tab["samp"][real], dense["samp"])
+    for (_, _, b, e), (_, _, b0, e0) in zip(tab["chunks"], dense["chunks"]):
+        assert (int(e) - int(b) + 2047) // 2048 == (int(e0) - int(b0) + 2047) // 2048
+        assert int(e) - int(b) >= int(e0) - int(b0)
