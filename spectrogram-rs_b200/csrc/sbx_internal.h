@@ -71,6 +71,7 @@ struct sbx_plan {
     uint32_t *d_pan_lut = nullptr;      // stereo schemes: finer gradient table indexed by pan (sbx_plan_set_pan_gradient), else d_lut
     uint32_t pan_levels = 256;
     std::vector<uint8_t> h_pan_rgb;
+    std::vector<uint32_t *> retired_pan_luts;   // replaced tables, freed with the plan (live graphs may still hold them)
 
     // single-frame staging (host pinned + device)
     float *h_frame = nullptr;           // max(N, K) x 2 floats: N x 2 in, reused for K x 2 out

@@ -356,6 +356,7 @@ SBX_API void sbx_plan_destroy(sbx_plan *p)
     cudaFree(p->d_window); cudaFree(p->d_wtw); cudaFree(p->d_twp); cudaFree(p->d_wq); cudaFree(p->d_wq_real); cudaFree(p->d_rowmap); cudaFree(p->d_rowinfo); cudaFree(p->d_chunks);
     cudaFree(p->d_samp); cudaFree(p->d_f16_scratch); cudaFree(p->d_twm); cudaFree(p->d_bl_a); cudaFree(p->d_bl_bf); cudaFree(p->d_bl_c); cudaFree(p->d_twg); cudaFree(p->d_pos_tab); cudaFree(p->d_twp_block); cudaFree(p->d_zbuf); cudaFree(p->d_magbuf);
     cudaFree(p->d_thr); cudaFree(p->d_lut); cudaFree(p->d_pan_lut); cudaFree(p->d_ctab); cudaFree(p->d_twp_real); cudaFree(p->d_wtw4); cudaFree(p->d_rtw); cudaFree(p->d_cz_in); cudaFree(p->d_cz_out); cudaFree(p->d_frame); cudaFree(p->d_mags1); cudaFree(p->d_col);
+    for (uint32_t *old_table : p->retired_pan_luts) cudaFree(old_table);
     if (p->h_frame) cudaFreeHost(p->h_frame);
     if (p->h_col) cudaFreeHost(p->h_col);
     if (p->large_scratch_free) cudaEventDestroy(p->large_scratch_free);
@@ -717,7 +718,9 @@ SBX_API sbx_status sbx_plan_set_pan_gradient(sbx_plan *p, const uint8_t *rgb, ui
     SBX_CUDA(p, cudaMalloc(&d_new, (size_t)entries * sizeof(uint32_t)));
     const cudaError_t e = cudaMemcpy(d_new, packed.data(), (size_t)entries * sizeof(uint32_t), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(d_new); return cuda_fail(p, e, "pan gradient upload"); }
-    cudaFree(p->d_pan_lut);
+    // a live stream created earlier has captured the previous table's address in its graphs: keep that table alive
+    // until the plan goes (a few KB each), so a late call can make such a stream stale but never dangling
+    if (p->d_pan_lut) p->retired_pan_luts.push_back(p->d_pan_lut);
     p->d_pan_lut = d_new;
     p->pan_levels = entries;
     p->h_pan_rgb.assign(rgb, rgb + (size_t)entries * 3);
