@@ -202,6 +202,8 @@ __global__ void __launch_bounds__(LARGE_THREADS) large_split_kernel(const LargeA
     large_split_emit<LOG2N, LOG2PAD, CH>(la, blockIdx.x, own, par);
 }
 
+#endif  // SBX_EMU (the geometry of the cluster path is host-visible: tests/emu checks its column assignment)
+
 // ---- cluster path: the whole transform of a unit in the distributed shared memory of one thread-block cluster ------
 // M = 32768 .. 131072 (Q = M / 4096 = 8, 16, 32 blocks of 32 KB): a cluster of C = Q / 4 CTAs, four blocks (128 KB) each.
 // The three trips through the global scratch of the four-kernel path (Y out, Y in / Z out, Z in) become
@@ -366,6 +368,7 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) large_cluster_kernel(const
 }
 #endif  // SBX_EMU
 
+#ifndef SBX_EMU
 // grid = (units, row chunks): row chunks are independent, so each CTA resamples and colours one chunk of one
 // unit; mags by bin kk from global memory (magbuf, or a caller's K x (L,R) array shifted by one)
 template <bool PAIR>

@@ -330,6 +330,19 @@ int ilog2(uint32_t v) { int l = 0; while ((1u << l) < v) ++l; return (1u << l) =
 
 }  // namespace
 
+// column -> (owner CTA, slot) assignment of the cluster path (GeomC, stft_large.cuh) for M = 2^log2m: out[3 c] = owner,
+// out[3 c + 1] = slot, out[3 c + 2] = column_of_slot(owner, slot); returns Q (columns), 0 for an unsupported length
+template <int LOG2N, int LOG2PAD> static int cluster_layout_of(int32_t *out)
+{
+    using GC = sbx::GeomC<LOG2N, LOG2PAD>;
+    for (int c = 0; c < GC::Q; ++c) {
+        out[3 * c] = GC::owner_of_column(c);
+        out[3 * c + 1] = GC::slot_of_column(c);
+        out[3 * c + 2] = GC::column_of_slot(GC::owner_of_column(c), GC::slot_of_column(c));
+    }
+    return GC::Q;
+}
+
 extern "C" {
 
 // Whole batch through the emulated kernel.  pcm: n_samples x channels.  Outputs may be NULL.
@@ -472,6 +485,17 @@ int emu_tables(const sbx_config *cfg, float *window, float *f0, float *step, uin
     if (period) *period = t.period;
     if (thr512) memcpy(thr512, t.thr_raw.data(), 512 * sizeof(float));
     return 0;
+}
+
+__attribute__((visibility("default")))
+int emu_cluster_layout(int log2m, int32_t *out)
+{
+    switch (log2m) {
+        case 15: return cluster_layout_of<13, 2>(out);
+        case 16: return cluster_layout_of<14, 2>(out);
+        case 17: return cluster_layout_of<15, 2>(out);
+        default: return 0;
+    }
 }
 
 // the per-sample table, row chunks and row info (n | first slot << 16) of the product, for the CPU test of the

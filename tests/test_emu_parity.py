@@ -371,3 +371,24 @@ def test_budgeted_fillers_never_add_a_table_round(magma, monkeypatch, n, pad, ro
     for (_, _, b, e), (_, _, b0, e0) in zip(tab["chunks"], dense["chunks"]):
         assert (int(e) - int(b) + 2047) // 2048 == (int(e0) - int(b0) + 2047) // 2048
         assert int(e) - int(b) >= int(e0) - int(b0)
+
+
+@pytest.mark.parametrize("log2m", [15, 16, 17])
+def test_cluster_path_column_assignment(log2m):
+    """large_cluster_kernel (stft_large.cuh): the Q = M / 4096 blocks ("columns") of a transform are spread over
+    Q / 4 CTAs, four slots each; the L/R split of bin kk = k Q + c needs column Q - c (0 and Q / 2 pair with themselves),
+    so partners must share a CTA, in adjacent slots (the kernel reads the partner at slot ^ 1)."""
+    import ctypes as C
+    fn = emu.lib().emu_cluster_layout
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int, C.c_void_p]
+    out = np.zeros((64, 3), np.int32)
+    q = fn(log2m, out.ctypes.data)
+    assert q == (1 << log2m) // 4096
+    owner, slot, back = out[:q, 0], out[:q, 1], out[:q, 2]
+    assert np.array_equal(back, np.arange(q))                               # column_of_slot inverts the assignment
+    assert sorted(zip(owner.tolist(), slot.tolist())) == [(j, s) for j in range(q // 4) for s in range(4)]
+    for c in range(q):
+        partner = c if c in (0, q // 2) else q - c
+        assert owner[partner] == owner[c]
+        assert slot[partner] == (slot[c] if partner == c else slot[c] ^ 1)
