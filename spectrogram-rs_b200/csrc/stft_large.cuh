@@ -240,6 +240,107 @@ template <int LOG2N, int LOG2PAD> struct GeomC : GeomL<LOG2N, LOG2PAD> {
     }
 };
 
+// ---- the phases of the cluster kernel as functions of (CTA rank, unit): the kernel below strings them together; the
+// host emulation (tests/emu) runs the same code for every rank and thread id in turn ------------------------------------
+
+// phase A, one thread: its share of the first-pass butterflies; every output goes to store(owner CTA, float2 slot in
+// that CTA's [4][4096] buffer, value)
+template <int LOG2N, int LOG2PAD, int CH, class Store>
+__device__ __forceinline__ void cluster_phase_a(const LargeArgs &la, unsigned int rank, unsigned int unit, Store store)
+{
+    using GC = GeomC<LOG2N, LOG2PAD>;
+    using GL = GeomL<LOG2N, LOG2PAD>;
+    constexpr int R = GL::R0;
+    const KernelArgs &a = la.k;
+    const unsigned long long frame0 = la.frame_base + (unsigned long long)unit * (CH == 1 ? 2 : 1);
+    const bool second_valid = CH == 1 && frame0 + 1 < a.n_frames;
+    const float *pa = a.pcm + frame0 * (unsigned long long)a.hop * CH;
+    const float *pb = pa + a.hop;
+    // BFLY_PER_CTA / CLUSTER_THREADS butterflies of R inputs per thread = 16 inputs in every geometry: all loads
+    // are issued before the first butterfly (one CTA owns the SM here, nothing else hides their latency)
+    constexpr int PER_THREAD = GC::BFLY_PER_CTA / CLUSTER_THREADS;
+    static_assert(PER_THREAD * CLUSTER_THREADS == GC::BFLY_PER_CTA && PER_THREAD * R == 16, "16 inputs per thread");
+    float2 v[PER_THREAD][R];
+#pragma unroll
+    for (int t = 0; t < PER_THREAD; ++t) {
+        const int b = (int)rank * GC::BFLY_PER_CTA + t * CLUSTER_THREADS + (int)threadIdx.x;
+        const int q0 = b >> LARGE_LOG2_BLOCK, lo = b & (LARGE_BLOCK - 1);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int n = lo + r * LARGE_BLOCK;
+            float2 s;
+            if constexpr (CH == 2) {
+                s = __ldg(reinterpret_cast<const float2 *>(pa) + n);
+            } else {
+                s.x = __ldg(pa + n);
+                s.y = second_valid ? __ldg(pb + n) : 0.0f;
+            }
+            // q0 = 0: the plain window (fft.rs:57-63); q0 > 0: window * W_M^(n q0) from one table
+            const float2 w = q0 == 0 ? make_float2(__ldg(a.window + n), 0.0f) : __ldg(a.wtw + (size_t)(q0 - 1) * GL::N + n);
+            v[t][r] = q0 == 0 ? make_float2(s.x * w.x, s.y * w.x) : cmul(s, w);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < PER_THREAD; ++t) {
+        const int b = (int)rank * GC::BFLY_PER_CTA + t * CLUSTER_THREADS + (int)threadIdx.x;
+        const int q0 = b >> LARGE_LOG2_BLOCK, lo = b & (LARGE_BLOCK - 1);
+        Butterfly<R>::run(v[t]);
+        apply_twiddles<R>(v[t], a.twp + lo, LARGE_BLOCK);                     // W_N^(lo q)
+        const unsigned int slot_off = (unsigned int)G12::zsw(lo);
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            const int c = q * GL::PAD + q0;                                   // column of output d0 = q: bins kk = k Q + c
+            const int e = (c == 0 || c == GL::Q / 2) ? 0 : (c < GL::Q / 2 ? c : GL::Q - c);
+            const int slot = ((e & 1) << 1) + (e == 0 ? (c == 0 ? 0 : 1) : (c == e ? 0 : 1));
+            store((unsigned int)(e >> 1), (unsigned int)slot * (unsigned int)LARGE_BLOCK + slot_off, v[t][q]);
+        }
+    }
+}
+
+// phase B, pass P of the four local 4096-point blocks: thread group g = threadIdx.x / 256 owns block g
+template <int P>
+__device__ __forceinline__ void cluster_phase_b(float2 *zb, const LargeArgs &la)
+{
+    KernelArgs ab = la.k;
+    ab.twp = la.twp_block;
+    const int group = threadIdx.x >> 8, tid = threadIdx.x & 255;
+    pass_inplace_t<G12, P>(zb + group * LARGE_BLOCK, ab, tid);
+}
+
+// phase C: local L/R split -> global magnitudes by bin kk
+template <int LOG2N, int LOG2PAD, int CH>
+__device__ __forceinline__ void cluster_phase_c(const float2 *zb, const LargeArgs &la, unsigned int rank, unsigned int unit)
+{
+    using GC = GeomC<LOG2N, LOG2PAD>;
+    using GL = GeomL<LOG2N, LOG2PAD>;
+    const KernelArgs &a = la.k;
+    const unsigned long long frame0 = la.frame_base + (unsigned long long)unit * (CH == 1 ? 2 : 1);
+    const bool second_valid = CH == 1 && frame0 + 1 < a.n_frames;
+    float2 *mag_u = la.magbuf + (size_t)unit * (GL::M / 2);
+    for (int i = threadIdx.x; i < 4 * (LARGE_BLOCK / 2); i += CLUSTER_THREADS) {
+        const int slot = i >> (LARGE_LOG2_BLOCK - 1), k = i & (LARGE_BLOCK / 2 - 1);
+        const int c = GC::column_of_slot((int)rank, slot);
+        const int kk = k * GL::Q + c;
+        if (kk == 0) continue;                                                // DC is dropped (fft.rs:81)
+        const bool self = (c == 0 || c == GL::Q / 2);
+        const int pslot = self ? slot : (slot ^ 1);
+        const int kp = c != 0 ? LARGE_BLOCK - 1 - k : LARGE_BLOCK - k;        // partner index in block Q - c (c = 0: 4096 - k)
+        const float2 own = zb[slot * LARGE_BLOCK + G12::zsw(G12::pos_of_bin(k))];
+        const float2 par = zb[pslot * LARGE_BLOCK + G12::zsw(G12::pos_of_bin(kp))];
+        const float2 m = split_pair(own, par, a.scale);
+        mag_u[kk] = m;
+        if (a.mags_out != nullptr) {
+            float2 *out = reinterpret_cast<float2 *>(a.mags_out) + frame0 * a.k_out + (kk - 1);
+            if constexpr (CH == 1) {
+                out[0] = make_float2(m.x, m.x);
+                if (second_valid) out[a.k_out] = make_float2(m.y, m.y);
+            } else {
+                out[0] = m;
+            }
+        }
+    }
+}
+
 #ifndef SBX_EMU
 __device__ __forceinline__ unsigned int cluster_ctarank()
 {
@@ -268,103 +369,28 @@ template <int LOG2N, int LOG2PAD, int CH>
 __global__ void __launch_bounds__(CLUSTER_THREADS, 1) large_cluster_kernel(const LargeArgs la)
 {
     using GC = GeomC<LOG2N, LOG2PAD>;
-    using GL = GeomL<LOG2N, LOG2PAD>;
-    constexpr int R = GL::R0;
     extern __shared__ __align__(16) unsigned char cluster_smem[];
     float2 *zb = reinterpret_cast<float2 *>(cluster_smem);                    // [4][4096]
-    const KernelArgs &a = la.k;
     const unsigned int rank = cluster_ctarank();
     const unsigned int unit = blockIdx.x / GC::CTAS;
-    const unsigned long long frame0 = la.frame_base + (unsigned long long)unit * (CH == 1 ? 2 : 1);
-    const bool second_valid = CH == 1 && frame0 + 1 < a.n_frames;
 
     // ---- phase A: first-pass butterflies, outputs scattered over the cluster ------------------------------------
-    {
-        const float *pa = a.pcm + frame0 * (unsigned long long)a.hop * CH;
-        const float *pb = pa + a.hop;
-        const unsigned int smem_base = (unsigned int)__cvta_generic_to_shared(zb);
-        // BFLY_PER_CTA / CLUSTER_THREADS butterflies of R inputs per thread = 16 inputs in every geometry: all loads
-        // are issued before the first butterfly (one CTA owns the SM here, nothing else hides their latency)
-        constexpr int PER_THREAD = GC::BFLY_PER_CTA / CLUSTER_THREADS;
-        static_assert(PER_THREAD * CLUSTER_THREADS == GC::BFLY_PER_CTA && PER_THREAD * R == 16, "16 inputs per thread");
-        float2 v[PER_THREAD][R];
-#pragma unroll
-        for (int t = 0; t < PER_THREAD; ++t) {
-            const int b = (int)rank * GC::BFLY_PER_CTA + t * CLUSTER_THREADS + (int)threadIdx.x;
-            const int q0 = b >> LARGE_LOG2_BLOCK, lo = b & (LARGE_BLOCK - 1);
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int n = lo + r * LARGE_BLOCK;
-                float2 s;
-                if constexpr (CH == 2) {
-                    s = __ldg(reinterpret_cast<const float2 *>(pa) + n);
-                } else {
-                    s.x = __ldg(pa + n);
-                    s.y = second_valid ? __ldg(pb + n) : 0.0f;
-                }
-                // q0 = 0: the plain window (fft.rs:57-63); q0 > 0: window * W_M^(n q0) from one table
-                const float2 w = q0 == 0 ? make_float2(__ldg(a.window + n), 0.0f) : __ldg(a.wtw + (size_t)(q0 - 1) * GL::N + n);
-                v[t][r] = q0 == 0 ? make_float2(s.x * w.x, s.y * w.x) : cmul(s, w);
-            }
-        }
-#pragma unroll
-        for (int t = 0; t < PER_THREAD; ++t) {
-            const int b = (int)rank * GC::BFLY_PER_CTA + t * CLUSTER_THREADS + (int)threadIdx.x;
-            const int q0 = b >> LARGE_LOG2_BLOCK, lo = b & (LARGE_BLOCK - 1);
-            Butterfly<R>::run(v[t]);
-            apply_twiddles<R>(v[t], a.twp + lo, LARGE_BLOCK);                 // W_N^(lo q)
-            const unsigned int slot_off = (unsigned int)G12::zsw(lo) * 8u;
-#pragma unroll
-            for (int q = 0; q < R; ++q) {
-                const int c = q * GL::PAD + q0;                               // column of output d0 = q: bins kk = k Q + c
-                const int e = (c == 0 || c == GL::Q / 2) ? 0 : (c < GL::Q / 2 ? c : GL::Q - c);
-                const int slot = ((e & 1) << 1) + (e == 0 ? (c == 0 ? 0 : 1) : (c == e ? 0 : 1));
-                cluster_store(cluster_map(smem_base, (unsigned int)(e >> 1)) + (unsigned int)slot * (LARGE_BLOCK * 8u) + slot_off, v[t][q]);
-            }
-        }
-    }
+    const unsigned int smem_base = (unsigned int)__cvta_generic_to_shared(zb);
+    cluster_phase_a<LOG2N, LOG2PAD, CH>(la, rank, unit, [smem_base](unsigned int owner, unsigned int slot, float2 v) {
+        cluster_store(cluster_map(smem_base, owner) + slot * 8u, v);
+    });
     cluster_sync_all();
 
     // ---- phase B: four local 4096-point blocks, one thread group each -----------------------------------------
-    {
-        KernelArgs ab = a;
-        ab.twp = la.twp_block;
-        const int group = threadIdx.x >> 8, tid = threadIdx.x & 255;
-        float2 *z = zb + group * LARGE_BLOCK;
-        pass_inplace_t<G12, 0>(z, ab, tid);
-        __syncthreads();
-        pass_inplace_t<G12, 1>(z, ab, tid);
-        __syncthreads();
-        pass_inplace_t<G12, 2>(z, ab, tid);
-        __syncthreads();
-    }
+    cluster_phase_b<0>(zb, la);
+    __syncthreads();
+    cluster_phase_b<1>(zb, la);
+    __syncthreads();
+    cluster_phase_b<2>(zb, la);
+    __syncthreads();
 
     // ---- phase C: local L/R split -> global magnitudes by bin kk --------------------------------------------------
-    {
-        float2 *mag_u = la.magbuf + (size_t)unit * (GL::M / 2);
-        for (int i = threadIdx.x; i < 4 * (LARGE_BLOCK / 2); i += CLUSTER_THREADS) {
-            const int slot = i >> (LARGE_LOG2_BLOCK - 1), k = i & (LARGE_BLOCK / 2 - 1);
-            const int c = GC::column_of_slot((int)rank, slot);
-            const int kk = k * GL::Q + c;
-            if (kk == 0) continue;                                            // DC is dropped (fft.rs:81)
-            const bool self = (c == 0 || c == GL::Q / 2);
-            const int pslot = self ? slot : (slot ^ 1);
-            const int kp = c != 0 ? LARGE_BLOCK - 1 - k : LARGE_BLOCK - k;    // partner index in block Q - c (c = 0: 4096 - k)
-            const float2 own = zb[slot * LARGE_BLOCK + G12::zsw(G12::pos_of_bin(k))];
-            const float2 par = zb[pslot * LARGE_BLOCK + G12::zsw(G12::pos_of_bin(kp))];
-            const float2 m = split_pair(own, par, a.scale);
-            mag_u[kk] = m;
-            if (a.mags_out != nullptr) {
-                float2 *out = reinterpret_cast<float2 *>(a.mags_out) + frame0 * a.k_out + (kk - 1);
-                if constexpr (CH == 1) {
-                    out[0] = make_float2(m.x, m.x);
-                    if (second_valid) out[a.k_out] = make_float2(m.y, m.y);
-                } else {
-                    out[0] = m;
-                }
-            }
-        }
-    }
+    cluster_phase_c<LOG2N, LOG2PAD, CH>(zb, la, rank, unit);
 }
 #endif  // SBX_EMU
 

@@ -62,7 +62,7 @@ def make_config(lut_rgb, sample_rate=48000.0, window_n=4096, pad_factor=2, hop=5
     return cfg
 
 
-def batch(cfg, pcm, want_mags=True, want_rgba=True, staged=False, real=None, wide=False, q2=False):
+def batch(cfg, pcm, want_mags=True, want_rgba=True, staged=False, real=None, wide=False, q2=False, cluster=False):
     """staged=True emulates the persistent kernel's pass 0 (PCM span in a stage buffer).
     real: mono batches on the real-sequence geometry (one frame per CTA) -- None: the product's default choice,
     False / True: what SBX_REAL=0 / 1 selects in the product."""
@@ -70,6 +70,7 @@ def batch(cfg, pcm, want_mags=True, want_rgba=True, staged=False, real=None, wid
     lib().emu_set_real(2 if real is None else (1 if real else 0))
     lib().emu_set_q2(1 if q2 else 0)                       # pad factor 2: the packed-lane kernel of stft_q2.cuh
     lib().emu_set_wide(1 if wide else 0)                   # stereo: the WIDE single-frame geometries (more threads per CTA)
+    lib().emu_set_cluster(1 if cluster else 0)             # M = 32768 .. 131072: the cluster kernel's phases (stft_large.cuh)
     pcm = np.ascontiguousarray(pcm, dtype=np.float32)
     n_samples = pcm.shape[0]
     n, hop = cfg.window_n, cfg.hop

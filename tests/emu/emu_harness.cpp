@@ -14,6 +14,7 @@ bool g_emu_staged = false;
 bool g_emu_wide = false;                // stereo frames on the WIDE (single-frame latency) geometries
 bool g_emu_q2 = false;                  // pad factor 2 on the packed-lane kernel of stft_q2.cuh
 std::vector<uint32_t> g_emu_pan_lut;    // stereo schemes: finer pan gradient (sbx_plan_set_pan_gradient), empty = the 256-entry lut
+bool g_emu_cluster = false;             // large path: the cluster kernel's phases instead of the four kernels' (M <= 131072)
 int g_emu_real = 2;                     // mono batches on the REAL geometry: 0 never, 1 wherever its tables exist, 2 the product's default
 
 template <class G, int P, int END = G::NPASS> struct EmuPasses {
@@ -203,6 +204,29 @@ int emu_real(const sbx::KernelArgs &a, unsigned long long frames, float *mags, u
 }
 
 // ---- large path: the four kernels of stft_large.cuh, one block at a time ------------------------------
+// the cluster path (large_cluster_kernel): every CTA rank and thread id in turn through the kernel's own phase functions;
+// the st.shared::cluster scatter of phase A becomes a store into the owning rank's buffer
+template <int LOG2N, int LOG2PAD, int CH>
+void emu_cluster_unit(const sbx::LargeArgs &la)
+{
+    using GL = sbx::GeomL<LOG2N, LOG2PAD>;
+    if constexpr (GL::Q / 4 >= 2 && GL::Q / 4 <= 8) {
+        using GC = sbx::GeomC<LOG2N, LOG2PAD>;
+        std::vector<std::vector<float2>> zb(GC::CTAS, std::vector<float2>(4 * sbx::LARGE_BLOCK));
+        for (unsigned rank = 0; rank < (unsigned)GC::CTAS; ++rank)
+            for (int t = 0; t < sbx::CLUSTER_THREADS; ++t) {
+                threadIdx.x = t;
+                sbx::cluster_phase_a<LOG2N, LOG2PAD, CH>(la, rank, 0u, [&zb](unsigned owner, unsigned slot, float2 v) { zb[owner][slot] = v; });
+            }
+        for (unsigned rank = 0; rank < (unsigned)GC::CTAS; ++rank) {
+            for (int t = 0; t < sbx::CLUSTER_THREADS; ++t) { threadIdx.x = t; sbx::cluster_phase_b<0>(zb[rank].data(), la); }
+            for (int t = 0; t < sbx::CLUSTER_THREADS; ++t) { threadIdx.x = t; sbx::cluster_phase_b<1>(zb[rank].data(), la); }
+            for (int t = 0; t < sbx::CLUSTER_THREADS; ++t) { threadIdx.x = t; sbx::cluster_phase_b<2>(zb[rank].data(), la); }
+            for (int t = 0; t < sbx::CLUSTER_THREADS; ++t) { threadIdx.x = t; sbx::cluster_phase_c<LOG2N, LOG2PAD, CH>(zb[rank].data(), la, rank, 0u); }
+        }
+    }
+}
+
 template <int LOG2N, int LOG2PAD, int CH>
 int emu_large(sbx::LargeArgs la, float *mags_out, uint8_t *rgba)
 {
@@ -217,9 +241,12 @@ int emu_large(sbx::LargeArgs la, float *mags_out, uint8_t *rgba)
     la.units = 1;
     for (unsigned long long u = 0; u < units; ++u) {
         la.frame_base = u * per;
+        const bool cluster = g_emu_cluster && GL::Q / 4 >= 2 && GL::Q / 4 <= 8;
+        if (cluster) emu_cluster_unit<LOG2N, LOG2PAD, CH>(la);
+        else
         for (unsigned b = 0; b < GL::PAD * (sbx::LARGE_BLOCK / sbx::LARGE_THREADS); ++b)
             for (int t = 0; t < sbx::LARGE_THREADS; ++t) { threadIdx.x = t; sbx::large_first<LOG2N, LOG2PAD, CH>(la, b); }
-        for (unsigned b = 0; b < GL::M / sbx::LARGE_BLOCK; ++b) {
+        for (unsigned b = 0; !cluster && b < GL::M / sbx::LARGE_BLOCK; ++b) {
             std::vector<float2> z(sbx::LARGE_BLOCK);
             float2 *blk = la.zbuf + (size_t)b * sbx::LARGE_BLOCK;
             sbx::KernelArgs a = la.k;
@@ -229,7 +256,7 @@ int emu_large(sbx::LargeArgs la, float *mags_out, uint8_t *rgba)
             for (int t = 0; t < sbx::LARGE_THREADS; ++t) { threadIdx.x = t; sbx::pass_inplace<sbx::G12, 2>(z.data(), a); }
             for (int t = 0; t < sbx::LARGE_THREADS; ++t) { threadIdx.x = t; sbx::large_block_store(z.data(), blk); }
         }
-        for (unsigned b = 0; b < (unsigned)GL::Q / 2; ++b) {
+        for (unsigned b = 0; !cluster && b < (unsigned)GL::Q / 2; ++b) {
             std::vector<float2> own(GL::TK * (GL::Q + 1)), par(GL::TK * (GL::Q + 1));
             for (int t = 0; t < sbx::LARGE_THREADS; ++t) { threadIdx.x = t; sbx::large_split_load<LOG2N, LOG2PAD>(la, b, own.data(), par.data()); }
             for (int t = 0; t < sbx::LARGE_THREADS; ++t) { threadIdx.x = t; sbx::large_split_emit<LOG2N, LOG2PAD, CH>(la, b, own.data(), par.data()); }
@@ -461,6 +488,9 @@ void emu_set_wide(int wide) { g_emu_wide = wide != 0; }
 
 __attribute__((visibility("default")))
 void emu_set_q2(int q2) { g_emu_q2 = q2 != 0; }
+
+__attribute__((visibility("default")))
+void emu_set_cluster(int on) { g_emu_cluster = on != 0; }
 
 __attribute__((visibility("default")))
 void emu_set_pan_gradient(const uint8_t *rgb, uint32_t entries)

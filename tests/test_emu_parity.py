@@ -392,3 +392,24 @@ def test_cluster_path_column_assignment(log2m):
         partner = c if c in (0, q // 2) else q - c
         assert owner[partner] == owner[c]
         assert slot[partner] == (slot[c] if partner == c else slot[c] ^ 1)
+
+
+@pytest.mark.parametrize("n,pad,ch,hop,rows,interp", [(16384, 2, 2, 2048, 128, 0), (8192, 4, 2, 1000, 64, 1), (32768, 1, 1, 4095, 64, 0),
+                                                      (16384, 4, 1, 2048, 256, 0), (32768, 4, 2, 4096, 64, 0)])
+def test_cluster_kernel_phases_match_oracle(magma, n, pad, ch, hop, rows, interp):
+    """large_cluster_kernel's own phase functions, every CTA rank and thread id in turn (the st.shared::cluster scatter
+    becomes a store into the owning rank's buffer): against the oracle, and bit-identical to the four-kernel path's
+    phases (same butterflies in the same order; the host build contracts nothing)."""
+    frames = 3
+    ns = n + hop * (frames - 1)
+    lr = signals.stereo_loopback(ns)
+    x = lr if ch == 2 else lr[:, 0].copy()
+    cfg = emu.make_config(magma, window_n=n, pad_factor=pad, hop=hop, rows_h=rows, channels=ch, interp=interp)
+    mags_c, rgba_c = emu.batch(cfg, x, cluster=True, real=False)
+    mags_4, rgba_4 = emu.batch(cfg, x, cluster=False, real=False)
+    assert np.array_equal(mags_c, mags_4) and np.array_equal(rgba_c, rgba_4)
+    p = oracle.params(window_n=n, pad_factor=pad, hop=hop, rows_h=rows, interp=interp)
+    o_rgba, o_mags = oracle.batch(p, x, ch, magma, want_mags=True)
+    err = (np.abs(mags_c - o_mags) / np.abs(o_mags).max(axis=(1, 2), keepdims=True)).max()
+    assert err <= 1e-5, err
+    assert (rgba_c != o_rgba).any(axis=2).mean() <= 2e-3
