@@ -312,6 +312,13 @@ SBX_API sbx_plan  *sbx_multi_plan(sbx_multi *multi, uint32_t index);
  * [sample_lo, sample_hi) including the halo.  Any output pointer may be NULL. */
 SBX_API sbx_status sbx_multi_time_block(const sbx_multi *multi, uint64_t n_samples, uint32_t index, uint64_t *frame_lo,
                                         uint64_t *frame_hi, uint64_t *sample_lo, uint64_t *sample_hi);
+/* The same arithmetic without a handle or a GPU, for callers that run one process per device (MPI, torchrun) and hand
+ * shard `index` of `n_shards` its own block: frames [F*index/n, F*(index+1)/n) of the F frames of the recording,
+ * boundaries rounded down to even frames when channels == 1 (mono plans pair frames 2c, 2c+1), samples
+ * [frame_lo*hop, (frame_hi-1)*hop + N).  Any output pointer may be NULL. */
+SBX_API sbx_status sbx_shard_time_block(uint64_t n_samples, uint32_t window_n, uint32_t hop, uint32_t channels, uint32_t index,
+                                        uint32_t n_shards, uint64_t *frame_lo, uint64_t *frame_hi, uint64_t *sample_lo,
+                                        uint64_t *sample_hi);
 /* sbx_process_batch over all devices, time-block sharded.  pcm / rgba: HOST memory (pinned -- sbx_host_alloc,
  * sbx_host_register -- for copies that overlap; pageable works, slowly). */
 SBX_API sbx_status sbx_multi_process_batch(sbx_multi *multi, const float *pcm, uint64_t n_samples, uint8_t *rgba,

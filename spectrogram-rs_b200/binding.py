@@ -74,6 +74,7 @@ SYMBOLS = {
     "sbx_multi_device_count": (C.c_uint32, [_vp]),
     "sbx_multi_plan": (_vp, [_vp, C.c_uint32]),
     "sbx_multi_time_block": (C.c_int32, [_vp, C.c_uint64, C.c_uint32, _u64p, _u64p, _u64p, _u64p]),
+    "sbx_shard_time_block": (C.c_int32, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _u64p, _u64p, _u64p, _u64p]),
     "sbx_multi_process_batch": (C.c_int32, [_vp, _vp, C.c_uint64, _vp, C.c_uint64, _u64p]),
     "sbx_multi_process_batch_planar": (C.c_int32, [_vp, _vp, C.c_uint32, C.c_uint64, C.c_uint64, _vp, C.c_uint64, _u64p]),
     "sbx_multi_launch_count": (C.c_uint64, [_vp]),

@@ -144,18 +144,30 @@ SBX_API sbx_plan *sbx_multi_plan(sbx_multi *m, uint32_t index)
     return m && index < m->plans.size() ? m->plans[index] : nullptr;
 }
 
+SBX_API sbx_status sbx_shard_time_block(uint64_t n_samples, uint32_t window_n, uint32_t hop, uint32_t channels, uint32_t index,
+                                        uint32_t n_shards, uint64_t *frame_lo, uint64_t *frame_hi, uint64_t *sample_lo,
+                                        uint64_t *sample_hi)
+{
+    if (window_n == 0 || hop == 0 || n_shards == 0 || index >= n_shards || (channels != 1 && channels != 2))
+        return SBX_ERR_INVALID_ARGUMENT;
+    const uint64_t total = n_samples < window_n ? 0 : (n_samples - window_n) / hop + 1;    // audio_transform.rs:37-41
+    if (total >> 56) return SBX_ERR_INVALID_ARGUMENT;
+    uint64_t lo, hi;
+    frame_block(total, index, n_shards, channels == 1 ? 2 : 1, &lo, &hi);
+    if (frame_lo) *frame_lo = lo;
+    if (frame_hi) *frame_hi = hi;
+    if (sample_lo) *sample_lo = lo * hop;
+    if (sample_hi) *sample_hi = hi > lo ? (hi - 1) * hop + window_n : lo * hop;            // includes the N - hop halo
+    return SBX_OK;
+}
+
 SBX_API sbx_status sbx_multi_time_block(const sbx_multi *m, uint64_t n_samples, uint32_t index, uint64_t *frame_lo, uint64_t *frame_hi,
                                         uint64_t *sample_lo, uint64_t *sample_hi)
 {
     if (!m || index >= m->plans.size()) return SBX_ERR_INVALID_ARGUMENT;
     const sbx_plan *p = m->plans[0];
-    uint64_t lo, hi;
-    frame_block(sbx_num_frames(p, n_samples), index, (uint32_t)m->plans.size(), m->mono ? 2 : 1, &lo, &hi);
-    if (frame_lo) *frame_lo = lo;
-    if (frame_hi) *frame_hi = hi;
-    if (sample_lo) *sample_lo = lo * p->hop;
-    if (sample_hi) *sample_hi = hi > lo ? (hi - 1) * p->hop + p->n : lo * p->hop;       // includes the N - hop halo
-    return SBX_OK;
+    return sbx_shard_time_block(n_samples, p->n, p->hop, p->channels, index, (uint32_t)m->plans.size(), frame_lo, frame_hi,
+                                sample_lo, sample_hi);
 }
 
 SBX_API sbx_status sbx_multi_process_batch(sbx_multi *m, const float *pcm, uint64_t n_samples, uint8_t *rgba,

@@ -59,3 +59,16 @@ def max_over_ranks(value, dist=None, device=None):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device or "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def time_block_native(n_samples, window_n, hop, channels, rank, world):
+    """The same block from the C ABI (sbx_shard_time_block: host arithmetic, no GPU needed); channels == 1 aligns the
+    boundaries to even frames like time_blocks(frame_align=2)."""
+    import ctypes as C
+    from . import binding
+    v = [C.c_uint64() for _ in range(4)]
+    st = binding.load().sbx_shard_time_block(n_samples, window_n, hop, channels, rank, world, *[C.byref(x) for x in v])
+    if st != binding.SBX_OK:
+        raise ValueError(f"sbx_shard_time_block: status {st}")
+    lo, hi, s_lo, s_hi = (int(x.value) for x in v)
+    return TimeBlock(rank, lo, hi, s_lo, s_hi)

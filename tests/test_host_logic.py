@@ -165,3 +165,21 @@ def test_world_size_2_gloo_time_block_sharding(tmp_path):
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "SHARD_OK 2 42" in out.stdout
+
+
+def test_native_time_blocks_equal_sharding_py(sbx):
+    """sbx_shard_time_block (C ABI, no GPU needed) == sharding.time_blocks, over a randomised sweep incl. recordings
+    shorter than a window, one-frame recordings and more shards than frames."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.integers(0, 10 ** 7), st.integers(1, 70000), st.integers(1, 70000), st.sampled_from([1, 2]), st.integers(1, 16))
+    def check(n_samples, window_n, hop, channels, world):
+        blocks = sbx.sharding.time_blocks(n_samples, window_n, hop, world, frame_align=2 if channels == 1 else 1)
+        for b in blocks:
+            assert sbx.sharding.time_block_native(n_samples, window_n, hop, channels, b.rank, world) == b
+    check()
+    with pytest.raises(ValueError):
+        sbx.sharding.time_block_native(1000, 256, 64, 1, 3, 3)              # index out of range
+    with pytest.raises(ValueError):
+        sbx.sharding.time_block_native(1000, 256, 0, 1, 0, 2)               # hop 0
